@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — PairHMM throughput (GCUPS) of the B200 engine on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--regions R]
+
+One "step" = one pass of the hot path (quality capping + PCR-indel model, forward recurrence, FP64 recompute, and in the
+end-to-end leg packing, H2D, D2H and the host epilogue) over one batch of synthetic active regions:
+BASELINE.json configs[1], 150 bp reads x 300 bp haplotypes, 8 haplotypes and 64 reads per region, R regions per GPU
+(default 4096 = 94.4 G cells per GPU per step; raw inputs + packed rows + outputs ~ 270 MB > the 126 MB L2).
+Multi-GPU (torchrun, one rank per GPU): regions are independent, every rank runs its own R regions through its own
+engine, no data-path collective ("scaling": "weak"); torch.distributed is used for the barrier and the max-over-ranks.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the engine's stream) with inputs resident in HBM;
+`e2e` is the same metric through the public host-buffer call (phmm_run_flat) with pack/H2D/D2H/epilogue in the timed region.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "PairHMM GCUPS"
+FP32_INSTR_PER_CELL = 8            # 4 FMUL + 4 FFMA, SURVEY.md §8d
+FLOP_PER_CELL = 12                 # 8 mul + 4 add
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": statistics.median(busy), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def visible_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [x for x in vis.split(",") if x != ""]
+        if local_rank < len(ids):
+            return ids[local_rank]
+    return str(local_rank)
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+def cpu_reference_run(batch, n_threads, steps=1, warmup=0):
+    """The reference's own CPU PairHMM (oracle/_ref: its kernels + call_pairhmm wrapper compiled in place) over `batch` with
+    n_threads host threads; falls back to the scalar port (oracle/phmm_oracle.c) where oracle/_ref cannot run.
+    -> (kind, [seconds per step], isa)"""
+    from oracle import bindings as ob
+    ref = ob.ref()
+    times = []
+    if ref is not None:
+        isa = "avx512 (call_new_pairhmm002)" if ref.avx512 else "avx2 (call_old_pairhmm)"
+        for it in range(warmup + steps):
+            secs, _ = ref.bench_regions(batch, n_threads)
+            if it >= warmup:
+                times.append(secs)
+        return "reference", times, isa
+    from concurrent.futures import ThreadPoolExecutor
+    orc = ob.oracle()
+    regs = [batch.region(g) for g in range(batch.n_regions)]
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(n_threads) as ex:
+            list(ex.map(lambda rh: orc.region(rh[0], rh[1]), regs))
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return "port", times, "scalar C restatement"
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from rovaca_b200 import workloads
+    cores = host_threads()
+    n_regions = min(args.regions, max(64, 96 * cores))
+    batch = workloads.cfg2(n_regions, seed=2)
+    kind, times, isa = cpu_reference_run(batch, cores, args.steps, args.warmup)
+    t = max(statistics.mean(times), 1e-9)
+    gcups = batch.cells() / t / 1e9
+    sample = f"{n_regions} of {args.regions} cfg2 regions per step ({batch.cells() / 1e9:.1f} G cells), {isa}, whole regions per thread"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(gcups, 3), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cfg2: 150bp reads x 300bp haplotypes, 8 haps x 64 reads per region", "regions_per_step": n_regions,
+                   "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18},
+        "cpu_baseline": {"value": round(gcups, 3), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(gcups, 3), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def ours_arm(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    from rovaca_b200 import PairHmmEngine, workloads, sharding
+    from rovaca_b200.pairhmm import FlatResult
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K, W = args.steps, max(args.warmup, 0)
+    batch = workloads.cfg2(args.regions, seed=2 + rank)       # every rank its own regions: weak scaling
+    cells = batch.cells()
+    eng = PairHmmEngine(device=local_rank)
+    sampler = ClockSampler(visible_gpu_index(local_rank)) if rank == 0 else None
+
+    # ---- leg 1: device path only, inputs resident in HBM -----------------------------------------
+    resident = eng.upload(batch)
+    for _ in range(W):
+        resident.run()
+    st0 = eng.stats()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    all_ms, fwd_ms = [], []
+    for _ in range(K):
+        a, f = resident.run()
+        all_ms.append(a)
+        fwd_ms.append(f)
+    torch.cuda.synchronize()
+    sharding.barrier()
+    wall_dev = (time.perf_counter() - t0) / K
+    st1 = eng.stats()
+    launches = int(st1["kernel_launches"] - st0["kernel_launches"])
+    ms_step = sharding.max_over_ranks(sum(all_ms) / K)
+    fwd_step = sharding.max_over_ranks(sum(fwd_ms) / K)
+    total_cells = sharding.sum_over_ranks(float(cells))
+    value = total_cells / (ms_step * 1e-3) / 1e9
+    check = resident.download()
+    resident.free()
+
+    # ---- leg 2: end to end through the host-buffer call ------------------------------------------
+    out = FlatResult(batch)
+    for _ in range(max(1, min(W, 2))):
+        eng.run_flat(batch, out=out)
+    st2 = eng.stats()
+    sharding.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        eng.run_flat(batch, out=out)
+    torch.cuda.synchronize()
+    e2e_s = sharding.max_over_ranks((time.perf_counter() - t0) / K)
+    st3 = eng.stats()
+    e2e = total_cells / e2e_s / 1e9
+    same = bool(np.array_equal(out.likelihoods.view(np.uint64), check.likelihoods.view(np.uint64)))
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        eng.close()
+        return
+    # ---- roofline of the dominant kernel (forward wavefront) -------------------------------------
+    prop = torch.cuda.get_device_properties(local_rank)
+    peaks = measured_peaks()
+    sm_max = float(peaks.get("sm_max_mhz", (clocks or {}).get("sm_max_mhz", 1965.0)))
+    n_sm = prop.multi_processor_count
+    peak_tflops = 2 * 128 * n_sm * sm_max * 1e6 / 1e12                       # FP32 FMA peak at the max SM clock
+    achieved = cells * FP32_INSTR_PER_CELL * 2 / (fwd_step * 1e-3) / 1e12    # FMA-slot equivalents (8 FP32 instr/cell)
+    _, ffma = eng.ubench(0)
+    _, ffma2 = eng.ubench(1)
+    measured_peak = max(ffma, ffma2) * 2 / 1e12
+    regs, spill = eng.kernel_info(5)
+    roof = {"bound": "fp32", "achieved": round(achieved, 3), "peak": round(peak_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / peak_tflops, 4),
+            "traffic": None, "kernel": "phmm_fwd_kernel<RPT=5> (forward wavefront, cfg2 reads)",
+            "peak_source": f"2 x 128 lanes x {n_sm} SMs x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); no FP32 figure in that file",
+            "work_model": "8 FP32-pipe instructions per cell (4 FMUL + 4 FFMA) counted as FMA slots = 16 flop-equivalents; plain 12 flop/cell also given",
+            "fwd_kernel_ms": round(fwd_step, 3), "tcups": round(cells / (fwd_step * 1e-3) / 1e12, 4),
+            "plain_flop_tflops": round(cells * FLOP_PER_CELL / (fwd_step * 1e-3) / 1e12, 3),
+            "measured_ffma_peak_tflops": round(measured_peak, 3), "frac_of_measured_peak": round(achieved / measured_peak, 4),
+            "ubench_tflops": {"ffma": round(ffma * 2 / 1e12, 2), "ffma2": round(ffma2 * 2 / 1e12, 2)},
+            "regs_per_thread": regs, "spill_bytes": spill}
+    if clocks:
+        roof["frac_at_observed_clock"] = round(achieved / (2 * 128 * n_sm * clocks["sm_mhz"] * 1e6 / 1e12), 4)
+
+    # ---- CPU baseline beside it (N = 1 only) -----------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_threads()
+        n_cpu = min(args.regions, max(64, 128 * cores))
+        sample_batch = batch.subset(range(n_cpu)) if n_cpu < batch.n_regions else batch
+        kind, times, isa = cpu_reference_run(sample_batch, cores, 1, 0)
+        cpu = {"value": round(sample_batch.cells() / times[0] / 1e9, 3), "unit": "GCUPS", "cores": cores, "kind": kind,
+               "sample": f"first {n_cpu} of {args.regions} regions ({sample_batch.cells() / 1e9:.1f} G cells), {isa}, {times[0]:.2f} s wall"}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": "GCUPS", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "cfg2: 150bp reads x 300bp haplotypes, 8 haps x 64 reads per region (BASELINE.json configs[1])",
+                   "regions_per_gpu": args.regions, "cells_per_gpu_per_step": cells, "pairs_per_gpu_per_step": batch.pairs(),
+                   "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18, "fma_mode": "avx512-contracted",
+                   "l2_policy": "inputs larger than L2: ~270 MB touched per step (raw reads, packed rows, outputs) vs 126 MB L2",
+                   "parallelism": f"regions sharded over {world} GPU(s), no collective"},
+        "e2e": {"value": round(e2e, 2), "unit": "GCUPS", "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / K),
+                "d2h_bytes_per_step": int((st3["d2h_bytes"] - st2["d2h_bytes"]) / K), "ms_per_step": round(e2e_s * 1e3, 3),
+                "api": "phmm_run_flat (host buffers in, host likelihood matrices out)", "matches_resident_run": same},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "device_step_wall_ms": round(wall_dev * 1e3, 3),
+        "fp64_pairs_per_step": int((st1["fp64_pairs"] - st0["fp64_pairs"])),
+        "gpu": prop.name,
+    }
+    print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--regions", type=int, default=4096, help="cfg2 regions per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        print(f"bench.py: --gpus {args.gpus} needs torchrun (one rank per GPU); running 1 GPU", file=sys.stderr)
+    ours_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,189 @@
+/*
+ * phmm_b200.h — C ABI of the B200-native PairHMM likelihood engine (drop-in for Rovaca's call_pairhmm).
+ *
+ * Every entry point cites the reference interface it replaces; paths are relative to
+ * /root/reference/src/haplotypecaller/.  The library is libphmm_b200.so (rovaca_b200/); it needs an
+ * NVIDIA GPU of compute capability 10.0 (sm_100a) and has NO CPU fallback: without a device every
+ * call fails with PHMM_ERR_CUDA and phmm_last_error() says why.
+ *
+ * Results are bit-identical to the reference's CPU path on the same inputs: the raw forward sums
+ * match rovaca/avx_512_float.cc / core/avx512_s.cpp (or core/avx2_s.cpp with PHMM_FMA_NONE) and the
+ * post-processed matrix matches call_old_pairhmm / call_new_pairhmm002 byte for byte, including
+ * the NaN tail and the set of filtered reads.
+ */
+#ifndef PHMM_B200_H_
+#define PHMM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHMM_OK 0
+#define PHMM_ERR_ARG (-1)      /* bad argument */
+#define PHMM_ERR_CUDA (-2)     /* CUDA runtime / no usable device */
+#define PHMM_ERR_MEM (-3)      /* host or device allocation failed */
+#define PHMM_ERR_STATE (-4)    /* unknown ticket, engine shut down */
+
+/* PcrIndelModel — common/enum.h:8 (same numeric values). */
+#define PHMM_PCR_NONE 0
+#define PHMM_PCR_HOSTILE 1
+#define PHMM_PCR_AGGRESSIVE 2
+#define PHMM_PCR_CONSERVATIVE 3
+
+/* Which compiled flavour of the reference's FP32 kernel to reproduce bit for bit:
+ * the FMA-contracted AVX-512 translation units (what init_pairhmm_ptr binds on an AVX-512 host,
+ * pairhmm/pairhmm_engine.cpp:37-52) or the un-contracted AVX2 one (core/avx2_s.cpp). */
+#define PHMM_FMA_DEFAULT 0   /* = PHMM_FMA_AVX512 */
+#define PHMM_FMA_AVX512 1
+#define PHMM_FMA_NONE 2
+
+typedef struct phmm_engine phmm_engine;
+
+/* Replaces: PairhmmArgument (haplotypecaller_args.h:35-39) + the one-time binding done by
+ * rovaca::init_pairhmm_ptr (pairhmm/pairhmm_engine.cpp:21-53).  Zero-initialise for defaults. */
+typedef struct phmm_config
+{
+    int32_t device;               /* CUDA ordinal; -1 = current device */
+    int32_t fma_mode;             /* PHMM_FMA_* (0 = the AVX-512 flavour) */
+    uint32_t n_workers;           /* host worker threads = batches in flight (0 = 4) */
+    uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 12e9) */
+    uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
+    uint32_t rsv[9];
+} phmm_config;
+
+/* What the path reads of a ReadRecord (genotype/read_record.h:67-103, read_record.cpp:176-210). */
+typedef struct phmm_read
+{
+    const uint8_t* bases;         /* ASCII, decode_base() */
+    const uint8_t* qual;          /* raw phred, qual() / decode_qual() */
+    const uint8_t* ins;           /* insertion GOP; NULL = 45 ('-'), ins_gops() */
+    const uint8_t* del;           /* deletion GOP; NULL = the PCR-adjusted insertion array, as the
+                                     reference aliases it (pairhmm/pairhmm_internal.cpp:425,559) */
+    const uint8_t* gcp;           /* gap continuation; NULL = 10 ('+'-33), gap_conts() */
+    uint32_t len;                 /* seq_length() */
+    uint8_t mapq;                 /* mapping_quality() */
+} phmm_read;
+
+/* What the path reads of a Haplotype (genotype/allele.h:104,107): get_display_string(), length(). */
+typedef struct phmm_hap
+{
+    const uint8_t* bases;
+    uint32_t len;
+} phmm_hap;
+
+/* One call of rovaca::call_pairhmm(hs, rs, min_quality_threshold, pcr_option, pool)
+ * (pairhmm/pairhmm_engine.h:14-15). */
+typedef struct phmm_region
+{
+    const phmm_read* reads;
+    uint32_t n_reads;
+    const phmm_hap* haps;
+    uint32_t n_haps;
+    int32_t min_quality_threshold;    /* -Q, default 18 (rovaca_tool_args.h:194) */
+    int32_t pcr_model;                /* PHMM_PCR_*, default CONSERVATIVE (rovaca_tool_args.h:199) */
+} phmm_region;
+
+/* The DoubleVector2D call_pairhmm returns + its side effect on `rs`, in caller-owned memory
+ * (the adapter builds the pmr vectors from it). */
+typedef struct phmm_result
+{
+    double* likelihoods;   /* [n_haps][n_reads] row-major.  First n_kept columns of each row valid,
+                              tail columns NaN (pairhmm_internal.cpp:516,589-591) */
+    uint32_t* kept_idx;    /* [n_reads]: original indices of the reads filter_poorly_modelled_evidence
+                              (pairhmm_internal.cpp:161-182) left in `rs`, in order */
+    uint32_t n_kept;       /* out */
+    float* raw_f32;        /* optional [n_reads][n_haps]: raw forward sums (dump-level parity) */
+    double* raw_f64;       /* optional [n_reads][n_haps]: FP64 recompute, NaN where not taken */
+    uint32_t n_fp64;       /* out: pairs that took the FP64 branch (pairhmm_internal.cpp:578) */
+} phmm_result;
+
+/* Many regions at once, flat arrays (what a batching caller / the bench hands over).  Region g owns
+ * reads [reg_read_off[g], reg_read_off[g+1]) and haplotypes [reg_hap_off[g], reg_hap_off[g+1]);
+ * read k has its bytes at read_bases + read_off[k] (same offset in every read blob). */
+typedef struct phmm_flat_batch
+{
+    uint32_t n_regions;
+    const uint64_t* reg_read_off;     /* [n_regions + 1] */
+    const uint64_t* reg_hap_off;      /* [n_regions + 1] */
+    const uint32_t* read_len;
+    const uint8_t* read_mapq;
+    const uint64_t* read_off;
+    const uint8_t* read_bases;
+    const uint8_t* read_qual;
+    const uint8_t* read_ins;          /* NULL = default */
+    const uint8_t* read_del;          /* NULL = alias */
+    const uint8_t* read_gcp;          /* NULL = default */
+    const uint32_t* hap_len;
+    const uint64_t* hap_off;
+    const uint8_t* hap_bases;
+    int32_t min_quality_threshold;
+    int32_t pcr_model;
+} phmm_flat_batch;
+
+/* Region g writes its [n_haps][n_reads] matrix at likelihoods + lik_off[g] (lik_off[g] = sum over
+ * earlier regions of n_haps*n_reads), its kept indices at kept_idx + reg_read_off[g]. */
+typedef struct phmm_flat_result
+{
+    double* likelihoods;
+    const uint64_t* lik_off;          /* [n_regions + 1] */
+    uint32_t* kept_idx;               /* [total reads] */
+    uint32_t* n_kept;                 /* [n_regions] */
+    float* raw_f32;                   /* optional, [read][hap] per region at lik_off[g] */
+    double* raw_f64;                  /* optional */
+    uint64_t n_fp64;                  /* out */
+} phmm_flat_result;
+
+typedef struct phmm_stats
+{
+    uint64_t regions, pairs, cells;   /* processed so far */
+    uint64_t fp64_pairs;              /* pairs recomputed in FP64 */
+    uint64_t slow_pairs;              /* pairs outside the wavefront kernel's envelope (per-pair kernel) */
+    uint64_t h2d_bytes, d2h_bytes;
+    uint64_t batches;
+    double gpu_ms;                    /* sum of per-batch device time (CUDA events, kernels only) */
+    uint64_t kernel_launches;
+} phmm_stats;
+
+/* Replaces rovaca::init_pairhmm_ptr (pairhmm/pairhmm_engine.cpp:21): builds the libm tables of
+ * core/context.h:13-190 on the host, uploads them, starts the workers. */
+int phmm_create(const phmm_config* cfg, phmm_engine** out);
+void phmm_destroy(phmm_engine* e);
+
+/* Replaces one synchronous rovaca::call_pairhmm call (haplotypecaller_engine.cpp:250).
+ * = phmm_submit + phmm_wait.  Thread-safe; efficient only when many callers are in flight. */
+int phmm_call_region(phmm_engine* e, const phmm_region* region, phmm_result* result);
+
+/* Asynchronous form of the same call, so that the caller's region loop
+ * (haplotypecaller_engine.cpp:145-284) can keep the GPU full: inputs and `result` must stay valid
+ * until phmm_wait(ticket) returns. */
+int phmm_submit(phmm_engine* e, const phmm_region* region, phmm_result* result, uint64_t* ticket);
+int phmm_wait(phmm_engine* e, uint64_t ticket);
+int phmm_flush(phmm_engine* e);
+
+/* A whole stream of regions in one call, pipelined over the workers (bench / batch callers). */
+int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* batch, phmm_flat_result* result);
+
+/* Device-resident form for kernel-only timing: upload once, run the device path (prep + forward +
+ * FP64 recompute kernels, no host<->device copies) any number of times, download when wanted. */
+typedef struct phmm_resident phmm_resident;
+int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* batch, phmm_resident** out);
+int phmm_resident_run(phmm_engine* e, phmm_resident* r, float* gpu_ms, float* fwd_ms);
+int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* result);
+void phmm_resident_free(phmm_engine* e, phmm_resident* r);
+uint32_t phmm_resident_launches(const phmm_resident* r);   /* kernels one phmm_resident_run launches */
+
+int phmm_get_stats(phmm_engine* e, phmm_stats* out);
+/* Static facts about a forward-kernel instantiation (registers, spill bytes) for reports. */
+int phmm_kernel_info(int rpt, int fma_mode, int* regs, int* local_bytes);
+/* Measured FP32 rate of this GPU (issue-rate micro-benchmark: mode 0 scalar FFMA, 1 packed FFMA2, 2 FFMA2 + select,
+ * 3 + shuffle) in FMA lane-operations per second — the empirical denominator of the FP32 roofline. */
+int phmm_ubench(phmm_engine* e, int mode, uint32_t iters, float* ms, double* fma_per_s);
+const char* phmm_last_error(void);   /* thread-local */
+const char* phmm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1080 @@
+// phmm_engine.cpp — host side of the B200 PairHMM engine and its C ABI (include/phmm_b200.h).
+//
+// Mirrors what the reference's host wrapper does around its kernels (pairhmm/pairhmm_internal.cpp
+// call_old_pairhmm :505-594 / call_new_pairhmm002 :596-753), re-cut for a GPU:
+//   * regions from many callers are gathered into batches (the reference runs one region per call on
+//     a pool thread, haplotypecaller_engine.cpp:119,250 — far too little work for a B200);
+//   * per batch the host only *plans*: reads are binned by length (rows per lane), each region's
+//     haplotypes are dealt into two balanced column streams, CTAs of PHMM_WARPS same-bin reads are
+//     formed; the bytes (bases, quals, haplotypes) are gathered into one pinned arena and shipped
+//     with a single H2D copy;
+//   * quality capping, the PCR-indel model, the table look-ups, the forward recurrence and the FP64
+//     underflow recompute all run on the device (phmm_kernels.cu);
+//   * the raw sums come back and the host finishes exactly as the reference does: log10f/log10 with
+//     glibc (so the bits match, pairhmm_internal.cpp:578-584), normalize_likelihoods (:53-63),
+//     filter_poorly_modelled_evidence (:161-182), transpose into the NaN-initialised matrix (:184-193).
+// There is no CPU implementation of the recurrence in this library and no fallback.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+#include <xmmintrin.h>
+
+#include <cuda_runtime.h>
+
+#include "../../include/phmm_b200.h"
+#include "phmm_kernels.h"
+#include "phmm_types.h"
+
+void phmm_build_tables(PhmmTables* t);
+
+namespace
+{
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                          \
+    do {                                                                                                  \
+        cudaError_t _e = (call);                                                                          \
+        if (_e != cudaSuccess)                                                                            \
+            return fail(PHMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+constexpr uint32_t kTargetStreamCols = 5900;    // per stream and chunk: 4 CTAs/SM worth of shared memory
+constexpr uint32_t kMaxStreamCols = 24000;      // hard limit of one haplotype in the wavefront kernel (192 KB)
+constexpr uint32_t kPairThreads = 148 * 2 * 128;
+constexpr float kMinAccepted = 1e-28f;                     // MIN_ACCEPTED, rovaca/common.h:9
+constexpr float kLog10InitF = 36.1236000061f;              // LOG10_INITIAL_CONSTANT_F, adapter.h:25
+constexpr double kLog10InitD = 307.050595577260822;        // LOG10_INITIAL_CONSTANT_D, adapter.h:26
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct RegionIn
+{
+    const phmm_read* reads;
+    uint32_t n_reads;
+    const phmm_hap* haps;
+    uint32_t n_haps;
+    int32_t thr;
+    int32_t pcr;
+    phmm_result out;        // caller buffers
+    uint32_t* n_kept_out;   // where to store n_kept
+    uint64_t* n_fp64_out;   // accumulates (may be null)
+    uint32_t* n_fp64_out32; // per-region (may be null)
+};
+
+struct RegionPlan
+{
+    uint32_t read_begin, n_reads, hap_begin, n_haps;
+    uint64_t out_off;
+};
+
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PHMM_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cap = want;
+        return PHMM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return PHMM_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        cap = want;
+        return PHMM_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct FwdLaunch
+{
+    int bin;
+    uint32_t cta_base, n_ctas;
+    size_t smem;
+};
+
+// One batch in flight: its plan, its pinned staging, its device memory, its stream.
+struct Slot
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // kernels begin, forward begin, forward end, kernels end
+    HostBuf h_in, h_f32, h_f64, h_cnt;
+    DevBuf d_in, d_words, d_f32, d_f64, d_pairs, d_cnt, d_scr64, d_scr32;
+    PhmmBatchDev dev{};
+    std::vector<RegionPlan> regions;
+    std::vector<FwdLaunch> launches;
+    std::vector<uint32_t> read_len;      // per read (for the filter)
+    size_t in_bytes = 0;
+    uint64_t n_pairs = 0, n_cells = 0, n_words = 0;
+    uint32_t n_reads = 0, n_haps = 0, n_slow = 0, max_cols = 0;
+    uint32_t n_launches = 0;
+    float gpu_ms = 0.f, fwd_ms = 0.f;
+
+    int init()
+    {
+        CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& e : ev) CU(cudaEventCreate(&e));
+        return PHMM_OK;
+    }
+    void destroy()
+    {
+        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt}) b->release();
+        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32}) b->release();
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+    }
+};
+
+struct Stats
+{
+    std::atomic<uint64_t> regions{0}, pairs{0}, cells{0}, fp64_pairs{0}, slow_pairs{0}, h2d{0}, d2h{0}, batches{0}, launches{0};
+    std::mutex m;
+    double gpu_ms = 0.0;
+};
+
+int bin_of(uint32_t len)
+{
+    if (len == 0) return -1;
+    for (int b = 0; b < kPhmmNumBins; ++b)
+        if (len <= phmm_bin_capacity(b)) return b;
+    return -1;
+}
+
+}  // namespace
+
+struct phmm_resident
+{
+    Slot slot;
+    std::vector<RegionIn> regs;
+    std::vector<phmm_read> reads;
+    std::vector<phmm_hap> haps;
+};
+
+struct phmm_engine
+{
+    int device = 0;
+    bool fma = true;
+    uint32_t n_workers = 4;
+    uint64_t batch_cells = 12000000000ull;
+    uint32_t linger_us = 200;
+    DevBuf d_tables;
+    Stats stats;
+
+    // workers + job queue
+    std::vector<std::thread> workers;
+    std::vector<std::unique_ptr<Slot>> slots;
+    std::mutex qm;
+    std::condition_variable qcv;
+    std::deque<std::function<void(Slot&)>> jobs;
+    bool stopping = false;
+
+    // region (ticket) API
+    struct OpenBatch
+    {
+        uint64_t id = 0;
+        std::vector<RegionIn> regs;
+        uint64_t cells = 0;
+        std::chrono::steady_clock::time_point first;
+    };
+    struct Done
+    {
+        bool done = false;
+        int rc = PHMM_OK;
+        uint32_t waits = 0;     // regions submitted under this ticket that have not been waited for yet
+        std::string err;
+    };
+    std::mutex bm;
+    std::condition_variable bcv;
+    OpenBatch open;
+    uint64_t next_batch_id = 1;
+    std::unordered_map<uint64_t, Done> batch_state;
+
+    int plan(Slot& s, const std::vector<RegionIn>& regs);
+    int launch(Slot& s, bool copy_in);
+    int finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out);
+    int execute(Slot& s, const std::vector<RegionIn>& regs);
+    void worker_main(uint32_t idx);
+    void enqueue(std::function<void(Slot&)> fn);
+    void seal_locked();
+};
+
+// ------------------------------------------------------------------------------------------------
+// Planning + packing
+// ------------------------------------------------------------------------------------------------
+
+int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
+{
+    uint64_t n_reads = 0, n_haps = 0, read_bytes = 0, hap_bytes = 0, n_pairs = 0, n_cells = 0;
+    bool any_ins = false, any_del = false, any_gcp = false;
+    for (const RegionIn& r : regs) {
+        if (r.n_reads == 0 || r.n_haps == 0) continue;           // pairhmm_internal.cpp:508-510
+        uint64_t rb = 0, hb = 0;
+        for (uint32_t k = 0; k < r.n_reads; ++k) {
+            rb += r.reads[k].len;
+            any_ins |= r.reads[k].ins != nullptr;
+            any_del |= r.reads[k].del != nullptr;
+            any_gcp |= r.reads[k].gcp != nullptr;
+        }
+        for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
+        n_reads += r.n_reads;
+        n_haps += r.n_haps;
+        read_bytes += rb;
+        hap_bytes += hb;
+        n_pairs += (uint64_t)r.n_reads * r.n_haps;
+        n_cells += rb * hb;
+    }
+    if (n_pairs >= (1ull << 31) || read_bytes >= (1ull << 31) || hap_bytes >= (1ull << 31))
+        return fail(PHMM_ERR_ARG, "batch too large for 32-bit device offsets; lower batch_cells");
+
+    std::vector<PhmmRead> reads;
+    std::vector<PhmmHap> haps;
+    std::vector<PhmmChunk> chunks;
+    std::vector<PhmmPair> slow;
+    reads.reserve(n_reads);
+    haps.reserve(n_haps);
+    s.regions.clear();
+    s.regions.reserve(regs.size());
+    s.read_len.clear();
+    s.read_len.reserve(n_reads);
+    // per bin: (chunk, reads...) groups
+    struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first; uint32_t n; };
+    std::vector<std::vector<Group>> groups(kPhmmNumBins);
+    std::vector<std::vector<uint32_t>> group_reads(kPhmmNumBins);
+    std::vector<uint32_t> order, region_chunks;
+    std::vector<std::vector<uint32_t>> by_bin(kPhmmNumBins);
+
+    uint64_t raw_off = 0, hap_off = 0, out_off = 0;
+    uint32_t max_cols = 0;
+    for (const RegionIn& r : regs) {
+        RegionPlan rp{};
+        rp.read_begin = (uint32_t)reads.size();
+        rp.hap_begin = (uint32_t)haps.size();
+        rp.out_off = out_off;
+        if (r.n_reads == 0 || r.n_haps == 0) {
+            rp.n_reads = rp.n_haps = 0;
+            s.regions.push_back(rp);
+            continue;
+        }
+        rp.n_reads = r.n_reads;
+        rp.n_haps = r.n_haps;
+        s.regions.push_back(rp);
+        // haplotypes -> chunks of two balanced streams
+        for (uint32_t j = 0; j < r.n_haps; ++j) {
+            PhmmHap h{};
+            h.byte_off = (uint32_t)hap_off;
+            h.len = r.haps[j].len;
+            h.out_col = j;
+            hap_off += h.len;
+            max_cols = std::max(max_cols, h.len);
+            haps.push_back(h);
+        }
+        order.clear();
+        uint64_t total = 0;
+        for (uint32_t j = 0; j < r.n_haps; ++j)
+            if (r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols) {
+                order.push_back(j);
+                total += r.haps[j].len;
+            }
+        region_chunks.clear();
+        if (!order.empty()) {
+            const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (total + 2ull * kTargetStreamCols - 1) / (2ull * kTargetStreamCols));
+            const uint64_t per_chunk = (total + n_chunks - 1) / n_chunks;
+            size_t at = 0;
+            while (at < order.size()) {
+                // take haplotypes (in region order) until this chunk holds its share
+                size_t end = at;
+                uint64_t acc = 0;
+                while (end < order.size() && (end == at || acc + r.haps[order[end]].len <= per_chunk + kTargetStreamCols / 4)) {
+                    acc += r.haps[order[end]].len;
+                    ++end;
+                    if (acc >= per_chunk) break;
+                }
+                // longest first onto the lighter stream
+                std::vector<uint32_t> idx(order.begin() + at, order.begin() + end);
+                std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return r.haps[a].len > r.haps[b].len; });
+                uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
+                for (uint32_t j : idx) {
+                    const uint32_t e = (sum[1] < sum[0]) ? 1u : 0u;
+                    PhmmHap& h = haps[rp.hap_begin + j];
+                    h.pos = 32 + sum[e];
+                    h.ord_stream = (cnt[e] << 1) | e;
+                    sum[e] += h.len;
+                    ++cnt[e];
+                }
+                // the device walks haps[hap_begin .. +n_haps); empty or over-long haplotypes inside that range
+                // keep pos == 0, which the kernel skips (they are served by the per-pair kernel)
+                PhmmChunk c{};
+                c.hap_begin = rp.hap_begin + order[at];
+                c.n_haps = order[end - 1] - order[at] + 1;
+                c.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
+                c.n_x = cnt[0];
+                region_chunks.push_back((uint32_t)chunks.size());
+                chunks.push_back(c);
+                at = end;
+            }
+        }
+        // reads
+        for (auto& v : by_bin) v.clear();
+        for (uint32_t k = 0; k < r.n_reads; ++k) {
+            const phmm_read& in = r.reads[k];
+            PhmmRead d{};
+            d.raw_off = (uint32_t)raw_off;
+            d.word_off = (uint32_t)raw_off;
+            d.len = in.len;
+            d.out_off = (uint32_t)(out_off + (uint64_t)k * r.n_haps);
+            d.n_haps = r.n_haps;
+            d.hap_begin = rp.hap_begin;
+            d.thr = (int16_t)std::max(-32768, std::min(32767, r.thr));
+            d.mapq = in.mapq;
+            const uint32_t fl = (in.ins ? PHMM_RD_HAS_INS : 0u) | (in.del ? PHMM_RD_HAS_DEL : 0u) | (in.gcp ? PHMM_RD_HAS_GCP : 0u);
+            d.model_flags = (uint8_t)((r.pcr & 15) | (fl << 4));
+            raw_off += in.len;
+            const uint32_t rid = (uint32_t)reads.size();
+            reads.push_back(d);
+            s.read_len.push_back(in.len);
+            const int b = bin_of(in.len);
+            if (b >= 0) by_bin[b].push_back(rid);
+            for (uint32_t j = 0; j < r.n_haps; ++j) {
+                const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
+                if (b < 0 || !hap_ok) {
+                    PhmmPair p{};
+                    p.read = rid;
+                    p.hap = rp.hap_begin + j;
+                    p.out_idx = d.out_off + j;
+                    slow.push_back(p);
+                }
+            }
+        }
+        for (int b = 0; b < kPhmmNumBins; ++b) {
+            if (by_bin[b].empty()) continue;
+            for (uint32_t ci : region_chunks) {
+                Group g{};
+                g.chunk = ci;
+                g.stream_len = chunks[ci].stream_len;
+                g.first = (uint32_t)group_reads[b].size();
+                g.n = (uint32_t)by_bin[b].size();
+                group_reads[b].insert(group_reads[b].end(), by_bin[b].begin(), by_bin[b].end());
+                groups[b].push_back(g);
+            }
+        }
+        out_off += (uint64_t)r.n_reads * r.n_haps;
+    }
+
+    // CTAs per bin, longest streams first
+    std::vector<PhmmCta> ctas;
+    std::vector<uint32_t> task_reads;
+    s.launches.clear();
+    for (int b = 0; b < kPhmmNumBins; ++b) {
+        if (groups[b].empty()) continue;
+        std::stable_sort(groups[b].begin(), groups[b].end(), [](const Group& x, const Group& y) { return x.stream_len > y.stream_len; });
+        FwdLaunch fl{};
+        fl.bin = b;
+        fl.cta_base = (uint32_t)ctas.size();
+        size_t smem = 0;
+        for (const Group& g : groups[b]) {
+            smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps));
+            for (uint32_t at = 0; at < g.n; at += PHMM_WARPS) {
+                PhmmCta c{};
+                c.chunk = g.chunk;
+                c.read_begin = (uint32_t)task_reads.size();
+                c.n_reads = std::min<uint32_t>(PHMM_WARPS, g.n - at);
+                for (uint32_t k = 0; k < c.n_reads; ++k) task_reads.push_back(group_reads[b][g.first + at + k]);
+                ctas.push_back(c);
+            }
+        }
+        fl.n_ctas = (uint32_t)ctas.size() - fl.cta_base;
+        fl.smem = smem;
+        s.launches.push_back(fl);
+    }
+
+    // ---- arena layout ---------------------------------------------------------------------------
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
+    const size_t o_reads = place(reads.size() * sizeof(PhmmRead));
+    const size_t o_haps = place(haps.size() * sizeof(PhmmHap));
+    const size_t o_chunks = place(chunks.size() * sizeof(PhmmChunk));
+    const size_t o_ctas = place(ctas.size() * sizeof(PhmmCta));
+    const size_t o_tasks = place(task_reads.size() * sizeof(uint32_t));
+    const size_t o_slow = place(slow.size() * sizeof(PhmmPair));
+    const size_t o_rb = place(read_bytes + 16);
+    const size_t o_rq = place(read_bytes + 16);
+    const size_t o_ri = any_ins ? place(read_bytes + 16) : 0;
+    const size_t o_rd = any_del ? place(read_bytes + 16) : 0;
+    const size_t o_rg = any_gcp ? place(read_bytes + 16) : 0;
+    const size_t o_hb = place(hap_bytes + 16);
+    s.in_bytes = off;
+    int rc;
+    if ((rc = s.h_in.ensure(off)) != PHMM_OK) return rc;
+    if ((rc = s.d_in.ensure(off)) != PHMM_OK) return rc;
+    uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+    std::memcpy(h + o_reads, reads.data(), reads.size() * sizeof(PhmmRead));
+    std::memcpy(h + o_haps, haps.data(), haps.size() * sizeof(PhmmHap));
+    std::memcpy(h + o_chunks, chunks.data(), chunks.size() * sizeof(PhmmChunk));
+    std::memcpy(h + o_ctas, ctas.data(), ctas.size() * sizeof(PhmmCta));
+    std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
+    std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
+    {
+        size_t ro = 0, ho = 0;
+        for (const RegionIn& r : regs) {
+            if (r.n_reads == 0 || r.n_haps == 0) continue;
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const phmm_read& in = r.reads[k];
+                std::memcpy(h + o_rb + ro, in.bases, in.len);
+                std::memcpy(h + o_rq + ro, in.qual, in.len);
+                if (in.ins) std::memcpy(h + o_ri + ro, in.ins, in.len);
+                if (in.del) std::memcpy(h + o_rd + ro, in.del, in.len);
+                if (in.gcp) std::memcpy(h + o_rg + ro, in.gcp, in.len);
+                ro += in.len;
+            }
+            for (uint32_t j = 0; j < r.n_haps; ++j) {
+                std::memcpy(h + o_hb + ho, r.haps[j].bases, r.haps[j].len);
+                ho += r.haps[j].len;
+            }
+        }
+    }
+    // ---- device-only buffers --------------------------------------------------------------------
+    const size_t pairs_alloc = std::max<uint64_t>(n_pairs, 1);
+    if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t))) != PHMM_OK) return rc;
+    if ((rc = s.d_f32.ensure(pairs_alloc * sizeof(float))) != PHMM_OK) return rc;
+    if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
+    if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair))) != PHMM_OK) return rc;
+    if ((rc = s.d_cnt.ensure(256)) != PHMM_OK) return rc;
+    if ((rc = s.d_scr64.ensure((size_t)kPairThreads * (max_cols + 1) * 3 * sizeof(double))) != PHMM_OK) return rc;
+    if (!slow.empty())
+        if ((rc = s.d_scr32.ensure((size_t)kPairThreads * (max_cols + 1) * 3 * sizeof(float))) != PHMM_OK) return rc;
+    if ((rc = s.h_f32.ensure(pairs_alloc * sizeof(float))) != PHMM_OK) return rc;
+    if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
+    if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
+
+    uint8_t* d = static_cast<uint8_t*>(s.d_in.p);
+    PhmmBatchDev& b = s.dev;
+    b.reads = reinterpret_cast<const PhmmRead*>(d + o_reads);
+    b.haps = reinterpret_cast<const PhmmHap*>(d + o_haps);
+    b.chunks = reinterpret_cast<const PhmmChunk*>(d + o_chunks);
+    b.ctas = reinterpret_cast<const PhmmCta*>(d + o_ctas);
+    b.task_reads = reinterpret_cast<const uint32_t*>(d + o_tasks);
+    b.slow_pairs = reinterpret_cast<const PhmmPair*>(d + o_slow);
+    b.read_bases = d + o_rb;
+    b.read_qual = d + o_rq;
+    b.read_ins = any_ins ? d + o_ri : nullptr;
+    b.read_del = any_del ? d + o_rd : nullptr;
+    b.read_gcp = any_gcp ? d + o_rg : nullptr;
+    b.hap_bases = d + o_hb;
+    b.words = static_cast<uint32_t*>(s.d_words.p);
+    b.out_f32 = static_cast<float*>(s.d_f32.p);
+    b.out_f64 = static_cast<double*>(s.d_f64.p);
+    b.f64_pairs = static_cast<PhmmPair*>(s.d_pairs.p);
+    b.f64_count = static_cast<uint32_t*>(s.d_cnt.p);
+    b.tables = static_cast<const PhmmTables*>(d_tables.p);
+    b.n_reads = (uint32_t)reads.size();
+
+    s.n_pairs = n_pairs;
+    s.n_cells = n_cells;
+    s.n_words = read_bytes;
+    s.n_reads = (uint32_t)reads.size();
+    s.n_haps = (uint32_t)haps.size();
+    s.n_slow = (uint32_t)slow.size();
+    s.max_cols = max_cols;
+    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + 1;
+    return PHMM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device side of one batch
+// ------------------------------------------------------------------------------------------------
+
+int phmm_engine::launch(Slot& s, bool copy_in)
+{
+    if (copy_in && s.in_bytes) {
+        CU(cudaMemcpyAsync(s.d_in.p, s.h_in.p, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
+        stats.h2d += s.in_bytes;
+    }
+    CU(cudaMemsetAsync(s.d_cnt.p, 0, 4, s.stream));
+    CU(cudaEventRecord(s.ev[0], s.stream));
+    CU(phmm_launch_prep(s.dev, s.stream));
+    CU(cudaEventRecord(s.ev[1], s.stream));
+    for (const FwdLaunch& fl : s.launches) CU(phmm_launch_fwd(s.dev, fl.bin, fma, fl.cta_base, fl.n_ctas, fl.smem, s.stream));
+    CU(cudaEventRecord(s.ev[2], s.stream));
+    if (s.n_slow)
+        CU(phmm_launch_pairs_f32(s.dev, fma, s.dev.slow_pairs, s.n_slow, static_cast<float*>(s.d_scr32.p), kPairThreads, s.max_cols,
+                                 s.stream));
+    if (s.n_pairs)
+        CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
+                                 s.stream));
+    CU(cudaEventRecord(s.ev[3], s.stream));
+    stats.launches += s.n_launches;
+    return PHMM_OK;
+}
+
+// D2H + the reference's host epilogue.
+int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out)
+{
+    uint32_t n64 = 0;
+    if (copy_out && s.n_pairs) {
+        CU(cudaMemcpyAsync(s.h_f32.p, s.d_f32.p, s.n_pairs * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaMemcpyAsync(s.h_cnt.p, s.d_cnt.p, 4, cudaMemcpyDeviceToHost, s.stream));
+        stats.d2h += s.n_pairs * sizeof(float) + 4;
+    }
+    CU(cudaStreamSynchronize(s.stream));
+    if (s.n_pairs) {
+        n64 = *static_cast<uint32_t*>(s.h_cnt.p);
+        if (n64 > 0) {
+            CU(cudaMemcpyAsync(s.h_f64.p, s.d_f64.p, s.n_pairs * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            CU(cudaStreamSynchronize(s.stream));
+            stats.d2h += s.n_pairs * sizeof(double);
+        }
+    }
+    CU(cudaEventElapsedTime(&s.gpu_ms, s.ev[0], s.ev[3]));
+    CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
+
+    const unsigned old_csr = _mm_getcsr();
+    _mm_setcsr(old_csr | 0x8000u);                 // init_native, pairhmm_internal.cpp:21-25
+    const float* f32 = static_cast<const float*>(s.h_f32.p);
+    const double* f64 = static_cast<const double*>(s.h_f64.p);
+    std::vector<double> lk;
+    for (size_t g = 0; g < regs.size(); ++g) {
+        const RegionIn& r = regs[g];
+        const RegionPlan& rp = s.regions[g];
+        if (r.n_kept_out) *r.n_kept_out = 0;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = 0;
+        if (rp.n_reads == 0 || rp.n_haps == 0) continue;
+        const uint32_t nr = rp.n_reads, nh = rp.n_haps;
+        lk.resize((size_t)nr * nh);
+        uint32_t reg64 = 0;
+        for (uint32_t i = 0; i < nr; ++i) {
+            double* row = lk.data() + (size_t)i * nh;
+            const float* fr = f32 + rp.out_off + (size_t)i * nh;
+            for (uint32_t j = 0; j < nh; ++j) {
+                const float f = fr[j];
+                double v;
+                if (f < kMinAccepted) {                                              // :578
+                    v = log10(f64[rp.out_off + (size_t)i * nh + j]) - kLog10InitD;   // :580
+                    ++reg64;
+                } else {
+                    v = (double)(log10f(f) - kLog10InitF);                           // :583
+                }
+                row[j] = v;
+            }
+            if (r.out.raw_f32) std::memcpy(r.out.raw_f32 + (size_t)i * nh, fr, nh * sizeof(float));
+            if (r.out.raw_f64)
+                for (uint32_t j = 0; j < nh; ++j)
+                    r.out.raw_f64[(size_t)i * nh + j] = (fr[j] < kMinAccepted) ? f64[rp.out_off + (size_t)i * nh + j] : (double)NAN;
+            // normalize_likelihoods :53-63
+            double best = row[0];
+            for (uint32_t j = 1; j < nh; ++j)
+                if (best < row[j]) best = row[j];
+            const double cmp = best + (-4.5);                                        // adapter.h:23
+            for (uint32_t j = 0; j < nh; ++j) row[j] = row[j] < cmp ? cmp : row[j];
+        }
+        // filter_poorly_modelled_evidence :161-182
+        uint32_t kept = 0;
+        double* out = r.out.likelihoods;
+        for (size_t k = 0; k < (size_t)nh * nr; ++k) out[k] = (double)NAN;          // :516
+        for (uint32_t i = 0; i < nr; ++i) {
+            const double* row = lk.data() + (size_t)i * nh;
+            double best = row[0];
+            for (uint32_t j = 1; j < nh; ++j)
+                if (best < row[j]) best = row[j];
+            const double lim = std::min(2.0, std::ceil((int32_t)s.read_len[rp.read_begin + i] * 0.02)) * (-4.0);   // adapter.h:20-22
+            if (best < lim) continue;
+            for (uint32_t j = 0; j < nh; ++j) out[(size_t)j * nr + kept] = row[j];  // transpose :184-193
+            r.out.kept_idx[kept++] = i;
+        }
+        if (r.n_kept_out) *r.n_kept_out = kept;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
+        if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
+    }
+    _mm_setcsr(old_csr);
+
+    stats.regions += regs.size();
+    stats.pairs += s.n_pairs;
+    stats.cells += s.n_cells;
+    stats.fp64_pairs += n64;
+    stats.slow_pairs += s.n_slow;
+    stats.batches += 1;
+    {
+        std::lock_guard<std::mutex> lk2(stats.m);
+        stats.gpu_ms += s.gpu_ms;
+    }
+    return PHMM_OK;
+}
+
+int phmm_engine::execute(Slot& s, const std::vector<RegionIn>& regs)
+{
+    int rc;
+    if ((rc = plan(s, regs)) != PHMM_OK) return rc;
+    if ((rc = launch(s, true)) != PHMM_OK) return rc;
+    return finish(s, regs, true);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Workers
+// ------------------------------------------------------------------------------------------------
+
+void phmm_engine::worker_main(uint32_t idx)
+{
+    cudaSetDevice(device);
+    Slot& s = *slots[idx];
+    for (;;) {
+        std::function<void(Slot&)> job;
+        {
+            std::unique_lock<std::mutex> lk(qm);
+            qcv.wait(lk, [&] { return stopping || !jobs.empty(); });
+            if (jobs.empty()) return;
+            job = std::move(jobs.front());
+            jobs.pop_front();
+        }
+        job(s);
+    }
+}
+
+void phmm_engine::enqueue(std::function<void(Slot&)> fn)
+{
+    {
+        std::lock_guard<std::mutex> lk(qm);
+        jobs.push_back(std::move(fn));
+    }
+    qcv.notify_one();
+}
+
+// bm must be held
+void phmm_engine::seal_locked()
+{
+    if (open.regs.empty()) return;
+    auto regs = std::make_shared<std::vector<RegionIn>>(std::move(open.regs));
+    const uint64_t id = open.id;
+    open = OpenBatch{};
+    enqueue([this, regs, id](Slot& s) {
+        const int rc = execute(s, *regs);
+        std::string err = g_err;
+        {
+            std::lock_guard<std::mutex> lk(bm);
+            Done& d = batch_state[id];
+            d.done = true;
+            d.rc = rc;
+            d.err = err;
+        }
+        bcv.notify_all();
+    });
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+
+static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, std::vector<phmm_read>& reads, std::vector<phmm_hap>& haps,
+                            std::vector<RegionIn>& regs)
+{
+    const uint64_t nr = fb->reg_read_off[fb->n_regions], nh = fb->reg_hap_off[fb->n_regions];
+    reads.resize(nr);
+    haps.resize(nh);
+    for (uint64_t k = 0; k < nr; ++k) {
+        phmm_read& r = reads[k];
+        const uint64_t o = fb->read_off[k];
+        r.bases = fb->read_bases + o;
+        r.qual = fb->read_qual + o;
+        r.ins = fb->read_ins ? fb->read_ins + o : nullptr;
+        r.del = fb->read_del ? fb->read_del + o : nullptr;
+        r.gcp = fb->read_gcp ? fb->read_gcp + o : nullptr;
+        r.len = fb->read_len[k];
+        r.mapq = fb->read_mapq[k];
+    }
+    for (uint64_t j = 0; j < nh; ++j) {
+        haps[j].bases = fb->hap_bases + fb->hap_off[j];
+        haps[j].len = fb->hap_len[j];
+    }
+    regs.resize(fb->n_regions);
+    if (fr) fr->n_fp64 = 0;
+    for (uint32_t g = 0; g < fb->n_regions; ++g) {
+        RegionIn& r = regs[g];
+        const uint64_t r0 = fb->reg_read_off[g], h0 = fb->reg_hap_off[g];
+        r.reads = reads.data() + r0;
+        r.n_reads = (uint32_t)(fb->reg_read_off[g + 1] - r0);
+        r.haps = haps.data() + h0;
+        r.n_haps = (uint32_t)(fb->reg_hap_off[g + 1] - h0);
+        r.thr = fb->min_quality_threshold;
+        r.pcr = fb->pcr_model;
+        r.out = phmm_result{};
+        r.n_kept_out = nullptr;
+        r.n_fp64_out = nullptr;
+        r.n_fp64_out32 = nullptr;
+        if (fr) {
+            r.out.likelihoods = fr->likelihoods + fr->lik_off[g];
+            r.out.kept_idx = fr->kept_idx + r0;
+            r.out.raw_f32 = fr->raw_f32 ? fr->raw_f32 + fr->lik_off[g] : nullptr;
+            r.out.raw_f64 = fr->raw_f64 ? fr->raw_f64 + fr->lik_off[g] : nullptr;
+            r.n_kept_out = fr->n_kept + g;
+            r.n_fp64_out = &fr->n_fp64;
+        }
+    }
+}
+
+static uint64_t region_cells(const RegionIn& r)
+{
+    uint64_t rb = 0, hb = 0;
+    for (uint32_t k = 0; k < r.n_reads; ++k) rb += r.reads[k].len;
+    for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
+    return rb * hb;
+}
+
+extern "C" {
+
+const char* phmm_last_error(void) { return g_err.c_str(); }
+const char* phmm_version(void) { return "rovaca_b200 pairhmm 0.1 (sm_100a)"; }
+
+int phmm_create(const phmm_config* cfg, phmm_engine** out)
+{
+    if (!out) return fail(PHMM_ERR_ARG, "phmm_create: out is null");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(PHMM_ERR_CUDA, std::string("no CUDA device: ") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0") +
+                                       " (this engine has no CPU fallback)");
+    std::unique_ptr<phmm_engine> e(new phmm_engine());
+    int dev = cfg ? cfg->device : -1;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PHMM_ERR_ARG, "phmm_create: device ordinal out of range");
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail(PHMM_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                                       "; this library carries sm_100a code only");
+    e->device = dev;
+    if (cfg) {
+        e->fma = cfg->fma_mode != PHMM_FMA_NONE;
+        if (cfg->n_workers) e->n_workers = std::min<uint32_t>(cfg->n_workers, 32);
+        if (cfg->batch_cells) e->batch_cells = cfg->batch_cells;
+        if (cfg->linger_us) e->linger_us = cfg->linger_us;
+    }
+    std::unique_ptr<PhmmTables> t(new PhmmTables());
+    phmm_build_tables(t.get());
+    int rc = e->d_tables.ensure(sizeof(PhmmTables));
+    if (rc != PHMM_OK) return rc;
+    CU(cudaMemcpy(e->d_tables.p, t.get(), sizeof(PhmmTables), cudaMemcpyHostToDevice));
+    for (uint32_t i = 0; i < e->n_workers; ++i) {
+        e->slots.emplace_back(new Slot());
+        if ((rc = e->slots.back()->init()) != PHMM_OK) return rc;
+    }
+    for (uint32_t i = 0; i < e->n_workers; ++i) e->workers.emplace_back([p = e.get(), i] { p->worker_main(i); });
+    *out = e.release();
+    return PHMM_OK;
+}
+
+void phmm_destroy(phmm_engine* e)
+{
+    if (!e) return;
+    {
+        std::lock_guard<std::mutex> lk(e->bm);
+        e->seal_locked();
+    }
+    {
+        std::lock_guard<std::mutex> lk(e->qm);
+        e->stopping = true;
+    }
+    e->qcv.notify_all();
+    for (auto& t : e->workers) t.join();
+    cudaSetDevice(e->device);
+    for (auto& s : e->slots) s->destroy();
+    e->d_tables.release();
+    delete e;
+}
+
+int phmm_submit(phmm_engine* e, const phmm_region* region, phmm_result* result, uint64_t* ticket)
+{
+    if (!e || !region || !result || !ticket) return fail(PHMM_ERR_ARG, "phmm_submit: null argument");
+    if (region->n_reads && region->n_haps && (!result->likelihoods || !result->kept_idx))
+        return fail(PHMM_ERR_ARG, "phmm_submit: result buffers are null");
+    RegionIn r{};
+    r.reads = region->reads;
+    r.n_reads = region->n_reads;
+    r.haps = region->haps;
+    r.n_haps = region->n_haps;
+    r.thr = region->min_quality_threshold;
+    r.pcr = region->pcr_model;
+    r.out = *result;
+    r.n_kept_out = &result->n_kept;
+    r.n_fp64_out32 = &result->n_fp64;
+    const uint64_t cells = region_cells(r);
+    std::lock_guard<std::mutex> lk(e->bm);
+    if (e->open.regs.empty()) {
+        e->open.id = e->next_batch_id++;
+        e->open.first = std::chrono::steady_clock::now();
+        e->batch_state[e->open.id] = phmm_engine::Done{};
+    }
+    *ticket = e->open.id;
+    e->batch_state[e->open.id].waits += 1;
+    e->open.regs.push_back(r);
+    e->open.cells += cells;
+    if (e->open.cells >= e->batch_cells) e->seal_locked();
+    return PHMM_OK;
+}
+
+int phmm_flush(phmm_engine* e)
+{
+    if (!e) return fail(PHMM_ERR_ARG, "phmm_flush: null engine");
+    std::lock_guard<std::mutex> lk(e->bm);
+    e->seal_locked();
+    return PHMM_OK;
+}
+
+int phmm_wait(phmm_engine* e, uint64_t ticket)
+{
+    if (!e) return fail(PHMM_ERR_ARG, "phmm_wait: null engine");
+    std::unique_lock<std::mutex> lk(e->bm);
+    auto it = e->batch_state.find(ticket);
+    if (it == e->batch_state.end()) return fail(PHMM_ERR_STATE, "phmm_wait: unknown ticket");
+    if (e->open.id == ticket && !e->open.regs.empty()) {
+        // let other callers join this batch for a moment, then seal it ourselves
+        const auto deadline = e->open.first + std::chrono::microseconds(e->linger_us);
+        while (e->open.id == ticket && !e->open.regs.empty() && std::chrono::steady_clock::now() < deadline)
+            e->bcv.wait_until(lk, deadline);
+        if (e->open.id == ticket && !e->open.regs.empty()) e->seal_locked();
+    }
+    e->bcv.wait(lk, [&] { return e->batch_state[ticket].done; });
+    phmm_engine::Done& st = e->batch_state[ticket];
+    const int rc = st.rc;
+    if (rc != PHMM_OK) g_err = st.err;
+    if (st.waits <= 1) e->batch_state.erase(ticket); else st.waits -= 1;
+    return rc;
+}
+
+int phmm_call_region(phmm_engine* e, const phmm_region* region, phmm_result* result)
+{
+    uint64_t t = 0;
+    int rc = phmm_submit(e, region, result, &t);
+    if (rc != PHMM_OK) return rc;
+    return phmm_wait(e, t);
+}
+
+int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* fr)
+{
+    if (!e || !fb || !fr) return fail(PHMM_ERR_ARG, "phmm_run_flat: null argument");
+    auto reads = std::make_shared<std::vector<phmm_read>>();
+    auto haps = std::make_shared<std::vector<phmm_hap>>();
+    std::vector<RegionIn> regs;
+    flat_to_regions(fb, fr, *reads, *haps, regs);
+    // cut into sub-batches of about batch_cells / n_workers so that packing, device work and the host
+    // epilogue of different sub-batches overlap
+    const uint64_t target = std::max<uint64_t>(e->batch_cells, 1);
+    std::vector<std::shared_ptr<std::vector<RegionIn>>> parts;
+    {
+        auto cur = std::make_shared<std::vector<RegionIn>>();
+        uint64_t cells = 0;
+        for (RegionIn& r : regs) {
+            cur->push_back(r);
+            cells += region_cells(r);
+            if (cells >= target) {
+                parts.push_back(cur);
+                cur = std::make_shared<std::vector<RegionIn>>();
+                cells = 0;
+            }
+        }
+        if (!cur->empty()) parts.push_back(cur);
+    }
+    std::mutex m;
+    std::condition_variable cv;
+    size_t remaining = parts.size();
+    int rc_all = PHMM_OK;
+    std::string err_all;
+    for (auto& part : parts) {
+        e->enqueue([&, part](Slot& s) {
+            const int rc = e->execute(s, *part);
+            std::lock_guard<std::mutex> lk(m);
+            if (rc != PHMM_OK && rc_all == PHMM_OK) {
+                rc_all = rc;
+                err_all = g_err;
+            }
+            if (--remaining == 0) cv.notify_all();
+        });
+    }
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv.wait(lk, [&] { return remaining == 0; });
+    }
+    if (rc_all != PHMM_OK) g_err = err_all;
+    return rc_all;
+}
+
+int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* fb, phmm_resident** out)
+{
+    if (!e || !fb || !out) return fail(PHMM_ERR_ARG, "phmm_resident_upload: null argument");
+    CU(cudaSetDevice(e->device));
+    std::unique_ptr<phmm_resident> r(new phmm_resident());
+    int rc = r->slot.init();
+    if (rc != PHMM_OK) return rc;
+    flat_to_regions(fb, nullptr, r->reads, r->haps, r->regs);
+    if ((rc = e->plan(r->slot, r->regs)) != PHMM_OK) return rc;
+    CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.in_bytes, cudaMemcpyHostToDevice, r->slot.stream));
+    CU(cudaStreamSynchronize(r->slot.stream));
+    e->stats.h2d += r->slot.in_bytes;
+    *out = r.release();
+    return PHMM_OK;
+}
+
+int phmm_resident_run(phmm_engine* e, phmm_resident* r, float* gpu_ms, float* fwd_ms)
+{
+    if (!e || !r) return fail(PHMM_ERR_ARG, "phmm_resident_run: null argument");
+    CU(cudaSetDevice(e->device));
+    int rc = e->launch(r->slot, false);
+    if (rc != PHMM_OK) return rc;
+    CU(cudaStreamSynchronize(r->slot.stream));
+    CU(cudaEventElapsedTime(&r->slot.gpu_ms, r->slot.ev[0], r->slot.ev[3]));
+    CU(cudaEventElapsedTime(&r->slot.fwd_ms, r->slot.ev[1], r->slot.ev[2]));
+    if (gpu_ms) *gpu_ms = r->slot.gpu_ms;
+    if (fwd_ms) *fwd_ms = r->slot.fwd_ms;
+    return PHMM_OK;
+}
+
+int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* fr)
+{
+    if (!e || !r || !fr) return fail(PHMM_ERR_ARG, "phmm_resident_download: null argument");
+    CU(cudaSetDevice(e->device));
+    fr->n_fp64 = 0;
+    for (size_t g = 0; g < r->regs.size(); ++g) {
+        RegionIn& x = r->regs[g];
+        const uint64_t r0 = (uint64_t)(x.reads - r->reads.data());
+        x.out = phmm_result{};
+        x.out.likelihoods = fr->likelihoods + fr->lik_off[g];
+        x.out.kept_idx = fr->kept_idx + r0;
+        x.out.raw_f32 = fr->raw_f32 ? fr->raw_f32 + fr->lik_off[g] : nullptr;
+        x.out.raw_f64 = fr->raw_f64 ? fr->raw_f64 + fr->lik_off[g] : nullptr;
+        x.n_kept_out = fr->n_kept + g;
+        x.n_fp64_out = &fr->n_fp64;
+    }
+    return e->finish(r->slot, r->regs, true);
+}
+
+void phmm_resident_free(phmm_engine* e, phmm_resident* r)
+{
+    if (!r) return;
+    if (e) cudaSetDevice(e->device);
+    r->slot.destroy();
+    delete r;
+}
+
+uint32_t phmm_resident_launches(const phmm_resident* r) { return r ? r->slot.n_launches : 0; }
+
+int phmm_get_stats(phmm_engine* e, phmm_stats* out)
+{
+    if (!e || !out) return fail(PHMM_ERR_ARG, "phmm_get_stats: null argument");
+    out->regions = e->stats.regions;
+    out->pairs = e->stats.pairs;
+    out->cells = e->stats.cells;
+    out->fp64_pairs = e->stats.fp64_pairs;
+    out->slow_pairs = e->stats.slow_pairs;
+    out->h2d_bytes = e->stats.h2d;
+    out->d2h_bytes = e->stats.d2h;
+    out->batches = e->stats.batches;
+    out->kernel_launches = e->stats.launches;
+    {
+        std::lock_guard<std::mutex> lk(e->stats.m);
+        out->gpu_ms = e->stats.gpu_ms;
+    }
+    return PHMM_OK;
+}
+
+int phmm_kernel_info(int rpt, int fma_mode, int* regs, int* local_bytes)
+{
+    int bin = -1;
+    for (int b = 0; b < kPhmmNumBins; ++b)
+        if (kPhmmRptBins[b] == rpt) bin = b;
+    if (bin < 0) return fail(PHMM_ERR_ARG, "phmm_kernel_info: no such rows-per-lane bin");
+    PhmmKernelInfo ki{};
+    CU(phmm_fwd_kernel_info(bin, fma_mode != PHMM_FMA_NONE, &ki));
+    if (regs) *regs = ki.regs;
+    if (local_bytes) *local_bytes = ki.local_bytes;
+    return PHMM_OK;
+}
+
+// Measured FP32 peak for the roofline denominator: runs the issue-rate micro-benchmark (phmm_kernels.cu) on every SM
+// and returns the sustained rate in FMA lane-operations per second (one FFMA2 counts 2 per lane).
+int phmm_ubench(phmm_engine* e, int mode, uint32_t iters, float* ms_out, double* fma_per_s)
+{
+    if (!e) return fail(PHMM_ERR_ARG, "phmm_ubench: null engine");
+    CU(cudaSetDevice(e->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, e->device));
+    const uint32_t blocks = (uint32_t)prop.multiProcessorCount * 8;
+    Slot& s = *e->slots[0];
+    int rc = s.d_cnt.ensure(256);
+    if (rc != PHMM_OK) return rc;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(s.ev[0], s.stream));
+        CU(phmm_launch_ubench(mode, blocks, iters, static_cast<float*>(s.d_cnt.p), s.stream));
+        CU(cudaEventRecord(s.ev[3], s.stream));
+        CU(cudaStreamSynchronize(s.stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.ev[0], s.ev[3]));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    if (ms_out) *ms_out = best;
+    if (fma_per_s) *fma_per_s = (double)blocks * 256.0 * (double)iters * 32.0 * 2.0 / ((double)best * 1e-3);
+    return PHMM_OK;
+}
+
+// For tests: the host-built tables, to be compared with the reference's Context<float> (core/context.h).
+void phmm_debug_tables(float* ph2pr128, float* mm8256, double* ph2pr128_d, double* mm8256_d)
+{
+    std::unique_ptr<PhmmTables> t(new PhmmTables());
+    phmm_build_tables(t.get());
+    if (ph2pr128) std::memcpy(ph2pr128, t->ph2pr, sizeof(t->ph2pr));
+    if (mm8256) std::memcpy(mm8256, t->mm, sizeof(t->mm));
+    if (ph2pr128_d) std::memcpy(ph2pr128_d, t->ph2pr_d, sizeof(t->ph2pr_d));
+    if (mm8256_d) std::memcpy(mm8256_d, t->mm_d, sizeof(t->mm_d));
+}
+
+}  // extern "C"

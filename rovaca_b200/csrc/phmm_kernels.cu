@@ -1,0 +1,528 @@
+// phmm_kernels.cu — hand-written CUDA (sm_100a) for Rovaca's PairHMM likelihood path.
+//
+// What the reference computes per (read, haplotype) pair is the forward algorithm of
+// rovaca/avx_512_float.cc:29-181 (equivalently core/avx512_s.cpp:259-397): an R x H table of three
+// states M/I/D, 4 FMUL + 4 FFMA per cell in the exact order GCC gives the reference's AVX-512 TUs
+// (SURVEY.md §8a), flush-to-zero, result = (sum_c M[R][c]) + (sum_c I[R][c]).
+//
+// Mapping (B200-first, not a port of the AVX lane layout):
+//   * a warp owns one read; lane l owns rows l*RPT .. l*RPT+RPT-1 of the table, the read is
+//     top-padded to 32*RPT rows with "boundary generator" rows (prior = 0, dd = 1) that reproduce the
+//     reference's row -1 (M = I = 0, D = 2^120/H) for any garbage fed in from above, so lane 0 needs no
+//     special case and the last read row is always the last register row of lane 31;
+//   * the warp sweeps the columns as an anti-diagonal wavefront: at step s lane l is at stream
+//     position s - l and receives the bottom row (M, I, D) of lane l-1 with three __shfl_up_sync;
+//   * every thread carries TWO haplotype streams at once in the two halves of packed f32x2
+//     registers (FFMA2 / FMUL2 / FADD2, one issue slot for two cells); the per-row transition
+//     probabilities and priors stay scalar and enter the packed instructions as broadcast operands;
+//   * all haplotypes of a region are chained head to tail in the two streams, staged once per CTA in
+//     shared memory as ready-to-test one-hot words, so the 31-step fill/drain is paid once per
+//     region, not once per pair; the first column of each haplotype carries a flag bit that makes
+//     the lane emit the finished pair (lane 31) and re-seed its column -1 state;
+//   * read rows (packed q/ins/del/gcp/base words written by the prep kernel) are turned into the
+//     eight per-row floats once per read through host-built libm tables and then live in registers
+//     for the whole sweep.
+//
+// Toolchain hazard, checked by tests/test_build_audit.py: ptxas 12.9 contracts a single-use
+// mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 although both carry .rn.  Every packed product
+// below either feeds an FMA addend or has a second consumer; the un-contracted (AVX2) arithmetic
+// variant is therefore written with scalar intrinsics, which ptxas leaves alone.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "phmm_kernels.h"
+#include "phmm_types.h"
+
+namespace
+{
+
+__device__ __forceinline__ uint32_t onehot(uint32_t c)   // pairhmm_internal.cpp:27-41
+{
+    uint32_t v = 0;
+    v = (c == 'A') ? 0x1u : v;
+    v = (c == 'C') ? 0x2u : v;
+    v = (c == 'T') ? 0x4u : v;
+    v = (c == 'G') ? 0x8u : v;
+    v = (c == 'N') ? 0xFu : v;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Read preparation: quality capping (pairhmm_internal.cpp:434-439) and the PCR-indel model
+// (:65-159) as an integer pre-kernel, one warp per read, one lane per base.  Output: one u32 per
+// base = q | ins<<7 | del<<14 | gcp<<21 | onehot<<28, every quality already masked & 127 (:466-469).
+// ------------------------------------------------------------------------------------------------
+
+__constant__ uint8_t c_pcr_cache[4][21] = {   // adapter.h:13-15
+    {0},
+    {40, 40, 39, 38, 37, 36, 34, 32, 28, 23, 17, 10, 10, 10, 10, 10, 10, 10, 10, 10, 10},
+    {40, 40, 40, 39, 39, 39, 38, 38, 37, 37, 36, 35, 34, 33, 32, 30, 28, 26, 23, 20, 17},
+    {40, 40, 40, 40, 39, 39, 39, 39, 39, 38, 38, 38, 37, 37, 37, 36, 36, 35, 34, 33, 33}};
+
+__device__ __forceinline__ bool unit_equal(const uint8_t* a, const uint8_t* b, int len)
+{
+    for (int i = 0; i < len; ++i)
+        if (a[i] != b[i]) return false;
+    return true;
+}
+
+// find_tandem_repeat_units(bases, offset) for offset < n - 1, the only offsets apply_pcr_error_model
+// passes (:126-127).  There the backward unit (recorded at offset-str-1, :78) never equals the forward
+// unit (at offset+1, :98), so the result is always: trailing repeats of the *forward* unit in
+// bases[0..offset] plus its leading repeats in bases[offset+1..n) (:107-110), capped at 20.
+__device__ int repeat_length(const uint8_t* b, int n, int offset)
+{
+    int fw_len = 1, max_fw = 0;
+    const int test_len = n - offset - 1;
+    const uint8_t* t = b + offset + 1;
+    for (int str = 1; str <= 8; ++str) {
+        if (offset + str + 1 > n) break;
+        int cnt = 0;
+        for (int s = 0; s <= test_len - str; s += str) {
+            if (!unit_equal(t + s, t, str)) break;
+            ++cnt;
+        }
+        max_fw = cnt;
+        if (cnt > 1) { fw_len = str; break; }
+    }
+    int max_bw = 0;
+    for (int s = offset + 1 - fw_len; s >= 0; s -= fw_len) {
+        if (!unit_equal(b + s, t, fw_len)) break;
+        ++max_bw;
+    }
+    const int rl = max_bw + max_fw;
+    return rl > 20 ? 20 : rl;
+}
+
+__global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= p.n_reads) return;
+    const PhmmRead rd = p.reads[warp];
+    const int n = (int)rd.len;
+    const uint8_t* b = p.read_bases + rd.raw_off;
+    const uint8_t* q = p.read_qual + rd.raw_off;
+    const uint32_t flags = rd.model_flags >> 4;
+    const int model = rd.model_flags & 15;
+    const int thr = rd.thr;
+    for (int i = (int)lane; i < n; i += 32) {
+        uint32_t qq = q[i];
+        qq = qq < rd.mapq ? qq : rd.mapq;
+        qq = ((int)qq < thr) ? 6u : qq;                                     // MIN_QUALITY, adapter.h:5
+        uint32_t gi = (flags & PHMM_RD_HAS_INS) ? p.read_ins[rd.raw_off + i] : 45u;   // read_record.cpp:191-196
+        if (model != 0 && i + 1 < n) {
+            const uint32_t cap = c_pcr_cache[model][repeat_length(b, n, i)];
+            gi = gi < cap ? gi : cap;
+        }
+        const uint32_t gd = (flags & PHMM_RD_HAS_DEL) ? p.read_del[rd.raw_off + i] : gi;   // del aliases ins, :425,:559
+        const uint32_t gc = (flags & PHMM_RD_HAS_GCP) ? p.read_gcp[rd.raw_off + i] : 10u; // read_record.cpp:205-210
+        p.words[rd.word_off + i] = (qq & 127u) | ((gi & 127u) << 7) | ((gd & 127u) << 14) | ((gc & 127u) << 21) | (onehot(b[i]) << 28);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward wavefront kernel.
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+
+template <int RPT, bool FMA>
+__global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const PhmmCta cta = p.ctas[cta_base + blockIdx.x];
+    const PhmmChunk ch = p.chunks[cta.chunk];
+    const uint32_t L = ch.stream_len;
+    uint2* stream = reinterpret_cast<uint2*>(smem);                   // [L + 32] {x word, y word}
+    const uint32_t NI = ch.n_haps + 1;
+    float* info_init = reinterpret_cast<float*>(stream + L + 32);     // [2][NI]  2^120 / H
+    uint32_t* info_col = reinterpret_cast<uint32_t*>(info_init + 2 * NI);   // [2][NI] output column
+    uint32_t* info_hap = info_col + 2 * NI;                            // [2][NI] global haplotype id
+
+    // ---- stage the two haplotype streams of this chunk -------------------------------------
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) stream[i] = make_uint2(0u, 0u);
+    for (uint32_t i = threadIdx.x; i < 2 * NI; i += blockDim.x) { info_init[i] = 0.f; info_col[i] = 0u; info_hap[i] = 0u; }
+    __syncthreads();
+    {
+        uint32_t* sw = reinterpret_cast<uint32_t*>(stream);
+        if (threadIdx.x == 0) {                      // empty streams still need their end sentinel
+            if (ch.n_x == 0) sw[2 * 32 + 0] = PHMM_FLAG_BIT;
+            if (ch.n_x == ch.n_haps) sw[2 * 32 + 1] = PHMM_FLAG_BIT;
+        }
+        for (uint32_t j = 0; j < ch.n_haps; ++j) {
+            const PhmmHap hp = p.haps[ch.hap_begin + j];
+            if (hp.pos == 0) continue;               // not in a stream (empty / over-long: per-pair kernel)
+            const uint32_t e = hp.ord_stream & 1u, ord = hp.ord_stream >> 1;
+            const uint32_t n_e = e ? (ch.n_haps - ch.n_x) : ch.n_x;
+            const uint8_t* hb = p.hap_bases + hp.byte_off;
+            for (uint32_t c = threadIdx.x; c < hp.len; c += blockDim.x) {
+                uint32_t w = onehot(hb[c]) * 0x01111111u;                    // one-hot nibble replicated for 7 rows
+                if (c == 0) w |= PHMM_FLAG_BIT;
+                sw[2 * (hp.pos + c) + e] = w;
+            }
+            if (threadIdx.x == 0) {
+                info_init[e * NI + ord] = __fdiv_rn(__uint_as_float(0x7B800000u), (float)hp.len);   // 2^120 / H, avx_512_float.cc:33
+                info_col[e * NI + ord] = hp.out_col;
+                info_hap[e * NI + ord] = ch.hap_begin + j;
+                if (ord + 1 == n_e) sw[2 * (hp.pos + hp.len) + e] = PHMM_FLAG_BIT;   // end sentinel
+            }
+        }
+    }
+    __syncthreads();
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= cta.n_reads) return;
+    const uint32_t rid = p.task_reads[cta.read_begin + warp];
+    const PhmmRead rd = p.reads[rid];
+    const int npad = 32 * RPT - (int)rd.len;       // >= 1 by binning
+
+    // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers -------------------
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], dd[RPT], pm[RPT], pmm[RPT];
+    uint32_t rb[(RPT + 6) / 7];
+#pragma unroll
+    for (int k = 0; k < (RPT + 6) / 7; ++k) rb[k] = 0u;
+    uint32_t padmask = 0u;     // bit k: row k is a pad row; bit RPT: the row above row 0 is one
+    const PhmmTables* __restrict__ T = p.tables;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const int r = (int)lane * RPT + k - npad;
+        if (r >= 0) {
+            const uint32_t w = p.words[rd.word_off + r];
+            const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
+            const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+            mm[k] = __ldg(&T->mm[((hi * (hi + 1)) >> 1) + lo]);
+            gapm[k] = __ldg(&T->gapm[qc]);
+            mi[k] = __ldg(&T->ph2pr[qi]);
+            ii[k] = __ldg(&T->ph2pr[qc]);
+            md[k] = __ldg(&T->ph2pr[qd]);
+            dd[k] = ii[k];
+            pm[k] = __ldg(&T->pm[q]);
+            pmm[k] = __ldg(&T->pmm[q]);
+            rb[k / 7] |= (w >> 28) << (4 * (k % 7));
+        } else {                                   // boundary-generator row
+            mm[k] = 0.f; gapm[k] = 0.f; mi[k] = 0.f; ii[k] = 0.f; md[k] = 0.f; dd[k] = 1.f; pm[k] = 0.f; pmm[k] = 0.f;
+            padmask |= 1u << k;
+        }
+    }
+    if ((int)lane * RPT - 1 < npad) padmask |= 1u << RPT;
+
+    // ---- state ------------------------------------------------------------------------------
+    float2 Ml[RPT], Il[RPT], Dl[RPT];              // previous column, my rows
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = bc(0.f); Il[k] = bc(0.f); Dl[k] = bc(0.f); }
+    float2 upM = bc(0.f), upI = bc(0.f), upD = bc(0.f);   // row above my row 0, current column
+    float2 dgM = bc(0.f), dgI = bc(0.f), dgD = bc(0.f);   // same row, previous column
+    float2 sumM = bc(0.f), sumI = bc(0.f);
+    uint32_t jx = 0, jy = 0;                       // haplotypes begun so far in each stream
+    const uint2* sp = stream + 32 - lane;
+    const uint32_t nsteps = L - 1;
+    const bool writer = (lane == 31);
+
+#define PHMM_BOUNDARY(E, J, EI)                                                                         \
+    {                                                                                                   \
+        if (writer && J > 0) {                                                                          \
+            const float res = __fadd_rn(sumM.E, sumI.E);                                                \
+            const uint32_t oi = rd.out_off + info_col[EI * NI + J - 1];                                 \
+            p.out_f32[oi] = res;                                                                        \
+            if (res < 1e-28f) {                                                                         \
+                const uint32_t slot = atomicAdd(p.f64_count, 1u);                                       \
+                PhmmPair pr; pr.read = rid; pr.hap = info_hap[EI * NI + J - 1]; pr.out_idx = oi;        \
+                p.f64_pairs[slot] = pr;                                                                 \
+            }                                                                                           \
+        }                                                                                               \
+        const float init = info_init[EI * NI + J];                                                      \
+        ++J;                                                                                            \
+        sumM.E = 0.f; sumI.E = 0.f;                                                                     \
+        _Pragma("unroll") for (int k = 0; k < RPT; ++k) {                                               \
+            Ml[k].E = 0.f; Il[k].E = 0.f; Dl[k].E = ((padmask >> k) & 1u) ? init : 0.f;                 \
+        }                                                                                               \
+        dgM.E = 0.f; dgI.E = 0.f; dgD.E = ((padmask >> RPT) & 1u) ? init : 0.f;                         \
+    }
+
+#pragma unroll 2
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        const uint2 w = sp[s];
+        if ((w.x | w.y) & PHMM_FLAG_BIT) {
+            if (w.x & PHMM_FLAG_BIT) PHMM_BOUNDARY(x, jx, 0)
+            if (w.y & PHMM_FLAG_BIT) PHMM_BOUNDARY(y, jy, 1)
+        }
+        float2 pM = dgM, pI = dgI, pD = dgD;       // diagonal inputs of row 0
+        float2 uM = upM, uI = upI;                 // inputs from above of row 0
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
+            const uint32_t msk = 0xFu << (4 * (k % 7));
+            float2 prior;
+            prior.x = (rb[k / 7] & w.x & msk) ? pm[k] : pmm[k];
+            prior.y = (rb[k / 7] & w.y & msk) ? pm[k] : pmm[k];
+            float2 nM, nI, nD;
+            if (FMA) {                              // SURVEY.md §8a, AVX-512 contraction
+                float2 t = __fmul2_rn(pM, bc(mm[k]));
+                t = __ffma2_rn(pI, bc(gapm[k]), t);
+                t = __ffma2_rn(pD, bc(gapm[k]), t);
+                nM = __fmul2_rn(t, prior);
+                nI = __ffma2_rn(uI, bc(ii[k]), __fmul2_rn(uM, bc(mi[k])));
+                nD = __ffma2_rn(oD, bc(dd[k]), __fmul2_rn(oM, bc(md[k])));
+            } else {                                // core/avx2_s.cpp:207-216, scalar on purpose (see header)
+                float tx = __fadd_rn(__fmul_rn(pM.x, mm[k]), __fmul_rn(pI.x, gapm[k]));
+                float ty = __fadd_rn(__fmul_rn(pM.y, mm[k]), __fmul_rn(pI.y, gapm[k]));
+                tx = __fadd_rn(tx, __fmul_rn(pD.x, gapm[k]));
+                ty = __fadd_rn(ty, __fmul_rn(pD.y, gapm[k]));
+                nM.x = __fmul_rn(tx, prior.x);
+                nM.y = __fmul_rn(ty, prior.y);
+                nI.x = __fadd_rn(__fmul_rn(uM.x, mi[k]), __fmul_rn(uI.x, ii[k]));
+                nI.y = __fadd_rn(__fmul_rn(uM.y, mi[k]), __fmul_rn(uI.y, ii[k]));
+                nD.x = __fadd_rn(__fmul_rn(oM.x, md[k]), __fmul_rn(oD.x, dd[k]));
+                nD.y = __fadd_rn(__fmul_rn(oM.y, md[k]), __fmul_rn(oD.y, dd[k]));
+            }
+            Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
+            pM = oM; pI = oI; pD = oD;
+            uM = nM; uI = nI;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        if (FMA) {
+            sumM = __fadd2_rn(sumM, Ml[RPT - 1]);   // avx_512_float.cc:166-171, ascending columns
+            sumI = __fadd2_rn(sumI, Il[RPT - 1]);
+        } else {
+            sumM.x = __fadd_rn(sumM.x, Ml[RPT - 1].x); sumM.y = __fadd_rn(sumM.y, Ml[RPT - 1].y);
+            sumI.x = __fadd_rn(sumI.x, Il[RPT - 1].x); sumI.y = __fadd_rn(sumI.y, Il[RPT - 1].y);
+        }
+        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1);
+        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1);
+        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1);
+        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1);
+        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1);
+        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1);
+    }
+#undef PHMM_BOUNDARY
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-pair kernel: one thread per (read, haplotype) pair, previous row kept in a global scratch
+// interleaved across threads.  Used for the FP64 recompute of pairs whose FP32 sum underflowed
+// (pairhmm_internal.cpp:578-581; init 2^1020/H, double tables — core/context.h:99-111) and, in FP32,
+// for shapes outside the wavefront kernel's envelope.  Same recurrence, same operation order.
+// ------------------------------------------------------------------------------------------------
+
+template <typename T> struct Num;
+template <> struct Num<float>
+{
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float init(uint32_t H) { return __fdiv_rn(__uint_as_float(0x7B800000u), (float)H); }
+};
+template <> struct Num<double>
+{
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double init(uint32_t H) { return __ddiv_rn(__longlong_as_double(0x7FB0000000000000LL), (double)H); }   // 2^1020 / H
+};
+
+template <typename T, bool FMA>
+__global__ void __launch_bounds__(128) phmm_pair_kernel(PhmmBatchDev p, const PhmmPair* pairs, const uint32_t* count_dev,
+                                                        uint32_t count, T* scratch, uint32_t max_cols, T* out)
+{
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nthr = gridDim.x * blockDim.x;
+    const uint32_t n = count_dev ? *count_dev : count;
+    T* Mr = scratch + tid;
+    T* Ir = Mr + (size_t)(max_cols + 1) * nthr;
+    T* Dr = Ir + (size_t)(max_cols + 1) * nthr;
+    const PhmmTables* __restrict__ tb = p.tables;
+    for (uint32_t pi = tid; pi < n; pi += nthr) {
+        const PhmmPair pr = pairs[pi];
+        const PhmmRead rd = p.reads[pr.read];
+        const PhmmHap hp = p.haps[pr.hap];
+        const uint32_t H = hp.len, R = rd.len;
+        const uint8_t* hb = p.hap_bases + hp.byte_off;
+        const T init = Num<T>::init(H);
+        for (uint32_t c = 0; c <= H; ++c) { Mr[(size_t)c * nthr] = (T)0; Ir[(size_t)c * nthr] = (T)0; Dr[(size_t)c * nthr] = init; }
+        for (uint32_t r = 0; r < R; ++r) {
+            const uint32_t w = p.words[rd.word_off + r];
+            const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u, rbase = w >> 28;
+            const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+            T mm, gapm, mi, ii, md, dd, pm, pmm;
+            if (sizeof(T) == 4) {
+                mm = tb->mm[((hi * (hi + 1)) >> 1) + lo]; gapm = tb->gapm[qc]; mi = tb->ph2pr[qi]; ii = tb->ph2pr[qc];
+                md = tb->ph2pr[qd]; dd = ii; pm = tb->pm[q]; pmm = tb->pmm[q];
+            } else {
+                mm = (T)tb->mm_d[((hi * (hi + 1)) >> 1) + lo]; gapm = (T)__dsub_rn(1.0, tb->ph2pr_d[qc]); mi = (T)tb->ph2pr_d[qi];
+                ii = (T)tb->ph2pr_d[qc]; md = (T)tb->ph2pr_d[qd]; dd = ii;
+                pm = (T)__dsub_rn(1.0, tb->ph2pr_d[q]); pmm = (T)__ddiv_rn(tb->ph2pr_d[q], 3.0);
+            }
+            T dM = Mr[0], dI = Ir[0], dD = Dr[0];          // row r-1, column 0
+            Mr[0] = (T)0; Ir[0] = (T)0; Dr[0] = (T)0;       // row r, column 0
+            T lM = (T)0, lI = (T)0, lD = (T)0;
+            for (uint32_t c = 1; c <= H; ++c) {
+                const T uM = Mr[(size_t)c * nthr], uI = Ir[(size_t)c * nthr], uD = Dr[(size_t)c * nthr];
+                const T prior = (rbase & onehot(hb[c - 1])) ? pm : pmm;
+                T m, i, d;
+                if (FMA) {
+                    T t = Num<T>::mul(dM, mm);
+                    t = Num<T>::fma(dI, gapm, t);
+                    t = Num<T>::fma(dD, gapm, t);
+                    m = Num<T>::mul(t, prior);
+                    i = Num<T>::fma(uI, ii, Num<T>::mul(uM, mi));
+                    d = Num<T>::fma(lD, dd, Num<T>::mul(lM, md));
+                } else {
+                    T t = Num<T>::add(Num<T>::mul(dM, mm), Num<T>::mul(dI, gapm));
+                    t = Num<T>::add(t, Num<T>::mul(dD, gapm));
+                    m = Num<T>::mul(t, prior);
+                    i = Num<T>::add(Num<T>::mul(uM, mi), Num<T>::mul(uI, ii));
+                    d = Num<T>::add(Num<T>::mul(lM, md), Num<T>::mul(lD, dd));
+                }
+                Mr[(size_t)c * nthr] = m; Ir[(size_t)c * nthr] = i; Dr[(size_t)c * nthr] = d;
+                dM = uM; dI = uI; dD = uD;
+                lM = m; lI = i; lD = d;
+            }
+        }
+        T sM = (T)0, sI = (T)0;
+        for (uint32_t c = 1; c <= H; ++c) { sM = Num<T>::add(sM, Mr[(size_t)c * nthr]); sI = Num<T>::add(sI, Ir[(size_t)c * nthr]); }
+        const T res = Num<T>::add(sM, sI);
+        out[pr.out_idx] = res;
+        if (sizeof(T) == 4 && res < (T)1e-28f) {            // pairhmm_internal.cpp:578: queue the FP64 recompute
+            const uint32_t slot = atomicAdd(p.f64_count, 1u);
+            p.f64_pairs[slot] = pr;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Issue-rate micro-benchmarks (bench.py's measured FP32 peak; DESIGN.md's pipe model).  Every thread runs
+// independent dependency chains long enough to hide the 4-cycle FMA latency.
+//   mode 0: scalar FFMA                     mode 1: packed FFMA2 (two FMAs per instruction)
+//   mode 2: FFMA2 + (LOP3->P, FSEL) 2:1     mode 3: mode 2 + one SHFL.UP per 8 FFMA2
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t iters, float a, float b, uint32_t m)
+{
+    const float t = (float)threadIdx.x * 1e-6f;
+    float2 x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = make_float2(t + (float)k, t - (float)k);
+    const float2 aa = make_float2(a, a), bb = make_float2(b, b);
+    uint32_t w = m + threadIdx.x;
+    float sel = 0.f;
+    for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                if (MODE == 0) {
+                    x[k].x = __fmaf_rn(x[k].x, a, b);
+                    x[k].y = __fmaf_rn(x[k].y, a, b);
+                } else {
+                    x[k] = __ffma2_rn(x[k], aa, bb);
+                }
+                if (MODE >= 2 && (k & 1)) {
+                    sel += ((w >> (k + r)) & m) ? a : b;     // LOP3 -> predicate, FSEL (+ the FADD, FP32 pipe)
+                }
+            }
+            if (MODE == 3) x[r].x = __shfl_up_sync(0xffffffffu, x[r].x, 1);
+            w = w * 1664525u + 1013904223u;
+        }
+    }
+    float acc = sel;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += x[k].x + x[k].y;
+    if (acc == 123.456f) out[0] = acc;
+}
+
+template <int RPT, bool FMA>
+cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, size_t smem, cudaStream_t st)
+{
+    auto kern = phmm_fwd_kernel<RPT, FMA>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<n_ctas, PHMM_WARPS * 32, smem, st>>>(b, cta_base);
+    return cudaGetLastError();
+}
+
+template <int RPT, bool FMA>
+cudaError_t info_t(PhmmKernelInfo* info)
+{
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, FMA>);
+    if (e != cudaSuccess) return e;
+    info->regs = a.numRegs;
+    info->local_bytes = (int)a.localSizeBytes;
+    info->max_threads = a.maxThreadsPerBlock;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
+{
+    if (b.n_reads == 0) return cudaSuccess;
+    const uint32_t warps_per_block = 8;
+    const uint32_t blocks = (b.n_reads + warps_per_block - 1) / warps_per_block;
+    phmm_prep_kernel<<<blocks, warps_per_block * 32, 0, st>>>(b);
+    return cudaGetLastError();
+}
+
+#define PHMM_DISPATCH_BIN(FN, ...)                                                    \
+    switch (kPhmmRptBins[bin]) {                                                      \
+        case 1: return fma ? FN<1, true>(__VA_ARGS__) : FN<1, false>(__VA_ARGS__);    \
+        case 2: return fma ? FN<2, true>(__VA_ARGS__) : FN<2, false>(__VA_ARGS__);    \
+        case 3: return fma ? FN<3, true>(__VA_ARGS__) : FN<3, false>(__VA_ARGS__);    \
+        case 4: return fma ? FN<4, true>(__VA_ARGS__) : FN<4, false>(__VA_ARGS__);    \
+        case 5: return fma ? FN<5, true>(__VA_ARGS__) : FN<5, false>(__VA_ARGS__);    \
+        case 6: return fma ? FN<6, true>(__VA_ARGS__) : FN<6, false>(__VA_ARGS__);    \
+        case 7: return fma ? FN<7, true>(__VA_ARGS__) : FN<7, false>(__VA_ARGS__);    \
+        case 8: return fma ? FN<8, true>(__VA_ARGS__) : FN<8, false>(__VA_ARGS__);    \
+        case 10: return fma ? FN<10, true>(__VA_ARGS__) : FN<10, false>(__VA_ARGS__); \
+        case 12: return fma ? FN<12, true>(__VA_ARGS__) : FN<12, false>(__VA_ARGS__); \
+        default: return cudaErrorInvalidValue;                                        \
+    }
+
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, size_t smem_bytes,
+                            cudaStream_t st)
+{
+    if (n_ctas == 0) return cudaSuccess;
+    if (bin < 0 || bin >= kPhmmNumBins) return cudaErrorInvalidValue;
+    PHMM_DISPATCH_BIN(launch_fwd_t, b, cta_base, n_ctas, smem_bytes, st)
+}
+
+cudaError_t phmm_fwd_kernel_info(int bin, bool fma, PhmmKernelInfo* info)
+{
+    if (bin < 0 || bin >= kPhmmNumBins) return cudaErrorInvalidValue;
+    PHMM_DISPATCH_BIN(info_t, info)
+}
+
+cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
+                                  uint32_t threads, uint32_t max_cols, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    const uint32_t blocks = threads / 128;
+    if (fma)
+        phmm_pair_kernel<float, true><<<blocks, 128, 0, st>>>(b, pairs, nullptr, count, scratch, max_cols, b.out_f32);
+    else
+        phmm_pair_kernel<float, false><<<blocks, 128, 0, st>>>(b, pairs, nullptr, count, scratch, max_cols, b.out_f32);
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_pairs_f64(const PhmmBatchDev& b, const PhmmPair* pairs, const uint32_t* count_dev, double* scratch,
+                                  uint32_t threads, uint32_t max_cols, cudaStream_t st)
+{
+    const uint32_t blocks = threads / 128;
+    phmm_pair_kernel<double, true><<<blocks, 128, 0, st>>>(b, pairs, count_dev, 0u, scratch, max_cols, b.out_f64);
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_ubench(int mode, uint32_t blocks, uint32_t iters, float* out, cudaStream_t st)
+{
+    switch (mode) {
+        case 0: phmm_ubench_kernel<0><<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-3f, 0x1u); break;
+        case 1: phmm_ubench_kernel<1><<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-3f, 0x1u); break;
+        case 2: phmm_ubench_kernel<2><<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-3f, 0x1u); break;
+        case 3: phmm_ubench_kernel<3><<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-3f, 0x1u); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}

@@ -1,0 +1,322 @@
+"""Python door to ``libphmm_b200.so`` — mirrors the reference's PairHMM interface.
+
+Reference seam: ``rovaca::call_pairhmm(hs, rs, min_quality_threshold, pcr_option, pool)``
+(/root/reference/src/haplotypecaller/pairhmm/pairhmm_engine.h:14-15), bound once by
+``init_pairhmm_ptr`` (pairhmm_engine.cpp:21-53).  Here: ``PairHmmEngine()`` is the binding,
+``PairHmmEngine.call_pairhmm(haps, reads, min_quality_threshold, pcr_option)`` the call; it returns
+the ``[hap][read]`` log10 likelihood matrix with the reference's NaN tail plus the indices of the reads
+the call left in ``rs``.  All arithmetic happens in the CUDA library; nothing here computes
+likelihoods and nothing falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from .workloads import RegionBatch, _as_u8
+
+PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE, PCR_CONSERVATIVE = 0, 1, 2, 3      # common/enum.h:8
+FMA_AVX512, FMA_NONE = 1, 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_u64p = C.POINTER(C.c_uint64)
+_f32p = C.POINTER(C.c_float)
+_f64p = C.POINTER(C.c_double)
+
+
+class PhmmError(RuntimeError):
+    pass
+
+
+class _Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
+                ("linger_us", C.c_uint32), ("rsv", C.c_uint32 * 9)]
+
+
+class _Read(C.Structure):
+    _fields_ = [("bases", _u8p), ("qual", _u8p), ("ins", _u8p), ("del_", _u8p), ("gcp", _u8p), ("len", C.c_uint32),
+                ("mapq", C.c_uint8)]
+
+
+class _Hap(C.Structure):
+    _fields_ = [("bases", _u8p), ("len", C.c_uint32)]
+
+
+class _Region(C.Structure):
+    _fields_ = [("reads", C.POINTER(_Read)), ("n_reads", C.c_uint32), ("haps", C.POINTER(_Hap)), ("n_haps", C.c_uint32),
+                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32)]
+
+
+class _Result(C.Structure):
+    _fields_ = [("likelihoods", _f64p), ("kept_idx", _u32p), ("n_kept", C.c_uint32), ("raw_f32", _f32p), ("raw_f64", _f64p),
+                ("n_fp64", C.c_uint32)]
+
+
+class _FlatBatch(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("reg_read_off", _u64p), ("reg_hap_off", _u64p), ("read_len", _u32p),
+                ("read_mapq", _u8p), ("read_off", _u64p), ("read_bases", _u8p), ("read_qual", _u8p), ("read_ins", _u8p),
+                ("read_del", _u8p), ("read_gcp", _u8p), ("hap_len", _u32p), ("hap_off", _u64p), ("hap_bases", _u8p),
+                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32)]
+
+
+class _FlatResult(C.Structure):
+    _fields_ = [("likelihoods", _f64p), ("lik_off", _u64p), ("kept_idx", _u32p), ("n_kept", _u32p), ("raw_f32", _f32p),
+                ("raw_f64", _f64p), ("n_fp64", C.c_uint64)]
+
+
+class _Stats(C.Structure):
+    _fields_ = [("regions", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64),
+                ("slow_pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("batches", C.c_uint64),
+                ("gpu_ms", C.c_double), ("kernel_launches", C.c_uint64)]
+
+
+EXPORTS = ["phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
+           "phmm_resident_upload", "phmm_resident_run", "phmm_resident_download", "phmm_resident_free",
+           "phmm_resident_launches", "phmm_get_stats", "phmm_kernel_info", "phmm_ubench", "phmm_last_error", "phmm_version"]
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libphmm_b200.so")
+
+
+def build_library(force: bool = False) -> str:
+    """Compile the CUDA kernels (sm_100a) and the host engine in-tree.  nvcc cross-compiles without a GPU."""
+    if force:
+        subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc"), "clean"], check=True)
+    subprocess.run(["make", "-s", "-C", os.path.join(_HERE, "csrc")], check=True)
+    return library_path()
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libphmm_b200.so; raises PhmmError (never falls back) if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise PhmmError(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                        "rovaca_b200 has no CPU fallback")
+    L = C.CDLL(path)
+    L.phmm_last_error.restype = C.c_char_p
+    L.phmm_version.restype = C.c_char_p
+    L.phmm_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.phmm_destroy.argtypes = [C.c_void_p]
+    L.phmm_destroy.restype = None
+    L.phmm_call_region.argtypes = [C.c_void_p, C.POINTER(_Region), C.POINTER(_Result)]
+    L.phmm_submit.argtypes = [C.c_void_p, C.POINTER(_Region), C.POINTER(_Result), _u64p]
+    L.phmm_wait.argtypes = [C.c_void_p, C.c_uint64]
+    L.phmm_flush.argtypes = [C.c_void_p]
+    L.phmm_run_flat.argtypes = [C.c_void_p, C.POINTER(_FlatBatch), C.POINTER(_FlatResult)]
+    L.phmm_resident_upload.argtypes = [C.c_void_p, C.POINTER(_FlatBatch), C.POINTER(C.c_void_p)]
+    L.phmm_resident_run.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p]
+    L.phmm_resident_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_FlatResult)]
+    L.phmm_resident_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.phmm_resident_free.restype = None
+    L.phmm_resident_launches.argtypes = [C.c_void_p]
+    L.phmm_resident_launches.restype = C.c_uint32
+    L.phmm_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
+    L.phmm_kernel_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.phmm_ubench.argtypes = [C.c_void_p, C.c_int, C.c_uint32, _f32p, _f64p]
+    L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
+    L.phmm_debug_tables.restype = None
+    _lib = L
+    return L
+
+
+def host_tables():
+    """The libm tables the engine uploads (core/context.h) — host-only, for table-level tests."""
+    L = load_library()
+    ph, mm = np.zeros(128, np.float32), np.zeros(8256, np.float32)
+    phd, mmd = np.zeros(128, np.float64), np.zeros(8256, np.float64)
+    L.phmm_debug_tables(ph.ctypes.data_as(_f32p), mm.ctypes.data_as(_f32p), phd.ctypes.data_as(_f64p), mmd.ctypes.data_as(_f64p))
+    return ph, mm, phd, mmd
+
+
+def _ptr(a: Optional[np.ndarray], t):
+    return a.ctypes.data_as(t) if a is not None else t()
+
+
+class FlatResult:
+    """Host buffers one flat call fills; ``matrix(g)`` gives region g's [n_haps][n_reads] view."""
+
+    def __init__(self, batch: RegionBatch, raw: bool = False):
+        self.batch = batch
+        self.lik_off = batch.lik_off()
+        n = int(self.lik_off[-1])
+        self.likelihoods = np.empty(max(n, 1), np.float64)
+        self.kept_idx = np.zeros(max(batch.n_reads, 1), np.uint32)
+        self.n_kept = np.zeros(max(batch.n_regions, 1), np.uint32)
+        self.raw_f32 = np.zeros(max(n, 1), np.float32) if raw else None
+        self.raw_f64 = np.zeros(max(n, 1), np.float64) if raw else None
+        self.n_fp64 = 0
+        self.c = _FlatResult(_ptr(self.likelihoods, _f64p), _ptr(self.lik_off, _u64p), _ptr(self.kept_idx, _u32p),
+                             _ptr(self.n_kept, _u32p), _ptr(self.raw_f32, _f32p), _ptr(self.raw_f64, _f64p), 0)
+
+    def _dims(self, g: int) -> Tuple[int, int]:
+        b = self.batch
+        return int(b.reg_hap_off[g + 1] - b.reg_hap_off[g]), int(b.reg_read_off[g + 1] - b.reg_read_off[g])
+
+    def matrix(self, g: int) -> np.ndarray:
+        nh, nr = self._dims(g)
+        o = int(self.lik_off[g])
+        return self.likelihoods[o:o + nh * nr].reshape(nh, nr)
+
+    def kept(self, g: int) -> np.ndarray:
+        r0 = int(self.batch.reg_read_off[g])
+        return self.kept_idx[r0:r0 + int(self.n_kept[g])]
+
+    def raw32(self, g: int) -> np.ndarray:
+        nh, nr = self._dims(g)
+        o = int(self.lik_off[g])
+        return self.raw_f32[o:o + nh * nr].reshape(nr, nh)
+
+    def raw64(self, g: int) -> np.ndarray:
+        nh, nr = self._dims(g)
+        o = int(self.lik_off[g])
+        return self.raw_f64[o:o + nh * nr].reshape(nr, nh)
+
+
+def _flat_c(batch: RegionBatch, thr: int, pcr: int) -> _FlatBatch:
+    return _FlatBatch(batch.n_regions, _ptr(batch.reg_read_off, _u64p), _ptr(batch.reg_hap_off, _u64p), _ptr(batch.read_len, _u32p),
+                      _ptr(batch.read_mapq, _u8p), _ptr(batch.read_off, _u64p), _ptr(batch.read_bases, _u8p),
+                      _ptr(batch.read_qual, _u8p), _ptr(batch.read_ins, _u8p), _ptr(batch.read_del, _u8p), _ptr(batch.read_gcp, _u8p),
+                      _ptr(batch.hap_len, _u32p), _ptr(batch.hap_off, _u64p), _ptr(batch.hap_bases, _u8p), thr, pcr)
+
+
+class Resident:
+    """A batch living in HBM: ``run()`` executes the device path only (kernel-timing leg of the bench)."""
+
+    def __init__(self, eng: "PairHmmEngine", batch: RegionBatch, thr: int, pcr: int):
+        self.eng, self.batch = eng, batch
+        self.h = C.c_void_p()
+        fb = _flat_c(batch, thr, pcr)
+        eng._check(eng.L.phmm_resident_upload(eng.h, C.byref(fb), C.byref(self.h)))
+        self.launches = int(eng.L.phmm_resident_launches(self.h))
+
+    def run(self) -> Tuple[float, float]:
+        """-> (all kernels ms, forward kernels ms) from CUDA events on the batch's stream."""
+        a, b = C.c_float(0), C.c_float(0)
+        self.eng._check(self.eng.L.phmm_resident_run(self.eng.h, self.h, C.byref(a), C.byref(b)))
+        return float(a.value), float(b.value)
+
+    def download(self, raw: bool = False) -> FlatResult:
+        res = FlatResult(self.batch, raw)
+        self.eng._check(self.eng.L.phmm_resident_download(self.eng.h, self.h, C.byref(res.c)))
+        res.n_fp64 = int(res.c.n_fp64)
+        return res
+
+    def free(self):
+        if self.h:
+            self.eng.L.phmm_resident_free(self.eng.h, self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PairHmmEngine:
+    """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
+
+    def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
+                 linger_us: int = 0):
+        self.L = load_library()
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us)
+        self.h = C.c_void_p()
+        rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise PhmmError(f"phmm_create failed ({rc}): {self.L.phmm_last_error().decode()}")
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PhmmError(f"libphmm_b200 error {rc}: {self.L.phmm_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.phmm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- the reference's call ---------------------------------------------------------------------
+    def call_pairhmm(self, haps: Sequence, reads: Sequence[dict], min_quality_threshold: int = 18,
+                     pcr_option: int = PCR_CONSERVATIVE, raw: bool = False):
+        """One region.  reads: dicts with bases, qual, mapq and optionally ins/del/gcp (bytes / uint8 arrays).
+        Returns (matrix[n_haps, n_reads] with NaN tail, kept_idx) and, with raw=True, also (raw_f32, raw_f64, n_fp64)."""
+        n_r, n_h = len(reads), len(haps)
+        keep = []
+        ra = (_Read * max(n_r, 1))()
+        for k, r in enumerate(reads):
+            b, q = _as_u8(r["bases"]), _as_u8(r["qual"])
+            if len(b) != len(q):
+                raise ValueError("bases and qual differ in length")
+            keep += [b, q]
+            ra[k].bases, ra[k].qual = b.ctypes.data_as(_u8p), q.ctypes.data_as(_u8p)
+            for name, field in (("ins", "ins"), ("del", "del_"), ("gcp", "gcp")):
+                v = r.get(name)
+                if v is not None:
+                    a = _as_u8(v)
+                    keep.append(a)
+                    setattr(ra[k], field, a.ctypes.data_as(_u8p))
+            ra[k].len, ra[k].mapq = len(b), int(r.get("mapq", 60))
+        ha = (_Hap * max(n_h, 1))()
+        for j, h in enumerate(haps):
+            a = _as_u8(h)
+            keep.append(a)
+            ha[j].bases, ha[j].len = a.ctypes.data_as(_u8p), len(a)
+        out = np.full((n_h, n_r), np.nan, np.float64)
+        kept = np.zeros(max(n_r, 1), np.uint32)
+        raw32 = np.zeros((n_r, n_h), np.float32) if raw else None
+        raw64 = np.zeros((n_r, n_h), np.float64) if raw else None
+        reg = _Region(ra, n_r, ha, n_h, min_quality_threshold, pcr_option)
+        res = _Result(_ptr(out, _f64p), _ptr(kept, _u32p), 0, _ptr(raw32, _f32p), _ptr(raw64, _f64p), 0)
+        self._check(self.L.phmm_call_region(self.h, C.byref(reg), C.byref(res)))
+        if n_r == 0 or n_h == 0:       # pairhmm_internal.cpp:508-510 returns an empty matrix
+            out = np.zeros((0, 0), np.float64)
+        if raw:
+            return out, kept[: res.n_kept].copy(), raw32, raw64, int(res.n_fp64)
+        return out, kept[: res.n_kept].copy()
+
+    # -- batch forms ------------------------------------------------------------------------------
+    def run_flat(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE,
+                 raw: bool = False, out: Optional[FlatResult] = None) -> FlatResult:
+        """Host buffers in, host buffers out: packing, H2D, kernels, D2H and the host epilogue, pipelined."""
+        res = out or FlatResult(batch, raw)
+        fb = _flat_c(batch, min_quality_threshold, pcr_option)
+        self._check(self.L.phmm_run_flat(self.h, C.byref(fb), C.byref(res.c)))
+        res.n_fp64 = int(res.c.n_fp64)
+        return res
+
+    def upload(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE) -> Resident:
+        return Resident(self, batch, min_quality_threshold, pcr_option)
+
+    def stats(self) -> dict:
+        s = _Stats()
+        self._check(self.L.phmm_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def ubench(self, mode: int, iters: int = 4096) -> Tuple[float, float]:
+        """-> (ms, FMA lane-ops per second) of the FP32 issue-rate micro-benchmark."""
+        ms, rate = C.c_float(0), C.c_double(0)
+        self._check(self.L.phmm_ubench(self.h, mode, iters, C.byref(ms), C.byref(rate)))
+        return float(ms.value), float(rate.value)
+
+    def kernel_info(self, rpt: int, fma_mode: int = FMA_AVX512) -> Tuple[int, int]:
+        regs, loc = C.c_int(0), C.c_int(0)
+        self._check(self.L.phmm_kernel_info(rpt, fma_mode, C.byref(regs), C.byref(loc)))
+        return regs.value, loc.value

@@ -1,0 +1,52 @@
+"""Loaders for tests/golden/*.npz (made by tests/golden/make_golden.py from the compiled reference)."""
+import os
+
+import numpy as np
+
+from rovaca_b200.workloads import RegionBatch
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def pairs():
+    """-> list of dict(hap, rs, q, ins, del, gcp, ref_avx512, ref_avx2, ref_1xn) (raw sums as uint32 bit patterns)."""
+    z = np.load(os.path.join(HERE, "pairs.npz"))
+    out, ro, ho = [], 0, 0
+    for k, (R, H) in enumerate(z["lens"]):
+        R, H = int(R), int(H)
+        d = dict(hap=z["hap"][ho:ho + H], rs=z["rs"][ro:ro + R], q=z["q"][ro:ro + R], ins=z["ins"][ro:ro + R],
+                 dele=z["del"][ro:ro + R], gcp=z["gcp"][ro:ro + R], ref_avx512=z["ref_avx512"][k], ref_avx2=z["ref_avx2"][k],
+                 ref_1xn=z["ref_1xn"][k])
+        out.append(d)
+        ro += R
+        ho += H
+    return out
+
+
+def regions():
+    """-> (RegionBatch, meta[n,2] (threshold, pcr model), list of matrix bit patterns, list of kept idx)."""
+    z = np.load(os.path.join(HERE, "regions.npz"))
+    b = RegionBatch(reg_read_off=z["reg_read_off"], reg_hap_off=z["reg_hap_off"], read_len=z["read_len"], read_mapq=z["read_mapq"],
+                    read_off=z["read_off"], read_bases=z["read_bases"], read_qual=z["read_qual"], hap_len=z["hap_len"],
+                    hap_off=z["hap_off"], hap_bases=z["hap_bases"], name="golden regions")
+    lik = b.lik_off()
+    mats, kept, ko = [], [], 0
+    for g in range(b.n_regions):
+        mats.append(z["mats"][int(lik[g]):int(lik[g + 1])])
+        n = int(z["n_kept"][g])
+        kept.append(z["kept"][ko:ko + n])
+        ko += n
+    return b, z["meta"], mats, kept
+
+
+def pcr():
+    z = np.load(os.path.join(HERE, "pcr.npz"))
+    out, so, co = [], 0, 0
+    for n in z["seq_len"]:
+        n = int(n)
+        seq = z["seq"][so:so + n]
+        capped = [z["capped"][co + m * n: co + (m + 1) * n] for m in range(3)]
+        out.append(dict(seq=seq, capped=capped, repeats=z["repeats"][so:so + n]))
+        so += n
+        co += 3 * n
+    return out

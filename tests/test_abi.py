@@ -1,0 +1,97 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/phmm_b200.h declares, refuses to run without a
+GPU (no CPU fallback), carries the reference's tables, and its SASS has the expected instruction mix."""
+import os
+import re
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import rovaca_b200
+from rovaca_b200 import pairhmm as ph
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_header_symbols():
+    lib = ph.load_library()
+    header = open(os.path.join(ROOT, "include", "phmm_b200.h")).read()
+    declared = set(re.findall(r"\b(phmm_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(ph.EXPORTS), (declared ^ set(ph.EXPORTS))
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/phmm_b200.h but not exported"
+    assert b"sm_100a" in lib.phmm_version()
+
+
+def test_header_cites_reference_interfaces():
+    header = open(os.path.join(ROOT, "include", "phmm_b200.h")).read()
+    for cite in ("pairhmm_engine.h:14-15", "pairhmm_engine.cpp:21", "haplotypecaller_engine.cpp:250", "read_record.h:67-103",
+                 "pairhmm_internal.cpp:161-182"):
+        assert cite in header
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_fails_loudly_without_gpu():
+    with pytest.raises(ph.PhmmError) as ei:
+        rovaca_b200.PairHmmEngine()
+    assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_tables_match_oracle(orc):
+    p, mm, pd, mmd = ph.host_tables()
+    assert np.array_equal(p.view(np.uint32), orc.ph2pr_f32().view(np.uint32))
+    assert np.array_equal(mm.view(np.uint32), orc.mm_tri_f32().view(np.uint32))
+    assert np.array_equal(pd.view(np.uint64), orc.ph2pr_f64().view(np.uint64))
+    assert np.array_equal(mmd.view(np.uint64), orc.mm_tri_f64().view(np.uint64))
+
+
+def test_product_never_touches_oracle():
+    """The product path must not import, link or call anything under oracle/."""
+    pkg = os.path.join(ROOT, "rovaca_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".hpp", "Makefile")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("the oracle", "").lower() or f == "workloads.py", f
+    ldd = subprocess.run(["ldd", ph.library_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in ldd and "phmm_ref" not in ldd
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not on PATH")
+def test_sass_audit():
+    """Per step the forward kernel must issue exactly 4 FMUL2 + 4 FFMA2 per row (two cells each) and 2 FADD2, i.e. ptxas
+    has not contracted any rounded product into a neighbouring add (it does for single-use packed products), and the
+    code is sm_100a packed-FP32 (FFMA2/FMUL2), loop unrolled by two."""
+    sass = subprocess.run(["cuobjdump", "-sass", ph.library_path()], capture_output=True, text=True).stdout
+    cur, counts = None, {}
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            counts[cur] = dict(FFMA2=0, FMUL2=0, FADD2=0, SHFL=0)
+            continue
+        if cur:
+            for op in counts[cur]:
+                if re.search(r"\b%s\b" % op, line):
+                    counts[cur][op] += 1
+    seen = 0
+    for name, c in counts.items():
+        m = re.search(r"phmm_fwd_kernelILi(\d+)ELb1E", name)
+        if not m:
+            continue
+        rpt = int(m.group(1))
+        seen += 1
+        assert c["FFMA2"] == 8 * rpt and c["FMUL2"] == 8 * rpt, (name, c)
+        assert c["FADD2"] == 4, (name, c)
+        assert c["SHFL"] >= 12, (name, c)
+    assert seen >= 8

@@ -1,0 +1,235 @@
+"""GPU (B200): the CUDA path, called through the C ABI, against the CPU oracle and the golden vectors.
+
+Bars (integer/bit work unless said otherwise):
+  raw FP32 forward sums ........ bit-identical to the reference's AVX-512 (or AVX2) kernels
+  FP64 recompute ............... <= 1e-12 relative vs the scalar FP64 oracle (tolerance stated here; the reference's own
+                                 FP64 kernels are defective and unobservable downstream)
+  PCR model / quality capping .. covered through the region results (any slip changes the matrices)
+  post-processed matrix ........ byte-identical incl. NaN tail, and the same set of surviving reads
+"""
+import threading
+
+import numpy as np
+import pytest
+
+import _golden
+from oracle import bindings as ob
+from rovaca_b200 import workloads as wl
+from rovaca_b200 import PairHmmEngine, PCR_NONE, PCR_CONSERVATIVE, PCR_HOSTILE, PCR_AGGRESSIVE
+
+pytestmark = pytest.mark.gpu
+B = np.frombuffer(b"ACGT", np.uint8)
+F64_RTOL = 1e-12
+
+
+def _bits32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _bits64(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _check_region_vs_oracle(eng, orc, reads, haps, thr=18, model=PCR_CONSERVATIVE, fma=ob.FMA_AVX512):
+    m1, k1, r32, r64, n64 = eng.call_pairhmm(haps, reads, thr, model, raw=True)
+    m0, k0, o32, o64, o_n64 = orc.region(reads, haps, thr, model, fma)
+    assert np.array_equal(_bits32(r32), _bits32(o32)), "raw FP32 sums differ"
+    assert n64 == o_n64
+    took = o32 < np.float32(1e-28)
+    if took.any():
+        a, b = r64[took], o64[took]
+        nz = b != 0
+        assert np.all(np.abs(a[nz] - b[nz]) <= F64_RTOL * np.abs(b[nz])) and np.all(a[~nz] == 0)
+        assert np.all(np.isnan(r64[~took]))
+    assert np.array_equal(k1, k0), "different reads survive the filter"
+    assert np.array_equal(_bits64(m1), _bits64(m0)), "likelihood matrix bytes differ"
+    return n64
+
+
+def test_golden_pairs_raw_bits(engine, engine_nofma):
+    """Every golden pair as a 1x1 region with explicit ins/del/gcp and no read preparation (thr 0, mapq 255, PCR NONE)."""
+    gp = _golden.pairs()
+    regs = [([dict(bases=p["rs"], qual=p["q"], ins=p["ins"], gcp=p["gcp"], mapq=255, **{"del": p["dele"]})], [p["hap"]]) for p in gp]
+    batch = wl.RegionBatch.from_regions(regs)
+    res = engine.run_flat(batch, 0, PCR_NONE, raw=True)
+    got = np.array([res.raw32(g)[0, 0] for g in range(batch.n_regions)], np.float32)
+    assert np.array_equal(_bits32(got), np.array([p["ref_avx512"] for p in gp], np.uint32))
+    res2 = engine_nofma.run_flat(batch, 0, PCR_NONE, raw=True)
+    got2 = np.array([res2.raw32(g)[0, 0] for g in range(batch.n_regions)], np.float32)
+    assert np.array_equal(_bits32(got2), np.array([p["ref_avx2"] for p in gp], np.uint32))
+
+
+def test_golden_regions_byte_identical(engine):
+    batch, meta, mats, kept = _golden.regions()
+    for g in range(batch.n_regions):
+        reads, haps = batch.region(g)
+        m, k = engine.call_pairhmm(haps, reads, int(meta[g][0]), int(meta[g][1]))
+        assert np.array_equal(k, kept[g]), f"region {g}"
+        assert np.array_equal(_bits64(m).reshape(-1), mats[g]), f"region {g}"
+    # and all of them in one flat call per (threshold, model)
+    for model in sorted(set(int(x) for x in meta[:, 1])):
+        idx = [g for g in range(batch.n_regions) if int(meta[g][1]) == model]
+        sub = batch.subset(idx)
+        res = engine.run_flat(sub, 18, model)
+        for j, g in enumerate(idx):
+            assert np.array_equal(res.kept(j), kept[g])
+            assert np.array_equal(_bits64(res.matrix(j)).reshape(-1), mats[g])
+
+
+@pytest.mark.parametrize("spec", [
+    dict(n_reads=40, n_haps=6, hap_lo=300, hap_hi=300, read_lo=150, read_hi=150, junk=0.05),
+    dict(n_reads=37, n_haps=9, hap_lo=250, hap_hi=450, read_lo=100, read_hi=151, junk=0.1),       # odd haplotype count
+    dict(n_reads=25, n_haps=3, hap_lo=41, hap_hi=120, read_lo=1, read_hi=41, junk=0.1),           # post-trim short shapes
+    dict(n_reads=30, n_haps=16, hap_lo=1000, hap_hi=1000, read_lo=250, read_hi=250, junk=0.1),    # cfg4 shape
+    dict(n_reads=12, n_haps=1, hap_lo=200, hap_hi=200, read_lo=60, read_hi=151, junk=0.0),        # single haplotype
+    dict(n_reads=20, n_haps=4, hap_lo=500, hap_hi=700, read_lo=300, read_hi=420, junk=0.1),       # R above 255 / above the envelope
+])
+@pytest.mark.parametrize("model", [PCR_CONSERVATIVE, PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE])
+def test_random_regions_vs_oracle(engine, orc, spec, model):
+    rng = np.random.default_rng(hash((spec["n_reads"], spec["n_haps"], model)) % (2**32))
+    reads, haps = wl._one_region(rng, **spec)
+    _check_region_vs_oracle(engine, orc, reads, haps, 18, model)
+
+
+def test_uncontracted_variant(engine_nofma, orc):
+    rng = np.random.default_rng(5)
+    reads, haps = wl._one_region(rng, 40, 7, 200, 330, 90, 151, junk=0.05)
+    _check_region_vs_oracle(engine_nofma, orc, reads, haps, 18, PCR_CONSERVATIVE, fma=ob.FMA_NONE)
+
+
+def test_explicit_gap_qualities(engine, orc):
+    """Callers may hand in per-base ins/del/gcp (the generic path of the kernel, not just the reference's constants)."""
+    rng = np.random.default_rng(6)
+    reads, haps = wl._one_region(rng, 24, 5, 260, 300, 120, 151, junk=0.05)
+    for r in reads:
+        n = len(r["bases"])
+        r["ins"] = rng.integers(10, 60, n).astype(np.uint8)
+        r["del"] = rng.integers(10, 46, n).astype(np.uint8)
+        r["gcp"] = rng.integers(3, 40, n).astype(np.uint8)
+    _check_region_vs_oracle(engine, orc, reads, haps, 18, PCR_CONSERVATIVE)
+    _check_region_vs_oracle(engine, orc, reads, haps, 10, PCR_NONE)
+
+
+def test_edge_cases(engine, orc):
+    q = lambda n, v=30: np.full(n, v, np.uint8)
+    # empty inputs -> empty matrix (pairhmm_internal.cpp:508-510)
+    m, k = engine.call_pairhmm([b"ACGT"], [])
+    assert m.size == 0 and len(k) == 0
+    m, k = engine.call_pairhmm([], [dict(bases=b"ACGT", qual=q(4), mapq=60)])
+    assert m.size == 0 and len(k) == 0
+    # lengths on the bin boundaries of the wavefront kernel and beyond it
+    rng = np.random.default_rng(11)
+    hap = B[rng.integers(0, 4, 420)]
+    reads = []
+    for n in (1, 2, 31, 32, 63, 64, 159, 160, 255, 256, 319, 320, 383, 384, 400):
+        o = int(rng.integers(0, 420 - n + 1))
+        reads.append(dict(bases=hap[o:o + n].copy(), qual=q(n, 35), mapq=60))
+    _check_region_vs_oracle(engine, orc, reads, [hap, hap[:100].copy(), hap[5:6].copy()])
+    # N on either side, bytes outside ACGTN, lower case (match nothing: one-hot rule), quals with the top bit set
+    reads = [dict(bases=b"ACGTNNACGTACGTTTGACA", qual=q(20), mapq=60), dict(bases=b"acgtACGTXXACGTACGTAC", qual=q(20, 200), mapq=255),
+             dict(bases=b"ACGTACGTACGTACGTACGT", qual=q(20, 1), mapq=0)]
+    haps = [b"TTACGTNNACGTACGTTTGACATT", b"NNNNNNNNNNNNNNNNNNNNNNNN", b"TTACGTACACGTACGTTTGACATTGG"]
+    _check_region_vs_oracle(engine, orc, reads, haps)
+    _check_region_vs_oracle(engine, orc, reads, haps, thr=0, model=PCR_NONE)
+    # everything filtered: junk reads only -> n_kept == 0, matrix all NaN
+    reads = [dict(bases=B[rng.integers(0, 4, 120)], qual=q(120, 38), mapq=60) for _ in range(5)]
+    haps = [B[rng.integers(0, 4, 300)] for _ in range(3)]
+    n64 = _check_region_vs_oracle(engine, orc, reads, haps)
+    m, k = engine.call_pairhmm(haps, reads)
+    assert len(k) == 0 and np.all(np.isnan(m)) and n64 >= 0
+    # homopolymers / short tandem repeats drive the PCR model to its caps
+    reads = [dict(bases=b"A" * 150, qual=q(150), mapq=60), dict(bases=b"AC" * 75, qual=q(150), mapq=60),
+             dict(bases=b"ACGTTGCA" * 18 + b"ACGTTG", qual=q(150), mapq=60), dict(bases=b"G", qual=q(1), mapq=60)]
+    haps = [b"A" * 300, b"AC" * 150, (b"ACGTTGCA" * 40)[:300]]
+    for model in (PCR_CONSERVATIVE, PCR_HOSTILE, PCR_AGGRESSIVE):
+        _check_region_vs_oracle(engine, orc, reads, haps, 18, model)
+
+
+def test_fp64_recompute_exercised(engine, orc):
+    """cfg3-style: junk reads underflow FP32 (< 1e-28f) and are recomputed in FP64 on the device."""
+    rng = np.random.default_rng(12)
+    reads, haps = wl._one_region(rng, 60, 8, 300, 420, 120, 151, junk=0.4)
+    n64 = _check_region_vs_oracle(engine, orc, reads, haps)
+    assert n64 > 50
+
+
+def test_long_haplotypes_multi_chunk(engine, orc):
+    """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
+    rng = np.random.default_rng(13)
+    reads, haps = wl._one_region(rng, 6, 40, 900, 1000, 100, 151, junk=0.0)
+    _check_region_vs_oracle(engine, orc, reads, haps)
+
+
+def test_flat_equals_per_region_and_resident(engine, orc):
+    batch = wl.cfg5(40, seed=21)
+    flat = engine.run_flat(batch, raw=True)
+    resident = engine.upload(batch)
+    resident.run()
+    down = resident.download(raw=True)
+    resident.free()
+    assert np.array_equal(_bits32(flat.raw_f32), _bits32(down.raw_f32))
+    assert np.array_equal(flat.n_kept, down.n_kept)
+    for g in range(batch.n_regions):
+        reads, haps = batch.region(g)
+        m, k = engine.call_pairhmm(haps, reads)
+        assert np.array_equal(k, flat.kept(g)) and np.array_equal(k, down.kept(g))
+        assert np.array_equal(_bits64(m), _bits64(flat.matrix(g)))
+        assert np.array_equal(_bits64(m), _bits64(down.matrix(g)))
+    for g in (0, 7, 19, 33):
+        reads, haps = batch.region(g)
+        m0, k0, *_ = orc.region(reads, haps)
+        assert np.array_equal(k0, flat.kept(g)) and np.array_equal(_bits64(m0), _bits64(flat.matrix(g)))
+
+
+def test_concurrent_callers(engine, orc):
+    """The reference calls call_pairhmm from up to --nthreads pool workers; submit/wait must be re-entrant."""
+    batch = wl.cfg5(24, seed=22)
+    want = {}
+    for g in range(batch.n_regions):
+        reads, haps = batch.region(g)
+        want[g] = orc.region(reads, haps)[:2]
+    errs = []
+
+    def work(ids):
+        try:
+            for g in ids:
+                reads, haps = batch.region(g)
+                m, k = engine.call_pairhmm(haps, reads)
+                assert np.array_equal(k, want[g][1]) and np.array_equal(_bits64(m), _bits64(want[g][0]))
+        except Exception as e:       # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(list(range(t, batch.n_regions, 8)),)) for t in range(8)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[0]
+
+
+def test_full_size_cfg2_properties(engine, orc):
+    """BASELINE.json configs[1] at bench size: a sample of regions against the oracle, plus size-independent properties:
+    determinism across runs, independence from batching, and column permutation when the reads are permuted."""
+    batch = wl.cfg2(1024, seed=2)
+    r1 = engine.run_flat(batch, raw=True)
+    r2 = engine.run_flat(batch, raw=True)
+    assert np.array_equal(_bits32(r1.raw_f32), _bits32(r2.raw_f32)) and np.array_equal(_bits64(r1.likelihoods), _bits64(r2.likelihoods))
+    assert np.all(np.isfinite(r1.raw_f32)) and np.all(r1.raw_f32 >= 0)
+    rng = np.random.default_rng(3)
+    for g in rng.choice(batch.n_regions, 12, replace=False):
+        reads, haps = batch.region(int(g))
+        m0, k0, o32, *_ = orc.region(reads, haps)
+        assert np.array_equal(_bits32(r1.raw32(int(g))), _bits32(o32))
+        assert np.array_equal(k0, r1.kept(int(g))) and np.array_equal(_bits64(m0), _bits64(r1.matrix(int(g))))
+    g = 5
+    reads, haps = batch.region(g)
+    perm = rng.permutation(len(reads))
+    m, k, raw, _, _ = engine.call_pairhmm(haps[::-1], [reads[i] for i in perm], raw=True)
+    assert np.array_equal(_bits32(raw), _bits32(r1.raw32(g)[perm][:, ::-1]))
+
+
+def test_stats_and_kernel_info(engine):
+    s = engine.stats()
+    assert s["cells"] > 0 and s["kernel_launches"] > 0 and s["h2d_bytes"] > 0
+    regs, loc = engine.kernel_info(5)
+    assert 0 < regs <= 168 and loc == 0, "RPT=5 forward kernel must not spill and must keep >= 3 warps per scheduler"

@@ -233,9 +233,10 @@ def ours_arm(args, rank, world, local_rank):
     _, ffma = eng.ubench(0)
     _, ffma2 = eng.ubench(1)
     measured_peak = max(ffma, ffma2) * 2 / 1e12
-    regs, spill = eng.kernel_info(5)
+    ki = eng.kernel_info(150)
+    regs, spill = ki["regs"], ki["spill_bytes"]
     roof = {"bound": "fp32", "achieved": round(achieved, 3), "peak": round(peak_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / peak_tflops, 4),
-            "traffic": None, "kernel": "phmm_fwd_kernel<RPT=5> (forward wavefront, cfg2 reads)",
+            "traffic": None, "kernel": f"phmm_fwd_kernel<RPT={ki['rows_per_lane']}, LANES={ki['lanes_per_read']}> (forward wavefront, cfg2 reads)",
             "peak_source": f"2 x 128 lanes x {n_sm} SMs x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); no FP32 figure in that file",
             "work_model": "8 FP32-pipe instructions per cell (4 FMUL + 4 FFMA) counted as FMA slots = 16 flop-equivalents; plain 12 flop/cell also given",
             "fwd_kernel_ms": round(fwd_step, 3), "tcups": round(cells / (fwd_step * 1e-3) / 1e12, 4),

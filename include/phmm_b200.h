@@ -175,8 +175,9 @@ void phmm_resident_free(phmm_engine* e, phmm_resident* r);
 uint32_t phmm_resident_launches(const phmm_resident* r);   /* kernels one phmm_resident_run launches */
 
 int phmm_get_stats(phmm_engine* e, phmm_stats* out);
-/* Static facts about a forward-kernel instantiation (registers, spill bytes) for reports. */
-int phmm_kernel_info(int rpt, int fma_mode, int* regs, int* local_bytes);
+/* Static facts about the forward-kernel instantiation that serves reads of `read_len` bases (registers, spill bytes,
+ * lanes per read, read rows per lane) for reports. */
+int phmm_kernel_info(uint32_t read_len, int fma_mode, int* regs, int* local_bytes, int* lanes, int* rows_per_lane);
 /* Measured FP32 rate of this GPU (issue-rate micro-benchmark: mode 0 scalar FFMA, 1 packed FFMA2, 2 FFMA2 + select,
  * 3 + shuffle) in FMA lane-operations per second — the empirical denominator of the FP32 roofline. */
 int phmm_ubench(phmm_engine* e, int mode, uint32_t iters, float* ms, double* fma_per_s);

@@ -58,8 +58,8 @@ int fail(int code, const std::string& msg)
             return fail(PHMM_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
     } while (0)
 
-constexpr uint32_t kTargetStreamCols = 5900;    // per stream and chunk: 4 CTAs/SM worth of shared memory
-constexpr uint32_t kMaxStreamCols = 24000;      // hard limit of one haplotype in the wavefront kernel (192 KB)
+constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
+constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)
 constexpr uint32_t kPairThreads = 148 * 2 * 128;
 constexpr float kMinAccepted = 1e-28f;                     // MIN_ACCEPTED, rovaca/common.h:9
 constexpr float kLog10InitF = 36.1236000061f;              // LOG10_INITIAL_CONSTANT_F, adapter.h:25
@@ -423,12 +423,13 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
         for (const Group& g : groups[b]) {
-            smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps));
-            for (uint32_t at = 0; at < g.n; at += PHMM_WARPS) {
+            smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps, b));
+            const uint32_t per_cta = phmm_bin_reads_per_cta(b);
+            for (uint32_t at = 0; at < g.n; at += per_cta) {
                 PhmmCta c{};
                 c.chunk = g.chunk;
                 c.read_begin = (uint32_t)task_reads.size();
-                c.n_reads = std::min<uint32_t>(PHMM_WARPS, g.n - at);
+                c.n_reads = std::min<uint32_t>(per_cta, g.n - at);
                 for (uint32_t k = 0; k < c.n_reads; ++k) task_reads.push_back(group_reads[b][g.first + at + k]);
                 ctas.push_back(c);
             }
@@ -1026,16 +1027,16 @@ int phmm_get_stats(phmm_engine* e, phmm_stats* out)
     return PHMM_OK;
 }
 
-int phmm_kernel_info(int rpt, int fma_mode, int* regs, int* local_bytes)
+int phmm_kernel_info(uint32_t read_len, int fma_mode, int* regs, int* local_bytes, int* lanes, int* rows_per_lane)
 {
-    int bin = -1;
-    for (int b = 0; b < kPhmmNumBins; ++b)
-        if (kPhmmRptBins[b] == rpt) bin = b;
-    if (bin < 0) return fail(PHMM_ERR_ARG, "phmm_kernel_info: no such rows-per-lane bin");
+    const int bin = bin_of(read_len);
+    if (bin < 0) return fail(PHMM_ERR_ARG, "phmm_kernel_info: no wavefront bin holds reads of this length (per-pair kernel)");
     PhmmKernelInfo ki{};
     CU(phmm_fwd_kernel_info(bin, fma_mode != PHMM_FMA_NONE, &ki));
     if (regs) *regs = ki.regs;
     if (local_bytes) *local_bytes = ki.local_bytes;
+    if (lanes) *lanes = kPhmmBins[bin].lanes;
+    if (rows_per_lane) *rows_per_lane = kPhmmBins[bin].rpt;
     return PHMM_OK;
 }
 

@@ -127,9 +127,30 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
 
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 
-template <int RPT, bool FMA>
-__global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
+// base class of a haplotype byte: index into the per-thread prior tables.  Classes follow the one-hot test of
+// pairhmm_internal.cpp:27-41: A C T G match themselves and N, N matches every class but "other", other never matches.
+__device__ __forceinline__ uint32_t base_class(uint32_t c)
 {
+    uint32_t v = 5u;
+    v = (c == 'A') ? 0u : v;
+    v = (c == 'C') ? 1u : v;
+    v = (c == 'T') ? 2u : v;
+    v = (c == 'G') ? 3u : v;
+    v = (c == 'N') ? 4u : v;
+    return v;
+}
+__device__ __forceinline__ uint32_t class_onehot(uint32_t b) { return b < 4u ? (1u << b) : (b == 4u ? 0xFu : 0u); }
+
+// occupancy targets found with tools/phmm_ablate.cu: the kernel is bound by register-file reads and issue slots, not by
+// latency, so it wants enough registers to hold RPT rows x 2 streams x 3 states plus the row parameters without spilling.
+constexpr int fwd_min_blocks(int rpt) { return rpt <= 3 ? 6 : rpt <= 5 ? 5 : (rpt == 6 || rpt == 8) ? 4 : rpt <= 10 ? 3 : 2; }
+
+template <int RPT, int LANES, bool FMA>
+__global__ void __launch_bounds__(PHMM_WARPS * 32, fwd_min_blocks(RPT)) phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
+{
+    constexpr int NT = PHMM_WARPS * 32;
+    constexpr int G = (RPT + 3) / 4;                     // float4 groups of the prior table
+    constexpr uint32_t TSTRIDE = (uint32_t)G * NT * 16;   // bytes between the tables of two base classes
     extern __shared__ __align__(16) unsigned char smem[];
     const PhmmCta cta = p.ctas[cta_base + blockIdx.x];
     const PhmmChunk ch = p.chunks[cta.chunk];
@@ -139,10 +160,11 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
     float* info_init = reinterpret_cast<float*>(stream + L + 32);     // [2][NI]  2^120 / H
     uint32_t* info_col = reinterpret_cast<uint32_t*>(info_init + 2 * NI);   // [2][NI] output column
     uint32_t* info_hap = info_col + 2 * NI;                            // [2][NI] global haplotype id
+    float4* tbl = reinterpret_cast<float4*>(smem + ((((size_t)(L + 32) * 8 + (size_t)NI * 2 * 12) + 15) & ~(size_t)15));   // [6][G][NT]
 
-    // ---- stage the two haplotype streams of this chunk -------------------------------------
-    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) stream[i] = make_uint2(0u, 0u);
-    for (uint32_t i = threadIdx.x; i < 2 * NI; i += blockDim.x) { info_init[i] = 0.f; info_col[i] = 0u; info_hap[i] = 0u; }
+    // ---- stage the two haplotype streams of this chunk: word = class * TSTRIDE (| flag on a first column) ----
+    for (uint32_t i = threadIdx.x; i < L + 32; i += NT) stream[i] = make_uint2(0u, 0u);
+    for (uint32_t i = threadIdx.x; i < 2 * NI; i += NT) { info_init[i] = 0.f; info_col[i] = 0u; info_hap[i] = 0u; }
     __syncthreads();
     {
         uint32_t* sw = reinterpret_cast<uint32_t*>(stream);
@@ -156,8 +178,8 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
             const uint32_t e = hp.ord_stream & 1u, ord = hp.ord_stream >> 1;
             const uint32_t n_e = e ? (ch.n_haps - ch.n_x) : ch.n_x;
             const uint8_t* hb = p.hap_bases + hp.byte_off;
-            for (uint32_t c = threadIdx.x; c < hp.len; c += blockDim.x) {
-                uint32_t w = onehot(hb[c]) * 0x01111111u;                    // one-hot nibble replicated for 7 rows
+            for (uint32_t c = threadIdx.x; c < hp.len; c += NT) {
+                uint32_t w = base_class(hb[c]) * TSTRIDE;
                 if (c == 0) w |= PHMM_FLAG_BIT;
                 sw[2 * (hp.pos + c) + e] = w;
             }
@@ -171,41 +193,59 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
     }
     __syncthreads();
 
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp >= cta.n_reads) return;
-    const uint32_t rid = p.task_reads[cta.read_begin + warp];
+    // ---- which read is mine: LANES lanes per read, 32 / LANES reads per warp ---------------------
+    const uint32_t slot = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
+    if ((threadIdx.x >> 5) * (32 / LANES) >= cta.n_reads) return;      // whole warp has no read
+    const bool live = slot < cta.n_reads;                              // a dead half warp shadows the last read, never writes
+    const uint32_t rid = p.task_reads[cta.read_begin + (live ? slot : cta.n_reads - 1)];
     const PhmmRead rd = p.reads[rid];
-    const int npad = 32 * RPT - (int)rd.len;       // >= 1 by binning
+    const int npad = LANES * RPT - (int)rd.len;       // >= 1 by binning
 
-    // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers -------------------
-    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], dd[RPT], pm[RPT], pmm[RPT];
-    uint32_t rb[(RPT + 6) / 7];
-#pragma unroll
-    for (int k = 0; k < (RPT + 6) / 7; ++k) rb[k] = 0u;
+    // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers, priors into my table ----
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], dd[RPT];
     uint32_t padmask = 0u;     // bit k: row k is a pad row; bit RPT: the row above row 0 is one
-    const PhmmTables* __restrict__ T = p.tables;
+    {
+        const PhmmTables* __restrict__ T = p.tables;
+        float pm[G * 4], pmm[G * 4];
+        uint32_t rr[G * 4];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) {
-        const int r = (int)lane * RPT + k - npad;
-        if (r >= 0) {
-            const uint32_t w = p.words[rd.word_off + r];
-            const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
-            const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
-            mm[k] = __ldg(&T->mm[((hi * (hi + 1)) >> 1) + lo]);
-            gapm[k] = __ldg(&T->gapm[qc]);
-            mi[k] = __ldg(&T->ph2pr[qi]);
-            ii[k] = __ldg(&T->ph2pr[qc]);
-            md[k] = __ldg(&T->ph2pr[qd]);
-            dd[k] = ii[k];
-            pm[k] = __ldg(&T->pm[q]);
-            pmm[k] = __ldg(&T->pmm[q]);
-            rb[k / 7] |= (w >> 28) << (4 * (k % 7));
-        } else {                                   // boundary-generator row
-            mm[k] = 0.f; gapm[k] = 0.f; mi[k] = 0.f; ii[k] = 0.f; md[k] = 0.f; dd[k] = 1.f; pm[k] = 0.f; pmm[k] = 0.f;
-            padmask |= 1u << k;
+        for (int k = 0; k < G * 4; ++k) { pm[k] = 0.f; pmm[k] = 0.f; rr[k] = 0u; }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = (int)lane * RPT + k - npad;
+            if (r >= 0) {
+                const uint32_t w = p.words[rd.word_off + r];
+                const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
+                const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+                mm[k] = __ldg(&T->mm[((hi * (hi + 1)) >> 1) + lo]);
+                gapm[k] = __ldg(&T->gapm[qc]);
+                mi[k] = __ldg(&T->ph2pr[qi]);
+                ii[k] = __ldg(&T->ph2pr[qc]);
+                md[k] = __ldg(&T->ph2pr[qd]);
+                dd[k] = ii[k];
+                pm[k] = __ldg(&T->pm[q]);
+                pmm[k] = __ldg(&T->pmm[q]);
+                rr[k] = w >> 28;
+            } else {                                   // boundary-generator row: prior 0, D carried unchanged
+                mm[k] = 0.f; gapm[k] = 0.f; mi[k] = 0.f; ii[k] = 0.f; md[k] = 0.f; dd[k] = 1.f;
+                padmask |= 1u << k;
+            }
+        }
+        if ((int)lane * RPT - 1 < npad) padmask |= 1u << RPT;
+#pragma unroll
+        for (uint32_t b = 0; b < 6; ++b) {
+            const uint32_t hb = class_onehot(b);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4 v;
+                v.x = (rr[4 * g] & hb) ? pm[4 * g] : pmm[4 * g];
+                v.y = (rr[4 * g + 1] & hb) ? pm[4 * g + 1] : pmm[4 * g + 1];
+                v.z = (rr[4 * g + 2] & hb) ? pm[4 * g + 2] : pmm[4 * g + 2];
+                v.w = (rr[4 * g + 3] & hb) ? pm[4 * g + 3] : pmm[4 * g + 3];
+                tbl[(b * G + g) * NT + threadIdx.x] = v;
+            }
         }
     }
-    if ((int)lane * RPT - 1 < npad) padmask |= 1u << RPT;
 
     // ---- state ------------------------------------------------------------------------------
     float2 Ml[RPT], Il[RPT], Dl[RPT];              // previous column, my rows
@@ -216,8 +256,9 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
     float2 sumM = bc(0.f), sumI = bc(0.f);
     uint32_t jx = 0, jy = 0;                       // haplotypes begun so far in each stream
     const uint2* sp = stream + 32 - lane;
-    const uint32_t nsteps = L - 1;
-    const bool writer = (lane == 31);
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 16;
+    const uint32_t nsteps = L - 1 - (32 - LANES);  // the last lane of the group reaches the end sentinel at step L - 33 + LANES
+    const bool writer = live && (lane == LANES - 1);
 
 #define PHMM_BOUNDARY(E, J, EI)                                                                         \
     {                                                                                                   \
@@ -226,9 +267,9 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
             const uint32_t oi = rd.out_off + info_col[EI * NI + J - 1];                                 \
             p.out_f32[oi] = res;                                                                        \
             if (res < 1e-28f) {                                                                         \
-                const uint32_t slot = atomicAdd(p.f64_count, 1u);                                       \
+                const uint32_t slot64 = atomicAdd(p.f64_count, 1u);                                     \
                 PhmmPair pr; pr.read = rid; pr.hap = info_hap[EI * NI + J - 1]; pr.out_idx = oi;        \
-                p.f64_pairs[slot] = pr;                                                                 \
+                p.f64_pairs[slot64] = pr;                                                               \
             }                                                                                           \
         }                                                                                               \
         const float init = info_init[EI * NI + J];                                                      \
@@ -242,26 +283,44 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
 
 #pragma unroll 2
     for (uint32_t s = 0; s < nsteps; ++s) {
-        const uint2 w = sp[s];
-        if ((w.x | w.y) & PHMM_FLAG_BIT) {
-            if (w.x & PHMM_FLAG_BIT) PHMM_BOUNDARY(x, jx, 0)
-            if (w.y & PHMM_FLAG_BIT) PHMM_BOUNDARY(y, jy, 1)
+        uint2 w = sp[s];
+        if ((int)(w.x | w.y) < 0) {
+            if ((int)w.x < 0) PHMM_BOUNDARY(x, jx, 0)
+            if ((int)w.y < 0) PHMM_BOUNDARY(y, jy, 1)
+            w.x &= ~PHMM_FLAG_BIT;
+            w.y &= ~PHMM_FLAG_BIT;
+        }
+        // priors of my RPT rows against this column's base class, four rows per LDS (pairhmm_internal.cpp:479-480 values)
+        float px[G * 4], py[G * 4];
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            const unsigned char* ax = tb + w.x + g * (NT * 16);
+            const unsigned char* ay = tb + w.y + g * (NT * 16);
+            if (RPT - 4 * g >= 3) {
+                const float4 vx = *reinterpret_cast<const float4*>(ax), vy = *reinterpret_cast<const float4*>(ay);
+                px[4 * g] = vx.x; px[4 * g + 1] = vx.y; px[4 * g + 2] = vx.z; px[4 * g + 3] = vx.w;
+                py[4 * g] = vy.x; py[4 * g + 1] = vy.y; py[4 * g + 2] = vy.z; py[4 * g + 3] = vy.w;
+            } else if (RPT - 4 * g == 2) {
+                const float2 vx = *reinterpret_cast<const float2*>(ax), vy = *reinterpret_cast<const float2*>(ay);
+                px[4 * g] = vx.x; px[4 * g + 1] = vx.y;
+                py[4 * g] = vy.x; py[4 * g + 1] = vy.y;
+            } else {
+                px[4 * g] = *reinterpret_cast<const float*>(ax);
+                py[4 * g] = *reinterpret_cast<const float*>(ay);
+            }
         }
         float2 pM = dgM, pI = dgI, pD = dgD;       // diagonal inputs of row 0
         float2 uM = upM, uI = upI;                 // inputs from above of row 0
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
-            const uint32_t msk = 0xFu << (4 * (k % 7));
-            float2 prior;
-            prior.x = (rb[k / 7] & w.x & msk) ? pm[k] : pmm[k];
-            prior.y = (rb[k / 7] & w.y & msk) ? pm[k] : pmm[k];
             float2 nM, nI, nD;
             if (FMA) {                              // SURVEY.md §8a, AVX-512 contraction
                 float2 t = __fmul2_rn(pM, bc(mm[k]));
                 t = __ffma2_rn(pI, bc(gapm[k]), t);
                 t = __ffma2_rn(pD, bc(gapm[k]), t);
-                nM = __fmul2_rn(t, prior);
+                nM.x = __fmul_rn(t.x, px[k]);       // scalar on purpose: the priors arrive un-paired from the table
+                nM.y = __fmul_rn(t.y, py[k]);
                 nI = __ffma2_rn(uI, bc(ii[k]), __fmul2_rn(uM, bc(mi[k])));
                 nD = __ffma2_rn(oD, bc(dd[k]), __fmul2_rn(oM, bc(md[k])));
             } else {                                // core/avx2_s.cpp:207-216, scalar on purpose (see header)
@@ -269,8 +328,8 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
                 float ty = __fadd_rn(__fmul_rn(pM.y, mm[k]), __fmul_rn(pI.y, gapm[k]));
                 tx = __fadd_rn(tx, __fmul_rn(pD.x, gapm[k]));
                 ty = __fadd_rn(ty, __fmul_rn(pD.y, gapm[k]));
-                nM.x = __fmul_rn(tx, prior.x);
-                nM.y = __fmul_rn(ty, prior.y);
+                nM.x = __fmul_rn(tx, px[k]);
+                nM.y = __fmul_rn(ty, py[k]);
                 nI.x = __fadd_rn(__fmul_rn(uM.x, mi[k]), __fmul_rn(uI.x, ii[k]));
                 nI.y = __fadd_rn(__fmul_rn(uM.y, mi[k]), __fmul_rn(uI.y, ii[k]));
                 nD.x = __fadd_rn(__fmul_rn(oM.x, md[k]), __fmul_rn(oD.x, dd[k]));
@@ -288,12 +347,12 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32) phmm_fwd_kernel(PhmmBatchDev 
             sumM.x = __fadd_rn(sumM.x, Ml[RPT - 1].x); sumM.y = __fadd_rn(sumM.y, Ml[RPT - 1].y);
             sumI.x = __fadd_rn(sumI.x, Il[RPT - 1].x); sumI.y = __fadd_rn(sumI.y, Il[RPT - 1].y);
         }
-        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1);
-        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1);
-        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1);
-        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1);
-        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1);
-        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1);
+        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1, LANES);
+        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1, LANES);
+        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1, LANES);
+        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1, LANES);
+        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1, LANES);
+        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1, LANES);
     }
 #undef PHMM_BOUNDARY
 }
@@ -431,10 +490,10 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
     if (acc == 123.456f) out[0] = acc;
 }
 
-template <int RPT, bool FMA>
+template <int RPT, int LANES, bool FMA>
 cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, size_t smem, cudaStream_t st)
 {
-    auto kern = phmm_fwd_kernel<RPT, FMA>;
+    auto kern = phmm_fwd_kernel<RPT, LANES, FMA>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -443,11 +502,11 @@ cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ct
     return cudaGetLastError();
 }
 
-template <int RPT, bool FMA>
+template <int RPT, int LANES, bool FMA>
 cudaError_t info_t(PhmmKernelInfo* info)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, FMA>);
+    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, LANES, FMA>);
     if (e != cudaSuccess) return e;
     info->regs = a.numRegs;
     info->local_bytes = (int)a.localSizeBytes;
@@ -466,20 +525,16 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     return cudaGetLastError();
 }
 
-#define PHMM_DISPATCH_BIN(FN, ...)                                                    \
-    switch (kPhmmRptBins[bin]) {                                                      \
-        case 1: return fma ? FN<1, true>(__VA_ARGS__) : FN<1, false>(__VA_ARGS__);    \
-        case 2: return fma ? FN<2, true>(__VA_ARGS__) : FN<2, false>(__VA_ARGS__);    \
-        case 3: return fma ? FN<3, true>(__VA_ARGS__) : FN<3, false>(__VA_ARGS__);    \
-        case 4: return fma ? FN<4, true>(__VA_ARGS__) : FN<4, false>(__VA_ARGS__);    \
-        case 5: return fma ? FN<5, true>(__VA_ARGS__) : FN<5, false>(__VA_ARGS__);    \
-        case 6: return fma ? FN<6, true>(__VA_ARGS__) : FN<6, false>(__VA_ARGS__);    \
-        case 7: return fma ? FN<7, true>(__VA_ARGS__) : FN<7, false>(__VA_ARGS__);    \
-        case 8: return fma ? FN<8, true>(__VA_ARGS__) : FN<8, false>(__VA_ARGS__);    \
-        case 10: return fma ? FN<10, true>(__VA_ARGS__) : FN<10, false>(__VA_ARGS__); \
-        case 12: return fma ? FN<12, true>(__VA_ARGS__) : FN<12, false>(__VA_ARGS__); \
-        default: return cudaErrorInvalidValue;                                        \
-    }
+#define PHMM_CASE(R, LN, FN, ...) \
+    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN) return fma ? FN<R, LN, true>(__VA_ARGS__) : FN<R, LN, false>(__VA_ARGS__);
+#define PHMM_DISPATCH_BIN(FN, ...)                                                                              \
+    PHMM_CASE(1, 16, FN, __VA_ARGS__) PHMM_CASE(2, 16, FN, __VA_ARGS__) PHMM_CASE(3, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE(4, 16, FN, __VA_ARGS__) PHMM_CASE(5, 16, FN, __VA_ARGS__) PHMM_CASE(6, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE(7, 16, FN, __VA_ARGS__) PHMM_CASE(8, 16, FN, __VA_ARGS__) PHMM_CASE(9, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE(10, 16, FN, __VA_ARGS__) PHMM_CASE(11, 16, FN, __VA_ARGS__) PHMM_CASE(12, 16, FN, __VA_ARGS__)    \
+    PHMM_CASE(7, 32, FN, __VA_ARGS__) PHMM_CASE(8, 32, FN, __VA_ARGS__) PHMM_CASE(9, 32, FN, __VA_ARGS__)       \
+    PHMM_CASE(10, 32, FN, __VA_ARGS__) PHMM_CASE(11, 32, FN, __VA_ARGS__) PHMM_CASE(12, 32, FN, __VA_ARGS__)    \
+    return cudaErrorInvalidValue;
 
 cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, size_t smem_bytes,
                             cudaStream_t st)

@@ -31,16 +31,30 @@ struct PhmmBatchDev
     uint32_t n_reads;
 };
 
-// Read-length bins of the wavefront kernel: a warp owns one read, lane l owns rows l*RPT .. l*RPT+RPT-1
-// (top-padded), so a bin holds reads of length <= 32*RPT - 1.
-static const int kPhmmRptBins[] = {1, 2, 3, 4, 5, 6, 7, 8, 10, 12};
-static const int kPhmmNumBins = sizeof(kPhmmRptBins) / sizeof(kPhmmRptBins[0]);
-static inline uint32_t phmm_bin_capacity(int bin) { return 32u * (uint32_t)kPhmmRptBins[bin] - 1u; }
-
-// Shared memory one CTA of the forward kernel needs for a chunk.
-static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps)
+// Read-length bins of the wavefront kernel: a group of LANES lanes (a half warp or a whole warp) owns one read, lane l owns
+// rows l*RPT .. l*RPT+RPT-1 (top-padded with at least one boundary row), so a bin holds reads of length <= LANES*RPT - 1.
+// Half-warp bins come first: more rows per lane means fewer shuffles per cell (3 per RPT cells and stream), which is what
+// the issue/register-read budget of the SM rewards ("kernel budget"); whole-warp bins take over where a
+// half-warp read would need more than 12 rows per lane (register file).
+struct PhmmBin
 {
-    return (size_t)(stream_len + 32) * 8 + (size_t)(n_haps + 1) * 2 * 12;
+    int lanes;
+    int rpt;
+};
+static const PhmmBin kPhmmBins[] = {{16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9},
+                                    {16, 10}, {16, 11}, {16, 12}, {32, 7}, {32, 8}, {32, 9}, {32, 10}, {32, 11}, {32, 12}};
+static const int kPhmmNumBins = sizeof(kPhmmBins) / sizeof(kPhmmBins[0]);
+static inline uint32_t phmm_bin_capacity(int bin) { return (uint32_t)(kPhmmBins[bin].lanes * kPhmmBins[bin].rpt) - 1u; }
+static inline uint32_t phmm_bin_reads_per_cta(int bin) { return (uint32_t)(PHMM_WARPS * 32 / kPhmmBins[bin].lanes); }
+
+// Shared memory one CTA of the forward kernel needs for a chunk: the two column streams, the per-haplotype seam records and
+// the per-thread prior tables (6 base classes x ceil(RPT/4) float4 per thread).
+static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int bin)
+{
+    const size_t streams = (size_t)(stream_len + 32) * 8;
+    const size_t info = (((streams + (size_t)(n_haps + 1) * 2 * 12) + 15) & ~(size_t)15) - streams;
+    const size_t tables = (size_t)6 * ((kPhmmBins[bin].rpt + 3) / 4) * (PHMM_WARPS * 32) * 16;
+    return streams + info + tables;
 }
 
 cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st);

@@ -124,7 +124,7 @@ def load_library():
     L.phmm_resident_launches.argtypes = [C.c_void_p]
     L.phmm_resident_launches.restype = C.c_uint32
     L.phmm_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
-    L.phmm_kernel_info.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.phmm_kernel_info.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.phmm_ubench.argtypes = [C.c_void_p, C.c_int, C.c_uint32, _f32p, _f64p]
     L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
     L.phmm_debug_tables.restype = None
@@ -316,7 +316,8 @@ class PairHmmEngine:
         self._check(self.L.phmm_ubench(self.h, mode, iters, C.byref(ms), C.byref(rate)))
         return float(ms.value), float(rate.value)
 
-    def kernel_info(self, rpt: int, fma_mode: int = FMA_AVX512) -> Tuple[int, int]:
-        regs, loc = C.c_int(0), C.c_int(0)
-        self._check(self.L.phmm_kernel_info(rpt, fma_mode, C.byref(regs), C.byref(loc)))
-        return regs.value, loc.value
+    def kernel_info(self, read_len: int, fma_mode: int = FMA_AVX512) -> dict:
+        """Static facts of the forward-kernel instantiation serving reads of ``read_len`` bases."""
+        regs, loc, lanes, rpt = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self.L.phmm_kernel_info(read_len, fma_mode, C.byref(regs), C.byref(loc), C.byref(lanes), C.byref(rpt)))
+        return {"regs": regs.value, "spill_bytes": loc.value, "lanes_per_read": lanes.value, "rows_per_lane": rpt.value}

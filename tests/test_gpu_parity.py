@@ -121,7 +121,7 @@ def test_edge_cases(engine, orc):
     rng = np.random.default_rng(11)
     hap = B[rng.integers(0, 4, 420)]
     reads = []
-    for n in (1, 2, 31, 32, 63, 64, 159, 160, 255, 256, 319, 320, 383, 384, 400):
+    for n in (1, 2, 15, 16, 31, 32, 63, 64, 159, 160, 191, 192, 223, 224, 255, 256, 319, 320, 383, 384, 400):
         o = int(rng.integers(0, 420 - n + 1))
         reads.append(dict(bases=hap[o:o + n].copy(), qual=q(n, 35), mapq=60))
     _check_region_vs_oracle(engine, orc, reads, [hap, hap[:100].copy(), hap[5:6].copy()])
@@ -143,6 +143,31 @@ def test_edge_cases(engine, orc):
     haps = [b"A" * 300, b"AC" * 150, (b"ACGTTGCA" * 40)[:300]]
     for model in (PCR_CONSERVATIVE, PCR_HOSTILE, PCR_AGGRESSIVE):
         _check_region_vs_oracle(engine, orc, reads, haps, 18, model)
+
+
+def test_every_length_bin_and_partial_groups(engine, orc):
+    """One read on each side of every read-length bin of the wavefront kernel (16 x RPT - 1 and 32 x RPT - 1), and read
+    counts that leave half warps and whole warps of a CTA without a read (1, 2, 3, 7, 9 reads of one bin)."""
+    rng = np.random.default_rng(17)
+    hap = B[rng.integers(0, 4, 400)]
+    haps = [hap, hap[3:390].copy(), hap[::-1].copy()]
+    caps = [16 * r - 1 for r in range(1, 13)] + [32 * r - 1 for r in range(7, 13)]
+    reads = []
+    for c in caps:
+        for n in (c, c + 1):
+            if n > 400:
+                continue
+            o = int(rng.integers(0, 400 - n + 1))
+            rd = hap[o:o + n].copy()
+            rd[rng.integers(0, n, max(1, n // 40))] = B[rng.integers(0, 4, max(1, n // 40))]
+            reads.append(dict(bases=rd, qual=rng.integers(8, 41, n).astype(np.uint8), mapq=int(rng.integers(20, 61))))
+    _check_region_vs_oracle(engine, orc, reads, haps)
+    for count in (1, 2, 3, 7, 9, 17):
+        sub = [dict(bases=B[rng.integers(0, 4, 150)], qual=rng.integers(8, 41, 150).astype(np.uint8), mapq=60) for _ in range(count)]
+        for r in sub[: max(1, count // 2)]:           # half of them real reads of the haplotype, the rest junk
+            o = int(rng.integers(0, 250))
+            r["bases"] = hap[o:o + 150].copy()
+        _check_region_vs_oracle(engine, orc, sub, haps)
 
 
 def test_fp64_recompute_exercised(engine, orc):
@@ -231,5 +256,7 @@ def test_full_size_cfg2_properties(engine, orc):
 def test_stats_and_kernel_info(engine):
     s = engine.stats()
     assert s["cells"] > 0 and s["kernel_launches"] > 0 and s["h2d_bytes"] > 0
-    regs, loc = engine.kernel_info(5)
-    assert 0 < regs <= 168 and loc == 0, "RPT=5 forward kernel must not spill and must keep >= 3 warps per scheduler"
+    ki = engine.kernel_info(150)
+    assert ki["lanes_per_read"] == 16 and ki["rows_per_lane"] == 10
+    assert 0 < ki["regs"] <= 168 and ki["spill_bytes"] == 0, "the 150-bp forward kernel must not spill and must keep 3 CTAs per SM"
+    assert engine.kernel_info(250)["lanes_per_read"] == 32

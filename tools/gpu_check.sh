@@ -1,0 +1,7 @@
+#!/bin/bash
+# smoke + GPU parity tests + a short bench (no ncu).  Usage under gpurun: bash tools/gpu_check.sh <tag> [bench args]
+TAG=${1:-chk}; shift
+mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke exit $?"; tail -3 gpurun_out/${TAG}_smoke.log
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -15 gpurun_out/${TAG}_pytest.log
+timeout 900 python bench.py "$@" > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err

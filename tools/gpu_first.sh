@@ -12,8 +12,8 @@ e = PairHmmEngine()
 for mode, name in enumerate(["FFMA scalar", "FFMA2 packed", "FFMA2+LOP3/FSEL/FADD", "mode2+SHFL"]):
     ms, rate = e.ubench(mode, 8192)
     print(f"ubench mode {mode} {name:24s} {ms:8.3f} ms  {rate*2/1e12:7.2f} TFLOP/s (FMA flops)")
-for rpt in (1,2,3,4,5,6,7,8,10,12):
-    print("rpt", rpt, "regs/spill", e.kernel_info(rpt))
+for n in (15, 31, 47, 63, 79, 95, 111, 127, 143, 150, 175, 191, 223, 255, 287, 319, 351, 383):
+    print("read_len", n, e.kernel_info(n))
 e.close()
 PY
 } > gpurun_out/first.log 2>&1

@@ -1,0 +1,653 @@
+// phmm_ablate.cu — standalone issue-rate experiments for the forward wavefront step (NOT product code).
+//
+// Each variant runs the inner step of phmm_fwd_kernel (rovaca_b200/csrc/phmm_kernels.cu) on synthetic
+// register/shared-memory state, full chip, and reports the fraction of FP32 FMA-issue slots doing
+// algorithmic work (8 per cell) — the same figure bench.py's roofline reports.  Used to
+// attribute the gap between the product kernel and the FP32 pipe (which instruction class costs what)
+// and to try alternative layouts before moving them into the product.
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -ftz=true -fmad=false -lineinfo \
+//        -o tools/phmm_ablate tools/phmm_ablate.cu && tools/phmm_ablate
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
+
+enum { SEL_LOP = 0, SEL_NONE = 1, SEL_LDS32 = 2, SEL_LDS128 = 3 };
+
+// Layout A (product): thread = RPT rows of one read x two haplotype streams in the f32x2 halves.
+template <int RPT, int SEL, bool SHFL, int WARPS, int LANES = 32, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) layoutA(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint2* stream = reinterpret_cast<uint2*>(smem);                  // [L + 32]
+    float* tbl = reinterpret_cast<float*>(stream + L + 32);          // [5][RPT][threads] (SEL_LDS32)
+    const uint32_t lane = threadIdx.x & (LANES - 1);
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) {
+        const uint32_t bx = gbases[(i * 2 + blockIdx.x) % 4096] & 3, by = gbases[(i * 2 + 1 + blockIdx.x) % 4096] & 3;
+        if (SEL == SEL_LDS32)
+            stream[i] = make_uint2(bx * RPT * blockDim.x * 4, by * RPT * blockDim.x * 4);
+        else if (SEL == SEL_LDS128)
+            stream[i] = make_uint2(bx * ((RPT + 3) / 4) * blockDim.x * 16, by * ((RPT + 3) / 4) * blockDim.x * 16);
+        else
+            stream[i] = make_uint2((1u << bx) * 0x01111111u, (1u << by) * 0x01111111u);
+    }
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], pm[RPT], pmm[RPT];
+    uint32_t rb = 0;   // (SEL_LOP only valid for RPT <= 8)
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const float j = seed * (float)(k + 1 + lane);
+        mm[k] = 0.9998f + j; gapm[k] = 0.9f + j; mi[k] = 3e-5f + j; ii[k] = 0.1f + j; md[k] = 3.1e-5f + j;
+        pm[k] = 0.999f + j; pmm[k] = 3.3e-4f + j;
+        const uint32_t base = (lane * 7 + k * 3 + blockIdx.x) & 3;
+        rb |= (1u << base) << (4 * k);
+        if (SEL == SEL_LDS32)
+            for (uint32_t b = 0; b < 4; ++b) tbl[(b * RPT + k) * blockDim.x + threadIdx.x] = (b == base) ? pm[k] : pmm[k];
+        if (SEL == SEL_LDS128)
+            for (uint32_t b = 0; b < 6; ++b) tbl[((b * ((RPT + 3) / 4) + k / 4) * blockDim.x + threadIdx.x) * 4 + (k % 4)] = (b == base || b == 4) ? pm[k] : pmm[k];
+    }
+    __syncthreads();
+    float2 Ml[RPT], Il[RPT], Dl[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = bc(1.f); Il[k] = bc(0.5f); Dl[k] = bc(0.25f); }
+    float2 upM = bc(1.f), upI = bc(1.f), upD = bc(1.f), dgM = bc(1.f), dgI = bc(1.f), dgD = bc(1.f), sumM = bc(0.f), sumI = bc(0.f);
+    const uint2* sp = stream + 32 - lane;
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 4;
+    const unsigned char* tb4 = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 16;
+    uint32_t nb = 0;
+#pragma unroll 2
+    for (uint32_t s = 0; s < L; ++s) {
+        const uint2 w = sp[s];
+        if ((w.x | w.y) & 0x80000000u) { ++nb; sumM = bc(0.f); }
+        float px[((RPT + 3) / 4) * 4], py[((RPT + 3) / 4) * 4];
+        if (SEL == SEL_LDS128) {
+#pragma unroll
+            for (int g = 0; g < (RPT + 3) / 4; ++g) {
+                if (4 * g + 1 < RPT) {
+                    const float4 vx = *reinterpret_cast<const float4*>(tb4 + w.x + g * blockDim.x * 16);
+                    const float4 vy = *reinterpret_cast<const float4*>(tb4 + w.y + g * blockDim.x * 16);
+                    px[4 * g] = vx.x; px[4 * g + 1] = vx.y; px[4 * g + 2] = vx.z; px[4 * g + 3] = vx.w;
+                    py[4 * g] = vy.x; py[4 * g + 1] = vy.y; py[4 * g + 2] = vy.z; py[4 * g + 3] = vy.w;
+                } else {
+                    px[4 * g] = *reinterpret_cast<const float*>(tb4 + w.x + g * blockDim.x * 16);
+                    py[4 * g] = *reinterpret_cast<const float*>(tb4 + w.y + g * blockDim.x * 16);
+                }
+            }
+        }
+        float2 pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
+            float2 prior;
+            if (SEL == SEL_LDS128) {
+                prior = make_float2(px[k], py[k]);
+            } else if (SEL == SEL_LOP) {
+                const uint32_t msk = 0xFu << (4 * k);
+                prior.x = (rb & w.x & msk) ? pm[k] : pmm[k];
+                prior.y = (rb & w.y & msk) ? pm[k] : pmm[k];
+            } else if (SEL == SEL_LDS32) {
+                prior.x = *reinterpret_cast<const float*>(tb + w.x + k * blockDim.x * 4);
+                prior.y = *reinterpret_cast<const float*>(tb + w.y + k * blockDim.x * 4);
+            } else {
+                prior = bc(pm[k]);
+            }
+            float2 t = __fmul2_rn(pM, bc(mm[k]));
+            t = __ffma2_rn(pI, bc(gapm[k]), t);
+            t = __ffma2_rn(pD, bc(gapm[k]), t);
+            float2 nM;
+            if (SEL == SEL_LDS128) { nM.x = __fmul_rn(t.x, prior.x); nM.y = __fmul_rn(t.y, prior.y); } else nM = __fmul2_rn(t, prior);
+            const float2 nI = __ffma2_rn(uI, bc(ii[k]), __fmul2_rn(uM, bc(mi[k])));
+            const float2 nD = __ffma2_rn(oD, bc(ii[k]), __fmul2_rn(oM, bc(md[k])));
+            Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
+            pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        sumM = __fadd2_rn(sumM, Ml[RPT - 1]);
+        sumI = __fadd2_rn(sumI, Il[RPT - 1]);
+        if (SHFL) {
+            upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1, LANES); upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1, LANES);
+            upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1, LANES); upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1, LANES);
+            upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1, LANES); upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1, LANES);
+        } else {
+            upM = Ml[RPT - 1]; upI = Il[RPT - 1]; upD = Dl[RPT - 1];
+        }
+    }
+    const float r = sumM.x + sumM.y + sumI.x + sumI.y + (float)nb;
+    if (r == 123.456f) out[0] = r;
+}
+
+// Layout B: thread = RPT rows of TWO reads (f32x2 halves) x one haplotype stream.  Per-row parameters are
+// register pairs; the priors come from a per-thread shared-memory table indexed by the column's base,
+// already paired, fetched with LDS.128/LDS.64 — no LOP3/FSEL at all.
+template <int RPT, bool SHFL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) layoutB(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    constexpr int NQ = (RPT + 1) / 2;                                 // float4 slots per base (2 rows each)
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* stream = reinterpret_cast<uint32_t*>(smem);            // [L + 32] byte offset of the base's table
+    float4* tbl = reinterpret_cast<float4*>(smem + (((size_t)(L + 32) * 4 + 15) & ~(size_t)15));   // [5][NQ][threads]
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x)
+        stream[i] = (gbases[(i + blockIdx.x) % 4096] & 3) * NQ * blockDim.x * 16;
+    float2 mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const float j = seed * (float)(k + 1 + lane);
+        mm[k] = make_float2(0.9998f + j, 0.9997f + j); gapm[k] = make_float2(0.9f + j, 0.91f + j);
+        mi[k] = make_float2(3e-5f + j, 3.2e-5f + j); ii[k] = make_float2(0.1f + j, 0.11f + j); md[k] = make_float2(3.1e-5f + j, 3e-5f + j);
+    }
+    for (uint32_t b = 0; b < 4; ++b)
+        for (int q = 0; q < NQ; ++q) {
+            const uint32_t b0 = (lane * 7 + (2 * q) * 3 + blockIdx.x) & 3, b1 = (lane * 5 + (2 * q + 1) * 3 + blockIdx.x) & 3;
+            tbl[(b * NQ + q) * blockDim.x + threadIdx.x] = make_float4(b == b0 ? 0.999f : 3.3e-4f, b == b1 ? 0.998f : 3.2e-4f,
+                                                                       b == b1 ? 0.999f : 3.3e-4f, b == b0 ? 0.998f : 3.2e-4f);
+        }
+    __syncthreads();
+    float2 Ml[RPT], Il[RPT], Dl[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = bc(1.f); Il[k] = bc(0.5f); Dl[k] = bc(0.25f); }
+    float2 upM = bc(1.f), upI = bc(1.f), upD = bc(1.f), dgM = bc(1.f), dgI = bc(1.f), dgD = bc(1.f), sumM = bc(0.f), sumI = bc(0.f);
+    const uint32_t* sp = stream + 32 - lane;
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 16;
+    uint32_t nb = 0;
+#pragma unroll 2
+    for (uint32_t s = 0; s < L; ++s) {
+        const uint32_t w = sp[s];
+        if (w & 0x80000000u) { ++nb; sumM = bc(0.f); }
+        float4 pr[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) pr[q] = *reinterpret_cast<const float4*>(tb + w + q * blockDim.x * 16);
+        float2 pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
+            const float2 prior = (k & 1) ? make_float2(pr[k / 2].z, pr[k / 2].w) : make_float2(pr[k / 2].x, pr[k / 2].y);
+            float2 t = __fmul2_rn(pM, mm[k]);
+            t = __ffma2_rn(pI, gapm[k], t);
+            t = __ffma2_rn(pD, gapm[k], t);
+            const float2 nM = __fmul2_rn(t, prior);
+            const float2 nI = __ffma2_rn(uI, ii[k], __fmul2_rn(uM, mi[k]));
+            const float2 nD = __ffma2_rn(oD, ii[k], __fmul2_rn(oM, md[k]));
+            Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
+            pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        sumM = __fadd2_rn(sumM, Ml[RPT - 1]);
+        sumI = __fadd2_rn(sumI, Il[RPT - 1]);
+        if (SHFL) {
+            upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1); upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1);
+            upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1); upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1);
+            upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1); upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1);
+        } else {
+            upM = Ml[RPT - 1]; upI = Il[RPT - 1]; upD = Dl[RPT - 1];
+        }
+    }
+    const float r = sumM.x + sumM.y + sumI.x + sumI.y + (float)nb;
+    if (r == 123.456f) out[0] = r;
+}
+
+// Layout A4: as A but FOUR haplotype streams per thread (two f32x2 pairs).  Consecutive instructions of the two pairs
+// share their scalar row parameter in the same operand slot, so the second one can take it from the operand reuse
+// cache: FFMA2 then reads 2 registers per bank instead of 3 and issues at the pipe rate.
+template <int RPT, int SEL, bool SHFL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) layoutA4(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint4* stream = reinterpret_cast<uint4*>(smem);                  // [L + 32]
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) {
+        uint32_t b[4];
+        for (int e = 0; e < 4; ++e) b[e] = (1u << (gbases[(i * 4 + e + blockIdx.x) % 4096] & 3)) * 0x01111111u;
+        stream[i] = make_uint4(b[0], b[1], b[2], b[3]);
+    }
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], pm[RPT], pmm[RPT];
+    uint32_t rb = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const float j = seed * (float)(k + 1 + lane);
+        mm[k] = 0.9998f + j; gapm[k] = 0.9f + j; mi[k] = 3e-5f + j; ii[k] = 0.1f + j; md[k] = 3.1e-5f + j;
+        pm[k] = 0.999f + j; pmm[k] = 3.3e-4f + j;
+        rb |= (1u << ((lane * 7 + k * 3 + blockIdx.x) & 3)) << (4 * k);
+    }
+    __syncthreads();
+    float2 Ml[2][RPT], Il[2][RPT], Dl[2][RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k)
+        for (int a = 0; a < 2; ++a) { Ml[a][k] = bc(1.f); Il[a][k] = bc(0.5f); Dl[a][k] = bc(0.25f); }
+    float2 upM[2], upI[2], upD[2], dgM[2], dgI[2], dgD[2], sumM[2], sumI[2];
+    for (int a = 0; a < 2; ++a) { upM[a] = upI[a] = upD[a] = dgM[a] = dgI[a] = dgD[a] = bc(1.f); sumM[a] = sumI[a] = bc(0.f); }
+    const uint4* sp = stream + 32 - lane;
+    uint32_t nb = 0;
+#pragma unroll 1
+    for (uint32_t s = 0; s < L; ++s) {
+        const uint4 w4 = sp[s];
+        const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+        if ((w4.x | w4.y | w4.z | w4.w) & 0x80000000u) { ++nb; sumM[0] = bc(0.f); }
+        float2 pM[2], pI[2], pD[2], uM[2], uI[2];
+#pragma unroll
+        for (int a = 0; a < 2; ++a) { pM[a] = dgM[a]; pI[a] = dgI[a]; pD[a] = dgD[a]; uM[a] = upM[a]; uI[a] = upI[a]; }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            float2 oM[2], oI[2], oD[2], prior[2], t[2], nM[2], nI[2], nD[2], x[2], y[2];
+#pragma unroll
+            for (int a = 0; a < 2; ++a) { oM[a] = Ml[a][k]; oI[a] = Il[a][k]; oD[a] = Dl[a][k]; }
+            const uint32_t msk = 0xFu << (4 * k);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                if (SEL == SEL_LOP) {
+                    prior[a].x = (rb & w[2 * a] & msk) ? pm[k] : pmm[k];
+                    prior[a].y = (rb & w[2 * a + 1] & msk) ? pm[k] : pmm[k];
+                } else {
+                    prior[a] = bc(pm[k]);
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < 2; ++a) t[a] = __fmul2_rn(pM[a], bc(mm[k]));
+#pragma unroll
+            for (int a = 0; a < 2; ++a) t[a] = __ffma2_rn(pI[a], bc(gapm[k]), t[a]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) t[a] = __ffma2_rn(pD[a], bc(gapm[k]), t[a]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) x[a] = __fmul2_rn(uM[a], bc(mi[k]));
+#pragma unroll
+            for (int a = 0; a < 2; ++a) y[a] = __fmul2_rn(oM[a], bc(md[k]));
+#pragma unroll
+            for (int a = 0; a < 2; ++a) nI[a] = __ffma2_rn(uI[a], bc(ii[k]), x[a]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) nD[a] = __ffma2_rn(oD[a], bc(ii[k]), y[a]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) nM[a] = __fmul2_rn(t[a], prior[a]);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+                Ml[a][k] = nM[a]; Il[a][k] = nI[a]; Dl[a][k] = nD[a];
+                pM[a] = oM[a]; pI[a] = oI[a]; pD[a] = oD[a]; uM[a] = nM[a]; uI[a] = nI[a];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            dgM[a] = upM[a]; dgI[a] = upI[a]; dgD[a] = upD[a];
+            sumM[a] = __fadd2_rn(sumM[a], Ml[a][RPT - 1]);
+            sumI[a] = __fadd2_rn(sumI[a], Il[a][RPT - 1]);
+            if (SHFL) {
+                upM[a].x = __shfl_up_sync(0xffffffffu, Ml[a][RPT - 1].x, 1); upM[a].y = __shfl_up_sync(0xffffffffu, Ml[a][RPT - 1].y, 1);
+                upI[a].x = __shfl_up_sync(0xffffffffu, Il[a][RPT - 1].x, 1); upI[a].y = __shfl_up_sync(0xffffffffu, Il[a][RPT - 1].y, 1);
+                upD[a].x = __shfl_up_sync(0xffffffffu, Dl[a][RPT - 1].x, 1); upD[a].y = __shfl_up_sync(0xffffffffu, Dl[a][RPT - 1].y, 1);
+            } else {
+                upM[a] = Ml[a][RPT - 1]; upI[a] = Il[a][RPT - 1]; upD[a] = Dl[a][RPT - 1];
+            }
+        }
+    }
+    const float r = sumM[0].x + sumM[0].y + sumI[0].x + sumI[0].y + sumM[1].x + sumM[1].y + sumI[1].x + sumI[1].y + (float)nb;
+    if (r == 123.456f) out[0] = r;
+}
+
+// Layout S: scalar FP32 (one read x one stream per thread), the un-packed baseline.
+template <int RPT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) layoutS(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* stream = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) stream[i] = (1u << (gbases[(i + blockIdx.x) % 4096] & 3)) * 0x01111111u;
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], pm[RPT], pmm[RPT];
+    uint32_t rb = 0;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const float j = seed * (float)(k + 1 + lane);
+        mm[k] = 0.9998f + j; gapm[k] = 0.9f + j; mi[k] = 3e-5f + j; ii[k] = 0.1f + j; md[k] = 3.1e-5f + j; pm[k] = 0.999f + j; pmm[k] = 3.3e-4f + j;
+        rb |= (1u << ((lane * 7 + k * 3 + blockIdx.x) & 3)) << (4 * k);
+    }
+    __syncthreads();
+    float Ml[RPT], Il[RPT], Dl[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = 1.f; Il[k] = 0.5f; Dl[k] = 0.25f; }
+    float upM = 1.f, upI = 1.f, upD = 1.f, dgM = 1.f, dgI = 1.f, dgD = 1.f, sumM = 0.f, sumI = 0.f;
+    const uint32_t* sp = stream + 32 - lane;
+    uint32_t nb = 0;
+#pragma unroll 2
+    for (uint32_t s = 0; s < L; ++s) {
+        const uint32_t w = sp[s];
+        if (w & 0x80000000u) { ++nb; sumM = 0.f; }
+        float pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const float oM = Ml[k], oI = Il[k], oD = Dl[k];
+            const float prior = (rb & w & (0xFu << (4 * k))) ? pm[k] : pmm[k];
+            float t = __fmul_rn(pM, mm[k]);
+            t = __fmaf_rn(pI, gapm[k], t);
+            t = __fmaf_rn(pD, gapm[k], t);
+            const float nM = __fmul_rn(t, prior);
+            const float nI = __fmaf_rn(uI, ii[k], __fmul_rn(uM, mi[k]));
+            const float nD = __fmaf_rn(oD, ii[k], __fmul_rn(oM, md[k]));
+            Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
+            pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        sumM = __fadd_rn(sumM, Ml[RPT - 1]);
+        sumI = __fadd_rn(sumI, Il[RPT - 1]);
+        upM = __shfl_up_sync(0xffffffffu, Ml[RPT - 1], 1);
+        upI = __shfl_up_sync(0xffffffffu, Il[RPT - 1], 1);
+        upD = __shfl_up_sync(0xffffffffu, Dl[RPT - 1], 1);
+    }
+    const float r = sumM + sumI + (float)nb;
+    if (r == 123.456f) out[0] = r;
+}
+
+// Layout D: scalar FP32, thread = RPT rows of one read x ONE haplotype stream; LANES (16 or 32) lanes per read, so a warp
+// carries 32/LANES reads.  Priors come from a per-thread shared-memory table indexed by the column's base (LDS.128, four
+// rows each), multiplied in with scalar FMULs — no LOP3/FSEL.  Larger RPT => fewer SHFL per cell.
+enum { SELD_LDS = 0, SELD_LOP = 1, SELD_NONE = 2 };
+template <int RPT, int LANES, int SEL, bool SHFL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) layoutD(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    constexpr int G = (RPT + 3) / 4;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* stream = reinterpret_cast<uint32_t*>(smem);            // [L + 32]
+    float4* tbl = reinterpret_cast<float4*>(smem + (((size_t)(L + 32) * 4 + 15) & ~(size_t)15));   // [6][G][threads]
+    const uint32_t lane = threadIdx.x & (LANES - 1);
+    for (uint32_t i = threadIdx.x; i < L + 32; i += blockDim.x) {
+        const uint32_t b = gbases[(i + blockIdx.x) % 4096] & 3;
+        stream[i] = (SEL == SELD_LDS) ? b * G * blockDim.x * 16 : (1u << b) * 0x11111111u;
+    }
+    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], pm[RPT], pmm[RPT];
+    uint32_t rb[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) {
+        const float j = seed * (float)(k + 1 + lane);
+        mm[k] = 0.9998f + j; gapm[k] = 0.9f + j; mi[k] = 3e-5f + j; ii[k] = 0.1f + j; md[k] = 3.1e-5f + j; pm[k] = 0.999f + j; pmm[k] = 3.3e-4f + j;
+        const uint32_t base = (lane * 7 + k * 3 + blockIdx.x) & 3;
+        rb[k / 8] |= (1u << base) << (4 * (k % 8));
+        if (SEL == SELD_LDS)
+            for (uint32_t b = 0; b < 6; ++b)
+                reinterpret_cast<float*>(&tbl[(b * G + k / 4) * blockDim.x + threadIdx.x])[k % 4] = (b == base || b == 4) ? pm[k] : pmm[k];
+    }
+    __syncthreads();
+    float Ml[RPT], Il[RPT], Dl[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = 1.f; Il[k] = 0.5f; Dl[k] = 0.25f; }
+    float upM = 1.f, upI = 1.f, upD = 1.f, dgM = 1.f, dgI = 1.f, dgD = 1.f, sumM = 0.f, sumI = 0.f;
+    const uint32_t* sp = stream + 32 - lane;
+    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 16;
+    uint32_t nb = 0;
+#pragma unroll 2
+    for (uint32_t s = 0; s < L; ++s) {
+        uint32_t w = sp[s];
+        if ((int)w < 0) { ++nb; sumM = 0.f; w &= 0x7fffffffu; }
+        float pr[G * 4];
+        if (SEL == SELD_LDS) {
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const float4 v = *reinterpret_cast<const float4*>(tb + w + g * blockDim.x * 16);
+                pr[4 * g] = v.x; pr[4 * g + 1] = v.y; pr[4 * g + 2] = v.z; pr[4 * g + 3] = v.w;
+            }
+        }
+        float pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const float oM = Ml[k], oI = Il[k], oD = Dl[k];
+            float prior;
+            if (SEL == SELD_LDS) prior = pr[k];
+            else if (SEL == SELD_LOP) prior = (rb[k / 8] & w & (0xFu << (4 * (k % 8)))) ? pm[k] : pmm[k];
+            else prior = pm[k];
+            float t = __fmul_rn(pM, mm[k]);
+            t = __fmaf_rn(pI, gapm[k], t);
+            t = __fmaf_rn(pD, gapm[k], t);
+            const float nM = __fmul_rn(t, prior);
+            const float nI = __fmaf_rn(uI, ii[k], __fmul_rn(uM, mi[k]));
+            const float nD = __fmaf_rn(oD, ii[k], __fmul_rn(oM, md[k]));
+            Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
+            pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        sumM = __fadd_rn(sumM, Ml[RPT - 1]);
+        sumI = __fadd_rn(sumI, Il[RPT - 1]);
+        if (SHFL) {
+            upM = __shfl_up_sync(0xffffffffu, Ml[RPT - 1], 1, LANES);
+            upI = __shfl_up_sync(0xffffffffu, Il[RPT - 1], 1, LANES);
+            upD = __shfl_up_sync(0xffffffffu, Dl[RPT - 1], 1, LANES);
+        } else {
+            upM = Ml[RPT - 1]; upI = Il[RPT - 1]; upD = Dl[RPT - 1];
+        }
+    }
+    const float r = sumM + sumI + (float)nb;
+    if (r == 123.456f) out[0] = r;
+}
+
+// Layout T ("column strips, row streams"): thread = CPT columns of ONE haplotype tile x TWO read chains in the f32x2 halves;
+// the warp sweeps the chained read rows as a wavefront (lane l works on stream row s - l).  All cells a thread computes in
+// one step lie in the same read row, so every transition parameter is shared by the CPT instructions of an op group and can
+// come from the operand reuse cache; the per-row parameter records are fetched from shared memory once per step (LDS.128).
+template <int CPT, int CHUNK, bool SEL, bool SHFL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB) layoutT(const uint32_t* gbases, uint32_t L, float* out, float seed)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    float4* recA = reinterpret_cast<float4*>(smem);                  // [2][L + 32]  mm, gapm, mi, ii
+    float4* recB = recA + 2 * (L + 32);                              // [2][L + 32]  md, pm, pmm, base word
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i = threadIdx.x; i < 2 * (L + 32); i += blockDim.x) {
+        const float j = seed * (float)(i & 63);
+        recA[i] = make_float4(0.9998f + j, 0.9f + j, 3e-5f + j, 0.1f + j);
+        recB[i] = make_float4(3.1e-5f + j, 0.999f + j, 3.3e-4f + j, __uint_as_float((1u << (gbases[(i + blockIdx.x) % 4096] & 3)) * 0x11111111u));
+    }
+    uint32_t hm[(CPT + 7) / 8];
+#pragma unroll
+    for (int k = 0; k < (CPT + 7) / 8; ++k) hm[k] = 0;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) hm[k / 8] |= (1u << ((lane * 7 + k * 3 + blockIdx.x + (threadIdx.x >> 5)) & 3)) << (4 * (k % 8));
+    __syncthreads();
+    float2 M[CPT], I[CPT], D[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) { M[k] = bc(1.f); I[k] = bc(0.5f); D[k] = bc(0.25f); }
+    float2 LM = bc(1.f), LI = bc(1.f), LD = bc(1.f), PM = bc(1.f), PI = bc(1.f), PD = bc(1.f);   // left lane: row r / row r-1
+    const float4* ax = recA + 32 - lane; const float4* ay = ax + (L + 32);
+    const float4* bx = recB + 32 - lane; const float4* by = bx + (L + 32);
+    uint32_t nb = 0;
+    float2 acc = bc(0.f);
+#pragma unroll 1
+    for (uint32_t s = 0; s < L; ++s) {
+        const float4 a0 = ax[s], a1 = ay[s], b0 = bx[s], b1 = by[s];
+        const float2 mm = make_float2(a0.x, a1.x), gapm = make_float2(a0.y, a1.y), mi = make_float2(a0.z, a1.z), ii = make_float2(a0.w, a1.w);
+        const float2 md = make_float2(b0.x, b1.x);
+        const float pmx = b0.y, pmmx = b0.z, pmy = b1.y, pmmy = b1.z;
+        const uint32_t wx = __float_as_uint(b0.w), wy = __float_as_uint(b1.w);
+        if ((int)(wx | wy) < 0) { ++nb; acc = bc(0.f); }
+        float2 nM[CPT], nI[CPT], nD[CPT];
+#pragma unroll
+        for (int c0 = 0; c0 < CPT; c0 += CHUNK) {
+            float2 t[CHUNK], x[CHUNK], pr[CHUNK];
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) t[j] = __fmul2_rn(k == 0 ? PM : M[k - 1], mm); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) t[j] = __ffma2_rn(k == 0 ? PI : I[k - 1], gapm, t[j]); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) t[j] = __ffma2_rn(k == 0 ? PD : D[k - 1], gapm, t[j]); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) x[j] = __fmul2_rn(M[k], mi); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) nI[k] = __ffma2_rn(I[k], ii, x[j]); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) {
+                const int k = c0 + j;
+                if (k < CPT) {
+                    if (SEL) {
+                        const uint32_t msk = 0xFu << (4 * (k % 8));
+                        pr[j].x = (hm[k / 8] & wx & msk) ? pmx : pmmx;
+                        pr[j].y = (hm[k / 8] & wy & msk) ? pmy : pmmy;
+                    } else {
+                        pr[j] = make_float2(pmx, pmy);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) nM[k] = __fmul2_rn(t[j], pr[j]); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) x[j] = __fmul2_rn(k == 0 ? LM : nM[k - 1], md); }
+#pragma unroll
+            for (int j = 0; j < CHUNK; ++j) { const int k = c0 + j; if (k < CPT) nD[k] = __ffma2_rn(k == 0 ? LD : nD[k - 1], ii, x[j]); }
+        }
+        PM = LM; PI = LI; PD = LD;
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) { M[k] = nM[k]; I[k] = nI[k]; D[k] = nD[k]; }
+        if (SHFL) {
+            LM.x = __shfl_up_sync(0xffffffffu, M[CPT - 1].x, 1); LM.y = __shfl_up_sync(0xffffffffu, M[CPT - 1].y, 1);
+            LI.x = __shfl_up_sync(0xffffffffu, I[CPT - 1].x, 1); LI.y = __shfl_up_sync(0xffffffffu, I[CPT - 1].y, 1);
+            LD.x = __shfl_up_sync(0xffffffffu, D[CPT - 1].x, 1); LD.y = __shfl_up_sync(0xffffffffu, D[CPT - 1].y, 1);
+        } else {
+            LM = M[CPT - 1]; LI = I[CPT - 1]; LD = D[CPT - 1];
+        }
+    }
+    float r = acc.x + acc.y + (float)nb;
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) r += M[k].x + M[k].y + I[k].x + I[k].y + D[k].x + D[k].y;
+    if (r == 123.456f) out[0] = r;
+}
+
+static int g_sms = 148;
+static double g_clk = 1.965e9;
+static uint32_t* g_bases;
+static float* g_out;
+
+template <typename K>
+void run(const char* name, K kern, int warps, int rpt, int halves, size_t smem, uint32_t L)
+{
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, kern));
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, warps * 32, smem));
+    const int grid = g_sms * occ * 3;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, warps * 32, smem>>>(g_bases, L, g_out, 1e-9f);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep && ms < best) best = ms;
+    }
+    CK(cudaGetLastError());
+    const double cells = (double)grid * warps * 32.0 * rpt * halves * L;
+    const double frac = cells * 8.0 / (best * 1e-3 * g_sms * 128.0 * g_clk);
+    const double cyc_per_step = best * 1e-3 * g_clk / (3.0 * L) / ((double)occ * warps / 4.0);   // SMSP cycles per warp-step
+    printf("%-34s regs %3d occ %2d (%2d warps/SM) smem %6zu  %8.3f ms  %6.1f cyc/warp-step (ideal %3d)  frac %.4f  %.2f TCUPS\n", name,
+           fa.numRegs, occ, occ * warps, smem, best, cyc_per_step, rpt * halves * 8, frac, cells / (best * 1e-3) / 1e12);
+    fflush(stdout);
+}
+
+int main()
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    int khz = 0;
+    CK(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, 0));
+    g_clk = khz * 1e3;
+    printf("%s: %d SMs, %.0f MHz max\n", prop.name, g_sms, g_clk / 1e6);
+    std::vector<uint32_t> hb(4096);
+    uint64_t x = 88172645463325252ull;
+    for (auto& v : hb) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; v = (uint32_t)(x >> 33); }
+    CK(cudaMalloc(&g_bases, 4096 * 4));
+    CK(cudaMemcpy(g_bases, hb.data(), 4096 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&g_out, 256));
+    const uint32_t L = 1232;
+    const uint32_t LB = 2432;
+    const size_t sA = (size_t)(L + 32) * 8;
+#define A(R, SEL, SH, W) run("A rpt" #R " " #SEL " shfl=" #SH " w" #W, layoutA<R, SEL, SH, W>, W, R, 2, sA + ((SEL) == SEL_LDS32 ? 4 * R * W * 32 * 4 : (SEL) == SEL_LDS128 ? 6 * ((R + 3) / 4) * W * 32 * 16 : 0), L)
+#define AL(R, W, LN, MB) run("A rpt" #R " LDS128 w" #W " lanes" #LN " minb" #MB, layoutA<R, SEL_LDS128, true, W, LN, MB>, W, R, 2, sA + 6 * ((R + 3) / 4) * W * 32 * 16, L)
+    AL(10, 4, 16, 3);
+    AL(10, 4, 16, 4);
+    AL(10, 2, 16, 6);
+    AL(10, 8, 16, 1);
+    AL(8, 4, 16, 4);
+    AL(12, 4, 16, 3);
+    AL(7, 4, 16, 4);
+    AL(5, 4, 32, 5);
+    AL(5, 4, 32, 6);
+    AL(6, 4, 32, 5);
+    A(5, SEL_LDS128, true, 4);
+    A(5, SEL_LDS128, false, 4);
+    A(4, SEL_LDS128, true, 4);
+    A(6, SEL_LDS128, true, 4);
+    A(8, SEL_LDS128, true, 4);
+    A(3, SEL_LDS128, true, 4);
+    A(5, SEL_LDS128, true, 2);
+    A(5, SEL_LDS128, true, 8);
+    A(5, SEL_LOP, true, 4);
+    A(5, SEL_NONE, true, 4);
+    A(5, SEL_LOP, false, 4);
+    A(5, SEL_NONE, false, 4);
+    A(5, SEL_LDS32, true, 4);
+    A(5, SEL_LDS32, false, 4);
+    A(4, SEL_LOP, true, 4);
+    A(4, SEL_NONE, false, 4);
+    A(3, SEL_LOP, true, 4);
+    A(3, SEL_NONE, false, 4);
+    A(6, SEL_LOP, true, 4);
+    A(8, SEL_LOP, true, 4);
+    A(5, SEL_LOP, true, 2);
+    A(5, SEL_LOP, true, 8);
+    const uint32_t LT = 600;
+#define T(C, CH, SEL, SH, W, MB) run("T cpt" #C " chunk" #CH " sel=" #SEL " shfl=" #SH " w" #W " minb" #MB, layoutT<C, CH, SEL, SH, W, MB>, W, C, 2, (size_t)(LT + 32) * 64, LT)
+    T(10, 10, true, true, 4, 3);
+    T(10, 5, true, true, 4, 3);
+    T(10, 5, true, true, 4, 4);
+    T(10, 10, false, true, 4, 3);
+    T(10, 10, true, false, 4, 3);
+    T(10, 10, false, false, 4, 3);
+    T(10, 5, false, false, 4, 3);
+    T(8, 8, true, true, 4, 4);
+    T(8, 4, true, true, 4, 4);
+    T(6, 6, true, true, 4, 5);
+    T(5, 5, true, true, 4, 5);
+    T(12, 6, true, true, 4, 3);
+    T(12, 12, true, true, 4, 2);
+    T(10, 10, true, true, 2, 6);
+#define D(R, LN, SEL, SH, W, MB) run("D rpt" #R " lanes" #LN " " #SEL " shfl=" #SH " w" #W " minb" #MB, layoutD<R, LN, SEL, SH, W, MB>, W, R, 1, \
+        (((size_t)(LB + 32) * 4 + 15) & ~(size_t)15) + ((SEL) == SELD_LDS ? (size_t)6 * ((R + 3) / 4) * W * 32 * 16 : 0), LB)
+    D(10, 16, SELD_LDS, true, 4, 4);
+    D(10, 16, SELD_LDS, true, 4, 3);
+    D(10, 16, SELD_LDS, true, 4, 5);
+    D(10, 16, SELD_LOP, true, 4, 4);
+    D(10, 16, SELD_NONE, true, 4, 4);
+    D(10, 16, SELD_NONE, false, 4, 4);
+    D(10, 16, SELD_LDS, false, 4, 4);
+    D(5, 32, SELD_LDS, true, 4, 6);
+    D(5, 32, SELD_LOP, true, 4, 6);
+    D(5, 32, SELD_NONE, false, 4, 6);
+    D(8, 16, SELD_LDS, true, 4, 5);
+    D(12, 16, SELD_LDS, true, 4, 3);
+    D(16, 16, SELD_LDS, true, 4, 3);
+    D(10, 16, SELD_LDS, true, 2, 8);
+    D(10, 16, SELD_LDS, true, 8, 2);
+    const uint32_t L4 = 632;
+#define A4(R, SEL, SH, W, MB) run("A4 rpt" #R " " #SEL " shfl=" #SH " w" #W " minb" #MB, layoutA4<R, SEL, SH, W, MB>, W, R, 4, (size_t)(L4 + 32) * 16, L4)
+    A4(5, SEL_LOP, true, 4, 3);
+    A4(5, SEL_LOP, true, 4, 2);
+    A4(5, SEL_NONE, true, 4, 3);
+    A4(5, SEL_LOP, false, 4, 3);
+    A4(5, SEL_NONE, false, 4, 3);
+    A4(4, SEL_LOP, true, 4, 3);
+    A4(4, SEL_LOP, true, 4, 4);
+    A4(3, SEL_LOP, true, 4, 4);
+    A4(3, SEL_LOP, true, 4, 5);
+    A4(6, SEL_LOP, true, 4, 2);
+    A4(5, SEL_LOP, true, 2, 6);
+#define B(R, SH, W) run("B rpt" #R " lds128 shfl=" #SH " w" #W, layoutB<R, SH, W>, W, R, 2, (((size_t)(LB + 32) * 4 + 15) & ~(size_t)15) + (size_t)4 * ((R + 1) / 2) * W * 32 * 16, LB)
+    B(5, true, 4);
+    B(5, false, 4);
+    B(4, true, 4);
+    B(6, true, 4);
+    B(3, true, 4);
+    B(5, true, 2);
+#define S(R, W) run("S rpt" #R " scalar w" #W, layoutS<R, W>, W, R, 1, (size_t)(LB + 32) * 4, LB)
+    S(5, 4);
+    S(5, 8);
+    return 0;
+}

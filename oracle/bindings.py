@@ -275,6 +275,69 @@ class Ref:
         return float(secs), float(chk.value)
 
 
+class Adapter:
+    """rovaca_b200/adapter/call_pairhmm_b200.cpp (the drop-in with the reference's signature) driven through the reference's
+    own ReadRecord / Haplotype / RovacaMemoryPool objects (oracle/_ref/libphmm_adapter_test.so).  Needs a B200 to run."""
+
+    EXPORTS = ["adapter_init", "adapter_shutdown", "adapter_region", "adapter_last_error"]
+
+    def __init__(self, path: str):
+        L = self.lib = C.CDLL(path)
+        L.adapter_last_error.restype = C.c_char_p
+        L.adapter_init.restype, L.adapter_init.argtypes = C.c_int, [C.c_int]
+        L.adapter_shutdown.restype = None
+        L.adapter_region.restype = C.c_int
+        L.adapter_region.argtypes = [C.c_uint32, _u8p, _u8p, _u64p, _u32p, _u8p, C.c_uint32, _u8p, _u64p, _u32p, C.c_int32, C.c_int,
+                                     _f64p, _u32p, _u32p]
+
+    def init(self, device: int = -1):
+        rc = self.lib.adapter_init(device)
+        if rc != 0:
+            raise RuntimeError("init_pairhmm_ptr_b200 failed (%d): %s" % (rc, self.lib.adapter_last_error().decode()))
+
+    def shutdown(self):
+        self.lib.adapter_shutdown()
+
+    def region(self, reads: Sequence[dict], haps: Sequence, thr: int = 18, model: int = PCR_CONSERVATIVE):
+        """One region through the global rovaca::call_pairhmm pointer after init_pairhmm_ptr_b200 re-bound it."""
+        n_r, n_h = len(reads), len(haps)
+        rb = [_u8(r["bases"]) for r in reads]
+        rq = [_u8(r["qual"]) for r in reads]
+        rlen = np.array([len(b) for b in rb], np.uint32)
+        roff = np.zeros(n_r, np.uint64)
+        if n_r:
+            roff[1:] = np.cumsum(rlen[:-1], dtype=np.uint64)
+        rbase = np.concatenate(rb) if n_r else np.zeros(1, np.uint8)
+        rqual = np.concatenate(rq) if n_r else np.zeros(1, np.uint8)
+        rmapq = np.array([int(r.get("mapq", 60)) for r in reads], np.uint8)
+        hb = [_u8(h) for h in haps]
+        hlen = np.array([len(b) for b in hb], np.uint32)
+        hoff = np.zeros(n_h, np.uint64)
+        if n_h:
+            hoff[1:] = np.cumsum(hlen[:-1], dtype=np.uint64)
+        hbase = np.concatenate(hb) if n_h else np.zeros(1, np.uint8)
+        out = np.full((n_h, n_r), np.nan, np.float64)
+        kept = np.zeros(max(n_r, 1), np.uint32)
+        n_kept = C.c_uint32(0)
+        rc = self.lib.adapter_region(n_r, _p(rbase, _u8p), _p(rqual, _u8p), _p(roff, _u64p), _p(rlen, _u32p), _p(rmapq, _u8p), n_h,
+                                     _p(hbase, _u8p), _p(hoff, _u64p), _p(hlen, _u32p), thr, model, _p(out, _f64p), _p(kept, _u32p),
+                                     C.byref(n_kept))
+        if rc != 0:
+            raise RuntimeError("adapter_region failed rc=%d: %s" % (rc, self.lib.adapter_last_error().decode()))
+        return out, kept[: n_kept.value].copy()
+
+
+def adapter() -> Optional[Adapter]:
+    """The adapter test library, or None when oracle/_ref/libphmm_adapter_test.so is not there (needs /root/reference to build)."""
+    path = os.path.join(_HERE, "_ref", "libphmm_adapter_test.so")
+    if not os.path.exists(path):
+        return None
+    try:
+        return Adapter(path)
+    except OSError:
+        return None
+
+
 _oracle: Optional[Oracle] = None
 _ref: Optional[Ref] = None
 _ref_tried = False

@@ -19,41 +19,7 @@
  * binding pairhmm_engine.cpp:21-53 performs (that file needs the spdlog logger, so its ten lines
  * of binding logic are restated in bind_kernels()).
  */
-#include <algorithm>
-#include <atomic>
-#include <chrono>
-#include <cmath>
-#include <cstdint>
-#include <cstdlib>
-#include <cstring>
-#include <map>
-#include <memory_resource>
-#include <set>
-#include <string>
-#include <thread>
-#include <unordered_map>
-#include <unordered_set>
-#include <vector>
-#include <list>
-#include <bitset>
-#include <memory>
-#include <xmmintrin.h>
-
-#include "htslib/sam.h"
-
-/* Reach the two private fields of Allele the path reads (genotype/allele.h:66-67). */
-#define private public
-#define protected public
-#include "genotype/haplotype.h"
-#undef private
-#undef protected
-#include "genotype/read_record.h"
-#include "common/utils/rovaca_memory_pool.h"
-#include "pairhmm/pairhmm_internal.h"
-#include "pairhmm/core/avx.h"
-#include "pairhmm/core/avx_impl.h"
-#include "pairhmm/rovaca/avx_512_float.h"
-#include "pairhmm/rovaca/context.h"
+#include "ref_glue.h"
 
 /* ---- htslib symbols read_record.cpp references (sam.c / hts.c); not exercised by the path ---- */
 extern "C" {
@@ -107,42 +73,7 @@ struct CsrGuard
     ~CsrGuard() { _mm_setcsr(old); }
 };
 
-uint8_t nt16_code(uint8_t c)
-{
-    switch (c) {
-        case 'A': return 1;
-        case 'C': return 2;
-        case 'G': return 4;
-        case 'T': return 8;
-        case 'N': return 15;
-        default: return 15;
-    }
-}
-
-/* A BAM record carrying just what ReadRecord's accessors read (read_record.cpp:73-95,176-210). */
-struct FakeBam
-{
-    bam1_t b;
-    std::vector<uint8_t> data;
-    void build(const uint8_t* bases, const uint8_t* qual, uint32_t len, uint8_t mapq)
-    {
-        std::memset(&b, 0, sizeof(b));
-        const uint32_t l_qname = 4;
-        data.assign(l_qname + (len + 1) / 2 + len, 0);
-        data[0] = 'r';
-        uint8_t* seq = data.data() + l_qname;
-        for (uint32_t i = 0; i < len; ++i) seq[i >> 1] |= nt16_code(bases[i]) << ((~i & 1) << 2);
-        std::memcpy(seq + (len + 1) / 2, qual, len);
-        b.core.l_qname = l_qname;
-        b.core.l_extranul = 2;
-        b.core.n_cigar = 0;
-        b.core.l_qseq = (int32_t)len;
-        b.core.qual = mapq;
-        b.data = data.data();
-        b.l_data = (int)data.size();
-        b.m_data = (uint32_t)data.size();
-    }
-};
+using ref_glue::FakeBam;
 
 struct Region
 {

@@ -1,0 +1,118 @@
+// call_pairhmm_b200.cpp — see call_pairhmm_b200.h.  Host glue only: it hands the reference's objects to the C ABI
+// (include/phmm_b200.h) as plain pointers and rebuilds the reference's return value; no likelihood arithmetic here.
+#include "call_pairhmm_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <xmmintrin.h>
+
+#include "common/utils/rovaca_memory_pool.h"
+#include "genotype/genotype_struct.h"
+#include "genotype/haplotype.h"
+#include "genotype/read_record.h"
+#include "phmm_b200.h"
+
+namespace rovaca
+{
+
+// the reference's seam (pairhmm/pairhmm_engine.cpp:16-17); defined there, or by the test shim
+extern DoubleVector2D (*call_pairhmm)(const HaplotypeVector& hs, ReadVector& rs, int32_t min_quality_threshold, PcrIndelModel pcr_option,
+                                      pMemoryPool pool);
+
+namespace
+{
+phmm_engine* g_engine = nullptr;
+std::mutex g_engine_mutex;
+}  // namespace
+
+void init_pairhmm_ptr_b200(int device)
+{
+    std::lock_guard<std::mutex> lk(g_engine_mutex);
+    if (!g_engine) {
+        phmm_config cfg;
+        std::memset(&cfg, 0, sizeof(cfg));
+        cfg.device = device;
+        if (phmm_create(&cfg, &g_engine) != PHMM_OK)
+            throw std::runtime_error(std::string("init_pairhmm_ptr_b200: ") + phmm_last_error());
+    }
+    call_pairhmm = call_pairhmm_b200;
+}
+
+void shutdown_pairhmm_b200()
+{
+    std::lock_guard<std::mutex> lk(g_engine_mutex);
+    if (g_engine) phmm_destroy(g_engine);
+    g_engine = nullptr;
+}
+
+DoubleVector2D call_pairhmm_b200(const HaplotypeVector& hs, ReadVector& rs, int32_t min_quality_threshold, PcrIndelModel pcr_option,
+                                 pMemoryPool pool)
+{
+    if (hs.empty() || rs.empty()) return {};                           // pairhmm_internal.cpp:508-510
+    if (!g_engine) throw std::runtime_error("call_pairhmm_b200: init_pairhmm_ptr_b200 has not been called");
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);                        // init_native, :21-25: stays set on the caller thread
+
+    const size_t n_reads = rs.size(), n_haps = hs.size();
+    DoubleVector2D final_likelihood{n_haps, DoubleVector{n_reads, NAN, pool}, pool};   // :516, allocated before the guard
+    auto* lp = static_cast<RovacaMemoryPool*>(pool);
+    MemoryPoolGuard scratch_guard{lp};                                  // :517-518: everything below is rewound on return
+
+    size_t read_bytes = 0;
+    for (pReadRecord r : rs) read_bytes += (size_t)r->seq_length();
+    auto* reads = static_cast<phmm_read*>(pool->allocate(sizeof(phmm_read) * n_reads, alignof(phmm_read)));
+    auto* haps = static_cast<phmm_hap*>(pool->allocate(sizeof(phmm_hap) * n_haps, alignof(phmm_hap)));
+    auto* bases = static_cast<uint8_t*>(pool->allocate(read_bytes + 1, 8));
+    auto* flat = static_cast<double*>(pool->allocate(sizeof(double) * n_reads * n_haps, alignof(double)));
+    auto* kept = static_cast<uint32_t*>(pool->allocate(sizeof(uint32_t) * n_reads, alignof(uint32_t)));
+
+    size_t at = 0;
+    for (size_t i = 0; i < n_reads; ++i) {
+        pReadRecord r = rs[i];
+        const uint32_t len = (uint32_t)r->seq_length();
+        for (uint32_t k = 0; k < len; ++k) bases[at + k] = r->seq_i(k);   // decode_base, read_record.cpp:176-182
+        reads[i].bases = bases + at;
+        reads[i].qual = r->qual();                                      // :521-523
+        reads[i].ins = nullptr;                                         // ins_gops(): '-' everywhere, read_record.cpp:191-196
+        reads[i].del = nullptr;                                         // del aliases ins, pairhmm_internal.cpp:559
+        reads[i].gcp = nullptr;                                         // gap_conts(): '+'-33, read_record.cpp:205-210
+        reads[i].len = len;
+        reads[i].mapq = r->mapping_quality();
+        at += len;
+    }
+    for (size_t j = 0; j < n_haps; ++j) {
+        pBases b = hs[j]->get_display_string();                        // genotype/allele.h:104
+        haps[j].bases = b->data;
+        haps[j].len = b->num;
+    }
+
+    phmm_region region;
+    region.reads = reads;
+    region.n_reads = (uint32_t)n_reads;
+    region.haps = haps;
+    region.n_haps = (uint32_t)n_haps;
+    region.min_quality_threshold = min_quality_threshold;
+    region.pcr_model = static_cast<int32_t>(pcr_option);               // common/enum.h:8, same numeric values
+    phmm_result result;
+    std::memset(&result, 0, sizeof(result));
+    result.likelihoods = flat;
+    result.kept_idx = kept;
+    if (phmm_call_region(g_engine, &region, &result) != PHMM_OK)
+        throw std::runtime_error(std::string("call_pairhmm_b200: ") + phmm_last_error());   // caught at rovaca_main.cpp:39-42
+
+    for (size_t j = 0; j < n_haps; ++j) std::memcpy(final_likelihood[j].data(), flat + j * n_reads, sizeof(double) * n_reads);
+    // filter_poorly_modelled_evidence's side effect on `rs` (:178-181): erase, back to front, every read not kept
+    size_t k = result.n_kept;
+    for (size_t i = n_reads; i-- > 0;) {
+        if (k > 0 && kept[k - 1] == i) {
+            --k;
+            continue;
+        }
+        rs.erase(rs.begin() + (std::ptrdiff_t)i);
+    }
+    return final_likelihood;
+}
+
+}  // namespace rovaca

@@ -183,14 +183,6 @@ struct Stats
     double gpu_ms = 0.0;
 };
 
-int bin_of(uint32_t len)
-{
-    if (len == 0) return -1;
-    for (int b = 0; b < kPhmmNumBins; ++b)
-        if (len <= phmm_bin_capacity(b)) return b;
-    return -1;
-}
-
 }  // namespace
 
 struct phmm_resident
@@ -276,6 +268,9 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     }
     if (n_pairs >= (1ull << 31) || read_bytes >= (1ull << 31) || hap_bytes >= (1ull << 31))
         return fail(PHMM_ERR_ARG, "batch too large for 32-bit device offsets; lower batch_cells");
+    // What the reference itself feeds its kernels — deletion qualities aliasing the insertion ones, one gap-continuation
+    // quality per read (read_record.cpp:191-210, pairhmm_internal.cpp:425,559) — is served by the leaner kernel variant.
+    const bool refgaps = fma && !any_del && !any_gcp;
 
     std::vector<PhmmRead> reads;
     std::vector<PhmmHap> haps;
@@ -383,7 +378,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
             const uint32_t rid = (uint32_t)reads.size();
             reads.push_back(d);
             s.read_len.push_back(in.len);
-            const int b = bin_of(in.len);
+            const int b = phmm_bin_of(in.len, refgaps);
             if (b >= 0) by_bin[b].push_back(rid);
             for (uint32_t j = 0; j < r.n_haps; ++j) {
                 const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
@@ -1029,7 +1024,7 @@ int phmm_get_stats(phmm_engine* e, phmm_stats* out)
 
 int phmm_kernel_info(uint32_t read_len, int fma_mode, int* regs, int* local_bytes, int* lanes, int* rows_per_lane)
 {
-    const int bin = bin_of(read_len);
+    const int bin = phmm_bin_of(read_len, fma_mode != PHMM_FMA_NONE);
     if (bin < 0) return fail(PHMM_ERR_ARG, "phmm_kernel_info: no wavefront bin holds reads of this length (per-pair kernel)");
     PhmmKernelInfo ki{};
     CU(phmm_fwd_kernel_info(bin, fma_mode != PHMM_FMA_NONE, &ki));

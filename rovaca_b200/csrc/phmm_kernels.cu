@@ -144,10 +144,22 @@ __device__ __forceinline__ uint32_t class_onehot(uint32_t b) { return b < 4u ? (
 // occupancy targets found with tools/phmm_ablate.cu: the kernel is bound by register-file reads and issue slots, not by
 // latency, so it wants enough registers to hold RPT rows x 2 streams x 3 states plus the row parameters without spilling.
 constexpr int fwd_min_blocks(int rpt) { return rpt <= 3 ? 6 : rpt <= 5 ? 5 : (rpt == 6 || rpt == 8) ? 4 : rpt <= 10 ? 3 : 2; }
+constexpr int fwd_min_blocks_rg(int rpt) { return rpt <= 3 ? 6 : rpt <= 6 ? 5 : rpt <= 9 ? 4 : rpt <= 12 ? 3 : 2; }
 
-template <int RPT, int LANES, bool FMA>
-__global__ void __launch_bounds__(PHMM_WARPS * 32, fwd_min_blocks(RPT)) phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
+// VAR: PHMM_VAR_GENERIC_NOFMA — any per-base qualities, un-contracted AVX2 arithmetic (core/avx2_s.cpp:207-216);
+//      PHMM_VAR_GENERIC       — any per-base qualities, AVX-512 contraction;
+//      PHMM_VAR_REFGAPS       — what the reference itself feeds the kernel: deletion qualities alias the insertion ones and
+//                               the gap-continuation quality is one constant per read (read_record.cpp:191-210,
+//                               pairhmm_internal.cpp:425,559), so md == mi and gapm / ii / dd are per-read scalars: half the
+//                               parameter registers, which is what lets 19 rows per lane (8 lanes x 19 = 152 rows for 150/151-bp
+//                               reads, 1 % padding instead of 6 %) fit the register file.
+template <int RPT, int LANES, int VAR>
+__global__ void __launch_bounds__(PHMM_WARPS * 32, VAR == PHMM_VAR_REFGAPS ? fwd_min_blocks_rg(RPT) : fwd_min_blocks(RPT))
+phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 {
+    constexpr bool FMA = VAR != PHMM_VAR_GENERIC_NOFMA;
+    constexpr bool RG = VAR == PHMM_VAR_REFGAPS;
+    constexpr int NP = RG ? 1 : RPT;                      // per-row (generic) or per-read (reference gaps) gap parameters
     constexpr int NT = PHMM_WARPS * 32;
     constexpr int G = (RPT + 3) / 4;                     // float4 groups of the prior table
     constexpr uint32_t TSTRIDE = (uint32_t)G * NT * 16;   // bytes between the tables of two base classes
@@ -202,7 +214,8 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32, fwd_min_blocks(RPT)) phmm_fwd
     const int npad = LANES * RPT - (int)rd.len;       // >= 1 by binning
 
     // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers, priors into my table ----
-    float mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], dd[RPT];
+    float mm[RPT], mi[RPT], dd[RPT], gapm[NP], ii[NP], md[NP];
+    float ii0 = 0.f;           // RG: gap-continuation probability of row 0 (0 on lane 0, whose row 0 is always a pad row)
     uint32_t padmask = 0u;     // bit k: row k is a pad row; bit RPT: the row above row 0 is one
     {
         const PhmmTables* __restrict__ T = p.tables;
@@ -218,18 +231,30 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32, fwd_min_blocks(RPT)) phmm_fwd
                 const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
                 const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
                 mm[k] = __ldg(&T->mm[((hi * (hi + 1)) >> 1) + lo]);
-                gapm[k] = __ldg(&T->gapm[qc]);
                 mi[k] = __ldg(&T->ph2pr[qi]);
-                ii[k] = __ldg(&T->ph2pr[qc]);
-                md[k] = __ldg(&T->ph2pr[qd]);
-                dd[k] = ii[k];
+                dd[k] = __ldg(&T->ph2pr[qc]);
+                if (!RG) {
+                    gapm[k] = __ldg(&T->gapm[qc]);
+                    ii[k] = dd[k];
+                    md[k] = __ldg(&T->ph2pr[qd]);
+                }
                 pm[k] = __ldg(&T->pm[q]);
                 pmm[k] = __ldg(&T->pmm[q]);
                 rr[k] = w >> 28;
-            } else {                                   // boundary-generator row: prior 0, D carried unchanged
-                mm[k] = 0.f; gapm[k] = 0.f; mi[k] = 0.f; ii[k] = 0.f; md[k] = 0.f; dd[k] = 1.f;
+            } else {                                   // boundary-generator row: prior 0, I stays 0, D carried unchanged
+                mm[k] = 0.f; mi[k] = 0.f; dd[k] = 1.f;
+                if (!RG) { gapm[k] = 0.f; ii[k] = 0.f; md[k] = 0.f; }
                 padmask |= 1u << k;
             }
+        }
+        if (RG) {
+            // one gap-continuation quality per read.  Pad rows keep mi = 0 and dd = 1; with a shared ii their I is
+            // ii x (I of the pad row above) = 0, except on the very first row of the group, which sees lane 0's own
+            // shuffled-back bottom row: that row multiplies by ii0 = 0 instead.  Their M is (finite) x prior 0 = 0.
+            const uint32_t qc = (p.words[rd.word_off] >> 21) & 127u;
+            gapm[0] = __ldg(&T->gapm[qc]);
+            ii[0] = __ldg(&T->ph2pr[qc]);
+            ii0 = lane == 0 ? 0.f : ii[0];
         }
         if ((int)lane * RPT - 1 < npad) padmask |= 1u << RPT;
 #pragma unroll
@@ -315,7 +340,15 @@ __global__ void __launch_bounds__(PHMM_WARPS * 32, fwd_min_blocks(RPT)) phmm_fwd
         for (int k = 0; k < RPT; ++k) {
             const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
             float2 nM, nI, nD;
-            if (FMA) {                              // SURVEY.md §8a, AVX-512 contraction
+            if (RG) {                               // same operations, md == mi and one gapm / ii per read
+                float2 t = __fmul2_rn(pM, bc(mm[k]));
+                t = __ffma2_rn(pI, bc(gapm[0]), t);
+                t = __ffma2_rn(pD, bc(gapm[0]), t);
+                nM.x = __fmul_rn(t.x, px[k]);
+                nM.y = __fmul_rn(t.y, py[k]);
+                nI = __ffma2_rn(uI, bc(k == 0 ? ii0 : ii[0]), __fmul2_rn(uM, bc(mi[k])));
+                nD = __ffma2_rn(oD, bc(dd[k]), __fmul2_rn(oM, bc(mi[k])));
+            } else if (FMA) {                       // SURVEY.md §8a, AVX-512 contraction
                 float2 t = __fmul2_rn(pM, bc(mm[k]));
                 t = __ffma2_rn(pI, bc(gapm[k]), t);
                 t = __ffma2_rn(pD, bc(gapm[k]), t);
@@ -374,9 +407,13 @@ template <> struct Num<float>
 };
 template <> struct Num<double>
 {
-    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
-    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
-    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    // The reference runs its FP64 kernels on a thread whose MXCSR has flush-to-zero set (init_native,
+    // pairhmm_internal.cpp:21-25), which also flushes tiny *double* results; the GPU has no FP64 FTZ mode, so every
+    // result below DBL_MIN is flushed here (sign kept), as the SSE unit does.
+    static __device__ __forceinline__ double ftz(double x) { return fabs(x) < 2.2250738585072014e-308 ? copysign(0.0, x) : x; }
+    static __device__ __forceinline__ double mul(double a, double b) { return ftz(__dmul_rn(a, b)); }
+    static __device__ __forceinline__ double add(double a, double b) { return ftz(__dadd_rn(a, b)); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return ftz(__fma_rn(a, b, c)); }
     static __device__ __forceinline__ double init(uint32_t H) { return __ddiv_rn(__longlong_as_double(0x7FB0000000000000LL), (double)H); }   // 2^1020 / H
 };
 
@@ -490,10 +527,10 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
     if (acc == 123.456f) out[0] = acc;
 }
 
-template <int RPT, int LANES, bool FMA>
+template <int RPT, int LANES, int VAR>
 cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, size_t smem, cudaStream_t st)
 {
-    auto kern = phmm_fwd_kernel<RPT, LANES, FMA>;
+    auto kern = phmm_fwd_kernel<RPT, LANES, VAR>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -502,11 +539,11 @@ cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ct
     return cudaGetLastError();
 }
 
-template <int RPT, int LANES, bool FMA>
+template <int RPT, int LANES, int VAR>
 cudaError_t info_t(PhmmKernelInfo* info)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, LANES, FMA>);
+    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, LANES, VAR>);
     if (e != cudaSuccess) return e;
     info->regs = a.numRegs;
     info->local_bytes = (int)a.localSizeBytes;
@@ -525,15 +562,30 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     return cudaGetLastError();
 }
 
-#define PHMM_CASE(R, LN, FN, ...) \
-    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN) return fma ? FN<R, LN, true>(__VA_ARGS__) : FN<R, LN, false>(__VA_ARGS__);
-#define PHMM_DISPATCH_BIN(FN, ...)                                                                              \
-    PHMM_CASE(1, 16, FN, __VA_ARGS__) PHMM_CASE(2, 16, FN, __VA_ARGS__) PHMM_CASE(3, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE(4, 16, FN, __VA_ARGS__) PHMM_CASE(5, 16, FN, __VA_ARGS__) PHMM_CASE(6, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE(7, 16, FN, __VA_ARGS__) PHMM_CASE(8, 16, FN, __VA_ARGS__) PHMM_CASE(9, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE(10, 16, FN, __VA_ARGS__) PHMM_CASE(11, 16, FN, __VA_ARGS__) PHMM_CASE(12, 16, FN, __VA_ARGS__)    \
-    PHMM_CASE(7, 32, FN, __VA_ARGS__) PHMM_CASE(8, 32, FN, __VA_ARGS__) PHMM_CASE(9, 32, FN, __VA_ARGS__)       \
-    PHMM_CASE(10, 32, FN, __VA_ARGS__) PHMM_CASE(11, 32, FN, __VA_ARGS__) PHMM_CASE(12, 32, FN, __VA_ARGS__)    \
+// generic bins exist in both arithmetic flavours, reference-gap bins only in the (default) contracted one
+#define PHMM_CASE_G(R, LN, FN, ...)                                                    \
+    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN && !kPhmmBins[bin].refgaps) \
+        return fma ? FN<R, LN, PHMM_VAR_GENERIC>(__VA_ARGS__) : FN<R, LN, PHMM_VAR_GENERIC_NOFMA>(__VA_ARGS__);
+#define PHMM_CASE_R(R, LN, FN, ...) \
+    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN && kPhmmBins[bin].refgaps && fma) return FN<R, LN, PHMM_VAR_REFGAPS>(__VA_ARGS__);
+#define PHMM_DISPATCH_BIN(FN, ...)                                                                                    \
+    PHMM_CASE_G(1, 16, FN, __VA_ARGS__) PHMM_CASE_G(2, 16, FN, __VA_ARGS__) PHMM_CASE_G(3, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_G(4, 16, FN, __VA_ARGS__) PHMM_CASE_G(5, 16, FN, __VA_ARGS__) PHMM_CASE_G(6, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_G(7, 16, FN, __VA_ARGS__) PHMM_CASE_G(8, 16, FN, __VA_ARGS__) PHMM_CASE_G(9, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_G(10, 16, FN, __VA_ARGS__) PHMM_CASE_G(11, 16, FN, __VA_ARGS__) PHMM_CASE_G(12, 16, FN, __VA_ARGS__)    \
+    PHMM_CASE_G(7, 32, FN, __VA_ARGS__) PHMM_CASE_G(8, 32, FN, __VA_ARGS__) PHMM_CASE_G(9, 32, FN, __VA_ARGS__)       \
+    PHMM_CASE_G(10, 32, FN, __VA_ARGS__) PHMM_CASE_G(11, 32, FN, __VA_ARGS__) PHMM_CASE_G(12, 32, FN, __VA_ARGS__)    \
+    PHMM_CASE_R(1, 8, FN, __VA_ARGS__) PHMM_CASE_R(2, 8, FN, __VA_ARGS__) PHMM_CASE_R(3, 8, FN, __VA_ARGS__)          \
+    PHMM_CASE_R(4, 8, FN, __VA_ARGS__) PHMM_CASE_R(5, 8, FN, __VA_ARGS__) PHMM_CASE_R(6, 8, FN, __VA_ARGS__)          \
+    PHMM_CASE_R(7, 8, FN, __VA_ARGS__) PHMM_CASE_R(8, 8, FN, __VA_ARGS__) PHMM_CASE_R(9, 8, FN, __VA_ARGS__)          \
+    PHMM_CASE_R(10, 8, FN, __VA_ARGS__) PHMM_CASE_R(11, 8, FN, __VA_ARGS__) PHMM_CASE_R(12, 8, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(13, 8, FN, __VA_ARGS__) PHMM_CASE_R(14, 8, FN, __VA_ARGS__) PHMM_CASE_R(15, 8, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(16, 8, FN, __VA_ARGS__) PHMM_CASE_R(17, 8, FN, __VA_ARGS__) PHMM_CASE_R(18, 8, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(19, 8, FN, __VA_ARGS__)                                                                               \
+    PHMM_CASE_R(10, 16, FN, __VA_ARGS__) PHMM_CASE_R(12, 16, FN, __VA_ARGS__) PHMM_CASE_R(14, 16, FN, __VA_ARGS__)    \
+    PHMM_CASE_R(16, 16, FN, __VA_ARGS__) PHMM_CASE_R(18, 16, FN, __VA_ARGS__) PHMM_CASE_R(19, 16, FN, __VA_ARGS__)    \
+    PHMM_CASE_R(10, 32, FN, __VA_ARGS__) PHMM_CASE_R(12, 32, FN, __VA_ARGS__) PHMM_CASE_R(14, 32, FN, __VA_ARGS__)    \
+    PHMM_CASE_R(16, 32, FN, __VA_ARGS__) PHMM_CASE_R(18, 32, FN, __VA_ARGS__) PHMM_CASE_R(19, 32, FN, __VA_ARGS__)    \
     return cudaErrorInvalidValue;
 
 cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, size_t smem_bytes,

@@ -36,16 +36,38 @@ struct PhmmBatchDev
 // Half-warp bins come first: more rows per lane means fewer shuffles per cell (3 per RPT cells and stream), which is what
 // the issue/register-read budget of the SM rewards ("kernel budget"); whole-warp bins take over where a
 // half-warp read would need more than 12 rows per lane (register file).
+#define PHMM_VAR_GENERIC_NOFMA 0
+#define PHMM_VAR_GENERIC 1
+#define PHMM_VAR_REFGAPS 2
+
 struct PhmmBin
 {
     int lanes;
     int rpt;
+    int refgaps;   // 1: the reference-gap-quality variant of the kernel (deletion = insertion qualities, one gcp per read)
 };
-static const PhmmBin kPhmmBins[] = {{16, 1}, {16, 2}, {16, 3}, {16, 4}, {16, 5}, {16, 6}, {16, 7}, {16, 8}, {16, 9},
-                                    {16, 10}, {16, 11}, {16, 12}, {32, 7}, {32, 8}, {32, 9}, {32, 10}, {32, 11}, {32, 12}};
+// generic bins (any per-base qualities; both arithmetic flavours) ...
+static const PhmmBin kPhmmBins[] = {
+    {16, 1, 0}, {16, 2, 0}, {16, 3, 0}, {16, 4, 0}, {16, 5, 0}, {16, 6, 0}, {16, 7, 0}, {16, 8, 0}, {16, 9, 0}, {16, 10, 0}, {16, 11, 0},
+    {16, 12, 0}, {32, 7, 0}, {32, 8, 0}, {32, 9, 0}, {32, 10, 0}, {32, 11, 0}, {32, 12, 0},
+    // ... and the bins of the reference-gap variant: 8 lanes up to 151 bp (8 x 19 = 152 rows hold a 150/151-bp read with
+    // 1-2 pad rows), 16 lanes up to 303 bp, 32 lanes up to 607 bp
+    {8, 1, 1}, {8, 2, 1}, {8, 3, 1}, {8, 4, 1}, {8, 5, 1}, {8, 6, 1}, {8, 7, 1}, {8, 8, 1}, {8, 9, 1}, {8, 10, 1}, {8, 11, 1}, {8, 12, 1},
+    {8, 13, 1}, {8, 14, 1}, {8, 15, 1}, {8, 16, 1}, {8, 17, 1}, {8, 18, 1}, {8, 19, 1},
+    {16, 10, 1}, {16, 12, 1}, {16, 14, 1}, {16, 16, 1}, {16, 18, 1}, {16, 19, 1},
+    {32, 10, 1}, {32, 12, 1}, {32, 14, 1}, {32, 16, 1}, {32, 18, 1}, {32, 19, 1}};
 static const int kPhmmNumBins = sizeof(kPhmmBins) / sizeof(kPhmmBins[0]);
+static const int kPhmmFirstRefGapBin = 18;
 static inline uint32_t phmm_bin_capacity(int bin) { return (uint32_t)(kPhmmBins[bin].lanes * kPhmmBins[bin].rpt) - 1u; }
 static inline uint32_t phmm_bin_reads_per_cta(int bin) { return (uint32_t)(PHMM_WARPS * 32 / kPhmmBins[bin].lanes); }
+// The bin that serves a read: the first one of its family (reference gaps or generic) that holds it; -1 = none (per-pair kernel).
+static inline int phmm_bin_of(uint32_t len, bool refgaps)
+{
+    if (len == 0) return -1;
+    for (int b = refgaps ? kPhmmFirstRefGapBin : 0; b < (refgaps ? kPhmmNumBins : kPhmmFirstRefGapBin); ++b)
+        if (len <= phmm_bin_capacity(b)) return b;
+    return -1;
+}
 
 // Shared memory one CTA of the forward kernel needs for a chunk: the two column streams, the per-haplotype seam records and
 // the per-thread prior tables (6 base classes x ceil(RPT/4) float4 per thread).

@@ -82,7 +82,8 @@ def test_golden_regions_byte_identical(engine):
     dict(n_reads=25, n_haps=3, hap_lo=41, hap_hi=120, read_lo=1, read_hi=41, junk=0.1),           # post-trim short shapes
     dict(n_reads=30, n_haps=16, hap_lo=1000, hap_hi=1000, read_lo=250, read_hi=250, junk=0.1),    # cfg4 shape
     dict(n_reads=12, n_haps=1, hap_lo=200, hap_hi=200, read_lo=60, read_hi=151, junk=0.0),        # single haplotype
-    dict(n_reads=20, n_haps=4, hap_lo=500, hap_hi=700, read_lo=300, read_hi=420, junk=0.1),       # R above 255 / above the envelope
+    dict(n_reads=20, n_haps=4, hap_lo=500, hap_hi=700, read_lo=300, read_hi=420, junk=0.1),       # whole-warp bins
+    dict(n_reads=6, n_haps=3, hap_lo=800, hap_hi=900, read_lo=600, read_hi=700, junk=0.2),        # above the envelope: per-pair kernel
 ])
 @pytest.mark.parametrize("model", [PCR_CONSERVATIVE, PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE])
 def test_random_regions_vs_oracle(engine, orc, spec, model):
@@ -121,7 +122,7 @@ def test_edge_cases(engine, orc):
     rng = np.random.default_rng(11)
     hap = B[rng.integers(0, 4, 420)]
     reads = []
-    for n in (1, 2, 15, 16, 31, 32, 63, 64, 159, 160, 191, 192, 223, 224, 255, 256, 319, 320, 383, 384, 400):
+    for n in (1, 2, 7, 8, 15, 16, 31, 32, 63, 64, 151, 152, 159, 160, 191, 192, 255, 256, 303, 304, 319, 320, 383, 384, 400):
         o = int(rng.integers(0, 420 - n + 1))
         reads.append(dict(bases=hap[o:o + n].copy(), qual=q(n, 35), mapq=60))
     _check_region_vs_oracle(engine, orc, reads, [hap, hap[:100].copy(), hap[5:6].copy()])
@@ -145,28 +146,44 @@ def test_edge_cases(engine, orc):
         _check_region_vs_oracle(engine, orc, reads, haps, 18, model)
 
 
-def test_every_length_bin_and_partial_groups(engine, orc):
-    """One read on each side of every read-length bin of the wavefront kernel (16 x RPT - 1 and 32 x RPT - 1), and read
-    counts that leave half warps and whole warps of a CTA without a read (1, 2, 3, 7, 9 reads of one bin)."""
-    rng = np.random.default_rng(17)
-    hap = B[rng.integers(0, 4, 400)]
-    haps = [hap, hap[3:390].copy(), hap[::-1].copy()]
-    caps = [16 * r - 1 for r in range(1, 13)] + [32 * r - 1 for r in range(7, 13)]
+def _bin_boundary_reads(rng, hap, caps, explicit_gaps):
     reads = []
     for c in caps:
         for n in (c, c + 1):
-            if n > 400:
+            if n > len(hap):
                 continue
-            o = int(rng.integers(0, 400 - n + 1))
+            o = int(rng.integers(0, len(hap) - n + 1))
             rd = hap[o:o + n].copy()
             rd[rng.integers(0, n, max(1, n // 40))] = B[rng.integers(0, 4, max(1, n // 40))]
-            reads.append(dict(bases=rd, qual=rng.integers(8, 41, n).astype(np.uint8), mapq=int(rng.integers(20, 61))))
-    _check_region_vs_oracle(engine, orc, reads, haps)
-    for count in (1, 2, 3, 7, 9, 17):
+            r = dict(bases=rd, qual=rng.integers(8, 41, n).astype(np.uint8), mapq=int(rng.integers(20, 61)))
+            if explicit_gaps:
+                r["ins"] = rng.integers(20, 50, n).astype(np.uint8)
+                r["del"] = rng.integers(20, 50, n).astype(np.uint8)
+                r["gcp"] = rng.integers(5, 30, n).astype(np.uint8)
+            reads.append(r)
+    return reads
+
+
+def test_every_length_bin_and_partial_groups(engine, engine_nofma, orc):
+    """One read on each side of every read-length bin of the wavefront kernel, for each of its three variants (reference
+    gap qualities: 8/16/32 lanes x up to 19 rows; generic per-base gap qualities; un-contracted arithmetic), and read
+    counts that leave sub-warp groups and whole warps of a CTA without a read."""
+    rng = np.random.default_rng(17)
+    hap = B[rng.integers(0, 4, 640)]
+    haps = [hap, hap[3:590].copy(), hap[::-1].copy()]
+    caps_ref = [8 * r - 1 for r in range(1, 20)] + [16 * r - 1 for r in (10, 12, 14, 16, 18, 19)] + [32 * r - 1 for r in (10, 12, 14, 16, 18, 19)]
+    caps_gen = [16 * r - 1 for r in range(1, 13)] + [32 * r - 1 for r in range(7, 13)]
+    _check_region_vs_oracle(engine, orc, _bin_boundary_reads(rng, hap, caps_ref, False), haps)
+    _check_region_vs_oracle(engine, orc, _bin_boundary_reads(rng, hap, caps_gen, True), haps)
+    _check_region_vs_oracle(engine_nofma, orc, _bin_boundary_reads(rng, hap, caps_gen, False), haps, fma=ob.FMA_NONE)
+    for count in (1, 2, 3, 5, 7, 9, 15, 17, 33):
         sub = [dict(bases=B[rng.integers(0, 4, 150)], qual=rng.integers(8, 41, 150).astype(np.uint8), mapq=60) for _ in range(count)]
         for r in sub[: max(1, count // 2)]:           # half of them real reads of the haplotype, the rest junk
             o = int(rng.integers(0, 250))
             r["bases"] = hap[o:o + 150].copy()
+        _check_region_vs_oracle(engine, orc, sub, haps)
+        for r in sub:
+            r["gcp"] = np.full(150, 12, np.uint8)      # explicit gcp: the generic variant, 16 lanes per read
         _check_region_vs_oracle(engine, orc, sub, haps)
 
 
@@ -257,6 +274,7 @@ def test_stats_and_kernel_info(engine):
     s = engine.stats()
     assert s["cells"] > 0 and s["kernel_launches"] > 0 and s["h2d_bytes"] > 0
     ki = engine.kernel_info(150)
-    assert ki["lanes_per_read"] == 16 and ki["rows_per_lane"] == 10
-    assert 0 < ki["regs"] <= 168 and ki["spill_bytes"] == 0, "the 150-bp forward kernel must not spill and must keep 3 CTAs per SM"
-    assert engine.kernel_info(250)["lanes_per_read"] == 32
+    assert ki["lanes_per_read"] == 8 and ki["rows_per_lane"] == 19
+    assert 0 < ki["regs"] <= 255 and ki["spill_bytes"] == 0, "the 150-bp forward kernel must not spill"
+    assert engine.kernel_info(151)["rows_per_lane"] == 19 and engine.kernel_info(152)["lanes_per_read"] == 16
+    assert engine.kernel_info(250)["lanes_per_read"] == 16 and engine.kernel_info(400)["lanes_per_read"] == 32

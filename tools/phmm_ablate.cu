@@ -21,7 +21,7 @@ __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 enum { SEL_LOP = 0, SEL_NONE = 1, SEL_LDS32 = 2, SEL_LDS128 = 3 };
 
 // Layout A (product): thread = RPT rows of one read x two haplotype streams in the f32x2 halves.
-template <int RPT, int SEL, bool SHFL, int WARPS, int LANES = 32, int MINB = 1>
+template <int RPT, int SEL, bool SHFL, int WARPS, int LANES = 32, int MINB = 1, int CG = 0>
 __global__ void __launch_bounds__(WARPS * 32, MINB) layoutA(const uint32_t* gbases, uint32_t L, float* out, float seed)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -97,12 +97,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) layoutA(const uint32_t* gbas
                 prior = bc(pm[k]);
             }
             float2 t = __fmul2_rn(pM, bc(mm[k]));
-            t = __ffma2_rn(pI, bc(gapm[k]), t);
-            t = __ffma2_rn(pD, bc(gapm[k]), t);
+            t = __ffma2_rn(pI, bc(CG ? gapm[0] : gapm[k]), t);
+            t = __ffma2_rn(pD, bc(CG ? gapm[0] : gapm[k]), t);
             float2 nM;
             if (SEL == SEL_LDS128) { nM.x = __fmul_rn(t.x, prior.x); nM.y = __fmul_rn(t.y, prior.y); } else nM = __fmul2_rn(t, prior);
-            const float2 nI = __ffma2_rn(uI, bc(ii[k]), __fmul2_rn(uM, bc(mi[k])));
-            const float2 nD = __ffma2_rn(oD, bc(ii[k]), __fmul2_rn(oM, bc(md[k])));
+            const float2 nI = __ffma2_rn(uI, bc(CG ? (k == 0 ? ii[1] : ii[0]) : ii[k]), __fmul2_rn(uM, bc(mi[k])));
+            const float2 nD = __ffma2_rn(oD, bc(CG == 1 ? md[k] : CG == 2 ? ii[0] : ii[k]), __fmul2_rn(oM, bc(CG ? mi[k] : md[k])));
             Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
             pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
         }
@@ -561,6 +561,26 @@ int main()
     const size_t sA = (size_t)(L + 32) * 8;
 #define A(R, SEL, SH, W) run("A rpt" #R " " #SEL " shfl=" #SH " w" #W, layoutA<R, SEL, SH, W>, W, R, 2, sA + ((SEL) == SEL_LDS32 ? 4 * R * W * 32 * 4 : (SEL) == SEL_LDS128 ? 6 * ((R + 3) / 4) * W * 32 * 16 : 0), L)
 #define AL(R, W, LN, MB) run("A rpt" #R " LDS128 w" #W " lanes" #LN " minb" #MB, layoutA<R, SEL_LDS128, true, W, LN, MB>, W, R, 2, sA + 6 * ((R + 3) / 4) * W * 32 * 16, L)
+#define AC(R, W, LN, MB, CG) run("A rpt" #R " LDS128 w" #W " lanes" #LN " minb" #MB " constgcp" #CG, layoutA<R, SEL_LDS128, true, W, LN, MB, CG>, W, R, 2, sA + 6 * ((R + 3) / 4) * W * 32 * 16, L)
+    AC(10, 4, 16, 3, 1);
+    AC(10, 4, 16, 4, 1);
+    AC(10, 4, 16, 4, 2);
+    AC(19, 4, 8, 2, 1);
+    AC(19, 4, 8, 3, 1);
+    AC(19, 4, 8, 2, 2);
+    AC(16, 4, 16, 3, 1);
+    AC(12, 4, 16, 4, 1);
+    AC(5, 4, 32, 6, 1);
+    AC(8, 4, 32, 5, 1);
+    AL(19, 4, 8, 2);
+    AL(19, 2, 8, 4);
+    AL(20, 4, 8, 2);
+    AL(16, 4, 16, 2);
+    AL(19, 4, 16, 2);
+    AL(14, 4, 8, 2);
+    AL(16, 4, 8, 2);
+    AL(12, 4, 8, 3);
+    AL(10, 4, 8, 3);
     AL(10, 4, 16, 3);
     AL(10, 4, 16, 4);
     AL(10, 2, 16, 6);

@@ -144,6 +144,8 @@ typedef struct phmm_stats
     uint64_t batches;
     double gpu_ms;                    /* sum of per-batch device time (CUDA events, kernels only) */
     uint64_t kernel_launches;
+    double host_plan_ms;              /* sum over batches of host planning + packing time (worker threads, wall) */
+    double host_epilogue_ms;          /* sum over batches of the host epilogue (log10, cap, filter, transpose) */
 } phmm_stats;
 
 /* Replaces rovaca::init_pairhmm_ptr (pairhmm/pairhmm_engine.cpp:21): builds the libm tables of

@@ -180,7 +180,7 @@ struct Stats
 {
     std::atomic<uint64_t> regions{0}, pairs{0}, cells{0}, fp64_pairs{0}, slow_pairs{0}, h2d{0}, d2h{0}, batches{0}, launches{0};
     std::mutex m;
-    double gpu_ms = 0.0;
+    double gpu_ms = 0.0, plan_ms = 0.0, epilogue_ms = 0.0;
 };
 
 }  // namespace
@@ -461,23 +461,48 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
     std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
     {
+        // gather the raw bytes; callers that keep their reads back to back (flat batches, BAM-like buffers) get one
+        // memcpy per contiguous run instead of one per read
+        struct Run
+        {
+            const uint8_t* src = nullptr;
+            size_t len = 0, dst = 0;
+            void add(uint8_t* base, const uint8_t* p, size_t n, size_t at)
+            {
+                if (src && p == src + len && at == dst + len) {
+                    len += n;
+                    return;
+                }
+                if (src) std::memcpy(base + dst, src, len);
+                src = p;
+                len = n;
+                dst = at;
+            }
+            void flush(uint8_t* base)
+            {
+                if (src) std::memcpy(base + dst, src, len);
+                src = nullptr;
+            }
+        } rb_run, rq_run, ri_run, rd_run, rg_run, hb_run;
         size_t ro = 0, ho = 0;
         for (const RegionIn& r : regs) {
             if (r.n_reads == 0 || r.n_haps == 0) continue;
             for (uint32_t k = 0; k < r.n_reads; ++k) {
                 const phmm_read& in = r.reads[k];
-                std::memcpy(h + o_rb + ro, in.bases, in.len);
-                std::memcpy(h + o_rq + ro, in.qual, in.len);
-                if (in.ins) std::memcpy(h + o_ri + ro, in.ins, in.len);
-                if (in.del) std::memcpy(h + o_rd + ro, in.del, in.len);
-                if (in.gcp) std::memcpy(h + o_rg + ro, in.gcp, in.len);
+                rb_run.add(h + o_rb, in.bases, in.len, ro);
+                rq_run.add(h + o_rq, in.qual, in.len, ro);
+                if (in.ins) ri_run.add(h + o_ri, in.ins, in.len, ro);
+                if (in.del) rd_run.add(h + o_rd, in.del, in.len, ro);
+                if (in.gcp) rg_run.add(h + o_rg, in.gcp, in.len, ro);
                 ro += in.len;
             }
             for (uint32_t j = 0; j < r.n_haps; ++j) {
-                std::memcpy(h + o_hb + ho, r.haps[j].bases, r.haps[j].len);
+                hb_run.add(h + o_hb, r.haps[j].bases, r.haps[j].len, ho);
                 ho += r.haps[j].len;
             }
         }
+        rb_run.flush(h + o_rb); rq_run.flush(h + o_rq); ri_run.flush(h + o_ri); rd_run.flush(h + o_rd); rg_run.flush(h + o_rg);
+        hb_run.flush(h + o_hb);
     }
     // ---- device-only buffers --------------------------------------------------------------------
     const size_t pairs_alloc = std::max<uint64_t>(n_pairs, 1);
@@ -574,6 +599,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     CU(cudaEventElapsedTime(&s.gpu_ms, s.ev[0], s.ev[3]));
     CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
 
+    const auto t_epi = std::chrono::steady_clock::now();
     const unsigned old_csr = _mm_getcsr();
     _mm_setcsr(old_csr | 0x8000u);                 // init_native, pairhmm_internal.cpp:21-25
     const float* f32 = static_cast<const float*>(s.h_f32.p);
@@ -642,6 +668,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     {
         std::lock_guard<std::mutex> lk2(stats.m);
         stats.gpu_ms += s.gpu_ms;
+        stats.epilogue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epi).count();
     }
     return PHMM_OK;
 }
@@ -649,9 +676,16 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
 int phmm_engine::execute(Slot& s, const std::vector<RegionIn>& regs)
 {
     int rc;
+    const auto t0 = std::chrono::steady_clock::now();
     if ((rc = plan(s, regs)) != PHMM_OK) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
     if ((rc = launch(s, true)) != PHMM_OK) return rc;
-    return finish(s, regs, true);
+    rc = finish(s, regs, true);
+    {
+        std::lock_guard<std::mutex> lk(stats.m);
+        stats.plan_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    }
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -709,35 +743,37 @@ void phmm_engine::seal_locked()
 // C ABI
 // ------------------------------------------------------------------------------------------------
 
-static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, std::vector<phmm_read>& reads, std::vector<phmm_hap>& haps,
-                            std::vector<RegionIn>& regs)
+// Regions [g0, g1) of a flat batch as RegionIn records (pointers into the caller's blobs).  reads/haps are resized to the
+// range; region g's reads start at reads[reg_read_off[g] - reg_read_off[g0]].
+static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_read>& reads,
+                            std::vector<phmm_hap>& haps, std::vector<RegionIn>& regs)
 {
-    const uint64_t nr = fb->reg_read_off[fb->n_regions], nh = fb->reg_hap_off[fb->n_regions];
+    const uint64_t rbeg = fb->reg_read_off[g0], hbeg = fb->reg_hap_off[g0];
+    const uint64_t nr = fb->reg_read_off[g1] - rbeg, nh = fb->reg_hap_off[g1] - hbeg;
     reads.resize(nr);
     haps.resize(nh);
     for (uint64_t k = 0; k < nr; ++k) {
         phmm_read& r = reads[k];
-        const uint64_t o = fb->read_off[k];
+        const uint64_t o = fb->read_off[rbeg + k];
         r.bases = fb->read_bases + o;
         r.qual = fb->read_qual + o;
         r.ins = fb->read_ins ? fb->read_ins + o : nullptr;
         r.del = fb->read_del ? fb->read_del + o : nullptr;
         r.gcp = fb->read_gcp ? fb->read_gcp + o : nullptr;
-        r.len = fb->read_len[k];
-        r.mapq = fb->read_mapq[k];
+        r.len = fb->read_len[rbeg + k];
+        r.mapq = fb->read_mapq[rbeg + k];
     }
     for (uint64_t j = 0; j < nh; ++j) {
-        haps[j].bases = fb->hap_bases + fb->hap_off[j];
-        haps[j].len = fb->hap_len[j];
+        haps[j].bases = fb->hap_bases + fb->hap_off[hbeg + j];
+        haps[j].len = fb->hap_len[hbeg + j];
     }
-    regs.resize(fb->n_regions);
-    if (fr) fr->n_fp64 = 0;
-    for (uint32_t g = 0; g < fb->n_regions; ++g) {
-        RegionIn& r = regs[g];
+    regs.resize(g1 - g0);
+    for (uint32_t g = g0; g < g1; ++g) {
+        RegionIn& r = regs[g - g0];
         const uint64_t r0 = fb->reg_read_off[g], h0 = fb->reg_hap_off[g];
-        r.reads = reads.data() + r0;
+        r.reads = reads.data() + (r0 - rbeg);
         r.n_reads = (uint32_t)(fb->reg_read_off[g + 1] - r0);
-        r.haps = haps.data() + h0;
+        r.haps = haps.data() + (h0 - hbeg);
         r.n_haps = (uint32_t)(fb->reg_hap_off[g + 1] - h0);
         r.thr = fb->min_quality_threshold;
         r.pcr = fb->pcr_model;
@@ -754,6 +790,19 @@ static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, std
             r.n_fp64_out = &fr->n_fp64;
         }
     }
+}
+
+// cells of regions [0, n) of a flat batch as a running sum (read lengths x haplotype lengths per region)
+static std::vector<uint64_t> flat_cells_prefix(const phmm_flat_batch* fb)
+{
+    std::vector<uint64_t> pre(fb->n_regions + 1, 0);
+    for (uint32_t g = 0; g < fb->n_regions; ++g) {
+        uint64_t rb = 0, hb = 0;
+        for (uint64_t k = fb->reg_read_off[g]; k < fb->reg_read_off[g + 1]; ++k) rb += fb->read_len[k];
+        for (uint64_t j = fb->reg_hap_off[g]; j < fb->reg_hap_off[g + 1]; ++j) hb += fb->hap_len[j];
+        pre[g + 1] = pre[g] + rb * hb;
+    }
+    return pre;
 }
 
 static uint64_t region_cells(const RegionIn& r)
@@ -898,36 +947,41 @@ int phmm_call_region(phmm_engine* e, const phmm_region* region, phmm_result* res
 int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* fr)
 {
     if (!e || !fb || !fr) return fail(PHMM_ERR_ARG, "phmm_run_flat: null argument");
-    auto reads = std::make_shared<std::vector<phmm_read>>();
-    auto haps = std::make_shared<std::vector<phmm_hap>>();
-    std::vector<RegionIn> regs;
-    flat_to_regions(fb, fr, *reads, *haps, regs);
-    // cut into sub-batches of about batch_cells / n_workers so that packing, device work and the host
-    // epilogue of different sub-batches overlap
-    const uint64_t target = std::max<uint64_t>(e->batch_cells, 1);
-    std::vector<std::shared_ptr<std::vector<RegionIn>>> parts;
+    fr->n_fp64 = 0;
+    // Cut the stream into sub-batches that the workers plan, ship, run and finish independently, so that packing, H2D,
+    // kernels, D2H and the host epilogue of different sub-batches overlap.  Sizes ramp up from batch_cells / 8 and down
+    // again at the end: the GPU starts after one small plan and only a small epilogue is left when it finishes.
+    const std::vector<uint64_t> pre = flat_cells_prefix(fb);
+    const uint64_t total = pre[fb->n_regions];
+    const uint64_t full = std::max<uint64_t>(e->batch_cells, 1);
+    std::vector<std::pair<uint32_t, uint32_t>> parts;
     {
-        auto cur = std::make_shared<std::vector<RegionIn>>();
-        uint64_t cells = 0;
-        for (RegionIn& r : regs) {
-            cur->push_back(r);
-            cells += region_cells(r);
-            if (cells >= target) {
-                parts.push_back(cur);
-                cur = std::make_shared<std::vector<RegionIn>>();
-                cells = 0;
-            }
+        uint32_t g = 0;
+        int ramp = 3;                                    // next sizes: full/8, full/4, full/2, then full
+        while (g < fb->n_regions) {
+            const uint64_t left = total - pre[g];
+            uint64_t want = ramp > 0 ? (full >> ramp) : full;
+            if (ramp > 0) --ramp;
+            // ramp down: never take more than half of what is left while more than full/8 remains
+            if (left > (full >> 3)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 3));
+            uint32_t end = g + 1;
+            while (end < fb->n_regions && pre[end] - pre[g] < want) ++end;
+            parts.emplace_back(g, end);
+            g = end;
         }
-        if (!cur->empty()) parts.push_back(cur);
     }
     std::mutex m;
     std::condition_variable cv;
     size_t remaining = parts.size();
     int rc_all = PHMM_OK;
     std::string err_all;
-    for (auto& part : parts) {
+    for (const auto& part : parts) {
         e->enqueue([&, part](Slot& s) {
-            const int rc = e->execute(s, *part);
+            std::vector<phmm_read> reads;
+            std::vector<phmm_hap> haps;
+            std::vector<RegionIn> regs;
+            flat_to_regions(fb, fr, part.first, part.second, reads, haps, regs);
+            const int rc = e->execute(s, regs);
             std::lock_guard<std::mutex> lk(m);
             if (rc != PHMM_OK && rc_all == PHMM_OK) {
                 rc_all = rc;
@@ -951,7 +1005,7 @@ int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* fb, phmm_residen
     std::unique_ptr<phmm_resident> r(new phmm_resident());
     int rc = r->slot.init();
     if (rc != PHMM_OK) return rc;
-    flat_to_regions(fb, nullptr, r->reads, r->haps, r->regs);
+    flat_to_regions(fb, nullptr, 0, fb->n_regions, r->reads, r->haps, r->regs);
     if ((rc = e->plan(r->slot, r->regs)) != PHMM_OK) return rc;
     CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.in_bytes, cudaMemcpyHostToDevice, r->slot.stream));
     CU(cudaStreamSynchronize(r->slot.stream));
@@ -1018,6 +1072,8 @@ int phmm_get_stats(phmm_engine* e, phmm_stats* out)
     {
         std::lock_guard<std::mutex> lk(e->stats.m);
         out->gpu_ms = e->stats.gpu_ms;
+        out->host_plan_ms = e->stats.plan_ms;
+        out->host_epilogue_ms = e->stats.epilogue_ms;
     }
     return PHMM_OK;
 }

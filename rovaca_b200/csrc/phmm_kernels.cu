@@ -94,10 +94,72 @@ __device__ int repeat_length(const uint8_t* b, int n, int offset)
     return rl > 20 ? 20 : rl;
 }
 
+// Bit-parallel form of the same scan for reads that fit a warp's shared-memory scratch: E[str-1] holds, for every
+// position p, whether bases[p] == bases[p + str] (and p + str < n).  A unit of length str starting at t repeats at
+// t + s (s a multiple of str) exactly when the str-periodicity holds on [t, t + s), i.e. when the run of set bits of
+// E[str-1] starting at t is at least s long; the backward count is the run of set bits ending at `offset`.
+constexpr int PREP_MAX = 1024;                 // bases per read on the fast path
+constexpr int PREP_WORDS = PREP_MAX / 32;
+
+__device__ __forceinline__ int run_up(const uint32_t* e, int nwords, int p0, int cap)     // consecutive ones at p0, p0+1, ...
+{
+    int run = 0, w = p0 >> 5, b = p0 & 31;
+    while (w < nwords && run < cap) {
+        const uint32_t inv = ~(e[w] >> b);         // zeros shifted in at the top read as "stop"
+        const int avail = 32 - b;
+        const int z = inv ? __ffs((int)inv) - 1 : 32;
+        if (z < avail) return run + z;
+        run += avail;
+        ++w;
+        b = 0;
+    }
+    return run;
+}
+
+__device__ __forceinline__ int run_down(const uint32_t* e, int p0, int cap)              // consecutive ones at p0, p0-1, ...
+{
+    int run = 0, w = p0 >> 5, b = p0 & 31;
+    while (w >= 0 && run < cap) {
+        const uint32_t inv = ~(e[w] << (31 - b));   // zeros shifted in at the bottom read as "stop"
+        const int avail = b + 1;
+        const int z = inv ? __clz((int)inv) : 32;
+        if (z < avail) return run + z;
+        run += avail;
+        --w;
+        b = 31;
+    }
+    return run;
+}
+
+__device__ __forceinline__ int repeat_length_bits(const uint32_t (*E)[PREP_WORDS], int nwords, int n, int offset)
+{
+    int fw_len = 1, max_fw = 0;
+    const int test_len = n - offset - 1;
+    const int p0 = offset + 1, w0 = p0 >> 5, b0 = p0 & 31;
+    for (int str = 1; str <= 8; ++str) {
+        if (str > test_len) break;                                   // :126-127 offsets only; unit must fit
+        // does the unit repeat at all?  (the next `str` periodicity bits all set)  Only then count the whole run.
+        const uint32_t lo = E[str - 1][w0], hi = (w0 + 1 < nwords) ? E[str - 1][w0 + 1] : 0u;
+        const uint32_t need = (1u << str) - 1u;
+        max_fw = 1;
+        if ((__funnelshift_r(lo, hi, b0) & need) == need) {
+            const int run = run_up(E[str - 1], nwords, p0, 21 * str);
+            max_fw = run / str + 1;                                  // bounded by test_len / str through E's validity bit
+            fw_len = str;
+            break;
+        }
+    }
+    const int max_bw = run_down(E[fw_len - 1], offset, 21 * fw_len) / fw_len;
+    const int rl = max_bw + max_fw;
+    return rl > 20 ? 20 : rl;
+}
+
 __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
 {
+    __shared__ uint8_t s_bases[8][PREP_MAX + 16];
+    __shared__ uint32_t s_eq[8][8][PREP_WORDS];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (warp >= p.n_reads) return;
     const PhmmRead rd = p.reads[warp];
     const int n = (int)rd.len;
@@ -106,18 +168,34 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
     const uint32_t flags = rd.model_flags >> 4;
     const int model = rd.model_flags & 15;
     const int thr = rd.thr;
+    const bool fast = model != 0 && n <= PREP_MAX;
+    const int nwords = (n + 31) >> 5;
+    if (fast) {
+        uint8_t* sb = s_bases[wib];
+        for (int i = (int)lane; i < nwords * 32 + 8; i += 32) sb[i] = i < n ? b[i] : 0;
+        __syncwarp();
+        for (int str = 1; str <= 8; ++str)
+            for (int w = 0; w < nwords; ++w) {
+                const int pos = w * 32 + (int)lane;
+                const uint32_t m = __ballot_sync(0xffffffffu, pos + str < n && sb[pos] == sb[pos + str]);
+                if (lane == 0) s_eq[wib][str - 1][w] = m;
+            }
+        __syncwarp();
+    }
     for (int i = (int)lane; i < n; i += 32) {
         uint32_t qq = q[i];
         qq = qq < rd.mapq ? qq : rd.mapq;
         qq = ((int)qq < thr) ? 6u : qq;                                     // MIN_QUALITY, adapter.h:5
         uint32_t gi = (flags & PHMM_RD_HAS_INS) ? p.read_ins[rd.raw_off + i] : 45u;   // read_record.cpp:191-196
         if (model != 0 && i + 1 < n) {
-            const uint32_t cap = c_pcr_cache[model][repeat_length(b, n, i)];
+            const int rl = fast ? repeat_length_bits(s_eq[wib], nwords, n, i) : repeat_length(b, n, i);
+            const uint32_t cap = c_pcr_cache[model][rl];
             gi = gi < cap ? gi : cap;
         }
         const uint32_t gd = (flags & PHMM_RD_HAS_DEL) ? p.read_del[rd.raw_off + i] : gi;   // del aliases ins, :425,:559
         const uint32_t gc = (flags & PHMM_RD_HAS_GCP) ? p.read_gcp[rd.raw_off + i] : 10u; // read_record.cpp:205-210
-        p.words[rd.word_off + i] = (qq & 127u) | ((gi & 127u) << 7) | ((gd & 127u) << 14) | ((gc & 127u) << 21) | (onehot(b[i]) << 28);
+        const uint32_t base = fast ? s_bases[wib][i] : b[i];
+        p.words[rd.word_off + i] = (qq & 127u) | ((gi & 127u) << 7) | ((gd & 127u) << 14) | ((gc & 127u) << 21) | (onehot(base) << 28);
     }
 }
 

@@ -187,6 +187,33 @@ def test_every_length_bin_and_partial_groups(engine, engine_nofma, orc):
         _check_region_vs_oracle(engine, orc, sub, haps)
 
 
+def test_pcr_model_tandem_repeats(engine, orc):
+    """The PCR-indel model's tandem-repeat scan (pairhmm_internal.cpp:65-159) on reads built from repeats of every unit
+    length 1..9 and count 1..25 between random flanks, at lengths on both sides of the prep kernel's bit-parallel limit
+    (1024 bases); any slip in a repeat length changes an insertion quality and with it the raw sums."""
+    rng = np.random.default_rng(23)
+    reads = []
+    for unit_len in range(1, 10):
+        for _ in range(3):
+            unit = B[rng.integers(0, 4, unit_len)]
+            parts = []
+            while sum(len(x) for x in parts) < 140:
+                parts.append(B[rng.integers(0, 4, int(rng.integers(0, 7)))])
+                parts.append(np.tile(unit, int(rng.integers(1, 26))))
+            rs = np.concatenate(parts)[: int(rng.integers(100, 152))]
+            reads.append(dict(bases=rs, qual=rng.integers(10, 41, len(rs)).astype(np.uint8), mapq=60))
+    hap = np.concatenate([r["bases"] for r in reads[:3]])[:400]
+    for model in (PCR_CONSERVATIVE, PCR_HOSTILE, PCR_AGGRESSIVE):
+        _check_region_vs_oracle(engine, orc, reads, [hap, hap[::-1].copy()], 18, model)
+    long_reads = []
+    for n in (1023, 1024, 1025, 1100):
+        unit = B[rng.integers(0, 4, 3)]
+        rs = np.concatenate([B[rng.integers(0, 4, 200)], np.tile(unit, 30), B[rng.integers(0, 4, 900)]])[:n]
+        rs[-40:] = rs[-41]                               # homopolymer running into the end of the read
+        long_reads.append(dict(bases=rs, qual=rng.integers(10, 41, n).astype(np.uint8), mapq=60))
+    _check_region_vs_oracle(engine, orc, long_reads, [long_reads[0]["bases"][100:700].copy()], 18, PCR_CONSERVATIVE)
+
+
 def test_fp64_recompute_exercised(engine, orc):
     """cfg3-style: junk reads underflow FP32 (< 1e-28f) and are recomputed in FP64 on the device."""
     rng = np.random.default_rng(12)

@@ -60,7 +60,7 @@ int fail(int code, const std::string& msg)
 
 constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
 constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)
-constexpr uint32_t kPairThreads = 148 * 2 * 128;
+constexpr uint32_t kPairThreads = 148 * 3 * 128;   // per-pair wavefront kernel: one warp per pair, 12 warps per SM
 constexpr float kMinAccepted = 1e-28f;                     // MIN_ACCEPTED, rovaca/common.h:9
 constexpr float kLog10InitF = 36.1236000061f;              // LOG10_INITIAL_CONSTANT_F, adapter.h:25
 constexpr double kLog10InitD = 307.050595577260822;        // LOG10_INITIAL_CONSTANT_D, adapter.h:26
@@ -97,7 +97,7 @@ struct DevBuf
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        size_t want = align_up(std::max(bytes + bytes / 2, (size_t)4 << 20), 1 << 20);   // grow in big steps: (re)allocation stalls the device
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
         cap = want;
@@ -121,7 +121,7 @@ struct HostBuf
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(bytes + bytes / 4, 1 << 20);
+        size_t want = align_up(std::max(bytes + bytes / 2, (size_t)4 << 20), 1 << 20);   // grow in big steps: (re)allocation stalls the device
         cudaError_t e = cudaMallocHost(&p, want);
         if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
         cap = want;
@@ -138,7 +138,7 @@ struct HostBuf
 struct FwdLaunch
 {
     int bin;
-    uint32_t cta_base, n_ctas;
+    uint32_t cta_base, n_ctas, cta_warps;
     size_t smem;
 };
 
@@ -183,6 +183,59 @@ struct Stats
     double gpu_ms = 0.0, plan_ms = 0.0, epilogue_ms = 0.0;
 };
 
+// Fill the read slots of a region's CTAs.  A warp of the forward kernel holds 32 / LANES reads of ONE bin; a region whose
+// reads scatter over many length bins would run many part-empty warps.  A read may run in any higher bin of its lane family
+// (more top padding, same result), so the remainder of a bin can be carried up into the next occupied one.  Cost of a warp
+// = rows per lane of its bin; the small DP below picks, per family, which remainders to carry (f[i][c]: best cost of bins
+// i.. with c reads carried in).
+void promote_remainders(std::vector<std::vector<uint32_t>>& by_bin, int first, int last)
+{
+    constexpr int kMaxBins = 24, kMaxS = 4;
+    const int S = 32 / kPhmmBins[first].lanes;            // reads per warp in this family
+    const int nb = last - first + 1;
+    if (S <= 1 || nb < 2 || nb > kMaxBins || S > kMaxS) return;
+    int occupied = 0;
+    bool ragged = false;
+    for (int i = 0; i < nb; ++i) {
+        const size_t n = by_bin[first + i].size();
+        occupied += n != 0;
+        ragged |= n % S != 0;
+    }
+    if (occupied < 2 || !ragged) return;                   // nothing to merge
+    uint32_t f[kMaxBins + 1][kMaxS] = {};
+    uint8_t carry[kMaxBins][kMaxS] = {};
+    uint32_t own[kMaxBins];
+    for (int i = nb - 1; i >= 0; --i) {
+        const uint32_t rpt = (uint32_t)kPhmmBins[first + i].rpt;
+        own[i] = (uint32_t)by_bin[first + i].size();
+        for (int c = 0; c < S; ++c) {
+            const uint32_t t = (uint32_t)c + own[i];
+            uint32_t best = (t + S - 1) / S * rpt + f[i + 1][0];
+            uint8_t how = 0;
+            if (i + 1 < nb && t % S != 0) {
+                const uint32_t alt = t / S * rpt + f[i + 1][t % S];
+                if (alt < best) { best = alt; how = 1; }
+            }
+            f[i][c] = best;
+            carry[i][c] = how;
+        }
+    }
+    uint32_t c = 0;                                        // reads carried into bin i (already appended to its vector)
+    for (int i = 0; i + 1 < nb; ++i) {
+        auto& cur = by_bin[first + i];
+        const uint32_t t = c + own[i];                    // == cur.size()
+        if (carry[i][c]) {
+            const uint32_t rem = t % S;
+            auto& up = by_bin[first + i + 1];
+            up.insert(up.end(), cur.end() - rem, cur.end());
+            cur.resize(t - rem);
+            c = rem;
+        } else {
+            c = 0;
+        }
+    }
+}
+
 }  // namespace
 
 struct phmm_resident
@@ -197,9 +250,10 @@ struct phmm_engine
 {
     int device = 0;
     bool fma = true;
-    uint32_t n_workers = 4;
+    uint32_t n_workers = 6;
     uint64_t batch_cells = 12000000000ull;
     uint32_t linger_us = 200;
+    uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
     DevBuf d_tables;
     Stats stats;
 
@@ -321,6 +375,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
                 order.push_back(j);
                 total += r.haps[j].len;
             }
+        const bool all_haps_in_stream = order.size() == r.n_haps;
         region_chunks.clear();
         if (!order.empty()) {
             const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (total + 2ull * kTargetStreamCols - 1) / (2ull * kTargetStreamCols));
@@ -380,7 +435,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
             s.read_len.push_back(in.len);
             const int b = phmm_bin_of(in.len, refgaps);
             if (b >= 0) by_bin[b].push_back(rid);
-            for (uint32_t j = 0; j < r.n_haps; ++j) {
+            if (b < 0 || !all_haps_in_stream)
+                for (uint32_t j = 0; j < r.n_haps; ++j) {
                 const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
                 if (b < 0 || !hap_ok) {
                     PhmmPair p{};
@@ -390,6 +446,12 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
                     slow.push_back(p);
                 }
             }
+        }
+        for (int b0 = 0; b0 < kPhmmNumBins;) {           // one lane family at a time (bins of a family are contiguous)
+            int b1 = b0;
+            while (b1 + 1 < kPhmmNumBins && kPhmmBins[b1 + 1].lanes == kPhmmBins[b0].lanes && kPhmmBins[b1 + 1].refgaps == kPhmmBins[b0].refgaps) ++b1;
+            promote_remainders(by_bin, b0, b1);
+            b0 = b1 + 1;
         }
         for (int b = 0; b < kPhmmNumBins; ++b) {
             if (by_bin[b].empty()) continue;
@@ -417,9 +479,24 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         fl.bin = b;
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
+        // warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but their
+        // read slots come in bigger lumps; take the biggest size that wastes at most 8 % more slots than single-warp CTAs
+        uint32_t cta_warps = this->cta_warps;
+        if (cta_warps == 0) {
+            const uint32_t per_warp = phmm_bin_reads_per_cta(b, 1);
+            uint64_t slots[3] = {0, 0, 0};
+            for (const Group& g : groups[b])
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t per = per_warp << k;
+                    slots[k] += (uint64_t)((g.n + per - 1) / per) * per;
+                }
+            cta_warps = 1;
+            for (int k = 1; k < 3; ++k)
+                if (slots[k] * 100 <= slots[0] * 108) cta_warps = 1u << k;
+        }
         for (const Group& g : groups[b]) {
-            smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps, b));
-            const uint32_t per_cta = phmm_bin_reads_per_cta(b);
+            smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps, b, cta_warps));
+            const uint32_t per_cta = phmm_bin_reads_per_cta(b, cta_warps);
             for (uint32_t at = 0; at < g.n; at += per_cta) {
                 PhmmCta c{};
                 c.chunk = g.chunk;
@@ -430,6 +507,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
             }
         }
         fl.n_ctas = (uint32_t)ctas.size() - fl.cta_base;
+        fl.cta_warps = cta_warps;
         fl.smem = smem;
         s.launches.push_back(fl);
     }
@@ -511,9 +589,9 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
     if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair))) != PHMM_OK) return rc;
     if ((rc = s.d_cnt.ensure(256)) != PHMM_OK) return rc;
-    if ((rc = s.d_scr64.ensure((size_t)kPairThreads * (max_cols + 1) * 3 * sizeof(double))) != PHMM_OK) return rc;
+    if ((rc = s.d_scr64.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(double))) != PHMM_OK) return rc;
     if (!slow.empty())
-        if ((rc = s.d_scr32.ensure((size_t)kPairThreads * (max_cols + 1) * 3 * sizeof(float))) != PHMM_OK) return rc;
+        if ((rc = s.d_scr32.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(float))) != PHMM_OK) return rc;
     if ((rc = s.h_f32.ensure(pairs_alloc * sizeof(float))) != PHMM_OK) return rc;
     if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
     if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
@@ -565,7 +643,13 @@ int phmm_engine::launch(Slot& s, bool copy_in)
     CU(cudaEventRecord(s.ev[0], s.stream));
     CU(phmm_launch_prep(s.dev, s.stream));
     CU(cudaEventRecord(s.ev[1], s.stream));
-    for (const FwdLaunch& fl : s.launches) CU(phmm_launch_fwd(s.dev, fl.bin, fma, fl.cta_base, fl.n_ctas, fl.smem, s.stream));
+    for (const FwdLaunch& fl : s.launches) {
+        const cudaError_t le = phmm_launch_fwd(s.dev, fl.bin, fma, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, s.stream);
+        if (le != cudaSuccess)
+            return fail(PHMM_ERR_CUDA, std::string("forward kernel launch (") + std::to_string(kPhmmBins[fl.bin].lanes) + " lanes x " +
+                                           std::to_string(kPhmmBins[fl.bin].rpt) + " rows, " + std::to_string(fl.n_ctas) + " CTAs, " +
+                                           std::to_string(fl.smem) + " B shared): " + cudaGetErrorString(le));
+    }
     CU(cudaEventRecord(s.ev[2], s.stream));
     if (s.n_slow)
         CU(phmm_launch_pairs_f32(s.dev, fma, s.dev.slow_pairs, s.n_slow, static_cast<float*>(s.d_scr32.p), kPairThreads, s.max_cols,
@@ -792,15 +876,19 @@ static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uin
     }
 }
 
-// cells of regions [0, n) of a flat batch as a running sum (read lengths x haplotype lengths per region)
-static std::vector<uint64_t> flat_cells_prefix(const phmm_flat_batch* fb)
+// Work of regions [0, n) of a flat batch as a running sum, in cell units: the cells of a region (device time) plus a
+// per-pair charge for the host's share (planning + epilogue cost about as much per pair as 16 K cells cost the GPU), so that
+// streams of small regions are cut into enough sub-batches to keep the host workers and the GPU overlapped.
+constexpr uint64_t kPairWeight = 16384;
+static std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb)
 {
     std::vector<uint64_t> pre(fb->n_regions + 1, 0);
     for (uint32_t g = 0; g < fb->n_regions; ++g) {
         uint64_t rb = 0, hb = 0;
         for (uint64_t k = fb->reg_read_off[g]; k < fb->reg_read_off[g + 1]; ++k) rb += fb->read_len[k];
         for (uint64_t j = fb->reg_hap_off[g]; j < fb->reg_hap_off[g + 1]; ++j) hb += fb->hap_len[j];
-        pre[g + 1] = pre[g] + rb * hb;
+        const uint64_t pairs = (fb->reg_read_off[g + 1] - fb->reg_read_off[g]) * (fb->reg_hap_off[g + 1] - fb->reg_hap_off[g]);
+        pre[g + 1] = pre[g] + rb * hb + pairs * kPairWeight;
     }
     return pre;
 }
@@ -843,6 +931,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
         if (cfg->n_workers) e->n_workers = std::min<uint32_t>(cfg->n_workers, 32);
         if (cfg->batch_cells) e->batch_cells = cfg->batch_cells;
         if (cfg->linger_us) e->linger_us = cfg->linger_us;
+        if (cfg->cta_warps) e->cta_warps = std::min<uint32_t>(cfg->cta_warps, PHMM_WARPS);
     }
     std::unique_ptr<PhmmTables> t(new PhmmTables());
     phmm_build_tables(t.get());
@@ -951,7 +1040,7 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* f
     // Cut the stream into sub-batches that the workers plan, ship, run and finish independently, so that packing, H2D,
     // kernels, D2H and the host epilogue of different sub-batches overlap.  Sizes ramp up from batch_cells / 8 and down
     // again at the end: the GPU starts after one small plan and only a small epilogue is left when it finishes.
-    const std::vector<uint64_t> pre = flat_cells_prefix(fb);
+    const std::vector<uint64_t> pre = flat_work_prefix(fb);
     const uint64_t total = pre[fb->n_regions];
     const uint64_t full = std::max<uint64_t>(e->batch_cells, 1);
     std::vector<std::pair<uint32_t, uint32_t>> parts;

@@ -30,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+
 #include "phmm_kernels.h"
 #include "phmm_types.h"
 
@@ -238,9 +240,10 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     constexpr bool FMA = VAR != PHMM_VAR_GENERIC_NOFMA;
     constexpr bool RG = VAR == PHMM_VAR_REFGAPS;
     constexpr int NP = RG ? 1 : RPT;                      // per-row (generic) or per-read (reference gaps) gap parameters
-    constexpr int NT = PHMM_WARPS * 32;
     constexpr int G = (RPT + 3) / 4;                     // float4 groups of the prior table
-    constexpr uint32_t TSTRIDE = (uint32_t)G * NT * 16;   // bytes between the tables of two base classes
+    constexpr uint32_t TSTRIDE = phmm_prior_table_stride(RPT);   // bytes per thread and base class: G float4, padded to an odd count
+    const uint32_t NT = blockDim.x;                       // 1..PHMM_WARPS warps per CTA, chosen by the host per launch
+    const uint32_t CSTRIDE = NT * TSTRIDE;                // bytes between the tables of two base classes (a multiple of 512)
     extern __shared__ __align__(16) unsigned char smem[];
     const PhmmCta cta = p.ctas[cta_base + blockIdx.x];
     const PhmmChunk ch = p.chunks[cta.chunk];
@@ -250,9 +253,9 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     float* info_init = reinterpret_cast<float*>(stream + L + 32);     // [2][NI]  2^120 / H
     uint32_t* info_col = reinterpret_cast<uint32_t*>(info_init + 2 * NI);   // [2][NI] output column
     uint32_t* info_hap = info_col + 2 * NI;                            // [2][NI] global haplotype id
-    float4* tbl = reinterpret_cast<float4*>(smem + ((((size_t)(L + 32) * 8 + (size_t)NI * 2 * 12) + 15) & ~(size_t)15));   // [6][G][NT]
+    unsigned char* tbl = smem + ((((size_t)(L + 32) * 8 + (size_t)NI * 2 * 12) + 15) & ~(size_t)15);   // [6 classes][thread][G] float4
 
-    // ---- stage the two haplotype streams of this chunk: word = class * TSTRIDE (| flag on a first column) ----
+    // ---- stage the two haplotype streams of this chunk: word = class * CSTRIDE (| flag on a first column) ----
     for (uint32_t i = threadIdx.x; i < L + 32; i += NT) stream[i] = make_uint2(0u, 0u);
     for (uint32_t i = threadIdx.x; i < 2 * NI; i += NT) { info_init[i] = 0.f; info_col[i] = 0u; info_hap[i] = 0u; }
     __syncthreads();
@@ -269,7 +272,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             const uint32_t n_e = e ? (ch.n_haps - ch.n_x) : ch.n_x;
             const uint8_t* hb = p.hap_bases + hp.byte_off;
             for (uint32_t c = threadIdx.x; c < hp.len; c += NT) {
-                uint32_t w = base_class(hb[c]) * TSTRIDE;
+                uint32_t w = base_class(hb[c]) * CSTRIDE;
                 if (c == 0) w |= PHMM_FLAG_BIT;
                 sw[2 * (hp.pos + c) + e] = w;
             }
@@ -285,7 +288,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 
     // ---- which read is mine: LANES lanes per read, 32 / LANES reads per warp ---------------------
     const uint32_t slot = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
-    if ((threadIdx.x >> 5) * (32 / LANES) >= cta.n_reads) return;      // whole warp has no read
+    if ((threadIdx.x >> 5) * (32 / LANES) >= cta.n_reads) return;      // whole warp has no read (the host sizes CTAs so that this is rare)
     const bool live = slot < cta.n_reads;                              // a dead half warp shadows the last read, never writes
     const uint32_t rid = p.task_reads[cta.read_begin + (live ? slot : cta.n_reads - 1)];
     const PhmmRead rd = p.reads[rid];
@@ -345,7 +348,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
                 v.y = (rr[4 * g + 1] & hb) ? pm[4 * g + 1] : pmm[4 * g + 1];
                 v.z = (rr[4 * g + 2] & hb) ? pm[4 * g + 2] : pmm[4 * g + 2];
                 v.w = (rr[4 * g + 3] & hb) ? pm[4 * g + 3] : pmm[4 * g + 3];
-                tbl[(b * G + g) * NT + threadIdx.x] = v;
+                *reinterpret_cast<float4*>(tbl + b * CSTRIDE + threadIdx.x * TSTRIDE + g * 16) = v;
             }
         }
     }
@@ -359,7 +362,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     float2 sumM = bc(0.f), sumI = bc(0.f);
     uint32_t jx = 0, jy = 0;                       // haplotypes begun so far in each stream
     const uint2* sp = stream + 32 - lane;
-    const unsigned char* tb = reinterpret_cast<const unsigned char*>(tbl) + threadIdx.x * 16;
+    const unsigned char* tb = tbl + threadIdx.x * TSTRIDE;
     const uint32_t nsteps = L - 1 - (32 - LANES);  // the last lane of the group reaches the end sentinel at step L - 33 + LANES
     const bool writer = live && (lane == LANES - 1);
 
@@ -397,8 +400,8 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         float px[G * 4], py[G * 4];
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const unsigned char* ax = tb + w.x + g * (NT * 16);
-            const unsigned char* ay = tb + w.y + g * (NT * 16);
+            const unsigned char* ax = tb + w.x + g * 16;
+            const unsigned char* ay = tb + w.y + g * 16;
             if (RPT - 4 * g >= 3) {
                 const float4 vx = *reinterpret_cast<const float4*>(ax), vy = *reinterpret_cast<const float4*>(ay);
                 px[4 * g] = vx.x; px[4 * g + 1] = vx.y; px[4 * g + 2] = vx.z; px[4 * g + 3] = vx.w;
@@ -469,10 +472,13 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 }
 
 // ------------------------------------------------------------------------------------------------
-// Per-pair kernel: one thread per (read, haplotype) pair, previous row kept in a global scratch
-// interleaved across threads.  Used for the FP64 recompute of pairs whose FP32 sum underflowed
-// (pairhmm_internal.cpp:578-581; init 2^1020/H, double tables — core/context.h:99-111) and, in FP32,
-// for shapes outside the wavefront kernel's envelope.  Same recurrence, same operation order.
+// Per-pair wavefront kernel: one warp per (read, haplotype) pair, any read and haplotype length, FP32 or FP64.  Used for
+// the FP64 recompute of pairs whose FP32 sum underflowed (pairhmm_internal.cpp:578-581; init 2^1020/H, double tables —
+// core/context.h:99-111) and, in FP32, for shapes outside the batched kernel's envelope.  Same recurrence, same operation
+// order.  The read is cut into strips of 32 x PAIR_RPT rows (top-padded with boundary-generator rows like the batched
+// kernel); a strip sweeps the haplotype as a wavefront, its bottom row goes through a per-warp global scratch to the next
+// strip.  The pair list and its length live on the device (the forward kernels append to it), so the grid is fixed and
+// every warp strides over the list.
 // ------------------------------------------------------------------------------------------------
 
 template <typename T> struct Num;
@@ -495,71 +501,134 @@ template <> struct Num<double>
     static __device__ __forceinline__ double init(uint32_t H) { return __ddiv_rn(__longlong_as_double(0x7FB0000000000000LL), (double)H); }   // 2^1020 / H
 };
 
+constexpr int PAIR_RPT = 5;
+
+template <typename T> struct RowParams;
+template <> struct RowParams<float>
+{
+    static __device__ __forceinline__ void load(const PhmmTables* tb, uint32_t w, float& mm, float& gapm, float& mi, float& ii, float& md,
+                                                float& pm, float& pmm)
+    {
+        const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
+        const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+        mm = tb->mm[((hi * (hi + 1)) >> 1) + lo]; gapm = tb->gapm[qc]; mi = tb->ph2pr[qi]; ii = tb->ph2pr[qc];
+        md = tb->ph2pr[qd]; pm = tb->pm[q]; pmm = tb->pmm[q];
+    }
+};
+template <> struct RowParams<double>
+{
+    static __device__ __forceinline__ void load(const PhmmTables* tb, uint32_t w, double& mm, double& gapm, double& mi, double& ii,
+                                                double& md, double& pm, double& pmm)
+    {
+        const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
+        const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+        mm = tb->mm_d[((hi * (hi + 1)) >> 1) + lo]; gapm = __dsub_rn(1.0, tb->ph2pr_d[qc]); mi = tb->ph2pr_d[qi];
+        ii = tb->ph2pr_d[qc]; md = tb->ph2pr_d[qd]; pm = __dsub_rn(1.0, tb->ph2pr_d[q]); pmm = __ddiv_rn(tb->ph2pr_d[q], 3.0);
+    }
+};
+
 template <typename T, bool FMA>
 __global__ void __launch_bounds__(128) phmm_pair_kernel(PhmmBatchDev p, const PhmmPair* pairs, const uint32_t* count_dev,
                                                         uint32_t count, T* scratch, uint32_t max_cols, T* out)
 {
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t nthr = gridDim.x * blockDim.x;
+    constexpr int RPT = PAIR_RPT, ROWS = 32 * RPT;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t n = count_dev ? *count_dev : count;
-    T* Mr = scratch + tid;
-    T* Ir = Mr + (size_t)(max_cols + 1) * nthr;
-    T* Dr = Ir + (size_t)(max_cols + 1) * nthr;
+    T* sM = scratch + (size_t)wid * 3 * (max_cols + 1);        // bottom row of the previous strip, per column
+    T* sI = sM + (max_cols + 1);
+    T* sD = sI + (max_cols + 1);
     const PhmmTables* __restrict__ tb = p.tables;
-    for (uint32_t pi = tid; pi < n; pi += nthr) {
+    for (uint32_t pi = wid; pi < n; pi += nwarps) {
         const PhmmPair pr = pairs[pi];
         const PhmmRead rd = p.reads[pr.read];
         const PhmmHap hp = p.haps[pr.hap];
-        const uint32_t H = hp.len, R = rd.len;
+        const int H = (int)hp.len, R = (int)rd.len;
         const uint8_t* hb = p.hap_bases + hp.byte_off;
-        const T init = Num<T>::init(H);
-        for (uint32_t c = 0; c <= H; ++c) { Mr[(size_t)c * nthr] = (T)0; Ir[(size_t)c * nthr] = (T)0; Dr[(size_t)c * nthr] = init; }
-        for (uint32_t r = 0; r < R; ++r) {
-            const uint32_t w = p.words[rd.word_off + r];
-            const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u, rbase = w >> 28;
-            const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
-            T mm, gapm, mi, ii, md, dd, pm, pmm;
-            if (sizeof(T) == 4) {
-                mm = tb->mm[((hi * (hi + 1)) >> 1) + lo]; gapm = tb->gapm[qc]; mi = tb->ph2pr[qi]; ii = tb->ph2pr[qc];
-                md = tb->ph2pr[qd]; dd = ii; pm = tb->pm[q]; pmm = tb->pmm[q];
-            } else {
-                mm = (T)tb->mm_d[((hi * (hi + 1)) >> 1) + lo]; gapm = (T)__dsub_rn(1.0, tb->ph2pr_d[qc]); mi = (T)tb->ph2pr_d[qi];
-                ii = (T)tb->ph2pr_d[qc]; md = (T)tb->ph2pr_d[qd]; dd = ii;
-                pm = (T)__dsub_rn(1.0, tb->ph2pr_d[q]); pmm = (T)__ddiv_rn(tb->ph2pr_d[q], 3.0);
-            }
-            T dM = Mr[0], dI = Ir[0], dD = Dr[0];          // row r-1, column 0
-            Mr[0] = (T)0; Ir[0] = (T)0; Dr[0] = (T)0;       // row r, column 0
-            T lM = (T)0, lI = (T)0, lD = (T)0;
-            for (uint32_t c = 1; c <= H; ++c) {
-                const T uM = Mr[(size_t)c * nthr], uI = Ir[(size_t)c * nthr], uD = Dr[(size_t)c * nthr];
-                const T prior = (rbase & onehot(hb[c - 1])) ? pm : pmm;
-                T m, i, d;
-                if (FMA) {
-                    T t = Num<T>::mul(dM, mm);
-                    t = Num<T>::fma(dI, gapm, t);
-                    t = Num<T>::fma(dD, gapm, t);
-                    m = Num<T>::mul(t, prior);
-                    i = Num<T>::fma(uI, ii, Num<T>::mul(uM, mi));
-                    d = Num<T>::fma(lD, dd, Num<T>::mul(lM, md));
-                } else {
-                    T t = Num<T>::add(Num<T>::mul(dM, mm), Num<T>::mul(dI, gapm));
-                    t = Num<T>::add(t, Num<T>::mul(dD, gapm));
-                    m = Num<T>::mul(t, prior);
-                    i = Num<T>::add(Num<T>::mul(uM, mi), Num<T>::mul(uI, ii));
-                    d = Num<T>::add(Num<T>::mul(lM, md), Num<T>::mul(lD, dd));
+        const T init = Num<T>::init((uint32_t)H);
+        const int nstrips = (R + 1 + ROWS - 1) / ROWS;         // at least one generator row on top
+        const int npad = nstrips * ROWS - R;
+        T sumM = (T)0, sumI = (T)0;
+        for (int strip = 0; strip < nstrips; ++strip) {
+            T mm[RPT], gapm[RPT], mi[RPT], ii[RPT], md[RPT], dd[RPT], pm[RPT], pmm[RPT];
+            uint32_t rb[RPT];
+            bool pad[RPT];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) {
+                const int r = strip * ROWS + (int)lane * RPT + k - npad;
+                pad[k] = r < 0;
+                if (r >= 0) {
+                    const uint32_t w = p.words[rd.word_off + r];
+                    RowParams<T>::load(tb, w, mm[k], gapm[k], mi[k], ii[k], md[k], pm[k], pmm[k]);
+                    dd[k] = ii[k];
+                    rb[k] = w >> 28;
+                } else {                                       // boundary-generator row
+                    mm[k] = gapm[k] = mi[k] = ii[k] = md[k] = pm[k] = pmm[k] = (T)0;
+                    dd[k] = (T)1;
+                    rb[k] = 0u;
                 }
-                Mr[(size_t)c * nthr] = m; Ir[(size_t)c * nthr] = i; Dr[(size_t)c * nthr] = d;
-                dM = uM; dI = uI; dD = uD;
-                lM = m; lI = i; lD = d;
             }
+            const bool above_pad = strip * ROWS + (int)lane * RPT - 1 < npad;
+            const bool from_scratch = strip > 0 && lane == 0;
+            const bool to_scratch = strip + 1 < nstrips && lane == 31;
+            const bool last = strip + 1 == nstrips && lane == 31;
+            T Ml[RPT], Il[RPT], Dl[RPT];
+            T upM = (T)0, upI = (T)0, upD = (T)0, dgM = (T)0, dgI = (T)0, dgD = (T)0;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) { Ml[k] = (T)0; Il[k] = (T)0; Dl[k] = (T)0; }
+            for (int s = 0; s < H + 31; ++s) {
+                const int c = s - (int)lane;                   // my column this step; outside [0, H): idle work, never stored
+                if (c == 0) {                                  // column -1 state: M = I = D = 0, generator rows hold D = init
+#pragma unroll
+                    for (int k = 0; k < RPT; ++k) { Ml[k] = (T)0; Il[k] = (T)0; Dl[k] = pad[k] ? init : (T)0; }
+                    dgM = (T)0; dgI = (T)0; dgD = above_pad ? init : (T)0;
+                }
+                const bool valid = c >= 0 && c < H;
+                if (from_scratch && valid) { upM = sM[c]; upI = sI[c]; upD = sD[c]; }
+                const uint32_t hbase = onehot(valid ? hb[c] : 0);
+                T pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+#pragma unroll
+                for (int k = 0; k < RPT; ++k) {
+                    const T oM = Ml[k], oI = Il[k], oD = Dl[k];
+                    const T prior = (rb[k] & hbase) ? pm[k] : pmm[k];
+                    T m, i, d;
+                    if (FMA) {
+                        T t = Num<T>::mul(pM, mm[k]);
+                        t = Num<T>::fma(pI, gapm[k], t);
+                        t = Num<T>::fma(pD, gapm[k], t);
+                        m = Num<T>::mul(t, prior);
+                        i = Num<T>::fma(uI, ii[k], Num<T>::mul(uM, mi[k]));
+                        d = Num<T>::fma(oD, dd[k], Num<T>::mul(oM, md[k]));
+                    } else {
+                        T t = Num<T>::add(Num<T>::mul(pM, mm[k]), Num<T>::mul(pI, gapm[k]));
+                        t = Num<T>::add(t, Num<T>::mul(pD, gapm[k]));
+                        m = Num<T>::mul(t, prior);
+                        i = Num<T>::add(Num<T>::mul(uM, mi[k]), Num<T>::mul(uI, ii[k]));
+                        d = Num<T>::add(Num<T>::mul(oM, md[k]), Num<T>::mul(oD, dd[k]));
+                    }
+                    Ml[k] = m; Il[k] = i; Dl[k] = d;
+                    pM = oM; pI = oI; pD = oD;
+                    uM = m; uI = i;
+                }
+                dgM = upM; dgI = upI; dgD = upD;
+                if (valid) {
+                    if (last) { sumM = Num<T>::add(sumM, Ml[RPT - 1]); sumI = Num<T>::add(sumI, Il[RPT - 1]); }
+                    if (to_scratch) { sM[c] = Ml[RPT - 1]; sI[c] = Il[RPT - 1]; sD[c] = Dl[RPT - 1]; }
+                }
+                const T nuM = __shfl_up_sync(0xffffffffu, Ml[RPT - 1], 1);
+                const T nuI = __shfl_up_sync(0xffffffffu, Il[RPT - 1], 1);
+                const T nuD = __shfl_up_sync(0xffffffffu, Dl[RPT - 1], 1);
+                if (lane != 0) { upM = nuM; upI = nuI; upD = nuD; }
+            }
+            __syncwarp();                                      // scratch written by lane 31 is read by lane 0 of the next strip
         }
-        T sM = (T)0, sI = (T)0;
-        for (uint32_t c = 1; c <= H; ++c) { sM = Num<T>::add(sM, Mr[(size_t)c * nthr]); sI = Num<T>::add(sI, Ir[(size_t)c * nthr]); }
-        const T res = Num<T>::add(sM, sI);
-        out[pr.out_idx] = res;
-        if (sizeof(T) == 4 && res < (T)1e-28f) {            // pairhmm_internal.cpp:578: queue the FP64 recompute
-            const uint32_t slot = atomicAdd(p.f64_count, 1u);
-            p.f64_pairs[slot] = pr;
+        if (lane == 31) {
+            const T res = Num<T>::add(sumM, sumI);
+            out[pr.out_idx] = res;
+            if (sizeof(T) == 4 && res < (T)1e-28f) {            // pairhmm_internal.cpp:578: queue the FP64 recompute
+                const uint32_t slot = atomicAdd(p.f64_count, 1u);
+                p.f64_pairs[slot] = pr;
+            }
         }
     }
 }
@@ -606,14 +675,24 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
 }
 
 template <int RPT, int LANES, int VAR>
-cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, size_t smem, cudaStream_t st)
+cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps, size_t smem, cudaStream_t st)
 {
     auto kern = phmm_fwd_kernel<RPT, LANES, VAR>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // Raise the dynamic shared-memory limit of this instantiation once, to the device maximum: several host workers launch
+    // concurrently, and a per-launch "set to what I need" lets one worker lower the limit under another's launch.
+    static std::atomic<uint64_t> limit_set{0};            // one bit per device ordinal
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const uint64_t bit = 1ull << (dev & 63);
+    if (!(limit_set.load(std::memory_order_acquire) & bit)) {
+        int optin = 0;
+        e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
         if (e != cudaSuccess) return e;
+        limit_set.fetch_or(bit, std::memory_order_release);
     }
-    kern<<<n_ctas, PHMM_WARPS * 32, smem, st>>>(b, cta_base);
+    kern<<<n_ctas, cta_warps * 32, smem, st>>>(b, cta_base);
     return cudaGetLastError();
 }
 
@@ -666,12 +745,12 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     PHMM_CASE_R(16, 32, FN, __VA_ARGS__) PHMM_CASE_R(18, 32, FN, __VA_ARGS__) PHMM_CASE_R(19, 32, FN, __VA_ARGS__)    \
     return cudaErrorInvalidValue;
 
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, size_t smem_bytes,
-                            cudaStream_t st)
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
+                            size_t smem_bytes, cudaStream_t st)
 {
     if (n_ctas == 0) return cudaSuccess;
-    if (bin < 0 || bin >= kPhmmNumBins) return cudaErrorInvalidValue;
-    PHMM_DISPATCH_BIN(launch_fwd_t, b, cta_base, n_ctas, smem_bytes, st)
+    if (bin < 0 || bin >= kPhmmNumBins || cta_warps < 1 || cta_warps > PHMM_WARPS) return cudaErrorInvalidValue;
+    PHMM_DISPATCH_BIN(launch_fwd_t, b, cta_base, n_ctas, cta_warps, smem_bytes, st)
 }
 
 cudaError_t phmm_fwd_kernel_info(int bin, bool fma, PhmmKernelInfo* info)

@@ -59,7 +59,7 @@ static const PhmmBin kPhmmBins[] = {
 static const int kPhmmNumBins = sizeof(kPhmmBins) / sizeof(kPhmmBins[0]);
 static const int kPhmmFirstRefGapBin = 18;
 static inline uint32_t phmm_bin_capacity(int bin) { return (uint32_t)(kPhmmBins[bin].lanes * kPhmmBins[bin].rpt) - 1u; }
-static inline uint32_t phmm_bin_reads_per_cta(int bin) { return (uint32_t)(PHMM_WARPS * 32 / kPhmmBins[bin].lanes); }
+static inline uint32_t phmm_bin_reads_per_cta(int bin, uint32_t cta_warps) { return cta_warps * 32u / (uint32_t)kPhmmBins[bin].lanes; }
 // The bin that serves a read: the first one of its family (reference gaps or generic) that holds it; -1 = none (per-pair kernel).
 static inline int phmm_bin_of(uint32_t len, bool refgaps)
 {
@@ -69,20 +69,28 @@ static inline int phmm_bin_of(uint32_t len, bool refgaps)
     return -1;
 }
 
+// Prior tables in shared memory: [6 base classes][thread][ceil(RPT/4) float4].  The per-thread slice is padded to an odd number
+// of 16-byte chunks so that the eight chunks a quarter warp fetches with one LDS.128 fall into eight different bank groups
+// whatever classes the lanes ask for (a class offset is a multiple of 512 B).
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr uint32_t phmm_prior_table_stride(int rpt) { return (uint32_t)(((rpt + 3) / 4) | 1) * 16u; }
+
 // Shared memory one CTA of the forward kernel needs for a chunk: the two column streams, the per-haplotype seam records and
 // the per-thread prior tables (6 base classes x ceil(RPT/4) float4 per thread).
-static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int bin)
+static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int bin, uint32_t cta_warps)
 {
     const size_t streams = (size_t)(stream_len + 32) * 8;
     const size_t info = (((streams + (size_t)(n_haps + 1) * 2 * 12) + 15) & ~(size_t)15) - streams;
-    const size_t tables = (size_t)6 * ((kPhmmBins[bin].rpt + 3) / 4) * (PHMM_WARPS * 32) * 16;
+    const size_t tables = (size_t)6 * phmm_prior_table_stride(kPhmmBins[bin].rpt) * cta_warps * 32;
     return streams + info + tables;
 }
 
 cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st);
 // Forward wavefront kernel over ctas[cta_base .. cta_base + n_ctas) (all of one RPT bin).
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, size_t smem_bytes,
-                            cudaStream_t st);
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
+                            size_t smem_bytes, cudaStream_t st);
 // Per-pair kernels.  count_dev != null: the pair count is read on the device (FP64 recompute list).
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
                                   uint32_t threads, uint32_t max_cols, cudaStream_t st);

@@ -36,7 +36,7 @@ class PhmmError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
-                ("linger_us", C.c_uint32), ("rsv", C.c_uint32 * 9)]
+                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("rsv", C.c_uint32 * 8)]
 
 
 class _Read(C.Structure):
@@ -230,9 +230,9 @@ class PairHmmEngine:
     """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
 
     def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
-                 linger_us: int = 0):
+                 linger_us: int = 0, cta_warps: int = 0):
         self.L = load_library()
-        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us)
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps)
         self.h = C.c_void_p()
         rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

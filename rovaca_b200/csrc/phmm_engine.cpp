@@ -145,7 +145,10 @@ struct FwdLaunch
 // One batch in flight: its plan, its pinned staging, its device memory, its stream.
 struct Slot
 {
+    static constexpr int kAux = 3;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr};       // the per-bin forward launches of one batch run side by side
+    cudaEvent_t aux_done[kAux] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // kernels begin, forward begin, forward end, kernels end
     HostBuf h_in, h_f32, h_f64, h_cnt;
     DevBuf d_in, d_words, d_f32, d_f64, d_pairs, d_cnt, d_scr64, d_scr32;
@@ -162,6 +165,8 @@ struct Slot
     int init()
     {
         CU(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& a : aux) CU(cudaStreamCreateWithFlags(&a, cudaStreamNonBlocking));
+        for (auto& e : aux_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         for (auto& e : ev) CU(cudaEventCreate(&e));
         return PHMM_OK;
     }
@@ -171,6 +176,10 @@ struct Slot
         for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32}) b->release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
+        for (auto& e : aux_done)
+            if (e) cudaEventDestroy(e);
+        for (auto& a : aux)
+            if (a) cudaStreamDestroy(a);
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
     }
@@ -512,6 +521,11 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         s.launches.push_back(fl);
     }
 
+    // biggest launches first: the small ones fill the tails
+    std::stable_sort(s.launches.begin(), s.launches.end(), [](const FwdLaunch& x, const FwdLaunch& y) {
+        return (uint64_t)x.n_ctas * x.cta_warps * kPhmmBins[x.bin].rpt > (uint64_t)y.n_ctas * y.cta_warps * kPhmmBins[y.bin].rpt;
+    });
+
     // ---- arena layout ---------------------------------------------------------------------------
     size_t off = 0;
     auto place = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
@@ -643,12 +657,23 @@ int phmm_engine::launch(Slot& s, bool copy_in)
     CU(cudaEventRecord(s.ev[0], s.stream));
     CU(phmm_launch_prep(s.dev, s.stream));
     CU(cudaEventRecord(s.ev[1], s.stream));
-    for (const FwdLaunch& fl : s.launches) {
-        const cudaError_t le = phmm_launch_fwd(s.dev, fl.bin, fma, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, s.stream);
+    // One launch per read-length bin.  A batch of mixed lengths has many of them, none big enough to fill the GPU to the
+    // end of its last wave, so they go out on up to four streams (forked after the prep kernel, joined before the FP64 pass).
+    const size_t n_side = std::min<size_t>(Slot::kAux, s.launches.size() > 1 ? s.launches.size() - 1 : 0);
+    for (size_t a = 0; a < n_side; ++a) CU(cudaStreamWaitEvent(s.aux[a], s.ev[1], 0));
+    for (size_t i = 0; i < s.launches.size(); ++i) {
+        const FwdLaunch& fl = s.launches[i];
+        const size_t lane = i % (n_side + 1);
+        cudaStream_t st = lane == 0 ? s.stream : s.aux[lane - 1];
+        const cudaError_t le = phmm_launch_fwd(s.dev, fl.bin, fma, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, st);
         if (le != cudaSuccess)
             return fail(PHMM_ERR_CUDA, std::string("forward kernel launch (") + std::to_string(kPhmmBins[fl.bin].lanes) + " lanes x " +
                                            std::to_string(kPhmmBins[fl.bin].rpt) + " rows, " + std::to_string(fl.n_ctas) + " CTAs, " +
                                            std::to_string(fl.smem) + " B shared): " + cudaGetErrorString(le));
+    }
+    for (size_t a = 0; a < n_side; ++a) {
+        CU(cudaEventRecord(s.aux_done[a], s.aux[a]));
+        CU(cudaStreamWaitEvent(s.stream, s.aux_done[a], 0));
     }
     CU(cudaEventRecord(s.ev[2], s.stream));
     if (s.n_slow)

@@ -95,6 +95,18 @@ def visible_gpu_index(local_rank):
     return str(local_rank)
 
 
+def captured_traffic(regions):
+    """DRAM bytes (read + write) of one forward-kernel launch from the committed ncu --set full capture, if it was taken at
+    this workload size; None otherwise (traffic is per launch, like `achieved`)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "fwd_traffic.json")))
+        if int(t["regions"]) == int(regions):
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"]), t["source"]
+    except Exception:
+        pass
+    return None, None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -235,8 +247,12 @@ def ours_arm(args, rank, world, local_rank):
     measured_peak = max(ffma, ffma2) * 2 / 1e12
     ki = eng.kernel_info(150)
     regs, spill = ki["regs"], ki["spill_bytes"]
+    traffic, traffic_src = captured_traffic(args.regions)
     roof = {"bound": "fp32", "achieved": round(achieved, 3), "peak": round(peak_tflops, 3), "unit": "TFLOP/s", "frac": round(achieved / peak_tflops, 4),
-            "traffic": None, "kernel": f"phmm_fwd_kernel<RPT={ki['rows_per_lane']}, LANES={ki['lanes_per_read']}> (forward wavefront, cfg2 reads)",
+            "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per forward launch", "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": int(4 * int(batch.read_len.sum()) + int(batch.hap_len.sum()) + 32 * batch.n_reads + 24 * batch.n_haps + 4 * batch.pairs()),
+            "algorithmic_bytes_model": "4 B packed word per read base + 1 B per haplotype base + 32 B per read record + 24 B per haplotype record in, 4 B per pair out",
+            "kernel": f"phmm_fwd_kernel<RPT={ki['rows_per_lane']}, LANES={ki['lanes_per_read']}> (forward wavefront, cfg2 reads)",
             "peak_source": f"2 x 128 lanes x {n_sm} SMs x {sm_max:.0f} MHz (sm_max_mhz of MEASURED_PEAKS.json); no FP32 figure in that file",
             "work_model": "8 FP32-pipe instructions per cell (4 FMUL + 4 FFMA) counted as FMA slots = 16 flop-equivalents; plain 12 flop/cell also given",
             "fwd_kernel_ms": round(fwd_step, 3), "tcups": round(cells / (fwd_step * 1e-3) / 1e12, 4),

@@ -3,6 +3,8 @@
 #include "call_pairhmm_b200.h"
 
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <stdexcept>
@@ -26,6 +28,36 @@ namespace
 {
 phmm_engine* g_engine = nullptr;
 std::mutex g_engine_mutex;
+
+// Optional capture of what the call site hands over: when ROVACA_B200_DUMP names a file, every region
+// is appended to it as a PHMMREG1 record (format: rovaca_b200/dump.py) before it is computed, so that real-data batches can
+// be replayed wherever only this repository is available.
+std::mutex g_dump_mutex;
+void dump_region(const phmm_region& region)
+{
+    const char* path = std::getenv("ROVACA_B200_DUMP");   // read per call: cheap next to a region, and tools may switch it on late
+    if (!path || !*path) return;
+    std::lock_guard<std::mutex> lk(g_dump_mutex);
+    FILE* f = std::fopen(path, "ab");
+    if (!f) return;
+    const int32_t head[2] = {region.min_quality_threshold, region.pcr_model};
+    std::fwrite("PHMMREG1", 1, 8, f);
+    std::fwrite(&region.n_reads, 4, 1, f);
+    std::fwrite(&region.n_haps, 4, 1, f);
+    std::fwrite(head, 4, 2, f);
+    for (uint32_t i = 0; i < region.n_reads; ++i) {
+        const phmm_read& r = region.reads[i];
+        std::fwrite(&r.len, 4, 1, f);
+        std::fwrite(&r.mapq, 1, 1, f);
+        std::fwrite(r.bases, 1, r.len, f);
+        std::fwrite(r.qual, 1, r.len, f);
+    }
+    for (uint32_t j = 0; j < region.n_haps; ++j) {
+        std::fwrite(&region.haps[j].len, 4, 1, f);
+        std::fwrite(region.haps[j].bases, 1, region.haps[j].len, f);
+    }
+    std::fclose(f);
+}
 }  // namespace
 
 void init_pairhmm_ptr_b200(int device)
@@ -95,6 +127,7 @@ DoubleVector2D call_pairhmm_b200(const HaplotypeVector& hs, ReadVector& rs, int3
     region.n_haps = (uint32_t)n_haps;
     region.min_quality_threshold = min_quality_threshold;
     region.pcr_model = static_cast<int32_t>(pcr_option);               // common/enum.h:8, same numeric values
+    dump_region(region);
     phmm_result result;
     std::memset(&result, 0, sizeof(result));
     result.likelihoods = flat;

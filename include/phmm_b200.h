@@ -51,7 +51,8 @@ typedef struct phmm_config
     uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 12e9) */
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
-    uint32_t rsv[8];
+    uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 3) */
+    uint32_t rsv[7];
 } phmm_config;
 
 /* What the path reads of a ReadRecord (genotype/read_record.h:67-103, read_record.cpp:176-210). */

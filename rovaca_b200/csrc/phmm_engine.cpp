@@ -59,6 +59,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
+constexpr uint32_t kMinStreamCols = 200;        // small batches are cut finer (more, shorter warps), but never below this
 constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)
 constexpr uint32_t kPairThreads = 148 * 3 * 128;   // per-pair wavefront kernel: one warp per pair, 12 warps per SM
 constexpr float kMinAccepted = 1e-28f;                     // MIN_ACCEPTED, rovaca/common.h:9
@@ -263,6 +264,8 @@ struct phmm_engine
     uint64_t batch_cells = 12000000000ull;
     uint32_t linger_us = 200;
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
+    uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
+    std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     DevBuf d_tables;
     Stats stats;
 
@@ -280,20 +283,33 @@ struct phmm_engine
         uint64_t id = 0;
         std::vector<RegionIn> regs;
         uint64_t cells = 0;
+        uint32_t waiters = 0;          // threads blocked in phmm_wait on this batch
         std::chrono::steady_clock::time_point first;
     };
-    struct Done
+    struct BatchSync            // completion of one sealed batch; waiters block on the batch's own condition variable
     {
+        std::mutex m;
+        std::condition_variable cv;
         bool done = false;
         int rc = PHMM_OK;
-        uint32_t waits = 0;     // regions submitted under this ticket that have not been waited for yet
         std::string err;
     };
+    struct Pending
+    {
+        std::shared_ptr<BatchSync> sync;
+        uint32_t waits = 0;     // regions submitted under this ticket that have not been waited for yet
+    };
     std::mutex bm;
-    std::condition_variable bcv;
+    std::condition_variable open_cv;   // signalled when the open batch is sealed
     OpenBatch open;
     uint64_t next_batch_id = 1;
-    std::unordered_map<uint64_t, Done> batch_state;
+    std::unordered_map<uint64_t, Pending> batch_state;
+    // Sealing policy (the callers are the reference's synchronous pool workers, haplotypecaller_engine.cpp:250): batch while
+    // busy.  A batch with a waiter goes out at once while fewer than kPipelineDepth batches are in flight (the pipeline is
+    // starving: plan / GPU / epilogue of different batches overlap); otherwise it keeps collecting the callers that return
+    // from earlier batches and goes out when one of those completes, when it is big (batch_cells), or after linger_us.
+    uint32_t in_flight = 0;            // sealed batches that have not completed
+    uint32_t pipeline_depth = 3;       // batches the ticket path keeps in flight before it starts batching up
 
     int plan(Slot& s, const std::vector<RegionIn>& regs);
     int launch(Slot& s, bool copy_in);
@@ -334,6 +350,22 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     // What the reference itself feeds its kernels — deletion qualities aliasing the insertion ones, one gap-continuation
     // quality per read (read_record.cpp:191-210, pairhmm_internal.cpp:425,559) — is served by the leaner kernel variant.
     const bool refgaps = fma && !any_del && !any_gcp;
+    // A warp sweeps its chunk's columns one after the other (~0.2 us per column), so the chunk length is the latency of a
+    // batch and chunks x reads its parallelism.  A big batch fills the GPU with long chunks (fewest seams and staging); a
+    // small one (the synchronous per-region callers) is cut finer until it has about two warps per warp slot of the device.
+    uint32_t target_cols = kTargetStreamCols;
+    {
+        uint64_t est_warps = 0;
+        for (const RegionIn& r : regs) {
+            uint64_t hb = 0;
+            for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
+            est_warps += (uint64_t)((r.n_reads + 3) / 4) * std::max<uint64_t>(1, (hb + 2ull * kTargetStreamCols - 1) / (2ull * kTargetStreamCols));
+        }
+        // batches already on the device fill it too: share the target among them
+        const uint64_t want = 2ull * warp_slots / std::max<uint32_t>(1, busy_batches.load(std::memory_order_relaxed));
+        if (est_warps > 0 && est_warps < want)
+            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want);
+    }
 
     std::vector<PhmmRead> reads;
     std::vector<PhmmHap> haps;
@@ -387,14 +419,14 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         const bool all_haps_in_stream = order.size() == r.n_haps;
         region_chunks.clear();
         if (!order.empty()) {
-            const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (total + 2ull * kTargetStreamCols - 1) / (2ull * kTargetStreamCols));
+            const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols));
             const uint64_t per_chunk = (total + n_chunks - 1) / n_chunks;
             size_t at = 0;
             while (at < order.size()) {
                 // take haplotypes (in region order) until this chunk holds its share
                 size_t end = at;
                 uint64_t acc = 0;
-                while (end < order.size() && (end == at || acc + r.haps[order[end]].len <= per_chunk + kTargetStreamCols / 4)) {
+                while (end < order.size() && (end == at || acc + r.haps[order[end]].len <= per_chunk + target_cols / 4)) {
                     acc += r.haps[order[end]].len;
                     ++end;
                     if (acc >= per_chunk) break;
@@ -696,7 +728,18 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
         CU(cudaMemcpyAsync(s.h_cnt.p, s.d_cnt.p, 4, cudaMemcpyDeviceToHost, s.stream));
         stats.d2h += s.n_pairs * sizeof(float) + 4;
     }
-    CU(cudaStreamSynchronize(s.stream));
+    {
+        // short batches (the synchronous per-region callers) finish in tens of microseconds: poll before paying a blocking
+        // sync's wake-up latency
+        const auto t_poll = std::chrono::steady_clock::now();
+        cudaError_t q;
+        while ((q = cudaStreamQuery(s.stream)) == cudaErrorNotReady) {
+            if (std::chrono::steady_clock::now() - t_poll > std::chrono::microseconds(400)) break;
+            _mm_pause();
+        }
+        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PHMM_ERR_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
+        if (q == cudaErrorNotReady) CU(cudaStreamSynchronize(s.stream));
+    }
     if (s.n_pairs) {
         n64 = *static_cast<uint32_t*>(s.h_cnt.p);
         if (n64 > 0) {
@@ -786,10 +829,18 @@ int phmm_engine::execute(Slot& s, const std::vector<RegionIn>& regs)
 {
     int rc;
     const auto t0 = std::chrono::steady_clock::now();
-    if ((rc = plan(s, regs)) != PHMM_OK) return rc;
+    busy_batches.fetch_add(1, std::memory_order_relaxed);
+    if ((rc = plan(s, regs)) != PHMM_OK) {
+        busy_batches.fetch_sub(1, std::memory_order_relaxed);
+        return rc;
+    }
     const auto t1 = std::chrono::steady_clock::now();
-    if ((rc = launch(s, true)) != PHMM_OK) return rc;
+    if ((rc = launch(s, true)) != PHMM_OK) {
+        busy_batches.fetch_sub(1, std::memory_order_relaxed);
+        return rc;
+    }
     rc = finish(s, regs, true);
+    busy_batches.fetch_sub(1, std::memory_order_relaxed);
     {
         std::lock_guard<std::mutex> lk(stats.m);
         stats.plan_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
@@ -832,19 +883,23 @@ void phmm_engine::seal_locked()
 {
     if (open.regs.empty()) return;
     auto regs = std::make_shared<std::vector<RegionIn>>(std::move(open.regs));
-    const uint64_t id = open.id;
+    std::shared_ptr<BatchSync> sync = batch_state[open.id].sync;
     open = OpenBatch{};
-    enqueue([this, regs, id](Slot& s) {
+    ++in_flight;
+    open_cv.notify_all();
+    enqueue([this, regs, sync](Slot& s) {
         const int rc = execute(s, *regs);
-        std::string err = g_err;
+        const std::string err = rc != PHMM_OK ? g_err : std::string();
         {
-            std::lock_guard<std::mutex> lk(bm);
-            Done& d = batch_state[id];
-            d.done = true;
-            d.rc = rc;
-            d.err = err;
+            std::lock_guard<std::mutex> lk(sync->m);
+            sync->done = true;
+            sync->rc = rc;
+            sync->err = err;
         }
-        bcv.notify_all();
+        sync->cv.notify_all();
+        std::lock_guard<std::mutex> lk(bm);
+        --in_flight;
+        if (open.waiters > 0 && in_flight < pipeline_depth) seal_locked();   // a stage is free: send what has gathered meanwhile
     });
 }
 
@@ -951,12 +1006,14 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
         return fail(PHMM_ERR_CUDA, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
                                        "; this library carries sm_100a code only");
     e->device = dev;
+    e->warp_slots = (uint32_t)prop.multiProcessorCount * 8;
     if (cfg) {
         e->fma = cfg->fma_mode != PHMM_FMA_NONE;
         if (cfg->n_workers) e->n_workers = std::min<uint32_t>(cfg->n_workers, 32);
         if (cfg->batch_cells) e->batch_cells = cfg->batch_cells;
         if (cfg->linger_us) e->linger_us = cfg->linger_us;
         if (cfg->cta_warps) e->cta_warps = std::min<uint32_t>(cfg->cta_warps, PHMM_WARPS);
+        if (cfg->pipeline_depth) e->pipeline_depth = std::min<uint32_t>(cfg->pipeline_depth, 32);
     }
     std::unique_ptr<PhmmTables> t(new PhmmTables());
     phmm_build_tables(t.get());
@@ -1011,7 +1068,7 @@ int phmm_submit(phmm_engine* e, const phmm_region* region, phmm_result* result, 
     if (e->open.regs.empty()) {
         e->open.id = e->next_batch_id++;
         e->open.first = std::chrono::steady_clock::now();
-        e->batch_state[e->open.id] = phmm_engine::Done{};
+        e->batch_state[e->open.id].sync = std::make_shared<phmm_engine::BatchSync>();
     }
     *ticket = e->open.id;
     e->batch_state[e->open.id].waits += 1;
@@ -1032,21 +1089,40 @@ int phmm_flush(phmm_engine* e)
 int phmm_wait(phmm_engine* e, uint64_t ticket)
 {
     if (!e) return fail(PHMM_ERR_ARG, "phmm_wait: null engine");
-    std::unique_lock<std::mutex> lk(e->bm);
-    auto it = e->batch_state.find(ticket);
-    if (it == e->batch_state.end()) return fail(PHMM_ERR_STATE, "phmm_wait: unknown ticket");
-    if (e->open.id == ticket && !e->open.regs.empty()) {
-        // let other callers join this batch for a moment, then seal it ourselves
-        const auto deadline = e->open.first + std::chrono::microseconds(e->linger_us);
-        while (e->open.id == ticket && !e->open.regs.empty() && std::chrono::steady_clock::now() < deadline)
-            e->bcv.wait_until(lk, deadline);
-        if (e->open.id == ticket && !e->open.regs.empty()) e->seal_locked();
+    std::shared_ptr<phmm_engine::BatchSync> sync;
+    {
+        std::unique_lock<std::mutex> lk(e->bm);
+        auto it = e->batch_state.find(ticket);
+        if (it == e->batch_state.end()) return fail(PHMM_ERR_STATE, "phmm_wait: unknown ticket");
+        sync = it->second.sync;
+        if (e->open.id == ticket && !e->open.regs.empty()) {
+            if (e->in_flight < e->pipeline_depth) {
+                e->seal_locked();                                   // the pipeline is starving: go now
+            } else {
+                // busy: keep collecting returning callers; a completing batch, the size limit or the deadline seals it
+                ++e->open.waiters;
+                const auto deadline = e->open.first + std::chrono::microseconds(e->linger_us);
+                while (e->open.id == ticket && !e->open.regs.empty()) {
+                    if (std::chrono::steady_clock::now() >= deadline) {
+                        e->seal_locked();
+                        break;
+                    }
+                    e->open_cv.wait_until(lk, deadline);
+                }
+            }
+        }
     }
-    e->bcv.wait(lk, [&] { return e->batch_state[ticket].done; });
-    phmm_engine::Done& st = e->batch_state[ticket];
-    const int rc = st.rc;
-    if (rc != PHMM_OK) g_err = st.err;
-    if (st.waits <= 1) e->batch_state.erase(ticket); else st.waits -= 1;
+    {
+        std::unique_lock<std::mutex> lk(sync->m);
+        sync->cv.wait(lk, [&] { return sync->done; });
+    }
+    const int rc = sync->rc;
+    if (rc != PHMM_OK) g_err = sync->err;
+    std::lock_guard<std::mutex> lk(e->bm);
+    auto it = e->batch_state.find(ticket);
+    if (it != e->batch_state.end()) {
+        if (it->second.waits <= 1) e->batch_state.erase(it); else it->second.waits -= 1;
+    }
     return rc;
 }
 

@@ -36,7 +36,7 @@ class PhmmError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
-                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("rsv", C.c_uint32 * 8)]
+                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("rsv", C.c_uint32 * 7)]
 
 
 class _Read(C.Structure):

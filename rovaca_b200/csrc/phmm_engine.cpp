@@ -88,17 +88,31 @@ struct RegionPlan
     uint64_t out_off;
 };
 
+// Growing an arena means cudaFree + cudaMalloc (a device-wide sync) or re-pinning host pages (milliseconds), so arenas grow
+// in big steps and straight to the biggest size any worker of the engine has needed for that buffer (the high-water mark):
+// after a change of workload every slot reallocates at most once.
+inline size_t grow_to(size_t bytes, std::atomic<size_t>* high_water)
+{
+    size_t want = align_up(std::max(bytes + bytes / 2, (size_t)4 << 20), 1 << 20);
+    if (high_water) {
+        size_t seen = high_water->load(std::memory_order_relaxed);
+        while (seen < want && !high_water->compare_exchange_weak(seen, want, std::memory_order_relaxed)) {}
+        want = std::max(want, seen);
+    }
+    return want;
+}
+
 struct DevBuf
 {
     void* p = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes)
+    int ensure(size_t bytes, std::atomic<size_t>* high_water = nullptr)
     {
         if (bytes <= cap) return PHMM_OK;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(std::max(bytes + bytes / 2, (size_t)4 << 20), 1 << 20);   // grow in big steps: (re)allocation stalls the device
+        size_t want = grow_to(bytes, high_water);
         cudaError_t e = cudaMalloc(&p, want);
         if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
         cap = want;
@@ -116,13 +130,13 @@ struct HostBuf
 {
     void* p = nullptr;
     size_t cap = 0;
-    int ensure(size_t bytes)
+    int ensure(size_t bytes, std::atomic<size_t>* high_water = nullptr)
     {
         if (bytes <= cap) return PHMM_OK;
         if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
-        size_t want = align_up(std::max(bytes + bytes / 2, (size_t)4 << 20), 1 << 20);   // grow in big steps: (re)allocation stalls the device
+        size_t want = grow_to(bytes, high_water);
         cudaError_t e = cudaMallocHost(&p, want);
         if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
         cap = want;
@@ -266,6 +280,7 @@ struct phmm_engine
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
+    std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
     DevBuf d_tables;
     Stats stats;
 
@@ -575,8 +590,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     const size_t o_hb = place(hap_bytes + 16);
     s.in_bytes = off;
     int rc;
-    if ((rc = s.h_in.ensure(off)) != PHMM_OK) return rc;
-    if ((rc = s.d_in.ensure(off)) != PHMM_OK) return rc;
+    if ((rc = s.h_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
+    if ((rc = s.d_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
     uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
     std::memcpy(h + o_reads, reads.data(), reads.size() * sizeof(PhmmRead));
     std::memcpy(h + o_haps, haps.data(), haps.size() * sizeof(PhmmHap));
@@ -630,16 +645,16 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     }
     // ---- device-only buffers --------------------------------------------------------------------
     const size_t pairs_alloc = std::max<uint64_t>(n_pairs, 1);
-    if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t))) != PHMM_OK) return rc;
-    if ((rc = s.d_f32.ensure(pairs_alloc * sizeof(float))) != PHMM_OK) return rc;
-    if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
-    if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair))) != PHMM_OK) return rc;
+    if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t), &high_water[1])) != PHMM_OK) return rc;
+    if ((rc = s.d_f32.ensure(pairs_alloc * sizeof(float), &high_water[2])) != PHMM_OK) return rc;
+    if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
+    if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair), &high_water[4])) != PHMM_OK) return rc;
     if ((rc = s.d_cnt.ensure(256)) != PHMM_OK) return rc;
-    if ((rc = s.d_scr64.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(double))) != PHMM_OK) return rc;
+    if ((rc = s.d_scr64.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(double), &high_water[5])) != PHMM_OK) return rc;
     if (!slow.empty())
-        if ((rc = s.d_scr32.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(float))) != PHMM_OK) return rc;
-    if ((rc = s.h_f32.ensure(pairs_alloc * sizeof(float))) != PHMM_OK) return rc;
-    if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double))) != PHMM_OK) return rc;
+        if ((rc = s.d_scr32.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(float), &high_water[6])) != PHMM_OK) return rc;
+    if ((rc = s.h_f32.ensure(pairs_alloc * sizeof(float), &high_water[2])) != PHMM_OK) return rc;
+    if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
     if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
 
     uint8_t* d = static_cast<uint8_t*>(s.d_in.p);

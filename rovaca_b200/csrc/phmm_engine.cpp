@@ -746,13 +746,15 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     {
         // short batches (the synchronous per-region callers) finish in tens of microseconds: poll before paying a blocking
         // sync's wake-up latency
-        const auto t_poll = std::chrono::steady_clock::now();
-        cudaError_t q;
-        while ((q = cudaStreamQuery(s.stream)) == cudaErrorNotReady) {
-            if (std::chrono::steady_clock::now() - t_poll > std::chrono::microseconds(400)) break;
-            _mm_pause();
+        cudaError_t q = cudaErrorNotReady;
+        if (s.n_cells < 1500000000ull) {            // < ~0.5 ms of device work; big batches sleep instead of burning a core
+            const auto t_poll = std::chrono::steady_clock::now();
+            while ((q = cudaStreamQuery(s.stream)) == cudaErrorNotReady) {
+                if (std::chrono::steady_clock::now() - t_poll > std::chrono::microseconds(400)) break;
+                _mm_pause();
+            }
+            if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PHMM_ERR_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
         }
-        if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PHMM_ERR_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
         if (q == cudaErrorNotReady) CU(cudaStreamSynchronize(s.stream));
     }
     if (s.n_pairs) {
@@ -779,11 +781,14 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
         if (r.n_fp64_out32) *r.n_fp64_out32 = 0;
         if (rp.n_reads == 0 || rp.n_haps == 0) continue;
         const uint32_t nr = rp.n_reads, nh = rp.n_haps;
-        lk.resize((size_t)nr * nh);
-        uint32_t reg64 = 0;
+        lk.resize((size_t)nh);
+        uint32_t reg64 = 0, kept = 0;
+        double* out = r.out.likelihoods;                                             // [nh][nr], :516
         for (uint32_t i = 0; i < nr; ++i) {
-            double* row = lk.data() + (size_t)i * nh;
+            double* row = lk.data();
             const float* fr = f32 + rp.out_off + (size_t)i * nh;
+            double best = -INFINITY;
+            bool best_nan = false;
             for (uint32_t j = 0; j < nh; ++j) {
                 const float f = fr[j];
                 double v;
@@ -794,32 +799,25 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
                     v = (double)(log10f(f) - kLog10InitF);                           // :583
                 }
                 row[j] = v;
+                // std::max_element semantics of :56,:170 — the first element, replaced only by a strictly greater one
+                if (j == 0) { best = v; best_nan = v != v; }
+                else if (!best_nan && best < v) best = v;
             }
             if (r.out.raw_f32) std::memcpy(r.out.raw_f32 + (size_t)i * nh, fr, nh * sizeof(float));
             if (r.out.raw_f64)
                 for (uint32_t j = 0; j < nh; ++j)
                     r.out.raw_f64[(size_t)i * nh + j] = (fr[j] < kMinAccepted) ? f64[rp.out_off + (size_t)i * nh + j] : (double)NAN;
-            // normalize_likelihoods :53-63
-            double best = row[0];
-            for (uint32_t j = 1; j < nh; ++j)
-                if (best < row[j]) best = row[j];
-            const double cmp = best + (-4.5);                                        // adapter.h:23
-            for (uint32_t j = 0; j < nh; ++j) row[j] = row[j] < cmp ? cmp : row[j];
-        }
-        // filter_poorly_modelled_evidence :161-182
-        uint32_t kept = 0;
-        double* out = r.out.likelihoods;
-        for (size_t k = 0; k < (size_t)nh * nr; ++k) out[k] = (double)NAN;          // :516
-        for (uint32_t i = 0; i < nr; ++i) {
-            const double* row = lk.data() + (size_t)i * nh;
-            double best = row[0];
-            for (uint32_t j = 1; j < nh; ++j)
-                if (best < row[j]) best = row[j];
+            // normalize_likelihoods :53-63 caps at best - 4.5 (adapter.h:23); the maximum itself is unchanged, so
+            // filter_poorly_modelled_evidence :161-182 sees the same `best`
+            const double cmp = best + (-4.5);
             const double lim = std::min(2.0, std::ceil((int32_t)s.read_len[rp.read_begin + i] * 0.02)) * (-4.0);   // adapter.h:20-22
             if (best < lim) continue;
-            for (uint32_t j = 0; j < nh; ++j) out[(size_t)j * nr + kept] = row[j];  // transpose :184-193
+            for (uint32_t j = 0; j < nh; ++j) out[(size_t)j * nr + kept] = row[j] < cmp ? cmp : row[j];   // transpose :184-193
             r.out.kept_idx[kept++] = i;
         }
+        if (kept < nr)                                                               // the NaN tail of the filtered reads
+            for (uint32_t j = 0; j < nh; ++j)
+                for (uint32_t c = kept; c < nr; ++c) out[(size_t)j * nr + c] = (double)NAN;
         if (r.n_kept_out) *r.n_kept_out = kept;
         if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
         if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
@@ -1022,6 +1020,8 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
                                        "; this library carries sm_100a code only");
     e->device = dev;
     e->warp_slots = (uint32_t)prop.multiProcessorCount * 8;
+    // host workers: one rank per GPU is the deployment, so a rank may count on its share of the cores
+    e->n_workers = std::max(2u, std::min(6u, std::thread::hardware_concurrency() / (unsigned)std::max(ndev, 1)));
     if (cfg) {
         e->fma = cfg->fma_mode != PHMM_FMA_NONE;
         if (cfg->n_workers) e->n_workers = std::min<uint32_t>(cfg->n_workers, 32);

@@ -106,9 +106,10 @@ struct DevBuf
 {
     void* p = nullptr;
     size_t cap = 0;
+    bool host_only = false;     // planner self-check (phmm_debug_plan): no device behind it, nothing is allocated
     int ensure(size_t bytes, std::atomic<size_t>* high_water = nullptr)
     {
-        if (bytes <= cap) return PHMM_OK;
+        if (bytes <= cap || host_only) return PHMM_OK;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
@@ -120,7 +121,7 @@ struct DevBuf
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p && !host_only) cudaFree(p);
         p = nullptr;
         cap = 0;
     }
@@ -130,21 +131,27 @@ struct HostBuf
 {
     void* p = nullptr;
     size_t cap = 0;
+    bool host_only = false;     // planner self-check: plain malloc instead of pinned memory
     int ensure(size_t bytes, std::atomic<size_t>* high_water = nullptr)
     {
         if (bytes <= cap) return PHMM_OK;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
+        release();
         size_t want = grow_to(bytes, high_water);
-        cudaError_t e = cudaMallocHost(&p, want);
-        if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        if (host_only) {
+            p = std::malloc(want);
+            if (!p) return fail(PHMM_ERR_MEM, "malloc failed");
+        } else {
+            cudaError_t e = cudaMallocHost(&p, want);
+            if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+        }
         cap = want;
         return PHMM_OK;
     }
     void release()
     {
-        if (p) cudaFreeHost(p);
+        if (p) {
+            if (host_only) std::free(p); else cudaFreeHost(p);
+        }
         p = nullptr;
         cap = 0;
     }
@@ -176,6 +183,14 @@ struct Slot
     uint32_t n_reads = 0, n_haps = 0, n_slow = 0, max_cols = 0;
     uint32_t n_launches = 0;
     float gpu_ms = 0.f, fwd_ms = 0.f;
+    size_t o_reads = 0, o_haps = 0, o_chunks = 0, o_ctas = 0, o_tasks = 0, o_slow = 0;   // arena offsets of the record arrays
+    size_t n_chunks = 0, n_ctas = 0, n_tasks = 0;
+
+    void set_host_only()
+    {
+        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt}) b->host_only = true;
+        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32}) b->host_only = true;
+    }
 
     int init()
     {
@@ -589,6 +604,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     const size_t o_rg = any_gcp ? place(read_bytes + 16) : 0;
     const size_t o_hb = place(hap_bytes + 16);
     s.in_bytes = off;
+    s.o_reads = o_reads; s.o_haps = o_haps; s.o_chunks = o_chunks; s.o_ctas = o_ctas; s.o_tasks = o_tasks; s.o_slow = o_slow;
+    s.n_chunks = chunks.size(); s.n_ctas = ctas.size(); s.n_tasks = task_reads.size();
     int rc;
     if ((rc = s.h_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
     if ((rc = s.d_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
@@ -1320,6 +1337,79 @@ int phmm_ubench(phmm_engine* e, int mode, uint32_t iters, float* ms_out, double*
     }
     if (ms_out) *ms_out = best;
     if (fma_per_s) *fma_per_s = (double)blocks * 256.0 * (double)iters * 32.0 * 2.0 / ((double)best * 1e-3);
+    return PHMM_OK;
+}
+
+// For tests (no GPU needed): run the planner alone on a flat batch and audit what it produced.  Every (read, haplotype) pair
+// must be computed exactly once — by exactly one forward-kernel warp slot whose chunk holds the haplotype, or by the per-pair
+// kernel — every read must sit in a bin that holds it, every CTA must respect its launch's shape.  out[0..15]:
+//   0 pairs  1 pairs covered by the wavefront kernel  2 per-pair-kernel pairs  3 pairs covered more than once  4 pairs missed
+//   5 warps launched  6 read slots  7 read slots filled  8 reads in a bin too small for them  9 launches  10 chunks
+//   11 lane-steps (sum over warps of 32 x RPT x steps)  12 cells (sum R x H over wavefront pairs)  13 CTA shape violations
+int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps, uint32_t busy_batches, uint64_t* out)
+{
+    if (!fb || !out) return fail(PHMM_ERR_ARG, "phmm_debug_plan: null argument");
+    phmm_engine e;
+    e.fma = fma_mode != PHMM_FMA_NONE;
+    e.cta_warps = std::min<uint32_t>(cta_warps, PHMM_WARPS);
+    e.busy_batches.store(busy_batches);
+    Slot s;
+    s.set_host_only();
+    std::vector<phmm_read> reads;
+    std::vector<phmm_hap> haps;
+    std::vector<RegionIn> regs;
+    flat_to_regions(fb, nullptr, 0, fb->n_regions, reads, haps, regs);
+    int rc = e.plan(s, regs);
+    if (rc != PHMM_OK) return rc;
+    const uint8_t* h = static_cast<const uint8_t*>(s.h_in.p);
+    const PhmmRead* R = reinterpret_cast<const PhmmRead*>(h + s.o_reads);
+    const PhmmHap* H = reinterpret_cast<const PhmmHap*>(h + s.o_haps);
+    const PhmmChunk* C = reinterpret_cast<const PhmmChunk*>(h + s.o_chunks);
+    const PhmmCta* T = reinterpret_cast<const PhmmCta*>(h + s.o_ctas);
+    const uint32_t* tasks = reinterpret_cast<const uint32_t*>(h + s.o_tasks);
+    const PhmmPair* slow = reinterpret_cast<const PhmmPair*>(h + s.o_slow);
+    for (int k = 0; k < 16; ++k) out[k] = 0;
+    std::vector<uint8_t> seen(std::max<uint64_t>(s.n_pairs, 1), 0);
+    out[0] = s.n_pairs;
+    out[9] = s.launches.size();
+    out[10] = s.n_chunks;
+    for (const FwdLaunch& fl : s.launches) {
+        const PhmmBin bin = kPhmmBins[fl.bin];
+        const uint32_t per_warp = 32u / (uint32_t)bin.lanes, per_cta = per_warp * fl.cta_warps;
+        for (uint32_t c = fl.cta_base; c < fl.cta_base + fl.n_ctas; ++c) {
+            const PhmmCta& cta = T[c];
+            const PhmmChunk& ch = C[cta.chunk];
+            if (cta.n_reads == 0 || cta.n_reads > per_cta || cta.read_begin + cta.n_reads > s.n_tasks) ++out[13];
+            const uint32_t warps = (cta.n_reads + per_warp - 1) / per_warp;
+            const uint64_t steps = ch.stream_len - 1 - (32 - (uint32_t)bin.lanes);
+            out[5] += warps;
+            out[6] += (uint64_t)warps * per_warp;
+            out[7] += cta.n_reads;
+            out[11] += (uint64_t)warps * 32u * (uint32_t)bin.rpt * steps;
+            for (uint32_t k = 0; k < cta.n_reads; ++k) {
+                const PhmmRead& rd = R[tasks[cta.read_begin + k]];
+                if (rd.len + 1 > (uint32_t)(bin.lanes * bin.rpt)) ++out[8];
+                for (uint32_t j = 0; j < ch.n_haps; ++j) {
+                    const PhmmHap& hp = H[ch.hap_begin + j];
+                    if (hp.pos == 0) continue;
+                    const uint64_t idx = (uint64_t)rd.out_off + hp.out_col;
+                    if (idx >= s.n_pairs || hp.out_col >= rd.n_haps) { ++out[13]; continue; }
+                    if (seen[idx]++) ++out[3];
+                    ++out[1];
+                    out[12] += (uint64_t)rd.len * hp.len;
+                }
+            }
+        }
+    }
+    for (uint32_t k = 0; k < s.n_slow; ++k) {
+        const uint64_t idx = slow[k].out_idx;
+        if (idx >= s.n_pairs) { ++out[13]; continue; }
+        if (seen[idx]++) ++out[3];
+        ++out[2];
+    }
+    for (uint64_t k = 0; k < s.n_pairs; ++k)
+        if (!seen[k]) ++out[4];
+    for (auto* b : {&s.h_in, &s.h_f32, &s.h_f64, &s.h_cnt}) b->release();
     return PHMM_OK;
 }
 

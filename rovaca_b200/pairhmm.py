@@ -128,6 +128,7 @@ def load_library():
     L.phmm_ubench.argtypes = [C.c_void_p, C.c_int, C.c_uint32, _f32p, _f64p]
     L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
     L.phmm_debug_tables.restype = None
+    L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, _u64p]
     _lib = L
     return L
 
@@ -139,6 +140,27 @@ def host_tables():
     phd, mmd = np.zeros(128, np.float64), np.zeros(8256, np.float64)
     L.phmm_debug_tables(ph.ctypes.data_as(_f32p), mm.ctypes.data_as(_f32p), phd.ctypes.data_as(_f64p), mmd.ctypes.data_as(_f64p))
     return ph, mm, phd, mmd
+
+
+PLAN_AUDIT_FIELDS = ("pairs", "wavefront_pairs", "per_pair_kernel_pairs", "covered_twice", "missed", "warps", "read_slots",
+                     "read_slots_filled", "reads_in_too_small_a_bin", "launches", "chunks", "lane_steps", "wavefront_cells",
+                     "shape_violations")
+
+
+def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 0, busy_batches: int = 1,
+               min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE) -> dict:
+    """Host only (no GPU): run the engine's planner on ``batch`` and audit its output — every pair computed exactly once,
+    every read in a bin that holds it, CTA shapes respected — plus the numbers that tell how well the lanes are used."""
+    L = load_library()
+    fb = _flat_c(batch, min_quality_threshold, pcr_option)
+    out = np.zeros(16, np.uint64)
+    rc = L.phmm_debug_plan(C.byref(fb), fma_mode, cta_warps, busy_batches, out.ctypes.data_as(_u64p))
+    if rc != 0:
+        raise PhmmError(f"phmm_debug_plan failed ({rc}): {L.phmm_last_error().decode()}")
+    d = {k: int(v) for k, v in zip(PLAN_AUDIT_FIELDS, out)}
+    d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)
+    d["lane_utilisation"] = d["wavefront_cells"] / max(2 * d["lane_steps"], 1)      # two haplotype streams per lane
+    return d
 
 
 def _ptr(a: Optional[np.ndarray], t):

@@ -1,0 +1,74 @@
+"""CPU: the engine's planner (length binning, remainder promotion, chunking into column streams, CTA sizing) audited without a
+GPU through phmm_debug_plan: every (read, haplotype) pair is computed exactly once, every read sits in a bin that holds it,
+and the lanes are used as well as DESIGN.md says."""
+import numpy as np
+import pytest
+
+from rovaca_b200 import workloads as wl
+from rovaca_b200 import pairhmm as ph
+
+B = np.frombuffer(b"ACGT", np.uint8)
+
+
+def _sound(a):
+    assert a["covered_twice"] == 0 and a["missed"] == 0, a
+    assert a["wavefront_pairs"] + a["per_pair_kernel_pairs"] == a["pairs"], a
+    assert a["reads_in_too_small_a_bin"] == 0 and a["shape_violations"] == 0, a
+
+
+@pytest.mark.parametrize("cta_warps", [0, 1, 2, 4])
+def test_cfg2_plan_is_tight(cta_warps):
+    a = ph.plan_audit(wl.cfg2(48, seed=3), cta_warps=cta_warps, busy_batches=8)
+    _sound(a)
+    assert a["pairs"] == 48 * 64 * 8 and a["per_pair_kernel_pairs"] == 0
+    assert a["slot_fill"] == 1.0                      # 64 reads: whole warps of four 8-lane reads
+    assert a["lane_utilisation"] > 0.96, a            # 150 rows in 152, 7 fill steps per 1200 columns
+
+
+def test_small_batches_are_cut_finer():
+    few, many = ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=16)
+    _sound(few)
+    _sound(many)
+    assert few["chunks"] > many["chunks"] and few["warps"] > many["warps"]       # latency over staging when the GPU is empty
+
+
+@pytest.mark.parametrize("make", [lambda: wl.cfg3(2, seed=3, n_reads=120, n_haps=11), lambda: wl.cfg4(6, seed=4, mix=True),
+                                  lambda: wl.cfg5(60, seed=5, post_trim_fraction=0.5), lambda: wl.cfg5(40, seed=6, post_trim_fraction=1.0)])
+@pytest.mark.parametrize("fma", [ph.FMA_AVX512, ph.FMA_NONE])
+def test_mixed_workloads_cover_every_pair_once(make, fma):
+    b = make()
+    for cta_warps in (0, 1, 4):
+        a = ph.plan_audit(b, fma_mode=fma, cta_warps=cta_warps)
+        _sound(a)
+        assert a["pairs"] == b.pairs()
+
+
+def test_promotion_fills_read_slots():
+    """A region whose reads scatter over many length bins: remainders are promoted into higher bins instead of each bin
+    running its own part-empty warp."""
+    rng = np.random.default_rng(7)
+    hap = B[rng.integers(0, 4, 300)]
+    reads = [dict(bases=B[rng.integers(0, 4, n)], qual=np.full(n, 30, np.uint8), mapq=60) for n in range(60, 152, 3)]   # 31 reads, 12 bins
+    b = wl.RegionBatch.from_regions([(reads, [hap, hap[::-1].copy()])] * 20)
+    a = ph.plan_audit(b, cta_warps=1, busy_batches=64)   # a busy device: one chunk per region
+    _sound(a)
+    assert a["slot_fill"] > 0.95, a                   # 31 reads in 8 warps of 4, not 12+ warps
+    assert a["chunks"] == 20 and a["warps"] == 20 * 8
+
+
+def test_out_of_envelope_shapes_go_to_the_pair_kernel():
+    rng = np.random.default_rng(8)
+    long_hap = B[rng.integers(0, 4, 23000)]            # beyond one shared-memory stream
+    reads = [dict(bases=B[rng.integers(0, 4, n)], qual=np.full(n, 30, np.uint8), mapq=60) for n in (1, 7, 8, 151, 152, 607, 608, 900)]
+    regs = [(reads, [long_hap, long_hap[:300].copy(), long_hap[:1].copy()])]
+    a = ph.plan_audit(wl.RegionBatch.from_regions(regs))
+    _sound(a)
+    assert a["per_pair_kernel_pairs"] == 8 + 2 * 2     # every read x the long haplotype, the two long reads x the other two
+    for r in reads:                                    # explicit per-base gap qualities: the generic bins (<= 383 bp)
+        r["gcp"] = np.full(len(r["bases"]), 11, np.uint8)
+    a = ph.plan_audit(wl.RegionBatch.from_regions(regs))
+    _sound(a)
+    assert a["per_pair_kernel_pairs"] == 8 + 3 * 2
+    empty = wl.RegionBatch.from_regions([([], [long_hap[:50].copy()]), (reads[:2], [])])
+    a = ph.plan_audit(empty)
+    assert a["pairs"] == 0 and a["warps"] == 0

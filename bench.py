@@ -27,6 +27,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 METRIC = "PairHMM GCUPS"
+WORKLOAD = "cfg2: 150bp reads x 300bp haplotypes, 8 haps x 64 reads per region (BASELINE.json configs[1])"
 FP32_INSTR_PER_CELL = 8            # 4 FMUL + 4 FFMA, SURVEY.md §8d
 FLOP_PER_CELL = 12                 # 8 mul + 4 add
 
@@ -163,7 +164,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": round(gcups, 3), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cfg2: 150bp reads x 300bp haplotypes, 8 haps x 64 reads per region", "regions_per_step": n_regions,
+        "config": {"workload": WORKLOAD, "regions_per_step": n_regions, "regions_per_gpu": args.regions,
                    "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18},
         "cpu_baseline": {"value": round(gcups, 3), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(gcups, 3), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -277,7 +278,7 @@ def ours_arm(args, rank, world, local_rank):
         "metric": METRIC, "value": round(value, 2), "unit": "GCUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "cfg2: 150bp reads x 300bp haplotypes, 8 haps x 64 reads per region (BASELINE.json configs[1])",
+        "config": {"workload": WORKLOAD,
                    "regions_per_gpu": args.regions, "cells_per_gpu_per_step": cells, "pairs_per_gpu_per_step": batch.pairs(),
                    "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18, "fma_mode": "avx512-contracted",
                    "l2_policy": "inputs larger than L2: ~270 MB touched per step (raw reads, packed rows, outputs) vs 126 MB L2",

@@ -296,6 +296,7 @@ struct phmm_engine
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
+    float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
     DevBuf d_tables;
     Stats stats;
 
@@ -695,6 +696,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     b.f64_count = static_cast<uint32_t*>(s.d_cnt.p);
     b.tables = static_cast<const PhmmTables*>(d_tables.p);
     b.n_reads = (uint32_t)reads.size();
+    b.rg_gapm = default_gapm;      // gap_conts() is the constant '+' - 33 = 10 for every read, read_record.cpp:205-210
+    b.rg_ii = default_ii;
 
     s.n_pairs = n_pairs;
     s.n_cells = n_cells;
@@ -1052,6 +1055,8 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
     int rc = e->d_tables.ensure(sizeof(PhmmTables));
     if (rc != PHMM_OK) return rc;
     CU(cudaMemcpy(e->d_tables.p, t.get(), sizeof(PhmmTables), cudaMemcpyHostToDevice));
+    e->default_gapm = t->gapm[10];
+    e->default_ii = t->ph2pr[10];
     for (uint32_t i = 0; i < e->n_workers; ++i) {
         e->slots.emplace_back(new Slot());
         if ((rc = e->slots.back()->init()) != PHMM_OK) return rc;

@@ -329,13 +329,14 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             }
         }
         if (RG) {
-            // one gap-continuation quality per read.  Pad rows keep mi = 0 and dd = 1; with a shared ii their I is
-            // ii x (I of the pad row above) = 0, except on the very first row of the group, which sees lane 0's own
-            // shuffled-back bottom row: that row multiplies by ii0 = 0 instead.  Their M is (finite) x prior 0 = 0.
-            const uint32_t qc = (p.words[rd.word_off] >> 21) & 127u;
-            gapm[0] = __ldg(&T->gapm[qc]);
-            ii[0] = __ldg(&T->ph2pr[qc]);
-            ii0 = lane == 0 ? 0.f : ii[0];
+            // One gap-continuation quality for the whole launch (the reference's constant 10): gapm and ii are kernel
+            // parameters, i.e. uniform-register operands of FFMA2 that cost no register-file read.  Pad rows keep mi = 0 and
+            // dd = 1; with the shared ii their I is ii x (I of the pad row above) = 0, except on the very first row of the
+            // group, which sees lane 0's own shuffled-back bottom row: that row multiplies by ii0 = 0 instead.  Their M is
+            // (finite) x prior 0 = 0.
+            gapm[0] = p.rg_gapm;
+            ii[0] = p.rg_ii;
+            ii0 = lane == 0 ? 0.f : p.rg_ii;
         }
         if ((int)lane * RPT - 1 < npad) padmask |= 1u << RPT;
 #pragma unroll
@@ -423,11 +424,11 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             float2 nM, nI, nD;
             if (RG) {                               // same operations, md == mi and one gapm / ii per read
                 float2 t = __fmul2_rn(pM, bc(mm[k]));
-                t = __ffma2_rn(pI, bc(gapm[0]), t);
-                t = __ffma2_rn(pD, bc(gapm[0]), t);
+                t = __ffma2_rn(pI, bc(p.rg_gapm), t);
+                t = __ffma2_rn(pD, bc(p.rg_gapm), t);
                 nM.x = __fmul_rn(t.x, px[k]);
                 nM.y = __fmul_rn(t.y, py[k]);
-                nI = __ffma2_rn(uI, bc(k == 0 ? ii0 : ii[0]), __fmul2_rn(uM, bc(mi[k])));
+                nI = __ffma2_rn(uI, bc(k == 0 ? ii0 : p.rg_ii), __fmul2_rn(uM, bc(mi[k])));
                 nD = __ffma2_rn(oD, bc(dd[k]), __fmul2_rn(oM, bc(mi[k])));
             } else if (FMA) {                       // SURVEY.md §8a, AVX-512 contraction
                 float2 t = __fmul2_rn(pM, bc(mm[k]));

@@ -29,6 +29,7 @@ struct PhmmBatchDev
     const PhmmPair* slow_pairs;   // out-of-envelope pairs routed to the per-pair kernel by the host
     const PhmmTables* tables;
     uint32_t n_reads;
+    float rg_gapm, rg_ii;         // reference-gap variant: 1 - ph2pr[gcp] and ph2pr[gcp] of the launch-wide gcp (10)
 };
 
 // Read-length bins of the wavefront kernel: a group of LANES lanes (a half warp or a whole warp) owns one read, lane l owns

@@ -19,6 +19,7 @@
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 
 enum { SEL_LOP = 0, SEL_NONE = 1, SEL_LDS32 = 2, SEL_LDS128 = 3 };
+__constant__ float c_gap[2];
 
 // Layout A (product): thread = RPT rows of one read x two haplotype streams in the f32x2 halves.
 template <int RPT, int SEL, bool SHFL, int WARPS, int LANES = 32, int MINB = 1, int CG = 0>
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) layoutA(const uint32_t* gbas
             for (uint32_t b = 0; b < 6; ++b) tbl[((b * ((RPT + 3) / 4) + k / 4) * blockDim.x + threadIdx.x) * 4 + (k % 4)] = (b == base || b == 4) ? pm[k] : pmm[k];
     }
     __syncthreads();
+    const float gapm_u = c_gap[0], ii_u = c_gap[1];           // kernel-wide constants (CG >= 3): constant-bank operands
     float2 Ml[RPT], Il[RPT], Dl[RPT];
 #pragma unroll
     for (int k = 0; k < RPT; ++k) { Ml[k] = bc(1.f); Il[k] = bc(0.5f); Dl[k] = bc(0.25f); }
@@ -97,12 +99,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) layoutA(const uint32_t* gbas
                 prior = bc(pm[k]);
             }
             float2 t = __fmul2_rn(pM, bc(mm[k]));
-            t = __ffma2_rn(pI, bc(CG ? gapm[0] : gapm[k]), t);
-            t = __ffma2_rn(pD, bc(CG ? gapm[0] : gapm[k]), t);
+            t = __ffma2_rn(pI, bc(CG >= 3 ? gapm_u : CG ? gapm[0] : gapm[k]), t);
+            t = __ffma2_rn(pD, bc(CG >= 3 ? gapm_u : CG ? gapm[0] : gapm[k]), t);
             float2 nM;
             if (SEL == SEL_LDS128) { nM.x = __fmul_rn(t.x, prior.x); nM.y = __fmul_rn(t.y, prior.y); } else nM = __fmul2_rn(t, prior);
-            const float2 nI = __ffma2_rn(uI, bc(CG ? (k == 0 ? ii[1] : ii[0]) : ii[k]), __fmul2_rn(uM, bc(mi[k])));
-            const float2 nD = __ffma2_rn(oD, bc(CG == 1 ? md[k] : CG == 2 ? ii[0] : ii[k]), __fmul2_rn(oM, bc(CG ? mi[k] : md[k])));
+            const float2 nI = __ffma2_rn(uI, bc(CG >= 3 ? (k == 0 ? ii[1] : ii_u) : CG ? (k == 0 ? ii[1] : ii[0]) : ii[k]), __fmul2_rn(uM, bc(mi[k])));
+            const float2 nD = __ffma2_rn(oD, bc(CG == 4 ? (k < 8 ? md[k] : ii_u) : (CG == 1 || CG == 3) ? md[k] : CG == 2 ? ii[0] : ii[k]), __fmul2_rn(oM, bc(CG ? mi[k] : md[k])));
             Ml[k] = nM; Il[k] = nI; Dl[k] = nD;
             pM = oM; pI = oI; pD = oD; uM = nM; uI = nI;
         }
@@ -556,12 +558,19 @@ int main()
     CK(cudaMalloc(&g_bases, 4096 * 4));
     CK(cudaMemcpy(g_bases, hb.data(), 4096 * 4, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&g_out, 256));
+    { const float hg[2] = {0.9f, 0.1f}; CK(cudaMemcpyToSymbol(c_gap, hg, sizeof(hg))); }
     const uint32_t L = 1232;
     const uint32_t LB = 2432;
     const size_t sA = (size_t)(L + 32) * 8;
 #define A(R, SEL, SH, W) run("A rpt" #R " " #SEL " shfl=" #SH " w" #W, layoutA<R, SEL, SH, W>, W, R, 2, sA + ((SEL) == SEL_LDS32 ? 4 * R * W * 32 * 4 : (SEL) == SEL_LDS128 ? 6 * ((R + 3) / 4) * W * 32 * 16 : 0), L)
 #define AL(R, W, LN, MB) run("A rpt" #R " LDS128 w" #W " lanes" #LN " minb" #MB, layoutA<R, SEL_LDS128, true, W, LN, MB>, W, R, 2, sA + 6 * ((R + 3) / 4) * W * 32 * 16, L)
 #define AC(R, W, LN, MB, CG) run("A rpt" #R " LDS128 w" #W " lanes" #LN " minb" #MB " constgcp" #CG, layoutA<R, SEL_LDS128, true, W, LN, MB, CG>, W, R, 2, sA + 6 * ((R + 3) / 4) * W * 32 * 16, L)
+    AC(19, 4, 8, 2, 3);
+    AC(19, 4, 8, 2, 4);
+    AC(16, 4, 8, 2, 4);
+    AC(16, 4, 8, 3, 4);
+    AC(12, 4, 8, 3, 4);
+    AC(10, 4, 8, 4, 4);
     AC(10, 4, 16, 3, 1);
     AC(10, 4, 16, 4, 1);
     AC(10, 4, 16, 4, 2);

@@ -355,8 +355,14 @@ struct phmm_engine
 // Planning + packing
 // ------------------------------------------------------------------------------------------------
 
+#ifndef PHMM_PLAN_TIMING      // section timers for tools/plan_timing.cpp; compiled out of the library
+#define PT_NOW() 0
+#define PT_ADD(i, a, b) (void)0
+#endif
+
 int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
 {
+    [[maybe_unused]] const auto pt0 = PT_NOW();
     uint64_t n_reads = 0, n_haps = 0, read_bytes = 0, hap_bytes = 0, n_pairs = 0, n_cells = 0;
     bool any_ins = false, any_del = false, any_gcp = false;
     for (const RegionIn& r : regs) {
@@ -412,11 +418,19 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first; uint32_t n; };
     std::vector<std::vector<Group>> groups(kPhmmNumBins);
     std::vector<std::vector<uint32_t>> group_reads(kPhmmNumBins);
-    std::vector<uint32_t> order, region_chunks;
+    std::vector<uint32_t> order, region_chunks, idx;
+    // read length -> bin, for the lengths the wavefront kernels take (a table instead of a search per read)
+    uint8_t bin_lut[640];
+    for (uint32_t len = 0; len < 640; ++len) {
+        const int b = phmm_bin_of(len, refgaps);
+        bin_lut[len] = b < 0 ? 255 : (uint8_t)b;
+    }
     std::vector<std::vector<uint32_t>> by_bin(kPhmmNumBins);
 
     uint64_t raw_off = 0, hap_off = 0, out_off = 0;
     uint32_t max_cols = 0;
+    [[maybe_unused]] const auto pt1 = PT_NOW();
+    PT_ADD(0, pt0, pt1);
     for (const RegionIn& r : regs) {
         RegionPlan rp{};
         rp.read_begin = (uint32_t)reads.size();
@@ -463,7 +477,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
                     if (acc >= per_chunk) break;
                 }
                 // longest first onto the lighter stream
-                std::vector<uint32_t> idx(order.begin() + at, order.begin() + end);
+                idx.assign(order.begin() + at, order.begin() + end);
                 std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return r.haps[a].len > r.haps[b].len; });
                 uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
                 for (uint32_t j : idx) {
@@ -505,7 +519,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
             const uint32_t rid = (uint32_t)reads.size();
             reads.push_back(d);
             s.read_len.push_back(in.len);
-            const int b = phmm_bin_of(in.len, refgaps);
+            const int b = in.len < 640 ? (bin_lut[in.len] == 255 ? -1 : (int)bin_lut[in.len]) : -1;
             if (b >= 0) by_bin[b].push_back(rid);
             if (b < 0 || !all_haps_in_stream)
                 for (uint32_t j = 0; j < r.n_haps; ++j) {
@@ -540,6 +554,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         out_off += (uint64_t)r.n_reads * r.n_haps;
     }
 
+    [[maybe_unused]] const auto pt2 = PT_NOW();
+    PT_ADD(1, pt1, pt2);
     // CTAs per bin, longest streams first
     std::vector<PhmmCta> ctas;
     std::vector<uint32_t> task_reads;
@@ -589,6 +605,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         return (uint64_t)x.n_ctas * x.cta_warps * kPhmmBins[x.bin].rpt > (uint64_t)y.n_ctas * y.cta_warps * kPhmmBins[y.bin].rpt;
     });
 
+    [[maybe_unused]] const auto pt3 = PT_NOW();
+    PT_ADD(2, pt2, pt3);
     // ---- arena layout ---------------------------------------------------------------------------
     size_t off = 0;
     auto place = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
@@ -617,6 +635,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::memcpy(h + o_ctas, ctas.data(), ctas.size() * sizeof(PhmmCta));
     std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
     std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
+    [[maybe_unused]] const auto pt4 = PT_NOW();
+    PT_ADD(3, pt3, pt4);
     {
         // gather the raw bytes; callers that keep their reads back to back (flat batches, BAM-like buffers) get one
         // memcpy per contiguous run instead of one per read
@@ -661,6 +681,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         rb_run.flush(h + o_rb); rq_run.flush(h + o_rq); ri_run.flush(h + o_ri); rd_run.flush(h + o_rd); rg_run.flush(h + o_rg);
         hb_run.flush(h + o_hb);
     }
+    PT_ADD(4, pt4, PT_NOW());
     // ---- device-only buffers --------------------------------------------------------------------
     const size_t pairs_alloc = std::max<uint64_t>(n_pairs, 1);
     if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t), &high_water[1])) != PHMM_OK) return rc;
@@ -1042,6 +1063,8 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
     e->warp_slots = (uint32_t)prop.multiProcessorCount * 8;
     // host workers: one rank per GPU is the deployment, so a rank may count on its share of the cores
     e->n_workers = std::max(2u, std::min(6u, std::thread::hardware_concurrency() / (unsigned)std::max(ndev, 1)));
+    if (const char* env = std::getenv("PHMM_B200_WORKERS"))          // deployment override of the default only
+        if (std::atoi(env) > 0) e->n_workers = std::min(32, std::atoi(env));
     if (cfg) {
         e->fma = cfg->fma_mode != PHMM_FMA_NONE;
         if (cfg->n_workers) e->n_workers = std::min<uint32_t>(cfg->n_workers, 32);

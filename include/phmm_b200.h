@@ -122,7 +122,13 @@ typedef struct phmm_flat_batch
     const uint8_t* hap_bases;
     int32_t min_quality_threshold;
     int32_t pcr_model;
+    uint32_t flags;                   /* PHMM_FLAT_* */
 } phmm_flat_batch;
+
+/* The byte blobs (read_bases, read_qual, read_ins/del/gcp, hap_bases) live in page-locked host memory (cudaHostAlloc,
+ * cudaHostRegister, a pinned torch tensor): the engine copies them to the device straight from there instead of gathering
+ * them into its own staging arena first. */
+#define PHMM_FLAT_PINNED 1u
 
 /* Region g writes its [n_haps][n_reads] matrix at likelihoods + lik_off[g] (lik_off[g] = sum over
  * earlier regions of n_haps*n_reads), its kept indices at kept_idx + reg_read_off[g]. */

@@ -80,6 +80,7 @@ struct RegionIn
     uint32_t* n_kept_out;   // where to store n_kept
     uint64_t* n_fp64_out;   // accumulates (may be null)
     uint32_t* n_fp64_out32; // per-region (may be null)
+    bool pinned_src;        // the read / haplotype bytes live in page-locked memory the device can read directly
 };
 
 struct RegionPlan
@@ -179,6 +180,9 @@ struct Slot
     std::vector<FwdLaunch> launches;
     std::vector<uint32_t> read_len;      // per read (for the filter)
     size_t in_bytes = 0;
+    size_t staged_bytes = 0;             // leading part of the arena that goes through the pinned staging copy
+    struct DirectCopy { size_t dst; const uint8_t* src; size_t len; };
+    std::vector<DirectCopy> direct;      // byte blobs copied straight from the caller's page-locked buffers
     uint64_t n_pairs = 0, n_cells = 0, n_words = 0;
     uint32_t n_reads = 0, n_haps = 0, n_slow = 0, max_cols = 0;
     uint32_t n_launches = 0;
@@ -639,47 +643,60 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     PT_ADD(3, pt3, pt4);
     {
         // gather the raw bytes; callers that keep their reads back to back (flat batches, BAM-like buffers) get one
-        // memcpy per contiguous run instead of one per read
+        // memcpy per contiguous run instead of one per read.  When the caller says its buffers are page-locked and the runs
+        // are few, nothing is gathered at all: the runs become host-to-device copies of their own (launch()).
         struct Run
         {
             const uint8_t* src = nullptr;
             size_t len = 0, dst = 0;
-            void add(uint8_t* base, const uint8_t* p, size_t n, size_t at)
+            std::vector<Slot::DirectCopy>* runs;
+            void add(const uint8_t* p, size_t n, size_t at)
             {
                 if (src && p == src + len && at == dst + len) {
                     len += n;
                     return;
                 }
-                if (src) std::memcpy(base + dst, src, len);
+                flush();
                 src = p;
                 len = n;
                 dst = at;
             }
-            void flush(uint8_t* base)
+            void flush()
             {
-                if (src) std::memcpy(base + dst, src, len);
+                if (src && len) runs->push_back(Slot::DirectCopy{dst, src, len});
                 src = nullptr;
             }
-        } rb_run, rq_run, ri_run, rd_run, rg_run, hb_run;
+        };
+        std::vector<Slot::DirectCopy> runs;
+        Run rb_run{nullptr, 0, 0, &runs}, rq_run = rb_run, ri_run = rb_run, rd_run = rb_run, rg_run = rb_run, hb_run = rb_run;
+        bool pinned = true;
         size_t ro = 0, ho = 0;
         for (const RegionIn& r : regs) {
             if (r.n_reads == 0 || r.n_haps == 0) continue;
+            pinned &= r.pinned_src;
             for (uint32_t k = 0; k < r.n_reads; ++k) {
                 const phmm_read& in = r.reads[k];
-                rb_run.add(h + o_rb, in.bases, in.len, ro);
-                rq_run.add(h + o_rq, in.qual, in.len, ro);
-                if (in.ins) ri_run.add(h + o_ri, in.ins, in.len, ro);
-                if (in.del) rd_run.add(h + o_rd, in.del, in.len, ro);
-                if (in.gcp) rg_run.add(h + o_rg, in.gcp, in.len, ro);
+                rb_run.add(in.bases, in.len, o_rb + ro);
+                rq_run.add(in.qual, in.len, o_rq + ro);
+                if (in.ins) ri_run.add(in.ins, in.len, o_ri + ro);
+                if (in.del) rd_run.add(in.del, in.len, o_rd + ro);
+                if (in.gcp) rg_run.add(in.gcp, in.len, o_rg + ro);
                 ro += in.len;
             }
             for (uint32_t j = 0; j < r.n_haps; ++j) {
-                hb_run.add(h + o_hb, r.haps[j].bases, r.haps[j].len, ho);
+                hb_run.add(r.haps[j].bases, r.haps[j].len, o_hb + ho);
                 ho += r.haps[j].len;
             }
         }
-        rb_run.flush(h + o_rb); rq_run.flush(h + o_rq); ri_run.flush(h + o_ri); rd_run.flush(h + o_rd); rg_run.flush(h + o_rg);
-        hb_run.flush(h + o_hb);
+        rb_run.flush(); rq_run.flush(); ri_run.flush(); rd_run.flush(); rg_run.flush(); hb_run.flush();
+        s.direct.clear();
+        s.staged_bytes = s.in_bytes;
+        if (pinned && !s.h_in.host_only && runs.size() <= 24) {
+            s.direct = std::move(runs);
+            s.staged_bytes = o_rb;                   // records only; the byte blobs follow them in the arena
+        } else {
+            for (const Slot::DirectCopy& c : runs) std::memcpy(h + c.dst, c.src, c.len);
+        }
     }
     PT_ADD(4, pt4, PT_NOW());
     // ---- device-only buffers --------------------------------------------------------------------
@@ -738,7 +755,9 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
 int phmm_engine::launch(Slot& s, bool copy_in)
 {
     if (copy_in && s.in_bytes) {
-        CU(cudaMemcpyAsync(s.d_in.p, s.h_in.p, s.in_bytes, cudaMemcpyHostToDevice, s.stream));
+        CU(cudaMemcpyAsync(s.d_in.p, s.h_in.p, s.staged_bytes, cudaMemcpyHostToDevice, s.stream));
+        for (const Slot::DirectCopy& c : s.direct)
+            CU(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_in.p) + c.dst, c.src, c.len, cudaMemcpyHostToDevice, s.stream));
         stats.h2d += s.in_bytes;
     }
     CU(cudaMemsetAsync(s.d_cnt.p, 0, 4, s.stream));
@@ -995,6 +1014,7 @@ static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uin
         r.n_haps = (uint32_t)(fb->reg_hap_off[g + 1] - h0);
         r.thr = fb->min_quality_threshold;
         r.pcr = fb->pcr_model;
+        r.pinned_src = (fb->flags & PHMM_FLAT_PINNED) != 0;
         r.out = phmm_result{};
         r.n_kept_out = nullptr;
         r.n_fp64_out = nullptr;
@@ -1257,7 +1277,9 @@ int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* fb, phmm_residen
     if (rc != PHMM_OK) return rc;
     flat_to_regions(fb, nullptr, 0, fb->n_regions, r->reads, r->haps, r->regs);
     if ((rc = e->plan(r->slot, r->regs)) != PHMM_OK) return rc;
-    CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.in_bytes, cudaMemcpyHostToDevice, r->slot.stream));
+    CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.staged_bytes, cudaMemcpyHostToDevice, r->slot.stream));
+    for (const Slot::DirectCopy& c : r->slot.direct)
+        CU(cudaMemcpyAsync(static_cast<uint8_t*>(r->slot.d_in.p) + c.dst, c.src, c.len, cudaMemcpyHostToDevice, r->slot.stream));
     CU(cudaStreamSynchronize(r->slot.stream));
     e->stats.h2d += r->slot.in_bytes;
     *out = r.release();

@@ -21,6 +21,7 @@ from .workloads import RegionBatch, _as_u8
 
 PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE, PCR_CONSERVATIVE = 0, 1, 2, 3      # common/enum.h:8
 FMA_AVX512, FMA_NONE = 1, 2
+FLAT_PINNED = 1                                                          # phmm_flat_batch.flags
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _u8p = C.POINTER(C.c_uint8)
@@ -62,7 +63,7 @@ class _FlatBatch(C.Structure):
     _fields_ = [("n_regions", C.c_uint32), ("reg_read_off", _u64p), ("reg_hap_off", _u64p), ("read_len", _u32p),
                 ("read_mapq", _u8p), ("read_off", _u64p), ("read_bases", _u8p), ("read_qual", _u8p), ("read_ins", _u8p),
                 ("read_del", _u8p), ("read_gcp", _u8p), ("hap_len", _u32p), ("hap_off", _u64p), ("hap_bases", _u8p),
-                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32)]
+                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32), ("flags", C.c_uint32)]
 
 
 class _FlatResult(C.Structure):
@@ -211,7 +212,8 @@ def _flat_c(batch: RegionBatch, thr: int, pcr: int) -> _FlatBatch:
     return _FlatBatch(batch.n_regions, _ptr(batch.reg_read_off, _u64p), _ptr(batch.reg_hap_off, _u64p), _ptr(batch.read_len, _u32p),
                       _ptr(batch.read_mapq, _u8p), _ptr(batch.read_off, _u64p), _ptr(batch.read_bases, _u8p),
                       _ptr(batch.read_qual, _u8p), _ptr(batch.read_ins, _u8p), _ptr(batch.read_del, _u8p), _ptr(batch.read_gcp, _u8p),
-                      _ptr(batch.hap_len, _u32p), _ptr(batch.hap_off, _u64p), _ptr(batch.hap_bases, _u8p), thr, pcr)
+                      _ptr(batch.hap_len, _u32p), _ptr(batch.hap_off, _u64p), _ptr(batch.hap_bases, _u8p), thr, pcr,
+                      FLAT_PINNED if getattr(batch, "pinned", False) else 0)
 
 
 class Resident:

@@ -33,6 +33,23 @@ class RegionBatch:
     read_del: Optional[np.ndarray] = None
     read_gcp: Optional[np.ndarray] = None
     name: str = ""
+    pinned: bool = False       # the byte blobs are views of page-locked memory (see pin())
+
+    def pin(self) -> "RegionBatch":
+        """Move the byte blobs into page-locked host memory (pinned torch tensors, viewed as numpy arrays) so that the
+        engine can copy them to the device without staging them first (PHMM_FLAT_PINNED)."""
+        import torch
+        keep = []
+        for name in ("read_bases", "read_qual", "read_ins", "read_del", "read_gcp", "hap_bases"):
+            a = getattr(self, name)
+            if a is None:
+                continue
+            t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+            keep.append(t)
+            setattr(self, name, t.numpy())
+        self._pinned_tensors = keep      # the tensors own the memory
+        self.pinned = True
+        return self
 
     @property
     def n_regions(self) -> int:

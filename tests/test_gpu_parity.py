@@ -250,6 +250,17 @@ def test_flat_equals_per_region_and_resident(engine, orc):
         assert np.array_equal(k0, flat.kept(g)) and np.array_equal(_bits64(m0), _bits64(flat.matrix(g)))
 
 
+def test_pinned_flat_batch_is_copied_directly(engine):
+    """PHMM_FLAT_PINNED: blobs in page-locked memory are copied to the device without the staging gather; same bytes out."""
+    batch = wl.cfg5(30, seed=23)
+    want = engine.run_flat(batch, raw=True)
+    s0 = engine.stats()
+    got = engine.run_flat(wl.cfg5(30, seed=23).pin(), raw=True)
+    s1 = engine.stats()
+    assert np.array_equal(_bits32(want.raw_f32), _bits32(got.raw_f32)) and np.array_equal(_bits64(want.likelihoods), _bits64(got.likelihoods))
+    assert np.array_equal(want.n_kept, got.n_kept) and s1["h2d_bytes"] > s0["h2d_bytes"]
+
+
 def test_concurrent_callers(engine, orc):
     """The reference calls call_pairhmm from up to --nthreads pool workers; submit/wait must be re-entrant."""
     batch = wl.cfg5(24, seed=22)

@@ -5,28 +5,30 @@
 // states M/I/D, 4 FMUL + 4 FFMA per cell in the exact order GCC gives the reference's AVX-512 TUs
 // (SURVEY.md §8a), flush-to-zero, result = (sum_c M[R][c]) + (sum_c I[R][c]).
 //
-// Mapping (B200-first, not a port of the AVX lane layout):
-//   * a warp owns one read; lane l owns rows l*RPT .. l*RPT+RPT-1 of the table, the read is
-//     top-padded to 32*RPT rows with "boundary generator" rows (prior = 0, dd = 1) that reproduce the
-//     reference's row -1 (M = I = 0, D = 2^120/H) for any garbage fed in from above, so lane 0 needs no
-//     special case and the last read row is always the last register row of lane 31;
-//   * the warp sweeps the columns as an anti-diagonal wavefront: at step s lane l is at stream
-//     position s - l and receives the bottom row (M, I, D) of lane l-1 with three __shfl_up_sync;
-//   * every thread carries TWO haplotype streams at once in the two halves of packed f32x2
-//     registers (FFMA2 / FMUL2 / FADD2, one issue slot for two cells); the per-row transition
-//     probabilities and priors stay scalar and enter the packed instructions as broadcast operands;
-//   * all haplotypes of a region are chained head to tail in the two streams, staged once per CTA in
-//     shared memory as ready-to-test one-hot words, so the 31-step fill/drain is paid once per
-//     region, not once per pair; the first column of each haplotype carries a flag bit that makes
-//     the lane emit the finished pair (lane 31) and re-seed its column -1 state;
-//   * read rows (packed q/ins/del/gcp/base words written by the prep kernel) are turned into the
-//     eight per-row floats once per read through host-built libm tables and then live in registers
-//     for the whole sweep.
+// Mapping (B200-first, not a port of the AVX lane layout; DESIGN.md §4-5 has the measurements behind each choice):
+//   * a group of LANES lanes (8, 16 or 32) owns one read; lane l owns rows l*RPT .. l*RPT+RPT-1 of the table, the read is
+//     top-padded to LANES*RPT rows with "boundary generator" rows (prior = 0, dd = 1) that reproduce the reference's row -1
+//     (M = I = 0, D = 2^120/H) for any garbage fed in from above, so lane 0 needs no special case and the last read row
+//     is always the last register row of the group's last lane.  Tall, narrow groups (8 x 19 rows for 150/151-bp reads)
+//     need the fewest shuffles per cell and the least padding;
+//   * the group sweeps the columns as an anti-diagonal wavefront: at step s lane l is at stream position s - l and
+//     receives the bottom row (M, I, D) of lane l-1 with three __shfl_up_sync per stream;
+//   * every thread carries TWO haplotype streams at once in the two halves of packed f32x2 registers (FFMA2 / FMUL2 /
+//     FADD2); the per-row transition probabilities stay scalar and enter the packed instructions as broadcast operands —
+//     from registers, or, for the gap parameters the reference keeps constant, from uniform registers (no register-file
+//     read: the register file's read bandwidth, not the FMA pipe, is what bounds this kernel);
+//   * all haplotypes of a region are chained head to tail in the two streams, staged once per CTA in shared memory as
+//     byte offsets of their base class's prior table, so the fill/drain is paid once per region, not once per pair; the
+//     first column of each haplotype carries a flag bit that makes the lane emit the finished pair (last lane) and re-seed
+//     its column -1 state;
+//   * the match / mismatch prior of a cell is not selected (LOP3 + FSEL per cell) but fetched: every thread keeps a private
+//     table prior[base class][row] in shared memory and reads four rows per LDS.128;
+//   * read rows (packed q/ins/del/gcp/base words written by the prep kernel) are turned into the per-row floats once per
+//     read through host-built libm tables and then live in registers for the whole sweep.
 //
-// Toolchain hazard, checked by tests/test_build_audit.py: ptxas 12.9 contracts a single-use
-// mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 although both carry .rn.  Every packed product
-// below either feeds an FMA addend or has a second consumer; the un-contracted (AVX2) arithmetic
-// variant is therefore written with scalar intrinsics, which ptxas leaves alone.
+// Toolchain hazard, checked by tests/test_abi.py::test_sass_audit: ptxas 12.9 contracts a single-use mul.rn.f32x2 feeding an
+// add.rn.f32x2 into FFMA2 although both carry .rn.  Every packed product below either feeds an FMA addend or has a second
+// consumer; the un-contracted (AVX2) arithmetic variant is therefore written with scalar intrinsics, which ptxas leaves alone.
 #include <cuda_runtime.h>
 #include <stdint.h>
 

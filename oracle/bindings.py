@@ -56,6 +56,18 @@ class _OrcHap(C.Structure):
     _fields_ = [("bases", _u8p), ("len", C.c_uint32)]
 
 
+SW_REALIGN = (10, -15, -30, -5)        # sw_parameters_genotype, common/base/lib/sw_avx/sw_avx.c:14
+SW_ASSEMBLE = (200, -150, -260, -11)   # sw_parameters_assemble, :13
+
+
+class _SwParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
+
+
+def cigar_string(cigar) -> str:
+    return "".join(f"{int(c) >> 4}{'MIDNSHP=X'[int(c) & 15]}" for c in cigar)
+
+
 class Oracle:
     """Scalar restatement (phmm_oracle.c)."""
 
@@ -82,6 +94,8 @@ class Oracle:
         L.orc_region.restype = C.c_int64
         L.orc_region.argtypes = [C.POINTER(_OrcRead), C.c_uint32, C.POINTER(_OrcHap), C.c_uint32, C.c_int32, C.c_int, C.c_int,
                                  _f64p, _u32p, _u32p, _f32p, _f64p]
+        L.orc_sw_align.restype = C.c_int32
+        L.orc_sw_align.argtypes = [_u8p, C.c_int32, _u8p, C.c_int32, C.c_void_p, _u32p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.orc_init()
 
     # tables -------------------------------------------------------------------------------
@@ -107,6 +121,16 @@ class Oracle:
         hap, rs, q, ins, dele, gcp = map(_u8, (hap, rs, q, ins, dele, gcp))
         return float(self.lib.orc_pair_f64(_p(hap, _u8p), len(hap), _p(rs, _u8p), _p(q, _u8p), _p(ins, _u8p),
                                            _p(dele, _u8p), _p(gcp, _u8p), len(rs)))
+
+    def sw_align(self, seq1, seq2, params=SW_REALIGN):
+        """Scalar restatement of the reference's Smith-Waterman (oracle/sw_oracle.c) -> (cigar, alignment_offset, score)."""
+        a, b = _u8(seq1), _u8(seq2)
+        cig = np.zeros(4096, np.uint32)
+        off, score = C.c_int32(0), C.c_int32(0)
+        prm = _SwParams(*params)
+        n = self.lib.orc_sw_align(_p(a, _u8p), len(a), _p(b, _u8p), len(b), C.byref(prm), _p(cig, _u32p), len(cig), C.byref(off),
+                                  C.byref(score))
+        return (None if n < 0 else cig[:n].copy()), int(off.value), int(score.value)
 
     def log10_likelihood(self, raw_f32, raw_f64=float("nan")) -> float:
         return float(self.lib.orc_log10_likelihood(C.c_float(float(raw_f32)), C.c_double(raw_f64)))
@@ -195,6 +219,21 @@ class Ref:
         L.ref_bench_regions.argtypes = [C.c_int, C.c_int, C.c_uint32, _u64p, _u64p, _u8p, _u8p, _u64p, _u32p, _u8p, _u8p, _u64p,
                                         _u32p, C.c_int32, C.c_int, _f64p]
         self.avx512 = bool(L.ref_has_avx512())
+        L.ref_sw_align.restype = C.c_int
+        L.ref_sw_align.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                   C.POINTER(C.c_int)]
+
+    def sw_align(self, seq1, seq2, assemble: bool = False, isa: int = -1):
+        """The reference's Smith-Waterman (sw_avx.c / sw_avx2.c): seq2 (read) against seq1 (haplotype).
+        -> (cigar uint32[], alignment_offset, score), cigar None where the reference gives up (>= 2048 bases)."""
+        a, b = _u8(seq1), _u8(seq2)
+        cig = np.zeros(4096, np.uint32)
+        off, score, bound = C.c_int(0), C.c_int(0), C.c_int(0)
+        n = self.lib.ref_sw_align(isa, int(assemble), _p(a, _u8p), len(a), _p(b, _u8p), len(b), _p(cig, _u32p), len(cig), C.byref(off),
+                                  C.byref(score), C.byref(bound))
+        if n == -2:
+            raise RuntimeError("ref_sw_align: bad arguments")
+        return (None if n < 0 else cig[:n].copy()), int(off.value), int(score.value)
 
     def pair_f32(self, isa: int, hap, rs, q, ins, dele, gcp) -> np.float32:
         hap, rs, q, ins, dele, gcp = map(_u8, (hap, rs, q, ins, dele, gcp))

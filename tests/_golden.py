@@ -50,3 +50,16 @@ def pcr():
         so += n
         co += 3 * n
     return out
+
+
+def sw():
+    """-> list of dict(hap, read, realign=(cigar, offset, score), assemble=(cigar, offset, score)) from the reference's sw_avx.c."""
+    z = np.load(os.path.join(HERE, "sw.npz"))
+    out = []
+    for k in range(int(z["n"][0])):
+        d = dict(hap=z[f"hap{k}"], read=z[f"read{k}"])
+        for tag, name in (("r", "realign"), ("a", "assemble")):
+            off, score = (int(x) for x in z[f"meta_{tag}{k}"])
+            d[name] = (z[f"cig_{tag}{k}"], off, score)
+        out.append(d)
+    return out

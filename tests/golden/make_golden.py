@@ -7,6 +7,7 @@ The reference ships no PairHMM vectors of its own, so these file
   pairs.npz    per-pair raw FP32 sums from core/avx512_s.cpp, core/avx2_s.cpp and rovaca/avx_512_float.cc
   regions.npz  whole-region outputs of call_old_pairhmm / call_new_pairhmm002 (matrix bits, kept reads)
   pcr.npz      apply_pcr_error_model / find_tandem_repeat_units outputs
+  sw.npz       score / alignment offset / CIGAR of common/base/lib/sw_avx/sw_avx.c (the step after the path)
 """
 import os
 import sys
@@ -130,5 +131,53 @@ def main():
     print("golden vectors written:", len(lens), "pairs,", len(regions), "regions,", len(seqs), "PCR sequences")
 
 
+def sw_cases(rng, n=160):
+    """(haplotype, read) pairs for the Smith-Waterman step after the path: true sub-sequences with SNPs / indels / overhangs,
+    unrelated sequences, low-complexity repeats (score ties), and the edge lengths."""
+    out = []
+    for t in range(n):
+        H, R = int(rng.integers(1, 420)), int(rng.integers(1, 200))
+        hap = B[rng.integers(0, 4, H)]
+        kind = t % 5
+        if kind == 4 or H < 8:
+            rd = B[rng.integers(0, 4, R)]
+        elif kind == 3:
+            hap = np.tile(B[rng.integers(0, 4, int(rng.integers(1, 4)))], 210)[:H]
+            rd = hap[: max(1, min(R, H))].copy()
+            if len(rd) > 4:
+                rd = np.delete(rd, int(rng.integers(1, len(rd) - 1)))
+        else:
+            o = int(rng.integers(0, H - 4))
+            rd = hap[o:o + R].copy()
+            m = rng.random(len(rd)) < 0.03
+            rd[m] = B[rng.integers(0, 4, int(m.sum()))]
+            if kind >= 1 and len(rd) > 10:
+                p, k = int(rng.integers(1, len(rd) - 1)), int(rng.integers(1, 12))
+                rd = np.concatenate([rd[:p], B[rng.integers(0, 4, k)], rd[p:]]) if rng.random() < 0.5 else np.concatenate([rd[:p], rd[p + k:]])
+            if kind == 2:
+                rd = np.concatenate([B[rng.integers(0, 4, int(rng.integers(1, 10)))], rd, B[rng.integers(0, 4, int(rng.integers(0, 6)))]])
+        out.append((hap, rd))
+    return out
+
+
+def make_sw():
+    """tests/golden/sw.npz: score, alignment offset and CIGAR of the UNMODIFIED reference Smith-Waterman
+    (common/base/lib/sw_avx/sw_avx.c, compiled in place) for both parameter sets."""
+    ref = ob.ref()
+    assert ref is not None, "needs oracle/_ref (make -C oracle with /root/reference present)"
+    rng = np.random.default_rng(20261018)
+    cases = sw_cases(rng)
+    rec = dict(n=np.array([len(cases)]))
+    for k, (hap, rd) in enumerate(cases):
+        rec[f"hap{k}"], rec[f"read{k}"] = hap, rd
+        for tag, asm in (("r", False), ("a", True)):
+            cig, off, score = ref.sw_align(hap, rd, asm)
+            rec[f"cig_{tag}{k}"], rec[f"meta_{tag}{k}"] = cig, np.array([off, score], np.int64)
+    np.savez_compressed(os.path.join(HERE, "sw.npz"), **rec)
+    print("sw.npz:", len(cases), "cases")
+
+
 if __name__ == "__main__":
-    main()
+    if "--sw" not in sys.argv:       # --sw: only the Smith-Waterman vectors
+        main()
+    make_sw()

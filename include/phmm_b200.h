@@ -184,6 +184,45 @@ int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* r
 void phmm_resident_free(phmm_engine* e, phmm_resident* r);
 uint32_t phmm_resident_launches(const phmm_resident* r);   /* kernels one phmm_resident_run launches */
 
+/* ---- the step after the path: read -> best-haplotype realignment ----------------------------
+ * Replaces the per-read call sw->avx_function(sw) (common/base/include/smithwaterman_common.h:95; sw_avx512_run /
+ * sw_avx2_run, common/base/lib/sw_avx/sw_avx.c:492-504) that AlignmentUtils::create_read_aligned_to_ref makes
+ * (genotype/utils/alignment_utils.cpp:574-579) for every read of a region — and the same call of the assembler
+ * (apply/assemble/hc_assemble_cigar_cacl.c:427) — by one batched call.  Score, alignment offset and CIGAR are identical to
+ * the reference's. */
+typedef struct phmm_sw_params       /* sw_parameters, smithwaterman_common.h:52-58 */
+{
+    int32_t match, mismatch, gap_open, gap_extend;
+} phmm_sw_params;
+/* the reference's two parameter sets (sw_avx.c:13-14) */
+#define PHMM_SW_PARAMS_REALIGN {10, -15, -30, -5}       /* sw_avx_init(0): read vs best haplotype */
+#define PHMM_SW_PARAMS_ASSEMBLE {200, -150, -260, -11}  /* sw_avx_init(1): haplotype vs reference */
+
+typedef struct phmm_sw_pair
+{
+    const uint8_t* ref;      /* lib_sw_avx.seq1 / len1: the haplotype (or reference) */
+    uint32_t ref_len;
+    const uint8_t* read;     /* lib_sw_avx.seq2 / len2: the read (or haplotype) */
+    uint32_t read_len;
+} phmm_sw_pair;
+
+typedef struct phmm_sw_result
+{
+    uint32_t* cigar;             /* caller buffer; element = length << 4 | op, op 0 M, 1 I, 2 D, 4 S (lib_sw_avx.cigar) */
+    uint32_t cigar_cap;
+    uint32_t n_cigar;            /* out: lib_sw_avx.cigar_count */
+    int32_t alignment_offset;    /* out: lib_sw_avx.alignment_offset */
+    int32_t score;               /* out: lib_sw_avx.score */
+    int32_t status;              /* out: 0 ok; 1 = a sequence of 2048 bases or more: the reference gives up with
+                                    alignment_offset = 1 and no CIGAR (sw_avx.c:494-499), so does this; 2 = cigar_cap too small */
+} phmm_sw_result;
+
+/* All pairs are aligned on the device in one pass (fill kernel: one warp per alignment; trace kernel: one thread per
+ * alignment).  Empty sequences are a PHMM_ERR_ARG.  Thread-safe (calls are serialised per engine). */
+int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, const phmm_sw_params* params, phmm_sw_result* results);
+/* Device time (CUDA events: fill + trace kernels) and cells (sum ref_len x read_len) of the last phmm_sw_align call. */
+int phmm_sw_last_timing(phmm_engine* e, float* gpu_ms, uint64_t* cells);
+
 int phmm_get_stats(phmm_engine* e, phmm_stats* out);
 /* Static facts about the forward-kernel instantiation that serves reads of `read_len` bases (registers, spill bytes,
  * lanes per read, read rows per lane) for reports. */

@@ -301,6 +301,18 @@ struct phmm_engine
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
     float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
+
+    // batched Smith-Waterman (phmm_sw_align): its own stream and arenas, one call at a time
+    struct SwContext
+    {
+        std::mutex m;
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        HostBuf h_in, h_out;
+        DevBuf d_in, d_bt, d_aux, d_cig, d_out;
+        float last_ms = 0.f;
+        uint64_t last_cells = 0;
+    } sw;
     DevBuf d_tables;
     Stats stats;
 
@@ -1124,6 +1136,11 @@ void phmm_destroy(phmm_engine* e)
     for (auto& t : e->workers) t.join();
     cudaSetDevice(e->device);
     for (auto& s : e->slots) s->destroy();
+    for (auto* b : {&e->sw.h_in, &e->sw.h_out}) b->release();
+    for (auto* b : {&e->sw.d_in, &e->sw.d_bt, &e->sw.d_aux, &e->sw.d_cig, &e->sw.d_out}) b->release();
+    for (auto& ev : e->sw.ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e->sw.stream) cudaStreamDestroy(e->sw.stream);
     e->d_tables.release();
     delete e;
 }
@@ -1328,6 +1345,154 @@ void phmm_resident_free(phmm_engine* e, phmm_resident* r)
 }
 
 uint32_t phmm_resident_launches(const phmm_resident* r) { return r ? r->slot.n_launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// Batched Smith-Waterman (include/phmm_b200.h; kernels in sw_kernels.cu)
+// ------------------------------------------------------------------------------------------------
+
+int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, const phmm_sw_params* params, phmm_sw_result* results)
+{
+    if (!e || !params || (n_pairs && (!pairs || !results))) return fail(PHMM_ERR_ARG, "phmm_sw_align: null argument");
+    if (n_pairs == 0) return PHMM_OK;
+    constexpr uint32_t kGiveUp = 2048;                                  // MAX_SEQ_LEN, sw_avx.c:17,494-499
+    constexpr size_t kBtBudget = (size_t)12 << 30;                       // back-track words held on the device at once
+    uint32_t cigar_cap = 0;
+    for (uint32_t k = 0; k < n_pairs; ++k) {
+        if (pairs[k].ref_len == 0 || pairs[k].read_len == 0 || !pairs[k].ref || !pairs[k].read)
+            return fail(PHMM_ERR_ARG, "phmm_sw_align: empty sequence");
+        if (results[k].cigar_cap && !results[k].cigar) return fail(PHMM_ERR_ARG, "phmm_sw_align: cigar buffer is null");
+        cigar_cap = std::max(cigar_cap, results[k].cigar_cap);
+    }
+    cigar_cap = std::max(cigar_cap, 1u);
+    phmm_engine::SwContext& c = e->sw;
+    std::lock_guard<std::mutex> lk(c.m);
+    CU(cudaSetDevice(e->device));
+    if (!c.stream) {
+        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
+    }
+    c.last_ms = 0.f;
+    c.last_cells = 0;
+    // sub-batches that fit the back-track budget
+    uint32_t at = 0;
+    while (at < n_pairs) {
+        std::vector<PhmmSwTask> tasks;
+        std::vector<uint32_t> src;                                      // task -> pair
+        size_t bytes = 0, bt_words = 0, aux_ints = 0;
+        while (at < n_pairs) {
+            const phmm_sw_pair& p = pairs[at];
+            phmm_sw_result& r = results[at];
+            if (std::max(p.ref_len, p.read_len) >= kGiveUp) {            // the reference returns alignment_offset = 1, no CIGAR
+                r.n_cigar = 0; r.alignment_offset = 1; r.score = 0; r.status = 1;
+                ++at;
+                continue;
+            }
+            int cpt = 0;
+            for (int q = 0; q < kPhmmSwNumCpt; ++q)
+                if (p.read_len <= 32u * (uint32_t)kPhmmSwCpt[q]) { cpt = kPhmmSwCpt[q]; break; }
+            const size_t words = (size_t)p.ref_len * 32 * ((cpt + 7) / 8);
+            if (!tasks.empty() && (bt_words + words) * 4 > kBtBudget) break;
+            PhmmSwTask t{};
+            t.ref_off = (uint32_t)bytes; t.ref_len = p.ref_len;
+            bytes += p.ref_len;
+            t.read_off = (uint32_t)bytes; t.read_len = p.read_len;
+            bytes += p.read_len;
+            t.bt_off = bt_words; bt_words += words;
+            t.aux_off = aux_ints; aux_ints += (size_t)p.ref_len + p.read_len;
+            t.cpt = (uint32_t)cpt;
+            if (bytes >= ((size_t)1 << 32)) return fail(PHMM_ERR_ARG, "phmm_sw_align: more than 4 GiB of sequence in one call");
+            tasks.push_back(t);
+            src.push_back(at);
+            ++at;
+        }
+        const uint32_t n = (uint32_t)tasks.size();
+        if (n == 0) continue;
+        // order by cpt (one fill launch per kernel instantiation), longest haplotypes first inside a group
+        std::vector<uint32_t> order(n);
+        for (uint32_t k = 0; k < n; ++k) order[k] = k;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) {
+            return tasks[a].cpt != tasks[b2].cpt ? tasks[a].cpt < tasks[b2].cpt : tasks[a].ref_len > tasks[b2].ref_len;
+        });
+        size_t off = 0;
+        auto place = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
+        const size_t o_tasks = place(n * sizeof(PhmmSwTask)), o_order = place(n * sizeof(uint32_t)), o_bytes = place(bytes + 16);
+        int rc;
+        if ((rc = c.h_in.ensure(off)) != PHMM_OK) return rc;
+        if ((rc = c.d_in.ensure(off)) != PHMM_OK) return rc;
+        if ((rc = c.d_bt.ensure(std::max<size_t>(bt_words, 1) * 4)) != PHMM_OK) return rc;
+        if ((rc = c.d_aux.ensure(std::max<size_t>(aux_ints, 1) * 4)) != PHMM_OK) return rc;
+        if ((rc = c.d_cig.ensure((size_t)n * cigar_cap * 4)) != PHMM_OK) return rc;
+        if ((rc = c.d_out.ensure((size_t)n * sizeof(PhmmSwOut))) != PHMM_OK) return rc;
+        if ((rc = c.h_out.ensure((size_t)n * (sizeof(PhmmSwOut) + (size_t)cigar_cap * 4))) != PHMM_OK) return rc;
+        uint8_t* h = static_cast<uint8_t*>(c.h_in.p);
+        std::memcpy(h + o_tasks, tasks.data(), n * sizeof(PhmmSwTask));
+        std::memcpy(h + o_order, order.data(), n * sizeof(uint32_t));
+        uint64_t cells = 0;
+        for (uint32_t k = 0; k < n; ++k) {
+            const phmm_sw_pair& p = pairs[src[k]];
+            std::memcpy(h + o_bytes + tasks[k].ref_off, p.ref, p.ref_len);
+            std::memcpy(h + o_bytes + tasks[k].read_off, p.read, p.read_len);
+            cells += (uint64_t)p.ref_len * p.read_len;
+        }
+        uint8_t* d = static_cast<uint8_t*>(c.d_in.p);
+        PhmmSwBatchDev b{};
+        b.tasks = reinterpret_cast<const PhmmSwTask*>(d + o_tasks);
+        b.order = reinterpret_cast<const uint32_t*>(d + o_order);
+        b.bytes = d + o_bytes;
+        b.bt = static_cast<uint32_t*>(c.d_bt.p);
+        b.aux = static_cast<int32_t*>(c.d_aux.p);
+        b.cigars = static_cast<uint32_t*>(c.d_cig.p);
+        b.outs = static_cast<PhmmSwOut*>(c.d_out.p);
+        b.cigar_cap = cigar_cap;
+        b.match = params->match; b.mismatch = params->mismatch; b.gap_open = params->gap_open; b.gap_extend = params->gap_extend;
+        CU(cudaMemcpyAsync(c.d_in.p, c.h_in.p, off, cudaMemcpyHostToDevice, c.stream));
+        CU(cudaEventRecord(c.ev[0], c.stream));
+        for (uint32_t g0 = 0; g0 < n;) {                                 // one fill launch per cpt group
+            uint32_t g1 = g0;
+            while (g1 < n && tasks[order[g1]].cpt == tasks[order[g0]].cpt) ++g1;
+            const uint32_t warps = std::min<uint32_t>(g1 - g0, e->warp_slots * 4);
+            CU(phmm_launch_sw_fill(b, (int)tasks[order[g0]].cpt, g0, g1 - g0, warps, c.stream));
+            g0 = g1;
+        }
+        CU(phmm_launch_sw_trace(b, 0, n, c.stream));
+        CU(cudaEventRecord(c.ev[1], c.stream));
+        uint8_t* ho = static_cast<uint8_t*>(c.h_out.p);
+        CU(cudaMemcpyAsync(ho, c.d_out.p, (size_t)n * sizeof(PhmmSwOut), cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaMemcpyAsync(ho + (size_t)n * sizeof(PhmmSwOut), c.d_cig.p, (size_t)n * cigar_cap * 4, cudaMemcpyDeviceToHost, c.stream));
+        CU(cudaStreamSynchronize(c.stream));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
+        c.last_ms += ms;
+        c.last_cells += cells;
+        const PhmmSwOut* outs = reinterpret_cast<const PhmmSwOut*>(ho);
+        const uint32_t* cig = reinterpret_cast<const uint32_t*>(ho + (size_t)n * sizeof(PhmmSwOut));
+        for (uint32_t k = 0; k < n; ++k) {
+            phmm_sw_result& r = results[src[k]];
+            r.alignment_offset = outs[k].alignment_offset;
+            r.score = outs[k].score;
+            r.status = outs[k].status;
+            r.n_cigar = outs[k].n_cigar;
+            if (outs[k].n_cigar > r.cigar_cap) {                          // the device buffer was sized for the largest caller buffer
+                r.status = 2;
+                r.n_cigar = r.cigar_cap;
+            }
+            if (r.n_cigar) std::memcpy(r.cigar, cig + (size_t)k * cigar_cap, (size_t)r.n_cigar * 4);
+        }
+        e->stats.launches += 2;
+        e->stats.h2d += off;
+        e->stats.d2h += (size_t)n * (sizeof(PhmmSwOut) + (size_t)cigar_cap * 4);
+    }
+    return PHMM_OK;
+}
+
+int phmm_sw_last_timing(phmm_engine* e, float* gpu_ms, uint64_t* cells)
+{
+    if (!e) return fail(PHMM_ERR_ARG, "phmm_sw_last_timing: null engine");
+    std::lock_guard<std::mutex> lk(e->sw.m);
+    if (gpu_ms) *gpu_ms = e->sw.last_ms;
+    if (cells) *cells = e->sw.last_cells;
+    return PHMM_OK;
+}
 
 int phmm_get_stats(phmm_engine* e, phmm_stats* out)
 {

@@ -106,6 +106,39 @@ struct PhmmKernelInfo
 };
 cudaError_t phmm_fwd_kernel_info(int bin, bool fma, PhmmKernelInfo* info);
 
+// ---- batched Smith-Waterman (sw_kernels.cu) -------------------------------------------------------------------------
+struct PhmmSwTask
+{
+    uint32_t ref_off, ref_len;     // haplotype (rows) in the byte blob
+    uint32_t read_off, read_len;   // read (columns)
+    uint64_t bt_off;               // first back-track word of this alignment, [row][lane][ceil(cpt/8)] u32
+    uint64_t aux_off;              // last row (read_len ints) then last column (ref_len ints) of H
+    uint32_t cpt;                  // columns per lane of the fill kernel that serves it
+    uint32_t rsv;
+};
+struct PhmmSwOut
+{
+    uint32_t n_cigar;
+    int32_t alignment_offset, score;
+    int32_t status;                // 0 ok, 2 CIGAR longer than the caller's buffer, 3 corrupt back-track (never)
+};
+struct PhmmSwBatchDev
+{
+    const PhmmSwTask* tasks;
+    const uint32_t* order;         // task ids grouped by cpt
+    const uint8_t* bytes;
+    uint32_t* bt;
+    int32_t* aux;
+    uint32_t* cigars;              // [task][cigar_cap]
+    PhmmSwOut* outs;
+    uint32_t cigar_cap;
+    int32_t match, mismatch, gap_open, gap_extend;
+};
+static const int kPhmmSwCpt[] = {2, 5, 8, 16, 32, 64};     // columns per lane: reads up to 64, 160, 256, 512, 1024, 2048 bases
+static const int kPhmmSwNumCpt = sizeof(kPhmmSwCpt) / sizeof(kPhmmSwCpt[0]);
+cudaError_t phmm_launch_sw_fill(const PhmmSwBatchDev& b, int cpt, uint32_t first, uint32_t count, uint32_t warps, cudaStream_t st);
+cudaError_t phmm_launch_sw_trace(const PhmmSwBatchDev& b, uint32_t first, uint32_t count, cudaStream_t st);
+
 // FP32 issue-rate micro-benchmark; each thread executes iters*32 FMA instructions on 2 lanes (see .cu).
 cudaError_t phmm_launch_ubench(int mode, uint32_t blocks, uint32_t iters, float* out, cudaStream_t st);
 

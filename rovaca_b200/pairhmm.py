@@ -71,13 +71,30 @@ class _FlatResult(C.Structure):
                 ("raw_f64", _f64p), ("n_fp64", C.c_uint64)]
 
 
+class _SwParams(C.Structure):
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
+
+
+class _SwPair(C.Structure):
+    _fields_ = [("ref", _u8p), ("ref_len", C.c_uint32), ("read", _u8p), ("read_len", C.c_uint32)]
+
+
+class _SwResult(C.Structure):
+    _fields_ = [("cigar", _u32p), ("cigar_cap", C.c_uint32), ("n_cigar", C.c_uint32), ("alignment_offset", C.c_int32),
+                ("score", C.c_int32), ("status", C.c_int32)]
+
+
+SW_REALIGN = (10, -15, -30, -5)        # sw_parameters_genotype, common/base/lib/sw_avx/sw_avx.c:14
+SW_ASSEMBLE = (200, -150, -260, -11)   # sw_parameters_assemble, :13
+
+
 class _Stats(C.Structure):
     _fields_ = [("regions", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64),
                 ("slow_pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("batches", C.c_uint64),
                 ("gpu_ms", C.c_double), ("kernel_launches", C.c_uint64), ("host_plan_ms", C.c_double), ("host_epilogue_ms", C.c_double)]
 
 
-EXPORTS = ["phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
+EXPORTS = ["phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
            "phmm_resident_upload", "phmm_resident_run", "phmm_resident_download", "phmm_resident_free",
            "phmm_resident_launches", "phmm_get_stats", "phmm_kernel_info", "phmm_ubench", "phmm_last_error", "phmm_version"]
 
@@ -127,6 +144,8 @@ def load_library():
     L.phmm_get_stats.argtypes = [C.c_void_p, C.POINTER(_Stats)]
     L.phmm_kernel_info.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.phmm_ubench.argtypes = [C.c_void_p, C.c_int, C.c_uint32, _f32p, _f64p]
+    L.phmm_sw_align.argtypes = [C.c_void_p, C.POINTER(_SwPair), C.c_uint32, C.POINTER(_SwParams), C.POINTER(_SwResult)]
+    L.phmm_sw_last_timing.argtypes = [C.c_void_p, _f32p, _u64p]
     L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
     L.phmm_debug_tables.restype = None
     L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, _u64p]
@@ -315,6 +334,29 @@ class PairHmmEngine:
         if raw:
             return out, kept[: res.n_kept].copy(), raw32, raw64, int(res.n_fp64)
         return out, kept[: res.n_kept].copy()
+
+    # -- the step after the path: batched Smith-Waterman ------------------------------------------
+    def sw_align(self, pairs: Sequence[Tuple], params=SW_REALIGN, cigar_cap: int = 64):
+        """pairs: (haplotype, read) byte sequences.  One device pass; per pair -> (cigar uint32[], alignment_offset, score,
+        status), exactly what the reference's sw->avx_function(sw) leaves in lib_sw_avx (alignment_utils.cpp:574-579)."""
+        n = len(pairs)
+        keep, arr = [], (_SwPair * max(n, 1))()
+        res = (_SwResult * max(n, 1))()
+        cig = np.zeros((max(n, 1), cigar_cap), np.uint32)
+        for k, (ref, read) in enumerate(pairs):
+            a, b = _as_u8(ref), _as_u8(read)
+            keep += [a, b]
+            arr[k] = _SwPair(a.ctypes.data_as(_u8p), len(a), b.ctypes.data_as(_u8p), len(b))
+            res[k].cigar = cig[k].ctypes.data_as(_u32p)
+            res[k].cigar_cap = cigar_cap
+        prm = _SwParams(*params)
+        self._check(self.L.phmm_sw_align(self.h, arr, n, C.byref(prm), res))
+        return [(cig[k, : res[k].n_cigar].copy(), int(res[k].alignment_offset), int(res[k].score), int(res[k].status)) for k in range(n)]
+
+    def sw_last_timing(self) -> Tuple[float, int]:
+        ms, cells = C.c_float(0), C.c_uint64(0)
+        self._check(self.L.phmm_sw_last_timing(self.h, C.byref(ms), C.byref(cells)))
+        return float(ms.value), int(cells.value)
 
     # -- batch forms ------------------------------------------------------------------------------
     def run_flat(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE,

@@ -223,6 +223,21 @@ class Ref:
         L.ref_sw_align.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int)]
 
+    def sw_bench(self, haps, reads, n_threads: int, assemble: bool = False):
+        """n alignments through the reference's Smith-Waterman on n_threads host threads -> (seconds, checksum)."""
+        hb = [_u8(h) for h in haps]
+        rb = [_u8(r) for r in reads]
+        hl, rl = np.array([len(x) for x in hb], np.uint32), np.array([len(x) for x in rb], np.uint32)
+        ho, ro = np.zeros(len(hb), np.uint64), np.zeros(len(rb), np.uint64)
+        ho[1:], ro[1:] = np.cumsum(hl[:-1], dtype=np.uint64), np.cumsum(rl[:-1], dtype=np.uint64)
+        hcat, rcat = np.concatenate(hb), np.concatenate(rb)
+        chk = C.c_longlong(0)
+        self.lib.ref_sw_bench.restype = C.c_double
+        self.lib.ref_sw_bench.argtypes = [C.c_int, C.c_int, C.c_uint32, _u8p, _u64p, _u32p, _u8p, _u64p, _u32p, C.POINTER(C.c_longlong)]
+        secs = self.lib.ref_sw_bench(n_threads, int(assemble), len(hb), _p(hcat, _u8p), _p(ho, _u64p), _p(hl, _u32p), _p(rcat, _u8p),
+                                     _p(ro, _u64p), _p(rl, _u32p), C.byref(chk))
+        return float(secs), int(chk.value)
+
     def sw_align(self, seq1, seq2, assemble: bool = False, isa: int = -1):
         """The reference's Smith-Waterman (sw_avx.c / sw_avx2.c): seq2 (read) against seq1 (haplotype).
         -> (cigar uint32[], alignment_offset, score), cigar None where the reference gives up (>= 2048 bases)."""

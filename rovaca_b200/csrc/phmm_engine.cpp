@@ -1390,7 +1390,7 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             int cpt = 0;
             for (int q = 0; q < kPhmmSwNumCpt; ++q)
                 if (p.read_len <= 32u * (uint32_t)kPhmmSwCpt[q]) { cpt = kPhmmSwCpt[q]; break; }
-            const size_t words = (size_t)p.ref_len * 32 * ((cpt + 7) / 8);
+            const size_t words = ((size_t)p.ref_len + 31) * 32 * ((cpt + 7) / 8);     // one line per wavefront step
             if (!tasks.empty() && (bt_words + words) * 4 > kBtBudget) break;
             PhmmSwTask t{};
             t.ref_off = (uint32_t)bytes; t.ref_len = p.ref_len;

@@ -111,7 +111,7 @@ struct PhmmSwTask
 {
     uint32_t ref_off, ref_len;     // haplotype (rows) in the byte blob
     uint32_t read_off, read_len;   // read (columns)
-    uint64_t bt_off;               // first back-track word of this alignment, [row][lane][ceil(cpt/8)] u32
+    uint64_t bt_off;               // first back-track word of this alignment, [step = row - 1 + lane][lane][ceil(cpt/8)] u32
     uint64_t aux_off;              // last row (read_len ints) then last column (ref_len ints) of H
     uint32_t cpt;                  // columns per lane of the fill kernel that serves it
     uint32_t rsv;

@@ -8,7 +8,8 @@
 //                        rows of the haplotype as an anti-diagonal wavefront (lane l is at row s - l + 1 in step s), H and E
 //                        of a lane's last column reach the next lane through two __shfl_up_sync per step.  Per cell the
 //                        reference's Gotoh recurrence with its 4-bit back-track code (sw_avx.c:40-76); the codes of a lane's
-//                        CPT cells are packed into words, the last row and last column of H are kept for the end-cell search.
+//                        CPT cells are packed into words and stored [step][lane] (the lanes of a step write one contiguous line),
+//                        the last row and last column of H are kept for the end-cell search.
 //   sw_trace_kernel      one thread per alignment: the reference's end-cell choice with its tie rules in anti-diagonal order
 //                        (sw_avx.c:196-217), its trace-back state machine and CIGAR compaction (:252-361).
 // Integer arithmetic only; nothing here depends on floating point.
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(128) sw_fill_kernel(PhmmSwBatchDev b, uint32_t
                 lastE = e;
                 diagH = inH;
 #pragma unroll
-                for (int w = 0; w < W; ++w) bt[((size_t)(i - 1) * 32 + lane) * W + w] = words[w];
+                for (int w = 0; w < W; ++w) bt[((size_t)s * 32 + lane) * W + w] = words[w];   // [step][lane]: one coalesced line per step
                 if (kcol >= 0 && kcol < CPT) hcol[i - 1] = hc;
                 if (i == nrow) {
 #pragma unroll
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(128) sw_fill_kernel(PhmmSwBatchDev b, uint32_t
 __device__ __forceinline__ uint32_t bt_code(const uint32_t* bt, int cpt, int i, int j)
 {
     const int w = (cpt + 7) / 8, lane = (j - 1) / cpt, k = (j - 1) % cpt;
-    return (bt[((size_t)(i - 1) * 32 + lane) * w + k / 8] >> (4 * (k % 8))) & 15u;
+    const int step = i - 1 + lane;                        // the fill kernel's lane `lane` was at row i in this step
+    return (bt[((size_t)step * 32 + lane) * w + k / 8] >> (4 * (k % 8))) & 15u;
 }
 
 __global__ void __launch_bounds__(128) sw_trace_kernel(PhmmSwBatchDev b, uint32_t first, uint32_t count)

@@ -2,17 +2,19 @@
 //
 // Mirrors what the reference's host wrapper does around its kernels (pairhmm/pairhmm_internal.cpp
 // call_old_pairhmm :505-594 / call_new_pairhmm002 :596-753), re-cut for a GPU:
-//   * regions from many callers are gathered into batches (the reference runs one region per call on
-//     a pool thread, haplotypecaller_engine.cpp:119,250 — far too little work for a B200);
-//   * per batch the host only *plans*: reads are binned by length (rows per lane), each region's
-//     haplotypes are dealt into two balanced column streams, CTAs of PHMM_WARPS same-bin reads are
-//     formed; the bytes (bases, quals, haplotypes) are gathered into one pinned arena and shipped
-//     with a single H2D copy;
-//   * quality capping, the PCR-indel model, the table look-ups, the forward recurrence and the FP64
-//     underflow recompute all run on the device (phmm_kernels.cu);
-//   * the raw sums come back and the host finishes exactly as the reference does: log10f/log10 with
-//     glibc (so the bits match, pairhmm_internal.cpp:578-584), normalize_likelihoods (:53-63),
-//     filter_poorly_modelled_evidence (:161-182), transpose into the NaN-initialised matrix (:184-193).
+//   * regions from many callers are gathered into batches (the reference runs one region per call on a pool thread,
+//     haplotypecaller_engine.cpp:119,250 — far too little work for a B200): tickets (phmm_submit / phmm_wait) with a
+//     batch-while-busy sealing policy for its synchronous callers, phmm_run_flat for whole streams;
+//   * per batch the host only *plans*: reads are binned by length (lanes per read x rows per lane), remainders of sparse bins
+//     are promoted so that warps run full, each region's haplotypes are dealt into chunks of two balanced column streams
+//     (shorter chunks when the device is idle: a chunk's length is a call's latency), CTAs of 1-4 warps are formed; the
+//     records go through one pinned arena, the read / haplotype bytes too, or straight from the caller's page-locked buffers;
+//   * quality capping, the PCR-indel model, the table look-ups, the forward recurrence and the FP64 underflow recompute all
+//     run on the device (phmm_kernels.cu), the per-bin launches side by side on four streams;
+//   * the raw sums come back and the host finishes exactly as the reference does: log10f/log10 with glibc (so the bits match,
+//     pairhmm_internal.cpp:578-584), normalize_likelihoods (:53-63), filter_poorly_modelled_evidence (:161-182), transpose
+//     into the NaN-tailed matrix (:184-193);
+//   * the step after the path, Smith-Waterman realignment of reads to their best haplotype, is phmm_sw_align (sw_kernels.cu).
 // There is no CPU implementation of the recurrence in this library and no fallback.
 #include <algorithm>
 #include <atomic>

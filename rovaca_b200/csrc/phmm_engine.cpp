@@ -70,6 +70,45 @@ constexpr double kLog10InitD = 307.050595577260822;        // LOG10_INITIAL_CONS
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// log10f is the host's biggest cost per pair (the reference's conversion, pairhmm_internal.cpp:583, must use the host's own
+// libm for the bits to match).  glibc up to 2.39 computes it the fdlibm way — split off the exponent, then
+// y*log10_2lo + ivln10*logf(m), + y*log10_2hi in float arithmetic — spending most of its time around a call of its own
+// (fast) logf.  The same formula inlined around the host's logf gives the same bits for less; whether this host's log10f IS
+// that formula is not assumed but tested when an engine is created (a million inputs across the range the path produces,
+// bit for bit); any difference and the engine keeps calling log10f itself.
+inline float log10f_fdlibm_form(float x)
+{
+    uint32_t ux;
+    std::memcpy(&ux, &x, 4);
+    int32_t hx = (int32_t)ux, k = 0;
+    if (hx < 0x00800000) {                                   // zero, negative or subnormal: leave those to libm
+        return log10f(x);
+    }
+    if (hx >= 0x7f800000) return x + x;
+    k += (hx >> 23) - 127;
+    const int32_t i = (int32_t)(((uint32_t)k & 0x80000000u) >> 31);
+    hx = (hx & 0x007fffff) | ((0x7f - i) << 23);
+    const float y = (float)(k + i);
+    ux = (uint32_t)hx;
+    std::memcpy(&x, &ux, 4);
+    const float ivln10 = 4.3429449201e-01f, log10_2hi = 3.0102920532e-01f, log10_2lo = 7.9034151668e-07f;
+    const float z = y * log10_2lo + ivln10 * logf(x);
+    return z + y * log10_2hi;
+}
+
+bool log10f_form_matches_libm()
+{
+    uint32_t bits = 0x0d800000u;                              // ~1e-30 ... up to 2^127, in a million prime-strided steps
+    for (int n = 0; n < 1000000; ++n, bits += 1913u + (uint32_t)(n & 7)) {
+        if (bits >= 0x7f000000u) bits = 0x0d800000u + (uint32_t)n;
+        float x;
+        std::memcpy(&x, &bits, 4);
+        const float a = log10f(x), b = log10f_fdlibm_form(x);
+        if (std::memcmp(&a, &b, 4) != 0) return false;
+    }
+    return true;
+}
+
 struct RegionIn
 {
     const phmm_read* reads;
@@ -300,6 +339,7 @@ struct phmm_engine
     uint32_t linger_us = 200;
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
+    bool inline_log10f = false;    // this host's log10f is the fdlibm formula around logf (checked at creation)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
     float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
@@ -870,7 +910,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
                     v = log10(f64[rp.out_off + (size_t)i * nh + j]) - kLog10InitD;   // :580
                     ++reg64;
                 } else {
-                    v = (double)(log10f(f) - kLog10InitF);                           // :583
+                    v = (double)((inline_log10f ? log10f_fdlibm_form(f) : log10f(f)) - kLog10InitF);   // :583
                 }
                 row[j] = v;
                 // std::max_element semantics of :56,:170 — the first element, replaced only by a strictly greater one
@@ -1112,6 +1152,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
     int rc = e->d_tables.ensure(sizeof(PhmmTables));
     if (rc != PHMM_OK) return rc;
     CU(cudaMemcpy(e->d_tables.p, t.get(), sizeof(PhmmTables), cudaMemcpyHostToDevice));
+    e->inline_log10f = std::getenv("PHMM_B200_LIBM_LOG10F") == nullptr && log10f_form_matches_libm();
     e->default_gapm = t->gapm[10];
     e->default_ii = t->ph2pr[10];
     for (uint32_t i = 0; i < e->n_workers; ++i) {
@@ -1628,6 +1669,23 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
         if (!seen[k]) ++out[4];
     for (auto* b : {&s.h_in, &s.h_f32, &s.h_f64, &s.h_cnt}) b->release();
     return PHMM_OK;
+}
+
+// For tests (no GPU needed): the inlined fdlibm form of log10f against this host's libm over every `stride`-th normal float.
+// Returns the number of inputs whose bits differ (0 on glibc <= 2.39); *would_use says what phmm_create would decide.
+uint64_t phmm_debug_log10f_check(uint32_t stride, int* would_use)
+{
+    uint64_t bad = 0;
+    if (stride == 0) stride = 1;
+    for (uint64_t b = 0x00800000u; b < 0x7f800000u; b += stride) {
+        const uint32_t bits = (uint32_t)b;
+        float x;
+        std::memcpy(&x, &bits, 4);
+        const float a = log10f(x), c = log10f_fdlibm_form(x);
+        bad += std::memcmp(&a, &c, 4) != 0;
+    }
+    if (would_use) *would_use = log10f_form_matches_libm() ? 1 : 0;
+    return bad;
 }
 
 // For tests: the host-built tables, to be compared with the reference's Context<float> (core/context.h).

@@ -148,6 +148,8 @@ def load_library():
     L.phmm_sw_last_timing.argtypes = [C.c_void_p, _f32p, _u64p]
     L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
     L.phmm_debug_tables.restype = None
+    L.phmm_debug_log10f_check.restype = C.c_uint64
+    L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.POINTER(C.c_int)]
     L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, _u64p]
     _lib = L
     return L

@@ -1,5 +1,6 @@
 """CPU: the C-ABI library builds, loads, exports every symbol include/phmm_b200.h declares, refuses to run without a
 GPU (no CPU fallback), carries the reference's tables, and its SASS has the expected instruction mix."""
+import ctypes
 import os
 import re
 import shutil
@@ -53,6 +54,15 @@ def test_tables_match_oracle(orc):
     assert np.array_equal(mm.view(np.uint32), orc.mm_tri_f32().view(np.uint32))
     assert np.array_equal(pd.view(np.uint64), orc.ph2pr_f64().view(np.uint64))
     assert np.array_equal(mmd.view(np.uint64), orc.mm_tri_f64().view(np.uint64))
+
+
+def test_inlined_log10f_is_libm_or_is_not_used():
+    """The host epilogue may inline the fdlibm form of log10f around libm's logf, but only on a host whose log10f has exactly
+    those bits: either the form matches libm on every sampled float, or the engine's creation-time check must refuse it."""
+    L = ph.load_library()
+    use = ctypes.c_int(-1)
+    differing = L.phmm_debug_log10f_check(257, ctypes.byref(use))
+    assert (differing == 0 and use.value == 1) or use.value == 0
 
 
 def test_product_never_touches_oracle():

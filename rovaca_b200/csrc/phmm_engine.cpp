@@ -1450,12 +1450,15 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
         }
         const uint32_t n = (uint32_t)tasks.size();
         if (n == 0) continue;
-        // order by cpt (one fill launch per kernel instantiation), longest haplotypes first inside a group
+        // order by cpt (one fill launch per kernel instantiation): a counting sort, input order kept inside a group
         std::vector<uint32_t> order(n);
-        for (uint32_t k = 0; k < n; ++k) order[k] = k;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b2) {
-            return tasks[a].cpt != tasks[b2].cpt ? tasks[a].cpt < tasks[b2].cpt : tasks[a].ref_len > tasks[b2].ref_len;
-        });
+        {
+            uint32_t count[kPhmmSwNumCpt + 1] = {};
+            auto group_of = [&](uint32_t cpt) { int q = 0; while (kPhmmSwCpt[q] != (int)cpt) ++q; return q; };
+            for (uint32_t k = 0; k < n; ++k) ++count[group_of(tasks[k].cpt) + 1];
+            for (int q = 0; q < kPhmmSwNumCpt; ++q) count[q + 1] += count[q];
+            for (uint32_t k = 0; k < n; ++k) order[count[group_of(tasks[k].cpt)]++] = k;
+        }
         size_t off = 0;
         auto place = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
         const size_t o_tasks = place(n * sizeof(PhmmSwTask)), o_order = place(n * sizeof(uint32_t)), o_bytes = place(bytes + 16);

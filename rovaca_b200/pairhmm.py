@@ -338,9 +338,8 @@ class PairHmmEngine:
         return out, kept[: res.n_kept].copy()
 
     # -- the step after the path: batched Smith-Waterman ------------------------------------------
-    def sw_align(self, pairs: Sequence[Tuple], params=SW_REALIGN, cigar_cap: int = 64):
-        """pairs: (haplotype, read) byte sequences.  One device pass; per pair -> (cigar uint32[], alignment_offset, score,
-        status), exactly what the reference's sw->avx_function(sw) leaves in lib_sw_avx (alignment_utils.cpp:574-579)."""
+    def sw_prepare(self, pairs: Sequence[Tuple], cigar_cap: int = 64):
+        """Marshal (haplotype, read) pairs into the C arrays phmm_sw_align takes (Python-side cost, kept out of timings)."""
         n = len(pairs)
         keep, arr = [], (_SwPair * max(n, 1))()
         res = (_SwResult * max(n, 1))()
@@ -351,9 +350,20 @@ class PairHmmEngine:
             arr[k] = _SwPair(a.ctypes.data_as(_u8p), len(a), b.ctypes.data_as(_u8p), len(b))
             res[k].cigar = cig[k].ctypes.data_as(_u32p)
             res[k].cigar_cap = cigar_cap
+        return dict(n=n, pairs=arr, results=res, cigars=cig, keep=keep)
+
+    def sw_run(self, prepared: dict, params=SW_REALIGN):
+        """One phmm_sw_align call on prepared arrays -> per pair (cigar, alignment_offset, score, status)."""
         prm = _SwParams(*params)
-        self._check(self.L.phmm_sw_align(self.h, arr, n, C.byref(prm), res))
-        return [(cig[k, : res[k].n_cigar].copy(), int(res[k].alignment_offset), int(res[k].score), int(res[k].status)) for k in range(n)]
+        self._check(self.L.phmm_sw_align(self.h, prepared["pairs"], prepared["n"], C.byref(prm), prepared["results"]))
+        res, cig = prepared["results"], prepared["cigars"]
+        return [(cig[k, : res[k].n_cigar].copy(), int(res[k].alignment_offset), int(res[k].score), int(res[k].status))
+                for k in range(prepared["n"])]
+
+    def sw_align(self, pairs: Sequence[Tuple], params=SW_REALIGN, cigar_cap: int = 64):
+        """pairs: (haplotype, read) byte sequences.  One device pass; per pair -> (cigar uint32[], alignment_offset, score,
+        status), exactly what the reference's sw->avx_function(sw) leaves in lib_sw_avx (alignment_utils.cpp:574-579)."""
+        return self.sw_run(self.sw_prepare(pairs, cigar_cap), params)
 
     def sw_last_timing(self) -> Tuple[float, int]:
         ms, cells = C.c_float(0), C.c_uint64(0)

@@ -1421,6 +1421,12 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
     while (at < n_pairs) {
         std::vector<PhmmSwTask> tasks;
         std::vector<uint32_t> src;                                      // task -> pair
+        struct SwCopy { size_t dst; const uint8_t* src; size_t len; };
+        std::vector<SwCopy> copies;                                     // what to gather into the byte blob
+        constexpr int kRefCache = 16;
+        struct RefSeen { const uint8_t* ptr; uint32_t len, off; } ref_cache[kRefCache] = {};
+        int ref_next = 0;
+        uint64_t cells = 0;
         size_t bytes = 0, bt_words = 0, aux_ints = 0;
         while (at < n_pairs) {
             const phmm_sw_pair& p = pairs[at];
@@ -1436,9 +1442,26 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             const size_t words = ((size_t)p.ref_len + 31) * 32 * ((cpt + 7) / 8);     // one line per wavefront step
             if (!tasks.empty() && (bt_words + words) * 4 > kBtBudget) break;
             PhmmSwTask t{};
-            t.ref_off = (uint32_t)bytes; t.ref_len = p.ref_len;
-            bytes += p.ref_len;
+            // a region's reads meet the same few haplotypes again and again: ship each distinct one once (a small cache of
+            // the latest haplotype buffers is enough, the callers walk region by region)
+            int hit = -1;
+            for (int q = 0; q < kRefCache; ++q)
+                if (ref_cache[q].ptr == p.ref && ref_cache[q].len == p.ref_len) { hit = q; break; }
+            if (hit >= 0) {
+                t.ref_off = ref_cache[hit].off;
+            } else {
+                t.ref_off = (uint32_t)bytes;
+                copies.push_back(SwCopy{bytes, p.ref, p.ref_len});
+                bytes += p.ref_len;
+                ref_cache[ref_next] = RefSeen{p.ref, p.ref_len, t.ref_off};
+                ref_next = (ref_next + 1) % kRefCache;
+            }
+            t.ref_len = p.ref_len;
             t.read_off = (uint32_t)bytes; t.read_len = p.read_len;
+            if (!copies.empty() && copies.back().src + copies.back().len == p.read && copies.back().dst + copies.back().len == bytes)
+                copies.back().len += p.read_len;                         // reads that sit back to back in the caller's memory
+            else
+                copies.push_back(SwCopy{bytes, p.read, p.read_len});
             bytes += p.read_len;
             t.bt_off = bt_words; bt_words += words;
             t.aux_off = aux_ints; aux_ints += (size_t)p.ref_len + p.read_len;
@@ -1446,6 +1469,7 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             if (bytes >= ((size_t)1 << 32)) return fail(PHMM_ERR_ARG, "phmm_sw_align: more than 4 GiB of sequence in one call");
             tasks.push_back(t);
             src.push_back(at);
+            cells += (uint64_t)p.ref_len * p.read_len;
             ++at;
         }
         const uint32_t n = (uint32_t)tasks.size();
@@ -1473,13 +1497,7 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
         uint8_t* h = static_cast<uint8_t*>(c.h_in.p);
         std::memcpy(h + o_tasks, tasks.data(), n * sizeof(PhmmSwTask));
         std::memcpy(h + o_order, order.data(), n * sizeof(uint32_t));
-        uint64_t cells = 0;
-        for (uint32_t k = 0; k < n; ++k) {
-            const phmm_sw_pair& p = pairs[src[k]];
-            std::memcpy(h + o_bytes + tasks[k].ref_off, p.ref, p.ref_len);
-            std::memcpy(h + o_bytes + tasks[k].read_off, p.read, p.read_len);
-            cells += (uint64_t)p.ref_len * p.read_len;
-        }
+        for (const SwCopy& cp : copies) std::memcpy(h + o_bytes + cp.dst, cp.src, cp.len);
         uint8_t* d = static_cast<uint8_t*>(c.d_in.p);
         PhmmSwBatchDev b{};
         b.tasks = reinterpret_cast<const PhmmSwTask*>(d + o_tasks);

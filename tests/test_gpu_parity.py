@@ -250,6 +250,26 @@ def test_flat_equals_per_region_and_resident(engine, orc):
         assert np.array_equal(k0, flat.kept(g)) and np.array_equal(_bits64(m0), _bits64(flat.matrix(g)))
 
 
+def test_flat_batches_with_empty_regions(engine, orc):
+    """Empty regions (no reads or no haplotypes) inside a flat batch, a batch of nothing but those, and an empty batch."""
+    rng = np.random.default_rng(29)
+    r1, h1 = wl._one_region(rng, 9, 3, 120, 160, 40, 100)
+    r2, h2 = wl._one_region(rng, 5, 2, 300, 300, 150, 150)
+    regs = [([], h1), (r1, h1), (r2, []), ([], []), (r2, h2)]
+    batch = wl.RegionBatch.from_regions(regs)
+    res = engine.run_flat(batch, raw=True)
+    for g, (reads, haps) in enumerate(regs):
+        if reads and haps:
+            m0, k0, *_ = orc.region(reads, haps)
+            assert np.array_equal(k0, res.kept(g)) and np.array_equal(_bits64(m0), _bits64(res.matrix(g)))
+        else:
+            assert res.n_kept[g] == 0
+    only_empty = engine.run_flat(wl.RegionBatch.from_regions([([], h1), (r1, [])]))
+    assert list(only_empty.n_kept[:2]) == [0, 0]
+    nothing = engine.run_flat(wl.RegionBatch.from_regions([]))
+    assert nothing.n_fp64 == 0
+
+
 def test_pinned_flat_batch_is_copied_directly(engine):
     """PHMM_FLAT_PINNED: blobs in page-locked memory are copied to the device without the staging gather; same bytes out."""
     batch = wl.cfg5(30, seed=23)

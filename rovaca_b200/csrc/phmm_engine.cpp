@@ -522,7 +522,9 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         const bool all_haps_in_stream = order.size() == r.n_haps;
         region_chunks.clear();
         if (!order.empty()) {
-            const uint32_t n_chunks = (uint32_t)std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols));
+            // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty
+            const uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / 2),
+                                                                 std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols)));
             const uint64_t per_chunk = (total + n_chunks - 1) / n_chunks;
             size_t at = 0;
             while (at < order.size()) {

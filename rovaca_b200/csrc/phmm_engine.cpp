@@ -1285,17 +1285,20 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* f
     // again at the end: the GPU starts after one small plan and only a small epilogue is left when it finishes.
     const std::vector<uint64_t> pre = flat_work_prefix(fb);
     const uint64_t total = pre[fb->n_regions];
-    const uint64_t full = std::max<uint64_t>(e->batch_cells, 1);
+    // sub-batch size: batch_cells at most, and small enough that every worker gets about two of them (host-bound streams of
+    // small regions need the planning and the epilogues spread over all workers), but not below a quarter of batch_cells
+    // (about a millisecond of device work: smaller batches are cut into finer chunks and run less efficiently)
+    const uint64_t full = std::max<uint64_t>(1, std::min<uint64_t>(e->batch_cells, std::max<uint64_t>(total / (2ull * e->n_workers), e->batch_cells >> 2)));
     std::vector<std::pair<uint32_t, uint32_t>> parts;
     {
         uint32_t g = 0;
-        int ramp = 3;                                    // next sizes: full/8, full/4, full/2, then full
+        int ramp = 2;                                    // next sizes: full/4, full/2, then full
         while (g < fb->n_regions) {
             const uint64_t left = total - pre[g];
             uint64_t want = ramp > 0 ? (full >> ramp) : full;
             if (ramp > 0) --ramp;
-            // ramp down: never take more than half of what is left while more than full/8 remains
-            if (left > (full >> 3)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 3));
+            // ramp down: never take more than half of what is left while more than full/4 remains
+            if (left > (full >> 2)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 2));
             uint32_t end = g + 1;
             while (end < fb->n_regions && pre[end] - pre[g] < want) ++end;
             parts.emplace_back(g, end);

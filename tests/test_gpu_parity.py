@@ -307,6 +307,33 @@ def test_concurrent_callers(engine, orc):
     assert not errs, errs[0]
 
 
+def test_many_synchronous_callers_match_the_flat_path(engine):
+    """48 threads calling call_pairhmm at once (the reference's pool workers; regions of different callers share GPU batches
+    under the batch-while-busy policy): every caller gets exactly what the flat path computes for its region."""
+    batch = wl.cfg5(48 * 8, seed=31)
+    flat = engine.run_flat(batch)
+    errs = []
+
+    def work(ids):
+        try:
+            for g in ids:
+                reads, haps = batch.region(g)
+                m, k = engine.call_pairhmm(haps, reads)
+                assert np.array_equal(k, flat.kept(g)), g
+                assert np.array_equal(_bits64(m), _bits64(flat.matrix(g))), g
+        except Exception as e:       # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(list(range(t, batch.n_regions, 48)),)) for t in range(48)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs[0]
+    s = engine.stats()
+    assert s["batches"] > 0
+
+
 def test_full_size_cfg2_properties(engine, orc):
     """BASELINE.json configs[1] at bench size: a sample of regions against the oracle, plus size-independent properties:
     determinism across runs, independence from batching, and column permutation when the reads are permuted."""

@@ -52,7 +52,9 @@ typedef struct phmm_config
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
     uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 3) */
-    uint32_t rsv[7];
+    uint32_t lanes_per_read;      /* 8, 16 or 32 lanes per read in the forward kernel; 0 = by batch size (small batches on an idle
+                                     device get the wide, low-latency layouts); tuning / test knob */
+    uint32_t rsv[6];
 } phmm_config;
 
 /* What the path reads of a ReadRecord (genotype/read_record.h:67-103, read_record.cpp:176-210). */

@@ -338,6 +338,7 @@ struct phmm_engine
     uint64_t batch_cells = 12000000000ull;
     uint32_t linger_us = 200;
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
+    uint32_t lanes_pref = 0;     // lanes per read of the reference-gap kernels: 0 = by batch size, else 8 / 16 / 32
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     bool inline_log10f = false;    // this host's log10f is the fdlibm formula around logf (checked at creation)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
@@ -449,6 +450,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     // batch and chunks x reads its parallelism.  A big batch fills the GPU with long chunks (fewest seams and staging); a
     // small one (the synchronous per-region callers) is cut finer until it has about two warps per warp slot of the device.
     uint32_t target_cols = kTargetStreamCols;
+    int min_lanes = 8;             // lanes per read of the reference-gap kernels
     {
         uint64_t est_warps = 0;
         for (const RegionIn& r : regs) {
@@ -458,10 +460,20 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         // batches already on the device fill it too: share the target among them
         const uint64_t want = 2ull * warp_slots / std::max<uint32_t>(1, busy_batches.load(std::memory_order_relaxed));
+        // First spread each read over more lanes (fewer rows per lane = a cheaper step: the latency bins), then cut the chunks
+        // shorter, until the batch has about `want` warps.
+        // (only while even the widened batch leaves half of its share of the device empty: the wide layouts do 10-15 % less
+        // work per issue slot, so a busy device wants the throughput layout)
+        if (lanes_pref)
+            min_lanes = (int)lanes_pref;
+        else if (est_warps * 8 <= want)
+            min_lanes = 32;
+        else if (est_warps * 4 <= want)
+            min_lanes = 16;
+        est_warps *= (uint64_t)min_lanes / 8;
         if (est_warps > 0 && est_warps < want)
             target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want);
     }
-
     std::vector<PhmmRead> reads;
     std::vector<PhmmHap> haps;
     std::vector<PhmmChunk> chunks;
@@ -480,7 +492,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     // read length -> bin, for the lengths the wavefront kernels take (a table instead of a search per read)
     uint8_t bin_lut[640];
     for (uint32_t len = 0; len < 640; ++len) {
-        const int b = phmm_bin_of(len, refgaps);
+        const int b = phmm_bin_of(len, refgaps, min_lanes);
         bin_lut[len] = b < 0 ? 255 : (uint8_t)b;
     }
     std::vector<std::vector<uint32_t>> by_bin(kPhmmNumBins);
@@ -1148,6 +1160,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
         if (cfg->linger_us) e->linger_us = cfg->linger_us;
         if (cfg->cta_warps) e->cta_warps = std::min<uint32_t>(cfg->cta_warps, PHMM_WARPS);
         if (cfg->pipeline_depth) e->pipeline_depth = std::min<uint32_t>(cfg->pipeline_depth, 32);
+        if (cfg->lanes_per_read == 8 || cfg->lanes_per_read == 16 || cfg->lanes_per_read == 32) e->lanes_pref = cfg->lanes_per_read;
     }
     std::unique_ptr<PhmmTables> t(new PhmmTables());
     phmm_build_tables(t.get());
@@ -1630,13 +1643,14 @@ int phmm_ubench(phmm_engine* e, int mode, uint32_t iters, float* ms_out, double*
 //   0 pairs  1 pairs covered by the wavefront kernel  2 per-pair-kernel pairs  3 pairs covered more than once  4 pairs missed
 //   5 warps launched  6 read slots  7 read slots filled  8 reads in a bin too small for them  9 launches  10 chunks
 //   11 lane-steps (sum over warps of 32 x RPT x steps)  12 cells (sum R x H over wavefront pairs)  13 CTA shape violations
-int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps, uint32_t busy_batches, uint64_t* out)
+int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps, uint32_t busy_batches, uint32_t lanes_per_read, uint64_t* out)
 {
     if (!fb || !out) return fail(PHMM_ERR_ARG, "phmm_debug_plan: null argument");
     phmm_engine e;
     e.fma = fma_mode != PHMM_FMA_NONE;
     e.cta_warps = std::min<uint32_t>(cta_warps, PHMM_WARPS);
     e.busy_batches.store(busy_batches);
+    e.lanes_pref = lanes_per_read;
     Slot s;
     s.set_host_only();
     std::vector<phmm_read> reads;

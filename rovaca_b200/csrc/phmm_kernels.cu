@@ -742,6 +742,12 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     PHMM_CASE_R(13, 8, FN, __VA_ARGS__) PHMM_CASE_R(14, 8, FN, __VA_ARGS__) PHMM_CASE_R(15, 8, FN, __VA_ARGS__)       \
     PHMM_CASE_R(16, 8, FN, __VA_ARGS__) PHMM_CASE_R(17, 8, FN, __VA_ARGS__) PHMM_CASE_R(18, 8, FN, __VA_ARGS__)       \
     PHMM_CASE_R(19, 8, FN, __VA_ARGS__)                                                                               \
+    PHMM_CASE_R(1, 16, FN, __VA_ARGS__) PHMM_CASE_R(2, 16, FN, __VA_ARGS__) PHMM_CASE_R(3, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(4, 16, FN, __VA_ARGS__) PHMM_CASE_R(5, 16, FN, __VA_ARGS__) PHMM_CASE_R(6, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(7, 16, FN, __VA_ARGS__) PHMM_CASE_R(8, 16, FN, __VA_ARGS__) PHMM_CASE_R(9, 16, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(1, 32, FN, __VA_ARGS__) PHMM_CASE_R(2, 32, FN, __VA_ARGS__) PHMM_CASE_R(3, 32, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(4, 32, FN, __VA_ARGS__) PHMM_CASE_R(5, 32, FN, __VA_ARGS__) PHMM_CASE_R(6, 32, FN, __VA_ARGS__)       \
+    PHMM_CASE_R(7, 32, FN, __VA_ARGS__) PHMM_CASE_R(8, 32, FN, __VA_ARGS__) PHMM_CASE_R(9, 32, FN, __VA_ARGS__)       \
     PHMM_CASE_R(10, 16, FN, __VA_ARGS__) PHMM_CASE_R(12, 16, FN, __VA_ARGS__) PHMM_CASE_R(14, 16, FN, __VA_ARGS__)    \
     PHMM_CASE_R(16, 16, FN, __VA_ARGS__) PHMM_CASE_R(18, 16, FN, __VA_ARGS__) PHMM_CASE_R(19, 16, FN, __VA_ARGS__)    \
     PHMM_CASE_R(10, 32, FN, __VA_ARGS__) PHMM_CASE_R(12, 32, FN, __VA_ARGS__) PHMM_CASE_R(14, 32, FN, __VA_ARGS__)    \

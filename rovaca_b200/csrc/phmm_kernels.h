@@ -51,22 +51,28 @@ struct PhmmBin
 static const PhmmBin kPhmmBins[] = {
     {16, 1, 0}, {16, 2, 0}, {16, 3, 0}, {16, 4, 0}, {16, 5, 0}, {16, 6, 0}, {16, 7, 0}, {16, 8, 0}, {16, 9, 0}, {16, 10, 0}, {16, 11, 0},
     {16, 12, 0}, {32, 7, 0}, {32, 8, 0}, {32, 9, 0}, {32, 10, 0}, {32, 11, 0}, {32, 12, 0},
-    // ... and the bins of the reference-gap variant: 8 lanes up to 151 bp (8 x 19 = 152 rows hold a 150/151-bp read with
-    // 1-2 pad rows), 16 lanes up to 303 bp, 32 lanes up to 607 bp
+    // ... and the bins of the reference-gap variant.  Throughput bins: 8 lanes up to 151 bp (8 x 19 = 152 rows hold a 150/151-bp
+    // read with 1-2 pad rows), 16 lanes up to 303 bp, 32 lanes up to 607 bp.  The short 16- and 32-lane bins are the latency
+    // bins: a read spread over more lanes has fewer rows per lane and so a cheaper wavefront step (the time of a sweep is
+    // steps x rows per lane), which is what a small batch on an idle device wants (phmm_engine::plan picks the family).
     {8, 1, 1}, {8, 2, 1}, {8, 3, 1}, {8, 4, 1}, {8, 5, 1}, {8, 6, 1}, {8, 7, 1}, {8, 8, 1}, {8, 9, 1}, {8, 10, 1}, {8, 11, 1}, {8, 12, 1},
     {8, 13, 1}, {8, 14, 1}, {8, 15, 1}, {8, 16, 1}, {8, 17, 1}, {8, 18, 1}, {8, 19, 1},
+    {16, 1, 1}, {16, 2, 1}, {16, 3, 1}, {16, 4, 1}, {16, 5, 1}, {16, 6, 1}, {16, 7, 1}, {16, 8, 1}, {16, 9, 1},
     {16, 10, 1}, {16, 12, 1}, {16, 14, 1}, {16, 16, 1}, {16, 18, 1}, {16, 19, 1},
+    {32, 1, 1}, {32, 2, 1}, {32, 3, 1}, {32, 4, 1}, {32, 5, 1}, {32, 6, 1}, {32, 7, 1}, {32, 8, 1}, {32, 9, 1},
     {32, 10, 1}, {32, 12, 1}, {32, 14, 1}, {32, 16, 1}, {32, 18, 1}, {32, 19, 1}};
 static const int kPhmmNumBins = sizeof(kPhmmBins) / sizeof(kPhmmBins[0]);
 static const int kPhmmFirstRefGapBin = 18;
 static inline uint32_t phmm_bin_capacity(int bin) { return (uint32_t)(kPhmmBins[bin].lanes * kPhmmBins[bin].rpt) - 1u; }
 static inline uint32_t phmm_bin_reads_per_cta(int bin, uint32_t cta_warps) { return cta_warps * 32u / (uint32_t)kPhmmBins[bin].lanes; }
-// The bin that serves a read: the first one of its family (reference gaps or generic) that holds it; -1 = none (per-pair kernel).
-static inline int phmm_bin_of(uint32_t len, bool refgaps)
+// The bin that serves a read: the first one of its family (reference gaps or generic) that holds it — for the reference-gap
+// family the first with at least min_lanes lanes per read (8 = throughput bins, 16 / 32 = latency bins); -1 = none (per-pair
+// kernel).
+static inline int phmm_bin_of(uint32_t len, bool refgaps, int min_lanes = 8)
 {
     if (len == 0) return -1;
     for (int b = refgaps ? kPhmmFirstRefGapBin : 0; b < (refgaps ? kPhmmNumBins : kPhmmFirstRefGapBin); ++b)
-        if (len <= phmm_bin_capacity(b)) return b;
+        if (len <= phmm_bin_capacity(b) && (!refgaps || kPhmmBins[b].lanes >= min_lanes)) return b;
     return -1;
 }
 

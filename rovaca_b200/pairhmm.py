@@ -37,7 +37,7 @@ class PhmmError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
-                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("rsv", C.c_uint32 * 7)]
+                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("lanes_per_read", C.c_uint32), ("rsv", C.c_uint32 * 6)]
 
 
 class _Read(C.Structure):
@@ -150,7 +150,7 @@ def load_library():
     L.phmm_debug_tables.restype = None
     L.phmm_debug_log10f_check.restype = C.c_uint64
     L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.POINTER(C.c_int)]
-    L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, _u64p]
+    L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u64p]
     _lib = L
     return L
 
@@ -170,13 +170,13 @@ PLAN_AUDIT_FIELDS = ("pairs", "wavefront_pairs", "per_pair_kernel_pairs", "cover
 
 
 def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 0, busy_batches: int = 1,
-               min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE) -> dict:
+               min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE, lanes_per_read: int = 0) -> dict:
     """Host only (no GPU): run the engine's planner on ``batch`` and audit its output — every pair computed exactly once,
     every read in a bin that holds it, CTA shapes respected — plus the numbers that tell how well the lanes are used."""
     L = load_library()
     fb = _flat_c(batch, min_quality_threshold, pcr_option)
     out = np.zeros(16, np.uint64)
-    rc = L.phmm_debug_plan(C.byref(fb), fma_mode, cta_warps, busy_batches, out.ctypes.data_as(_u64p))
+    rc = L.phmm_debug_plan(C.byref(fb), fma_mode, cta_warps, busy_batches, lanes_per_read, out.ctypes.data_as(_u64p))
     if rc != 0:
         raise PhmmError(f"phmm_debug_plan failed ({rc}): {L.phmm_last_error().decode()}")
     d = {k: int(v) for k, v in zip(PLAN_AUDIT_FIELDS, out)}
@@ -275,9 +275,9 @@ class PairHmmEngine:
     """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
 
     def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
-                 linger_us: int = 0, cta_warps: int = 0):
+                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0):
         self.L = load_library()
-        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps)
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read)
         self.h = C.c_void_p()
         rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -105,4 +105,4 @@ def test_sass_audit():
         assert c["FMUL"] >= 4 * rpt, (name, c)
         assert c["FADD2"] == 4, (name, c)
         assert c["SHFL"] >= 12, (name, c)
-    assert seen == 18 + 31
+    assert seen == 18 + 31 + 18          # generic, reference-gap throughput bins, reference-gap latency bins

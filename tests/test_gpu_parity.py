@@ -214,6 +214,26 @@ def test_pcr_model_tandem_repeats(engine, orc):
     _check_region_vs_oracle(engine, orc, long_reads, [long_reads[0]["bases"][100:700].copy()], 18, PCR_CONSERVATIVE)
 
 
+@pytest.mark.parametrize("lanes", [16, 32])
+def test_latency_lane_families(orc, lanes):
+    """The reference-gap kernels with 16 and 32 lanes per read (what a small batch on an idle device gets): every bin boundary,
+    odd read counts, a mixed region, and the default engine on a one-region batch (which picks them by itself)."""
+    eng = PairHmmEngine(lanes_per_read=lanes)
+    try:
+        rng = np.random.default_rng(100 + lanes)
+        hap = B[rng.integers(0, 4, 640)]
+        haps = [hap, hap[3:590].copy(), hap[::-1].copy()]
+        caps = [lanes * r - 1 for r in list(range(1, 10)) + [10, 12, 14, 16, 18, 19]]
+        _check_region_vs_oracle(eng, orc, _bin_boundary_reads(rng, hap, caps, False), haps)
+        for count in (1, 2, 3, 5):
+            sub = [dict(bases=hap[o:o + 150].copy(), qual=rng.integers(8, 41, 150).astype(np.uint8), mapq=60) for o in rng.integers(0, 400, count)]
+            _check_region_vs_oracle(eng, orc, sub, haps)
+        reads, hs = wl._one_region(rng, 37, 9, 250, 450, 30, 151, junk=0.1)
+        _check_region_vs_oracle(eng, orc, reads, hs)
+    finally:
+        eng.close()
+
+
 def test_fp64_recompute_exercised(engine, orc):
     """cfg3-style: junk reads underflow FP32 (< 1e-28f) and are recomputed in FP64 on the device."""
     rng = np.random.default_rng(12)

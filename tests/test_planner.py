@@ -25,6 +25,25 @@ def test_cfg2_plan_is_tight(cta_warps):
     assert a["lane_utilisation"] > 0.96, a            # 150 rows in 152, 7 fill steps per 1200 columns
 
 
+@pytest.mark.parametrize("lanes", [8, 16, 32])
+def test_every_lane_family_covers_every_pair(lanes):
+    b = wl.cfg5(40, seed=12, post_trim_fraction=0.5)
+    a = ph.plan_audit(b, lanes_per_read=lanes, busy_batches=4)
+    _sound(a)
+    assert a["read_slots"] % (32 // lanes) == 0
+
+
+def test_an_idle_device_gets_the_wide_layouts():
+    """One region on an idle device: reads spread over 32 lanes (5 rows per lane for 150 bp) — a quarter of the rows per lane of
+    the throughput layout, so a quarter of the time per wavefront step; a big batch keeps 8 lanes x 19 rows."""
+    one = ph.plan_audit(wl.cfg2(1, seed=3), busy_batches=1)
+    many = ph.plan_audit(wl.cfg2(256, seed=3), busy_batches=1)
+    _sound(one)
+    _sound(many)
+    assert one["read_slots"] == 64 * one["chunks"] and one["warps"] == 64 * one["chunks"]      # one read per warp
+    assert many["warps"] == 256 * 16                                                             # four reads per warp
+
+
 def test_small_batches_are_cut_finer():
     few, many = ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=16)
     _sound(few)

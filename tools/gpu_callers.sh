@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 OUT=gpurun_out/${1:-callers}.txt
 : > $OUT
-for t in 8 16 32 64 128 256; do tools/caller_bench --threads $t --regions $((4096 / t > 16 ? 4096 / t : 16)) >> $OUT 2>&1; done
-for w in 4 16 64; do tools/caller_bench --threads 16 --regions 256 --window $w >> $OUT 2>&1; done
+tools/caller_bench --threads 1 --regions 512 >> $OUT 2>&1
+for t in 8 16 32 64 128 256 512; do tools/caller_bench --threads $t --regions $((8192 / t > 64 ? 8192 / t : 64)) >> $OUT 2>&1; done
+for w in 4 16 64; do tools/caller_bench --threads 16 --regions 512 --window $w >> $OUT 2>&1; done
 cat $OUT

@@ -54,8 +54,17 @@ typedef struct phmm_config
     uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 3) */
     uint32_t lanes_per_read;      /* 8, 16 or 32 lanes per read in the forward kernel; 0 = by batch size (small batches on an idle
                                      device get the wide, low-latency layouts); tuning / test knob */
-    uint32_t rsv[6];
+    uint32_t fp64_mode;           /* PHMM_FP64_*: when pairs whose FP32 sum underflows (< 1e-28f) are recomputed in FP64 */
+    uint32_t rsv[5];
 } phmm_config;
+
+/* pairhmm_internal.cpp:578-584 recomputes an underflowing pair in FP64.  The value it gets is below -64 (log10) and never
+ * reaches the returned matrix: filter_poorly_modelled_evidence drops the read (best < -8, or -4 under 51 bp) or
+ * normalize_likelihoods caps the entry at best - 4.5 (SURVEY.md §8a "Consequence of a11-a14"); the reference's own FP64
+ * kernels return 0 for every such pair (a12) and its matrix is the same.  So by default the recompute runs only for a
+ * caller that can see the value (phmm_result.raw_f64 / phmm_flat_result.raw_f64). */
+#define PHMM_FP64_WHEN_OBSERVABLE 0u
+#define PHMM_FP64_ALWAYS 1u
 
 /* What the path reads of a ReadRecord (genotype/read_record.h:67-103, read_record.cpp:176-210). */
 typedef struct phmm_read

@@ -227,6 +227,8 @@ struct Slot
     uint64_t n_pairs = 0, n_cells = 0, n_words = 0;
     uint32_t n_reads = 0, n_haps = 0, n_slow = 0, max_cols = 0;
     uint32_t n_launches = 0;
+    bool want_f64 = false;               // the FP64 recompute goes out with the batch (someone will read its values)
+    bool f64_done = false;               // ... and has been launched for the sums now on the device
     float gpu_ms = 0.f, fwd_ms = 0.f;
     size_t o_reads = 0, o_haps = 0, o_chunks = 0, o_ctas = 0, o_tasks = 0, o_slow = 0;   // arena offsets of the record arrays
     size_t n_chunks = 0, n_ctas = 0, n_tasks = 0;
@@ -339,6 +341,7 @@ struct phmm_engine
     uint32_t linger_us = 200;
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
     uint32_t lanes_pref = 0;     // lanes per read of the reference-gap kernels: 0 = by batch size, else 8 / 16 / 32
+    bool fp64_always = false;    // PHMM_FP64_ALWAYS: recompute every underflowing pair even when nobody can see the value
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     bool inline_log10f = false;    // this host's log10f is the fdlibm formula around logf (checked at creation)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
@@ -424,8 +427,10 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     [[maybe_unused]] const auto pt0 = PT_NOW();
     uint64_t n_reads = 0, n_haps = 0, read_bytes = 0, hap_bytes = 0, n_pairs = 0, n_cells = 0;
     bool any_ins = false, any_del = false, any_gcp = false;
+    s.want_f64 = fp64_always;
     for (const RegionIn& r : regs) {
         if (r.n_reads == 0 || r.n_haps == 0) continue;           // pairhmm_internal.cpp:508-510
+        s.want_f64 |= r.out.raw_f64 != nullptr;
         uint64_t rb = 0, hb = 0;
         for (uint32_t k = 0; k < r.n_reads; ++k) {
             rb += r.reads[k].len;
@@ -854,7 +859,8 @@ int phmm_engine::launch(Slot& s, bool copy_in)
     if (s.n_slow)
         CU(phmm_launch_pairs_f32(s.dev, fma, s.dev.slow_pairs, s.n_slow, static_cast<float*>(s.d_scr32.p), kPairThreads, s.max_cols,
                                  s.stream));
-    if (s.n_pairs)
+    s.f64_done = s.want_f64 && s.n_pairs;
+    if (s.f64_done)
         CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
                                  s.stream));
     CU(cudaEventRecord(s.ev[3], s.stream));
@@ -885,9 +891,20 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
         }
         if (q == cudaErrorNotReady) CU(cudaStreamSynchronize(s.stream));
     }
+    // The FP64 sums are read only by a caller that asked for them (raw_f64) or under PHMM_FP64_ALWAYS; see `have64` below.
+    bool have64 = s.f64_done;
     if (s.n_pairs) {
         n64 = *static_cast<uint32_t*>(s.h_cnt.p);
-        if (n64 > 0) {
+        if (n64 > 0 && !have64) {
+            bool asked = false;                                 // a resident batch learns at download time who wants raw sums
+            for (const RegionIn& r : regs) asked |= r.out.raw_f64 != nullptr && r.n_reads && r.n_haps;
+            if (asked) {
+                CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads,
+                                         s.max_cols, s.stream));
+                s.f64_done = have64 = true;
+            }
+        }
+        if (n64 > 0 && have64) {
             CU(cudaMemcpyAsync(s.h_f64.p, s.d_f64.p, s.n_pairs * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
             CU(cudaStreamSynchronize(s.stream));
             stats.d2h += s.n_pairs * sizeof(double);
@@ -921,7 +938,10 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
                 const float f = fr[j];
                 double v;
                 if (f < kMinAccepted) {                                              // :578
-                    v = log10(f64[rp.out_off + (size_t)i * nh + j]) - kLog10InitD;   // :580
+                    // :580.  Without the FP64 sum the pair stands at -inf — which is also what the reference as built
+                    // computes here (its FP64 kernels return 0).  Either way the value is below -64 and
+                    // cannot reach the matrix: the read is dropped (best < -8 / -4) or the entry is capped at best - 4.5.
+                    v = have64 ? log10(f64[rp.out_off + (size_t)i * nh + j]) - kLog10InitD : -INFINITY;
                     ++reg64;
                 } else {
                     v = (double)((inline_log10f ? log10f_fdlibm_form(f) : log10f(f)) - kLog10InitF);   // :583
@@ -934,7 +954,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
             if (r.out.raw_f32) std::memcpy(r.out.raw_f32 + (size_t)i * nh, fr, nh * sizeof(float));
             if (r.out.raw_f64)
                 for (uint32_t j = 0; j < nh; ++j)
-                    r.out.raw_f64[(size_t)i * nh + j] = (fr[j] < kMinAccepted) ? f64[rp.out_off + (size_t)i * nh + j] : (double)NAN;
+                    r.out.raw_f64[(size_t)i * nh + j] = (fr[j] < kMinAccepted && have64) ? f64[rp.out_off + (size_t)i * nh + j] : (double)NAN;
             // normalize_likelihoods :53-63 caps at best - 4.5 (adapter.h:23); the maximum itself is unchanged, so
             // filter_poorly_modelled_evidence :161-182 sees the same `best`
             const double cmp = best + (-4.5);
@@ -1161,6 +1181,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
         if (cfg->cta_warps) e->cta_warps = std::min<uint32_t>(cfg->cta_warps, PHMM_WARPS);
         if (cfg->pipeline_depth) e->pipeline_depth = std::min<uint32_t>(cfg->pipeline_depth, 32);
         if (cfg->lanes_per_read == 8 || cfg->lanes_per_read == 16 || cfg->lanes_per_read == 32) e->lanes_pref = cfg->lanes_per_read;
+        e->fp64_always = cfg->fp64_mode == PHMM_FP64_ALWAYS;
     }
     std::unique_ptr<PhmmTables> t(new PhmmTables());
     phmm_build_tables(t.get());

@@ -22,6 +22,7 @@ from .workloads import RegionBatch, _as_u8
 PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE, PCR_CONSERVATIVE = 0, 1, 2, 3      # common/enum.h:8
 FMA_AVX512, FMA_NONE = 1, 2
 FLAT_PINNED = 1                                                          # phmm_flat_batch.flags
+FP64_WHEN_OBSERVABLE, FP64_ALWAYS = 0, 1                                     # phmm_config.fp64_mode
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _u8p = C.POINTER(C.c_uint8)
@@ -37,7 +38,7 @@ class PhmmError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
-                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("lanes_per_read", C.c_uint32), ("rsv", C.c_uint32 * 6)]
+                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("lanes_per_read", C.c_uint32), ("fp64_mode", C.c_uint32), ("rsv", C.c_uint32 * 5)]
 
 
 class _Read(C.Structure):
@@ -275,9 +276,9 @@ class PairHmmEngine:
     """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
 
     def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
-                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0):
+                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0, fp64_mode: int = 0):
         self.L = load_library()
-        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read)
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read, fp64_mode)
         self.h = C.c_void_p()
         rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:

@@ -242,6 +242,51 @@ def test_fp64_recompute_exercised(engine, orc):
     assert n64 > 50
 
 
+def test_matrix_does_not_depend_on_the_fp64_recompute(engine, orc):
+    """By default the FP64 recompute runs only when its values can be seen (raw_f64 asked for): an underflowing pair is
+    below -64, so its read is dropped or its entry capped at best - 4.5 (consequence of a11-a14).  The
+    matrices and the surviving reads must be the ones the oracle gets WITH the recompute, for reads on both sides of the
+    51-bp filter limit, all-junk regions, flat batches and device-resident batches; PHMM_FP64_ALWAYS gives the same bytes."""
+    from rovaca_b200.pairhmm import FP64_ALWAYS
+    always = PairHmmEngine(fp64_mode=FP64_ALWAYS)
+    try:
+        rng = np.random.default_rng(31)
+        specs = [dict(n_reads=60, n_haps=8, hap_lo=300, hap_hi=420, read_lo=120, read_hi=151, junk=0.4),
+                 dict(n_reads=40, n_haps=5, hap_lo=200, hap_hi=260, read_lo=20, read_hi=60, junk=0.5),     # limit -4 below 51 bp
+                 dict(n_reads=9, n_haps=3, hap_lo=300, hap_hi=300, read_lo=150, read_hi=150, junk=1.0),    # nothing survives
+                 dict(n_reads=30, n_haps=4, hap_lo=500, hap_hi=700, read_lo=300, read_hi=420, junk=0.3)]
+        seen = 0
+        for spec in specs:
+            reads, haps = wl._one_region(rng, **spec)
+            m0, k0, o32, _, o_n64 = orc.region(reads, haps)
+            seen += o_n64
+            for eng in (engine, always):
+                m, k = eng.call_pairhmm(haps, reads)
+                assert np.array_equal(k, k0)
+                assert np.array_equal(_bits64(m), _bits64(m0))
+        assert seen > 200
+        batch = wl.cfg3(2, seed=33, n_reads=120, n_haps=12)
+        before = engine.stats()["fp64_pairs"]
+        lazy, full, raw = engine.run_flat(batch), always.run_flat(batch), engine.run_flat(batch, raw=True)
+        assert lazy.n_fp64 == full.n_fp64 == raw.n_fp64 > 50                        # counted either way
+        assert engine.stats()["fp64_pairs"] - before == 2 * raw.n_fp64
+        assert np.array_equal(_bits64(lazy.likelihoods), _bits64(full.likelihoods))
+        assert np.array_equal(_bits64(lazy.likelihoods), _bits64(raw.likelihoods))
+        assert np.array_equal(lazy.n_kept, full.n_kept) and np.array_equal(lazy.kept_idx, full.kept_idx)
+        resident = engine.upload(batch)
+        resident.run()
+        d0 = resident.download()                  # no raw sums asked for: nothing recomputed
+        d1 = resident.download(raw=True)          # asked for after the run: recomputed now
+        resident.free()
+        assert np.array_equal(_bits64(d0.likelihoods), _bits64(raw.likelihoods))
+        assert np.array_equal(_bits64(d1.likelihoods), _bits64(raw.likelihoods))
+        assert np.array_equal(_bits64(d1.raw_f64), _bits64(raw.raw_f64))
+        took = raw.raw_f32 < np.float32(1e-28)
+        assert took.sum() == raw.n_fp64 and not np.isnan(raw.raw_f64[took]).any() and np.isnan(raw.raw_f64[~took]).all()
+    finally:
+        always.close()
+
+
 def test_long_haplotypes_multi_chunk(engine, orc):
     """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
     rng = np.random.default_rng(13)

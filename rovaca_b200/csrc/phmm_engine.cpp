@@ -38,6 +38,7 @@
 
 #include "../../include/phmm_b200.h"
 #include "phmm_kernels.h"
+#include "phmm_log10.h"
 #include "phmm_types.h"
 
 void phmm_build_tables(PhmmTables* t);
@@ -69,45 +70,6 @@ constexpr float kLog10InitF = 36.1236000061f;              // LOG10_INITIAL_CONS
 constexpr double kLog10InitD = 307.050595577260822;        // LOG10_INITIAL_CONSTANT_D, adapter.h:26
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-// log10f is the host's biggest cost per pair (the reference's conversion, pairhmm_internal.cpp:583, must use the host's own
-// libm for the bits to match).  glibc up to 2.39 computes it the fdlibm way — split off the exponent, then
-// y*log10_2lo + ivln10*logf(m), + y*log10_2hi in float arithmetic — spending most of its time around a call of its own
-// (fast) logf.  The same formula inlined around the host's logf gives the same bits for less; whether this host's log10f IS
-// that formula is not assumed but tested when an engine is created (a million inputs across the range the path produces,
-// bit for bit); any difference and the engine keeps calling log10f itself.
-inline float log10f_fdlibm_form(float x)
-{
-    uint32_t ux;
-    std::memcpy(&ux, &x, 4);
-    int32_t hx = (int32_t)ux, k = 0;
-    if (hx < 0x00800000) {                                   // zero, negative or subnormal: leave those to libm
-        return log10f(x);
-    }
-    if (hx >= 0x7f800000) return x + x;
-    k += (hx >> 23) - 127;
-    const int32_t i = (int32_t)(((uint32_t)k & 0x80000000u) >> 31);
-    hx = (hx & 0x007fffff) | ((0x7f - i) << 23);
-    const float y = (float)(k + i);
-    ux = (uint32_t)hx;
-    std::memcpy(&x, &ux, 4);
-    const float ivln10 = 4.3429449201e-01f, log10_2hi = 3.0102920532e-01f, log10_2lo = 7.9034151668e-07f;
-    const float z = y * log10_2lo + ivln10 * logf(x);
-    return z + y * log10_2hi;
-}
-
-bool log10f_form_matches_libm()
-{
-    uint32_t bits = 0x0d800000u;                              // ~1e-30 ... up to 2^127, in a million prime-strided steps
-    for (int n = 0; n < 1000000; ++n, bits += 1913u + (uint32_t)(n & 7)) {
-        if (bits >= 0x7f000000u) bits = 0x0d800000u + (uint32_t)n;
-        float x;
-        std::memcpy(&x, &bits, 4);
-        const float a = log10f(x), b = log10f_fdlibm_form(x);
-        if (std::memcmp(&a, &b, 4) != 0) return false;
-    }
-    return true;
-}
 
 struct RegionIn
 {
@@ -343,7 +305,7 @@ struct phmm_engine
     uint32_t lanes_pref = 0;     // lanes per read of the reference-gap kernels: 0 = by batch size, else 8 / 16 / 32
     bool fp64_always = false;    // PHMM_FP64_ALWAYS: recompute every underflowing pair even when nobody can see the value
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
-    bool inline_log10f = false;    // this host's log10f is the fdlibm formula around logf (checked at creation)
+    int log10_mode = 0;            // how raw sums become log10 doubles: phmm_log10.cpp, picked (and tested against libm) at creation
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
     float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
@@ -407,6 +369,7 @@ struct phmm_engine
     int plan(Slot& s, const std::vector<RegionIn>& regs);
     int launch(Slot& s, bool copy_in);
     int finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out);
+    void epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const;
     int execute(Slot& s, const std::vector<RegionIn>& regs);
     void worker_main(uint32_t idx);
     void enqueue(std::function<void(Slot&)> fn);
@@ -914,64 +877,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
 
     const auto t_epi = std::chrono::steady_clock::now();
-    const unsigned old_csr = _mm_getcsr();
-    _mm_setcsr(old_csr | 0x8000u);                 // init_native, pairhmm_internal.cpp:21-25
-    const float* f32 = static_cast<const float*>(s.h_f32.p);
-    const double* f64 = static_cast<const double*>(s.h_f64.p);
-    std::vector<double> lk;
-    for (size_t g = 0; g < regs.size(); ++g) {
-        const RegionIn& r = regs[g];
-        const RegionPlan& rp = s.regions[g];
-        if (r.n_kept_out) *r.n_kept_out = 0;
-        if (r.n_fp64_out32) *r.n_fp64_out32 = 0;
-        if (rp.n_reads == 0 || rp.n_haps == 0) continue;
-        const uint32_t nr = rp.n_reads, nh = rp.n_haps;
-        lk.resize((size_t)nh);
-        uint32_t reg64 = 0, kept = 0;
-        double* out = r.out.likelihoods;                                             // [nh][nr], :516
-        for (uint32_t i = 0; i < nr; ++i) {
-            double* row = lk.data();
-            const float* fr = f32 + rp.out_off + (size_t)i * nh;
-            double best = -INFINITY;
-            bool best_nan = false;
-            for (uint32_t j = 0; j < nh; ++j) {
-                const float f = fr[j];
-                double v;
-                if (f < kMinAccepted) {                                              // :578
-                    // :580.  Without the FP64 sum the pair stands at -inf — which is also what the reference as built
-                    // computes here (its FP64 kernels return 0, SURVEY.md §8 a12).  Either way the value is below -64 and
-                    // cannot reach the matrix: the read is dropped (best < -8 / -4) or the entry is capped at best - 4.5.
-                    v = have64 ? log10(f64[rp.out_off + (size_t)i * nh + j]) - kLog10InitD : -INFINITY;
-                    ++reg64;
-                } else {
-                    v = (double)((inline_log10f ? log10f_fdlibm_form(f) : log10f(f)) - kLog10InitF);   // :583
-                }
-                row[j] = v;
-                // std::max_element semantics of :56,:170 — the first element, replaced only by a strictly greater one
-                if (j == 0) { best = v; best_nan = v != v; }
-                else if (!best_nan && best < v) best = v;
-            }
-            if (r.out.raw_f32) std::memcpy(r.out.raw_f32 + (size_t)i * nh, fr, nh * sizeof(float));
-            if (r.out.raw_f64)
-                for (uint32_t j = 0; j < nh; ++j)
-                    r.out.raw_f64[(size_t)i * nh + j] = (fr[j] < kMinAccepted && have64) ? f64[rp.out_off + (size_t)i * nh + j] : (double)NAN;
-            // normalize_likelihoods :53-63 caps at best - 4.5 (adapter.h:23); the maximum itself is unchanged, so
-            // filter_poorly_modelled_evidence :161-182 sees the same `best`
-            const double cmp = best + (-4.5);
-            const double lim = std::min(2.0, std::ceil((int32_t)s.read_len[rp.read_begin + i] * 0.02)) * (-4.0);   // adapter.h:20-22
-            if (best < lim) continue;
-            for (uint32_t j = 0; j < nh; ++j) out[(size_t)j * nr + kept] = row[j] < cmp ? cmp : row[j];   // transpose :184-193
-            r.out.kept_idx[kept++] = i;
-        }
-        if (kept < nr)                                                               // the NaN tail of the filtered reads
-            for (uint32_t j = 0; j < nh; ++j)
-                for (uint32_t c = kept; c < nr; ++c) out[(size_t)j * nr + c] = (double)NAN;
-        if (r.n_kept_out) *r.n_kept_out = kept;
-        if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
-        if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
-    }
-    _mm_setcsr(old_csr);
-
+    epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
     stats.regions += regs.size();
     stats.pairs += s.n_pairs;
     stats.cells += s.n_cells;
@@ -984,6 +890,45 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
         stats.epilogue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epi).count();
     }
     return PHMM_OK;
+}
+
+// The reference's host side after the kernels (pairhmm_internal.cpp:578-584 conversion, :53-63 normalize, :161-182 filter,
+// :184-193 transpose), region by region, from the raw sums in batch order.
+void phmm_engine::epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const
+{
+    const unsigned old_csr = _mm_getcsr();
+    _mm_setcsr(old_csr | 0x8000u);                 // init_native, pairhmm_internal.cpp:21-25
+    std::vector<double> lk;
+    for (size_t g = 0; g < regs.size(); ++g) {
+        const RegionIn& r = regs[g];
+        const RegionPlan& rp = s.regions[g];
+        if (r.n_kept_out) *r.n_kept_out = 0;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = 0;
+        if (rp.n_reads == 0 || rp.n_haps == 0) continue;
+        const uint32_t nr = rp.n_reads, nh = rp.n_haps;
+        const size_t np = (size_t)nr * nh;
+        const float* fr = f32 + rp.out_off;
+        if (lk.size() < np + 8) lk.resize(np + 8);
+        // :583 for the whole region, [read][hap]; the pairs under MIN_ACCEPTED (:578) are redone below
+        const uint32_t reg64 = (uint32_t)phmm_log10_block(fr, lk.data(), np, log10_mode);
+        if (reg64)
+            for (size_t q = 0; q < np; ++q)
+                if (fr[q] < kMinAccepted)
+                    // :580.  Without the FP64 sum the pair stands at -inf — which is also what the reference as built
+                    // computes here (its FP64 kernels return 0, SURVEY.md §8 a12).  Either way the value is below -64 and
+                    // cannot reach the matrix: the read is dropped (best < -8 / -4) or the entry is capped at best - 4.5.
+                    lk[q] = have64 ? log10(f64[rp.out_off + q]) - kLog10InitD : -INFINITY;
+        if (r.out.raw_f32) std::memcpy(r.out.raw_f32, fr, np * sizeof(float));
+        if (r.out.raw_f64)
+            for (size_t q = 0; q < np; ++q) r.out.raw_f64[q] = (fr[q] < kMinAccepted && have64) ? f64[rp.out_off + q] : (double)NAN;
+        // normalize :53-63, filter :161-182, transpose :184-193 into the caller's [nh][nr] matrix (:516) with its NaN tail
+        const uint32_t kept = phmm_postprocess_region(lk.data(), nr, nh, s.read_len.data() + rp.read_begin, r.out.likelihoods,
+                                                      r.out.kept_idx, log10_mode);
+        if (r.n_kept_out) *r.n_kept_out = kept;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
+        if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
+    }
+    _mm_setcsr(old_csr);
 }
 
 int phmm_engine::execute(Slot& s, const std::vector<RegionIn>& regs)
@@ -1188,7 +1133,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
     int rc = e->d_tables.ensure(sizeof(PhmmTables));
     if (rc != PHMM_OK) return rc;
     CU(cudaMemcpy(e->d_tables.p, t.get(), sizeof(PhmmTables), cudaMemcpyHostToDevice));
-    e->inline_log10f = std::getenv("PHMM_B200_LIBM_LOG10F") == nullptr && log10f_form_matches_libm();
+    e->log10_mode = phmm_log10_pick_mode();
     e->default_gapm = t->gapm[10];
     e->default_ii = t->ph2pr[10];
     for (uint32_t i = 0; i < e->n_workers; ++i) {
@@ -1732,22 +1677,68 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
     return PHMM_OK;
 }
 
-// For tests (no GPU needed): the inlined fdlibm form of log10f against this host's libm over every `stride`-th normal float.
-// Returns the number of inputs whose bits differ (0 on glibc <= 2.39); *would_use says what phmm_create would decide.
-uint64_t phmm_debug_log10f_check(uint32_t stride, int* would_use)
+// For tests and host timing (no GPU needed): the engine's host epilogue on raw sums the caller brings (the oracle's, say), laid
+// out like phmm_flat_result.raw_f32 / raw_f64 (raw_f64 may be null: underflowing pairs then stand at -inf).  mode as in
+// phmm_debug_log10f_check; runs `reps` times and reports the mean wall time of one run.
+int phmm_debug_epilogue(const phmm_flat_batch* fb, const float* raw_f32, const double* raw_f64, phmm_flat_result* fr, int mode,
+                        uint32_t reps, double* ms)
 {
+    if (!fb || !raw_f32 || !fr) return fail(PHMM_ERR_ARG, "phmm_debug_epilogue: null argument");
+    phmm_engine e;
+    e.log10_mode = mode < 0 ? phmm_log10_pick_mode() : mode;
+    Slot s;
+    s.set_host_only();
+    std::vector<phmm_read> reads;
+    std::vector<phmm_hap> haps;
+    std::vector<RegionIn> regs;
+    flat_to_regions(fb, fr, 0, fb->n_regions, reads, haps, regs);
+    int rc = e.plan(s, regs);
+    if (rc != PHMM_OK) return rc;
+    for (size_t g = 0; g < regs.size(); ++g)
+        if (s.regions[g].n_reads && s.regions[g].n_haps && s.regions[g].out_off != fr->lik_off[g])
+            return fail(PHMM_ERR_ARG, "phmm_debug_epilogue: lik_off is not the running sum of reads x haplotypes");
+    fr->n_fp64 = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t k = 0; k < std::max(reps, 1u); ++k) {
+        fr->n_fp64 = 0;
+        e.epilogue(s, regs, raw_f32, raw_f64, raw_f64 != nullptr);
+    }
+    if (ms) *ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / std::max(reps, 1u);
+    for (auto* b : {&s.h_in, &s.h_f32, &s.h_f64, &s.h_cnt}) b->release();
+    return PHMM_OK;
+}
+
+// For tests (no GPU needed): the raw-sum -> log10 conversion in `mode` (phmm_log10.h; -1 = the mode phmm_create picks on this
+// host) against this host's libm over every `stride`-th normal float.  Returns the number of inputs whose bits differ (0 for
+// every mode on glibc <= 2.39); *picked says what phmm_create would use.
+uint64_t phmm_debug_log10f_check(uint32_t stride, int mode, int* picked)
+{
+    const int auto_mode = phmm_log10_pick_mode();
+    if (picked) *picked = auto_mode;
+    if (mode < 0) mode = auto_mode;
+    if (mode == 2 && phmm_log10_logf_mismatches(1u << 20) == UINT64_MAX) return UINT64_MAX;    // no AVX-512 here
     uint64_t bad = 0;
     if (stride == 0) stride = 1;
-    for (uint64_t b = 0x00800000u; b < 0x7f800000u; b += stride) {
-        const uint32_t bits = (uint32_t)b;
-        float x;
-        std::memcpy(&x, &bits, 4);
-        const float a = log10f(x), c = log10f_fdlibm_form(x);
-        bad += std::memcmp(&a, &c, 4) != 0;
+    float x[4096];
+    double got[4096];
+    uint64_t b = 0x00800000u;
+    while (b < 0x7f800000u) {
+        int n = 0;
+        for (; n < 4096 && b < 0x7f800000u; ++n, b += stride) {
+            const uint32_t bits = (uint32_t)b;
+            std::memcpy(&x[n], &bits, 4);
+        }
+        phmm_log10_block(x, got, (size_t)n, mode);
+        for (int k = 0; k < n; ++k) {
+            const double want = (double)(log10f(x[k]) - kLog10InitF);
+            bad += std::memcmp(&want, &got[k], 8) != 0;
+        }
     }
-    if (would_use) *would_use = log10f_form_matches_libm() ? 1 : 0;
     return bad;
 }
+
+// For tests: the restated logf against libm's on [0.5, 2), everything the log10f formula hands it (stride 1 = all 2^24).
+uint64_t phmm_debug_logf_check(uint32_t stride) { return phmm_log10_logf_mismatches(stride); }
 
 // For tests: the host-built tables, to be compared with the reference's Context<float> (core/context.h).
 void phmm_debug_tables(float* ph2pr128, float* mm8256, double* ph2pr128_d, double* mm8256_d)

@@ -150,8 +150,11 @@ def load_library():
     L.phmm_debug_tables.argtypes = [_f32p, _f32p, _f64p, _f64p]
     L.phmm_debug_tables.restype = None
     L.phmm_debug_log10f_check.restype = C.c_uint64
-    L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.POINTER(C.c_int)]
+    L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int)]
+    L.phmm_debug_logf_check.restype = C.c_uint64
+    L.phmm_debug_logf_check.argtypes = [C.c_uint32]
     L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u64p]
+    L.phmm_debug_epilogue.argtypes = [C.POINTER(_FlatBatch), _f32p, _f64p, C.POINTER(_FlatResult), C.c_int, C.c_uint32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -184,6 +187,24 @@ def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 
     d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)
     d["lane_utilisation"] = d["wavefront_cells"] / max(2 * d["lane_steps"], 1)      # two haplotype streams per lane
     return d
+
+
+def host_epilogue(batch: RegionBatch, raw_f32: np.ndarray, raw_f64: Optional[np.ndarray] = None, mode: int = -1, reps: int = 1,
+                  min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE):
+    """Host only (no GPU): the engine's epilogue — log10 conversion, normalisation, filter, transpose — on raw sums laid out
+    like ``FlatResult.raw_f32``.  ``mode``: how log10f is computed (0 libm, 1 around libm's logf, 2 AVX-512, -1 as an engine
+    would pick).  -> (FlatResult, mean milliseconds per run)."""
+    L = load_library()
+    fb = _flat_c(batch, min_quality_threshold, pcr_option)
+    res = FlatResult(batch)
+    f32 = np.ascontiguousarray(raw_f32, np.float32).reshape(-1)
+    f64 = None if raw_f64 is None else np.ascontiguousarray(raw_f64, np.float64).reshape(-1)
+    ms = C.c_double(0)
+    rc = L.phmm_debug_epilogue(C.byref(fb), _ptr(f32, _f32p), _ptr(f64, _f64p), C.byref(res.c), mode, reps, C.byref(ms))
+    if rc != 0:
+        raise PhmmError(f"phmm_debug_epilogue failed ({rc}): {L.phmm_last_error().decode()}")
+    res.n_fp64 = int(res.c.n_fp64)
+    return res, float(ms.value)
 
 
 def _ptr(a: Optional[np.ndarray], t):

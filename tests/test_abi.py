@@ -56,13 +56,24 @@ def test_tables_match_oracle(orc):
     assert np.array_equal(mmd.view(np.uint64), orc.mm_tri_f64().view(np.uint64))
 
 
-def test_inlined_log10f_is_libm_or_is_not_used():
-    """The host epilogue may inline the fdlibm form of log10f around libm's logf, but only on a host whose log10f has exactly
-    those bits: either the form matches libm on every sampled float, or the engine's creation-time check must refuse it."""
+def test_restated_log10f_is_libm_or_is_not_used():
+    """The host epilogue converts raw sums with the fastest restatement of log10f whose bits equal this host's libm — the
+    fdlibm formula around libm's logf (mode 1), or that formula with glibc's table-driven logf restated in AVX-512 (mode 2).
+    Whatever phmm_create picks must match libm on every sampled float; a mode that does not match must not be picked.  The
+    restated logf only ever sees inputs in [0.5, 2): checked there exhaustively, all 2^24 floats."""
     L = ph.load_library()
-    use = ctypes.c_int(-1)
-    differing = L.phmm_debug_log10f_check(257, ctypes.byref(use))
-    assert (differing == 0 and use.value == 1) or use.value == 0
+    picked = ctypes.c_int(-1)
+    assert L.phmm_debug_log10f_check(257, -1, ctypes.byref(picked)) == 0
+    assert picked.value in (0, 1, 2)
+    for mode in (1, 2):
+        bad = L.phmm_debug_log10f_check(263, mode, None)
+        if bad == 2**64 - 1:                       # mode 2 without AVX-512 on this host
+            assert picked.value < mode
+        elif bad:
+            assert picked.value < mode, f"mode {mode} differs from libm on {bad} inputs but would be used"
+    exhaustive = L.phmm_debug_logf_check(1)
+    if exhaustive != 2**64 - 1:
+        assert exhaustive == 0 or picked.value < 2
 
 
 def test_product_never_touches_oracle():

@@ -96,3 +96,33 @@ def test_two_rank_gather_gloo():
             assert np.array_equal(gathered, expect)
         assert t == 2.0
         assert total_cells == float(b.cells())
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, -1])
+def test_host_epilogue_on_the_oracles_raw_sums(orc, mode):
+    """The engine's host side after the kernels (pairhmm_internal.cpp:578-584 conversion, :53-63 normalize, :161-182 filter,
+    :184-193 transpose) fed with the ORACLE's raw sums must give the oracle's matrices byte for byte — in every log10f mode
+    (libm, the formula around libm's logf, the AVX-512 restatement), with the FP64 sums and without them (underflowing pairs
+    then stand at -inf and never reach the matrix), NaN tail and surviving reads included."""
+    import ctypes
+    from rovaca_b200 import pairhmm as ph
+    if mode == 2 and ph.load_library().phmm_debug_log10f_check(1 << 16, 2, None) == 2**64 - 1:
+        pytest.skip("no AVX-512 on this host")
+    rng = np.random.default_rng(41)
+    specs = [dict(n_reads=24, n_haps=5, hap_lo=120, hap_hi=160, read_lo=40, read_hi=76, junk=0.3),
+             dict(n_reads=17, n_haps=9, hap_lo=90, hap_hi=120, read_lo=20, read_hi=60, junk=0.4),      # limit -4 below 51 bp
+             dict(n_reads=6, n_haps=3, hap_lo=100, hap_hi=100, read_lo=70, read_hi=70, junk=1.0),      # nothing survives
+             dict(n_reads=9, n_haps=1, hap_lo=80, hap_hi=80, read_lo=30, read_hi=60, junk=0.0),
+             dict(n_reads=1, n_haps=17, hap_lo=60, hap_hi=90, read_lo=50, read_hi=50, junk=0.0)]
+    regs = [wl._one_region(rng, **sp) for sp in specs]
+    batch = wl.RegionBatch.from_regions(regs)
+    want = [orc.region(reads, haps) for reads, haps in regs]
+    raw32 = np.concatenate([w[2].reshape(-1) for w in want])
+    raw64 = np.concatenate([w[3].reshape(-1) for w in want])
+    assert sum(w[4] for w in want) > 30
+    for f64 in (raw64, None):
+        res, _ = ph.host_epilogue(batch, raw32, f64, mode=mode)
+        assert res.n_fp64 == sum(w[4] for w in want)
+        for g, (m0, k0, *_) in enumerate(want):
+            assert np.array_equal(res.kept(g), k0), (g, f64 is None)
+            assert np.array_equal(res.matrix(g).view(np.uint64), m0.view(np.uint64)), (g, f64 is None)

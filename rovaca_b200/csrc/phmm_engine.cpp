@@ -182,6 +182,20 @@ struct Slot
     std::vector<RegionPlan> regions;
     std::vector<FwdLaunch> launches;
     std::vector<uint32_t> read_len;      // per read (for the filter)
+    // plan()'s working storage: kept between batches so that a plan allocates nothing once its slot has seen a batch its size
+    struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first; uint32_t n; };
+    struct PlanScratch
+    {
+        std::vector<PhmmRead> reads;
+        std::vector<PhmmHap> haps;
+        std::vector<PhmmChunk> chunks;
+        std::vector<PhmmPair> slow;
+        std::vector<PhmmCta> ctas;
+        std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket;
+        std::vector<std::vector<Group>> groups;
+        std::vector<Group> sorted;
+        std::vector<std::vector<uint32_t>> group_reads, by_bin;
+    } ps;
     size_t in_bytes = 0;
     size_t staged_bytes = 0;             // leading part of the arena that goes through the pinned staging copy
     struct DirectCopy { size_t dst; const uint8_t* src; size_t len; };
@@ -442,10 +456,15 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         if (est_warps > 0 && est_warps < want)
             target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want);
     }
-    std::vector<PhmmRead> reads;
-    std::vector<PhmmHap> haps;
-    std::vector<PhmmChunk> chunks;
-    std::vector<PhmmPair> slow;
+    Slot::PlanScratch& ps = s.ps;
+    std::vector<PhmmRead>& reads = ps.reads;
+    std::vector<PhmmHap>& haps = ps.haps;
+    std::vector<PhmmChunk>& chunks = ps.chunks;
+    std::vector<PhmmPair>& slow = ps.slow;
+    reads.clear();
+    haps.clear();
+    chunks.clear();
+    slow.clear();
     reads.reserve(n_reads);
     haps.reserve(n_haps);
     s.regions.clear();
@@ -453,17 +472,30 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     s.read_len.clear();
     s.read_len.reserve(n_reads);
     // per bin: (chunk, reads...) groups
-    struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first; uint32_t n; };
-    std::vector<std::vector<Group>> groups(kPhmmNumBins);
-    std::vector<std::vector<uint32_t>> group_reads(kPhmmNumBins);
-    std::vector<uint32_t> order, region_chunks, idx;
+    using Group = Slot::Group;
+    std::vector<std::vector<Group>>& groups = ps.groups;
+    std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;
+    std::vector<std::vector<uint32_t>>& by_bin = ps.by_bin;
+    groups.resize(kPhmmNumBins);
+    group_reads.resize(kPhmmNumBins);
+    by_bin.resize(kPhmmNumBins);
+    for (int b = 0; b < kPhmmNumBins; ++b) {
+        groups[b].clear();
+        group_reads[b].clear();
+        by_bin[b].clear();
+    }
+    std::vector<uint32_t>&order = ps.order, &region_chunks = ps.region_chunks, &idx = ps.idx;
     // read length -> bin, for the lengths the wavefront kernels take (a table instead of a search per read)
     uint8_t bin_lut[640];
+    int bin_lo = kPhmmNumBins, bin_hi = -1;        // the bins this batch can use (one variant, lane families from min_lanes up)
     for (uint32_t len = 0; len < 640; ++len) {
         const int b = phmm_bin_of(len, refgaps, min_lanes);
         bin_lut[len] = b < 0 ? 255 : (uint8_t)b;
+        if (b >= 0) {
+            bin_lo = std::min(bin_lo, b);
+            bin_hi = std::max(bin_hi, b);
+        }
     }
-    std::vector<std::vector<uint32_t>> by_bin(kPhmmNumBins);
 
     uint64_t raw_off = 0, hap_off = 0, out_off = 0;
     uint32_t max_cols = 0;
@@ -518,7 +550,15 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
                 }
                 // longest first onto the lighter stream
                 idx.assign(order.begin() + at, order.begin() + end);
-                std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return r.haps[a].len > r.haps[b].len; });
+                for (size_t a = 1; a < idx.size(); ++a) {                  // stable insertion sort, longest first (a handful of entries)
+                    const uint32_t v = idx[a];
+                    size_t at2 = a;
+                    while (at2 > 0 && r.haps[idx[at2 - 1]].len < r.haps[v].len) {
+                        idx[at2] = idx[at2 - 1];
+                        --at2;
+                    }
+                    idx[at2] = v;
+                }
                 uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
                 for (uint32_t j : idx) {
                     const uint32_t e = (sum[1] < sum[0]) ? 1u : 0u;
@@ -541,7 +581,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
             }
         }
         // reads
-        for (auto& v : by_bin) v.clear();
+        for (int b = bin_lo; b <= bin_hi; ++b) by_bin[b].clear();
         for (uint32_t k = 0; k < r.n_reads; ++k) {
             const phmm_read& in = r.reads[k];
             PhmmRead d{};
@@ -573,23 +613,18 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
                 }
             }
         }
-        for (int b0 = 0; b0 < kPhmmNumBins;) {           // one lane family at a time (bins of a family are contiguous)
+        for (int b0 = bin_lo; b0 <= bin_hi;) {           // one lane family at a time (bins of a family are contiguous)
             int b1 = b0;
-            while (b1 + 1 < kPhmmNumBins && kPhmmBins[b1 + 1].lanes == kPhmmBins[b0].lanes && kPhmmBins[b1 + 1].refgaps == kPhmmBins[b0].refgaps) ++b1;
+            while (b1 + 1 <= bin_hi && kPhmmBins[b1 + 1].lanes == kPhmmBins[b0].lanes && kPhmmBins[b1 + 1].refgaps == kPhmmBins[b0].refgaps) ++b1;
             promote_remainders(by_bin, b0, b1);
             b0 = b1 + 1;
         }
-        for (int b = 0; b < kPhmmNumBins; ++b) {
+        for (int b = bin_lo; b <= bin_hi; ++b) {
             if (by_bin[b].empty()) continue;
-            for (uint32_t ci : region_chunks) {
-                Group g{};
-                g.chunk = ci;
-                g.stream_len = chunks[ci].stream_len;
-                g.first = (uint32_t)group_reads[b].size();
-                g.n = (uint32_t)by_bin[b].size();
-                group_reads[b].insert(group_reads[b].end(), by_bin[b].begin(), by_bin[b].end());
-                groups[b].push_back(g);
-            }
+            // every chunk of the region sweeps the same reads: one copy of the list, one group per chunk
+            const uint32_t first = (uint32_t)group_reads[b].size();
+            group_reads[b].insert(group_reads[b].end(), by_bin[b].begin(), by_bin[b].end());
+            for (uint32_t ci : region_chunks) groups[b].push_back(Group{ci, chunks[ci].stream_len, first, (uint32_t)by_bin[b].size()});
         }
         out_off += (uint64_t)r.n_reads * r.n_haps;
     }
@@ -597,12 +632,24 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     [[maybe_unused]] const auto pt2 = PT_NOW();
     PT_ADD(1, pt1, pt2);
     // CTAs per bin, longest streams first
-    std::vector<PhmmCta> ctas;
-    std::vector<uint32_t> task_reads;
+    std::vector<PhmmCta>& ctas = ps.ctas;
+    std::vector<uint32_t>& task_reads = ps.task_reads;
+    ctas.clear();
+    task_reads.clear();
     s.launches.clear();
-    for (int b = 0; b < kPhmmNumBins; ++b) {
+    for (int b = std::max(bin_lo, 0); b <= bin_hi; ++b) {
         if (groups[b].empty()) continue;
-        std::stable_sort(groups[b].begin(), groups[b].end(), [](const Group& x, const Group& y) { return x.stream_len > y.stream_len; });
+        {
+            // stable, longest stream first: a counting sort on the stream length (at most kMaxStreamCols + 33 values)
+            uint32_t longest = 0;
+            for (const Group& g : groups[b]) longest = std::max(longest, g.stream_len);
+            ps.bucket.assign((size_t)longest + 2, 0u);
+            for (const Group& g : groups[b]) ++ps.bucket[longest - g.stream_len + 1];
+            for (uint32_t k = 1; k <= longest + 1; ++k) ps.bucket[k] += ps.bucket[k - 1];
+            ps.sorted.resize(groups[b].size());
+            for (const Group& g : groups[b]) ps.sorted[ps.bucket[longest - g.stream_len]++] = g;
+            groups[b].swap(ps.sorted);
+        }
         FwdLaunch fl{};
         fl.bin = b;
         fl.cta_base = (uint32_t)ctas.size();

@@ -1,5 +1,5 @@
 // Times the sections of phmm_engine::plan on the CPU (host-only slot, no GPU), cfg2-shaped synthetic regions (NOT product).
-//   nvcc -O2 -std=c++17 -x cu -Irovaca_b200/csrc -Iinclude -o /tmp/plan_timing tools/plan_timing.cpp rovaca_b200/csrc/phmm_tables.cpp -Lrovaca_b200 -lphmm_b200 -Xlinker -rpath=$PWD/rovaca_b200
+//   nvcc -O2 -std=c++17 -x cu -Irovaca_b200/csrc -Iinclude -o build/plan_timing tools/plan_timing.cpp rovaca_b200/csrc/phmm_tables.cpp -Lrovaca_b200 -lphmm_b200 -Xlinker -rpath=$PWD/rovaca_b200
 #include <chrono>
 static double g_t[8];
 #define PT_NOW() std::chrono::steady_clock::now()
@@ -7,25 +7,41 @@ static double g_t[8];
 #define PHMM_PLAN_TIMING 1
 #include "../rovaca_b200/csrc/phmm_engine.cpp"
 #include <random>
-int main()
+#include <string>
+int main(int argc, char** argv)
 {
-    const int G = 4096, NR = 64, NH = 8, R = 150, H = 300;
-    std::vector<uint8_t> rb((size_t)G * NR * R), rq(rb.size()), hb((size_t)G * NH * H);
+    const bool mixed = argc > 1 && std::string(argv[1]) == "cfg5";     // cfg5-like: Poisson(41) reads of 60-151 bp, 2-24 haplotypes of 201-499
+    const int G = mixed ? 16384 : 4096;
     std::mt19937_64 rng(1);
+    std::vector<uint32_t> nr(G), nh(G);
+    std::vector<std::vector<uint32_t>> rl(G), hl(G);
+    size_t n_reads = 0, n_haps = 0, rbytes = 0, hbytes = 0, n_pairs = 0;
+    std::poisson_distribution<int> pr(41), ph(7.8);
+    for (int g = 0; g < G; ++g) {
+        nr[g] = mixed ? std::max(1, pr(rng)) : 64;
+        nh[g] = mixed ? std::min(24, std::max(2, ph(rng) + 1)) : 8;
+        const uint32_t H = mixed ? 201 + rng() % 299 : 300;
+        for (uint32_t k = 0; k < nr[g]; ++k) { rl[g].push_back(mixed ? 60 + rng() % 92 : 150); rbytes += rl[g].back(); }
+        for (uint32_t j = 0; j < nh[g]; ++j) { hl[g].push_back(H); hbytes += H; }
+        n_reads += nr[g]; n_haps += nh[g]; n_pairs += (size_t)nr[g] * nh[g];
+    }
+    std::vector<uint8_t> rb(rbytes), rq(rbytes), hb(hbytes);
     for (auto& x : rb) x = "ACGT"[rng() & 3];
     for (auto& x : rq) x = 30 + rng() % 10;
     for (auto& x : hb) x = "ACGT"[rng() & 3];
-    std::vector<phmm_read> reads((size_t)G * NR);
-    std::vector<phmm_hap> haps((size_t)G * NH);
-    for (size_t k = 0; k < reads.size(); ++k) reads[k] = phmm_read{rb.data() + k * R, rq.data() + k * R, nullptr, nullptr, nullptr, R, 60};
-    for (size_t j = 0; j < haps.size(); ++j) haps[j] = phmm_hap{hb.data() + j * H, H};
-    std::vector<double> out((size_t)G * NR * NH);
-    std::vector<uint32_t> kept((size_t)G * NR);
+    std::vector<phmm_read> reads(n_reads);
+    std::vector<phmm_hap> haps(n_haps);
+    std::vector<double> out(n_pairs);
+    std::vector<uint32_t> kept(n_reads);
     std::vector<RegionIn> regs(G);
+    size_t ro = 0, ho = 0, ri = 0, hi = 0, po = 0;
     for (int g = 0; g < G; ++g) {
         regs[g] = RegionIn{};
-        regs[g].reads = reads.data() + (size_t)g * NR; regs[g].n_reads = NR; regs[g].haps = haps.data() + (size_t)g * NH; regs[g].n_haps = NH;
-        regs[g].thr = 18; regs[g].pcr = 3; regs[g].out.likelihoods = out.data() + (size_t)g * NR * NH; regs[g].out.kept_idx = kept.data() + (size_t)g * NR;
+        regs[g].reads = reads.data() + ri; regs[g].n_reads = nr[g]; regs[g].haps = haps.data() + hi; regs[g].n_haps = nh[g];
+        regs[g].thr = 18; regs[g].pcr = 3; regs[g].out.likelihoods = out.data() + po; regs[g].out.kept_idx = kept.data() + ri;
+        for (uint32_t k = 0; k < nr[g]; ++k) { reads[ri++] = phmm_read{rb.data() + ro, rq.data() + ro, nullptr, nullptr, nullptr, rl[g][k], 60}; ro += rl[g][k]; }
+        for (uint32_t j = 0; j < nh[g]; ++j) { haps[hi++] = phmm_hap{hb.data() + ho, hl[g][j]}; ho += hl[g][j]; }
+        po += (size_t)nr[g] * nh[g];
     }
     phmm_engine e;
     e.busy_batches.store(16);
@@ -37,7 +53,7 @@ int main()
         if (e.plan(s, regs) != PHMM_OK) return 1;
         PT_ADD(7, a, PT_NOW());
     }
-    std::printf("plan total %.2f ms/call: count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f\n", g_t[7] / 5, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5,
-                g_t[3] / 5, g_t[4] / 5);
+    std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f\n", G,
+                n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5);
     return 0;
 }

@@ -55,8 +55,18 @@ typedef struct phmm_config
     uint32_t lanes_per_read;      /* 8, 16 or 32 lanes per read in the forward kernel; 0 = by batch size (small batches on an idle
                                      device get the wide, low-latency layouts); tuning / test knob */
     uint32_t fp64_mode;           /* PHMM_FP64_*: when pairs whose FP32 sum underflows (< 1e-28f) are recomputed in FP64 */
-    uint32_t rsv[5];
+    uint32_t epilogue;            /* PHMM_EPILOGUE_*: where log10 / normalize / filter / transpose / best-haplotype search run */
+    uint32_t rsv[4];
 } phmm_config;
+
+/* The reference's host side after its kernels (pairhmm_internal.cpp:578-584, :53-63, :161-182, :184-193) and the per-read
+ * best-haplotype search the next step opens with (genotype/allele_likelihoods.hpp:589-657) run either on the host or in
+ * one more kernel on the device.  log10f is whatever the HOST's libm says, so the device (and the host's vector path) use a
+ * restatement of glibc's algorithm that is tested bit for bit against this host's libm when the engine is created; AUTO
+ * takes the device only if that test passes, DEVICE fails phmm_create if it does not. */
+#define PHMM_EPILOGUE_AUTO 0u
+#define PHMM_EPILOGUE_HOST 1u
+#define PHMM_EPILOGUE_DEVICE 2u
 
 /* pairhmm_internal.cpp:578-584 recomputes an underflowing pair in FP64.  The value it gets is below -64 (log10) and never
  * reaches the returned matrix: filter_poorly_modelled_evidence drops the read (best < -8, or -4 under 51 bp) or
@@ -84,6 +94,9 @@ typedef struct phmm_hap
 {
     const uint8_t* bases;
     uint32_t len;
+    double priority;              /* only read when best_hap is asked for: breaks ties between haplotypes whose likelihoods
+                                     are within 0.2 of the best (allele_likelihoods.hpp:624-645); the reference passes
+                                     (is_reference ? 1 : 0) + (1 - cigar elements), assembly_based_caller_utils.cpp:150-155 */
 } phmm_hap;
 
 /* One call of rovaca::call_pairhmm(hs, rs, min_quality_threshold, pcr_option, pool)
@@ -110,6 +123,12 @@ typedef struct phmm_result
     float* raw_f32;        /* optional [n_reads][n_haps]: raw forward sums (dump-level parity) */
     double* raw_f64;       /* optional [n_reads][n_haps]: FP64 recompute, NaN where not taken */
     uint32_t n_fp64;       /* out: pairs that took the FP64 branch (pairhmm_internal.cpp:578) */
+    uint32_t* best_hap;    /* optional [n_reads], first n_kept valid: for the k-th surviving read the haplotype
+                              AlleleLikelihoods::search_best_allele (genotype/allele_likelihoods.hpp:589-657, as called by
+                              best_alleles_breaking_ties :364-383 with phmm_hap.priority) names best ... */
+    uint32_t* second_hap;  /* ... and second best; required when best_hap is given.  BestAllele's likelihood, second-best
+                              likelihood and confidence are likelihoods[best][k], likelihoods[second][k] (-inf if the two
+                              indices are equal) and their difference (:651-656) */
 } phmm_result;
 
 /* Many regions at once, flat arrays (what a batching caller / the bench hands over).  Region g owns
@@ -134,6 +153,7 @@ typedef struct phmm_flat_batch
     int32_t min_quality_threshold;
     int32_t pcr_model;
     uint32_t flags;                   /* PHMM_FLAT_* */
+    const double* hap_priority;       /* optional, per haplotype: phmm_hap.priority */
 } phmm_flat_batch;
 
 /* The byte blobs (read_bases, read_qual, read_ins/del/gcp, hap_bases) live in page-locked host memory (cudaHostAlloc,
@@ -152,6 +172,8 @@ typedef struct phmm_flat_result
     float* raw_f32;                   /* optional, [read][hap] per region at lik_off[g] */
     double* raw_f64;                  /* optional */
     uint64_t n_fp64;                  /* out */
+    uint32_t* best_hap;               /* optional, [total reads] at reg_read_off[g]: phmm_result.best_hap */
+    uint32_t* second_hap;             /* optional, with best_hap */
 } phmm_flat_result;
 
 typedef struct phmm_stats

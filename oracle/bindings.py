@@ -94,6 +94,8 @@ class Oracle:
         L.orc_region.restype = C.c_int64
         L.orc_region.argtypes = [C.POINTER(_OrcRead), C.c_uint32, C.POINTER(_OrcHap), C.c_uint32, C.c_int32, C.c_int, C.c_int,
                                  _f64p, _u32p, _u32p, _f32p, _f64p]
+        L.orc_best_alleles.restype = None
+        L.orc_best_alleles.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, _f64p, _u32p, _u32p, _f64p, _f64p, _f64p]
         L.orc_sw_align.restype = C.c_int32
         L.orc_sw_align.argtypes = [_u8p, C.c_int32, _u8p, C.c_int32, C.c_void_p, _u32p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.orc_init()
@@ -162,6 +164,18 @@ class Oracle:
         return q, i, d, c
 
     # region -------------------------------------------------------------------------------
+    def best_alleles(self, matrix: np.ndarray, n_evidence: int, priorities=None):
+        """search_best_allele for the first n_evidence columns of matrix[n_alleles, stride] ->
+        (best, second, best_lik, second_lik, confidence)."""
+        m = np.ascontiguousarray(matrix, np.float64)
+        na, stride = m.shape
+        pri = None if priorities is None else np.ascontiguousarray(priorities, np.float64)
+        best, second = np.zeros(max(n_evidence, 1), np.uint32), np.zeros(max(n_evidence, 1), np.uint32)
+        bl, sl, conf = (np.zeros(max(n_evidence, 1), np.float64) for _ in range(3))
+        self.lib.orc_best_alleles(_p(m, _f64p), na, stride, n_evidence, _p(pri, _f64p) if pri is not None else None,
+                                  _p(best, _u32p), _p(second, _u32p), _p(bl, _f64p), _p(sl, _f64p), _p(conf, _f64p))
+        return best[:n_evidence], second[:n_evidence], bl[:n_evidence], sl[:n_evidence], conf[:n_evidence]
+
     def region(self, reads: Sequence[dict], haps: Sequence, thr: int = 18, model: int = PCR_CONSERVATIVE,
                fma_mode: int = FMA_AVX512):
         """reads: dicts with bases, qual, mapq and optional ins/del/gcp.  Returns

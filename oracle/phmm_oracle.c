@@ -392,3 +392,57 @@ int64_t orc_region(const orc_read* reads, uint32_t n_reads, const orc_hap* haps,
     ftz_restore(csr);
     return n_fp64;
 }
+
+/* allele_likelihoods.hpp:589-657, one evidence at a time; names follow the reference's locals */
+void orc_best_alleles(const double* values, uint32_t n_alleles, uint32_t stride, uint32_t n_evidence, const double* priorities,
+                      uint32_t* best, uint32_t* second, double* best_lik, double* second_lik, double* confidence)
+{
+    const double informative_threshold = 0.2000;            /* s_log_10_informative_threshold, :27 */
+    for (uint32_t evidence_index = 0; evidence_index < n_evidence; evidence_index++) {
+#define SAMPLE_VALUE(a) values[(size_t)(a) * stride + evidence_index]
+        int32_t best_allele_index = 0;                       /* can_be_reference, :610 */
+        int32_t second_best_index = 0;
+        double best_likelihood = SAMPLE_VALUE(best_allele_index);
+        double second_best_likelihood = -INFINITY, candidate_likelihood;
+        for (int32_t a = best_allele_index + 1; a < (int32_t)n_alleles; a++) {            /* :614-622 */
+            candidate_likelihood = SAMPLE_VALUE(a);
+            if (candidate_likelihood > best_likelihood) {
+                second_best_index = best_allele_index;
+                best_allele_index = a;
+                second_best_likelihood = best_likelihood;
+                best_likelihood = candidate_likelihood;
+            } else if (candidate_likelihood > second_best_likelihood) {
+                second_best_index = a;
+                second_best_likelihood = candidate_likelihood;
+            }
+        }
+        if (priorities && best_likelihood - second_best_likelihood < informative_threshold) {   /* :624-645 */
+            double best_priority = priorities[best_allele_index];
+            double second_best_priority = priorities[second_best_index];
+            for (int32_t a = 0; a < (int32_t)n_alleles; a++) {
+                candidate_likelihood = SAMPLE_VALUE(a);
+                if (a == best_allele_index || best_likelihood - candidate_likelihood > informative_threshold) continue;
+                const double candidate_priority = priorities[a];
+                if (candidate_priority > best_priority) {
+                    second_best_index = best_allele_index;
+                    best_allele_index = a;
+                    second_best_priority = best_priority;
+                    best_priority = candidate_priority;
+                } else if (candidate_priority > second_best_priority) {
+                    second_best_index = a;
+                    second_best_priority = candidate_priority;
+                }
+            }
+        }
+        best_likelihood = SAMPLE_VALUE(best_allele_index);                                  /* :647-649 */
+        second_best_likelihood = second_best_index != best_allele_index ? SAMPLE_VALUE(second_best_index) : -INFINITY;
+#undef SAMPLE_VALUE
+        best[evidence_index] = (uint32_t)best_allele_index;
+        second[evidence_index] = (uint32_t)second_best_index;
+        if (best_lik) best_lik[evidence_index] = best_likelihood;
+        if (second_lik) second_lik[evidence_index] = second_best_likelihood;
+        if (confidence)                                                                     /* BestAllele, :52-62 */
+            confidence[evidence_index] =
+                fabs(best_likelihood - second_best_likelihood) < 2.220446049250313e-16 ? 0.0 : best_likelihood - second_best_likelihood;
+    }
+}

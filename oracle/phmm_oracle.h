@@ -85,6 +85,14 @@ int64_t orc_region(const orc_read* reads, uint32_t n_reads, const orc_hap* haps,
                    int32_t min_quality_threshold, int pcr_model, int fma_mode, double* out,
                    uint32_t* kept_idx, uint32_t* n_kept, float* raw_f32, double* raw_f64);
 
+/* AlleleLikelihoods::search_best_allele (genotype/allele_likelihoods.hpp:589-657) as best_alleles_breaking_ties (:364-383)
+ * calls it for every evidence of a sample: can_be_reference = true, one priority per allele (may be NULL = no
+ * priorities), log10 likelihoods (informative threshold 0.2, :27).  values is the [n_alleles][stride] matrix call_pairhmm
+ * returned; evidence runs over its first n_evidence columns.  Per evidence: best / second-best allele index, their
+ * likelihoods (second = -inf when both indices are equal, :651-652) and BestAllele's confidence (:59-62). */
+void orc_best_alleles(const double* values, uint32_t n_alleles, uint32_t stride, uint32_t n_evidence, const double* priorities,
+                      uint32_t* best, uint32_t* second, double* best_lik, double* second_lik, double* confidence);
+
 #ifdef __cplusplus
 }
 #endif

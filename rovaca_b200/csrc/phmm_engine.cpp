@@ -191,6 +191,8 @@ struct Slot
         std::vector<PhmmChunk> chunks;
         std::vector<PhmmPair> slow;
         std::vector<PhmmCta> ctas;
+        std::vector<PhmmRegionDev> regions_dev;
+        std::vector<double> pri;
         std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket;
         std::vector<std::vector<Group>> groups;
         std::vector<Group> sorted;
@@ -203,6 +205,14 @@ struct Slot
     uint64_t n_pairs = 0, n_cells = 0, n_words = 0;
     uint32_t n_reads = 0, n_haps = 0, n_slow = 0, max_cols = 0;
     uint32_t n_launches = 0;
+    // device epilogue: one buffer on each side, [lik | kept_idx | best | second | n_kept | n_under]
+    DevBuf d_epi;
+    HostBuf h_epi;
+    PhmmEpilogueDev epi{};
+    size_t e_kept = 0, e_best = 0, e_second = 0, e_nkept = 0, e_under = 0, epi_bytes = 0;
+    size_t o_regions = 0, o_pri = 0;
+    bool want_best = false;              // some region of the batch asks for best / second-best haplotypes
+    bool want_raw = false;               // ... for the raw FP32 sums
     bool want_f64 = false;               // the FP64 recompute goes out with the batch (someone will read its values)
     bool f64_done = false;               // ... and has been launched for the sums now on the device
     float gpu_ms = 0.f, fwd_ms = 0.f;
@@ -211,8 +221,8 @@ struct Slot
 
     void set_host_only()
     {
-        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt}) b->host_only = true;
-        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32}) b->host_only = true;
+        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt, &h_epi}) b->host_only = true;
+        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32, &d_epi}) b->host_only = true;
     }
 
     int init()
@@ -225,8 +235,8 @@ struct Slot
     }
     void destroy()
     {
-        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt}) b->release();
-        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32}) b->release();
+        for (auto* b : {&h_in, &h_f32, &h_f64, &h_cnt, &h_epi}) b->release();
+        for (auto* b : {&d_in, &d_words, &d_f32, &d_f64, &d_pairs, &d_cnt, &d_scr64, &d_scr32, &d_epi}) b->release();
         for (auto& e : ev)
             if (e) cudaEventDestroy(e);
         for (auto& e : aux_done)
@@ -319,6 +329,7 @@ struct phmm_engine
     uint32_t lanes_pref = 0;     // lanes per read of the reference-gap kernels: 0 = by batch size, else 8 / 16 / 32
     bool fp64_always = false;    // PHMM_FP64_ALWAYS: recompute every underflowing pair even when nobody can see the value
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
+    bool device_epilogue = false;  // log10 / normalize / filter / transpose / best haplotype in one more kernel (PHMM_EPILOGUE_*)
     int log10_mode = 0;            // how raw sums become log10 doubles: phmm_log10.cpp, picked (and tested against libm) at creation
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
@@ -384,6 +395,7 @@ struct phmm_engine
     int launch(Slot& s, bool copy_in);
     int finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out);
     void epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const;
+    void epilogue_from_device(const Slot& s, const std::vector<RegionIn>& regs, bool have64) const;
     int execute(Slot& s, const std::vector<RegionIn>& regs);
     void worker_main(uint32_t idx);
     void enqueue(std::function<void(Slot&)> fn);
@@ -405,9 +417,12 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     uint64_t n_reads = 0, n_haps = 0, read_bytes = 0, hap_bytes = 0, n_pairs = 0, n_cells = 0;
     bool any_ins = false, any_del = false, any_gcp = false;
     s.want_f64 = fp64_always;
+    s.want_best = s.want_raw = false;
     for (const RegionIn& r : regs) {
         if (r.n_reads == 0 || r.n_haps == 0) continue;           // pairhmm_internal.cpp:508-510
         s.want_f64 |= r.out.raw_f64 != nullptr;
+        s.want_raw |= r.out.raw_f32 != nullptr || r.out.raw_f64 != nullptr;
+        s.want_best |= r.out.best_hap != nullptr;
         uint64_t rb = 0, hb = 0;
         for (uint32_t k = 0; k < r.n_reads; ++k) {
             rb += r.reads[k].len;
@@ -465,6 +480,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     haps.clear();
     chunks.clear();
     slow.clear();
+    ps.pri.clear();
     reads.reserve(n_reads);
     haps.reserve(n_haps);
     s.regions.clear();
@@ -514,6 +530,8 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         rp.n_reads = r.n_reads;
         rp.n_haps = r.n_haps;
         s.regions.push_back(rp);
+        if (s.want_best)
+            for (uint32_t j = 0; j < r.n_haps; ++j) ps.pri.push_back(r.haps[j].priority);
         // haplotypes -> chunks of two balanced streams
         for (uint32_t j = 0; j < r.n_haps; ++j) {
             PhmmHap h{};
@@ -703,6 +721,12 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     const size_t o_ctas = place(ctas.size() * sizeof(PhmmCta));
     const size_t o_tasks = place(task_reads.size() * sizeof(uint32_t));
     const size_t o_slow = place(slow.size() * sizeof(PhmmPair));
+    ps.regions_dev.clear();
+    if (device_epilogue)
+        for (const RegionPlan& rp : s.regions)
+            ps.regions_dev.push_back(PhmmRegionDev{rp.read_begin, rp.n_reads, rp.hap_begin, rp.n_haps, (uint32_t)rp.out_off, {0, 0, 0}});
+    const size_t o_regions = place(ps.regions_dev.size() * sizeof(PhmmRegionDev));
+    const size_t o_pri = place((device_epilogue ? ps.pri.size() : 0) * sizeof(double));
     const size_t o_rb = place(read_bytes + 16);
     const size_t o_rq = place(read_bytes + 16);
     const size_t o_ri = any_ins ? place(read_bytes + 16) : 0;
@@ -722,6 +746,10 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::memcpy(h + o_ctas, ctas.data(), ctas.size() * sizeof(PhmmCta));
     std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
     std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
+    std::memcpy(h + o_regions, ps.regions_dev.data(), ps.regions_dev.size() * sizeof(PhmmRegionDev));
+    if (device_epilogue) std::memcpy(h + o_pri, ps.pri.data(), ps.pri.size() * sizeof(double));
+    s.o_regions = o_regions;
+    s.o_pri = o_pri;
     [[maybe_unused]] const auto pt4 = PT_NOW();
     PT_ADD(3, pt3, pt4);
     {
@@ -796,6 +824,21 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
     if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
 
+    if (device_epilogue) {
+        // [lik: one double per pair | kept_idx, best, second: one u32 per read | n_kept, n_under: one u32 per region]
+        size_t eo = 0;
+        auto eplace = [&](size_t bytes) { size_t at = eo; eo = align_up(eo + bytes, 256); return at; };
+        eplace(pairs_alloc * sizeof(double));
+        s.e_kept = eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t));
+        s.e_best = s.want_best ? eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t)) : 0;
+        s.e_second = s.want_best ? eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t)) : 0;
+        s.e_nkept = eplace(std::max<size_t>(regs.size(), 1) * sizeof(uint32_t));
+        s.e_under = eplace(std::max<size_t>(regs.size(), 1) * sizeof(uint32_t));
+        s.epi_bytes = eo;
+        if ((rc = s.d_epi.ensure(eo, &high_water[7])) != PHMM_OK) return rc;
+        if ((rc = s.h_epi.ensure(eo, &high_water[7])) != PHMM_OK) return rc;
+    }
+
     uint8_t* d = static_cast<uint8_t*>(s.d_in.p);
     PhmmBatchDev& b = s.dev;
     b.reads = reinterpret_cast<const PhmmRead*>(d + o_reads);
@@ -819,6 +862,21 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     b.n_reads = (uint32_t)reads.size();
     b.rg_gapm = default_gapm;      // gap_conts() is the constant '+' - 33 = 10 for every read, read_record.cpp:205-210
     b.rg_ii = default_ii;
+    if (device_epilogue) {
+        uint8_t* de = static_cast<uint8_t*>(s.d_epi.p);
+        PhmmEpilogueDev& ep = s.epi;
+        ep.regions = reinterpret_cast<const PhmmRegionDev*>(d + o_regions);
+        ep.reads = b.reads;
+        ep.raw = b.out_f32;
+        ep.hap_priority = s.want_best ? reinterpret_cast<const double*>(d + o_pri) : nullptr;
+        ep.lik = reinterpret_cast<double*>(de);
+        ep.kept_idx = reinterpret_cast<uint32_t*>(de + s.e_kept);
+        ep.best = s.want_best ? reinterpret_cast<uint32_t*>(de + s.e_best) : nullptr;
+        ep.second = s.want_best ? reinterpret_cast<uint32_t*>(de + s.e_second) : nullptr;
+        ep.n_kept = reinterpret_cast<uint32_t*>(de + s.e_nkept);
+        ep.n_under = reinterpret_cast<uint32_t*>(de + s.e_under);
+        ep.n_regions = (uint32_t)regs.size();
+    }
 
     s.n_pairs = n_pairs;
     s.n_cells = n_cells;
@@ -827,7 +885,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     s.n_haps = (uint32_t)haps.size();
     s.n_slow = (uint32_t)slow.size();
     s.max_cols = max_cols;
-    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + 1;
+    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + (s.want_f64 ? 1 : 0) + (device_epilogue ? 1 : 0);
     return PHMM_OK;
 }
 
@@ -873,6 +931,7 @@ int phmm_engine::launch(Slot& s, bool copy_in)
     if (s.f64_done)
         CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
                                  s.stream));
+    if (device_epilogue && s.n_pairs) CU(phmm_launch_epilogue(s.epi, s.stream));
     CU(cudaEventRecord(s.ev[3], s.stream));
     stats.launches += s.n_launches;
     return PHMM_OK;
@@ -882,10 +941,28 @@ int phmm_engine::launch(Slot& s, bool copy_in)
 int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out)
 {
     uint32_t n64 = 0;
+    bool asks_best = false, asks_raw = false, asks_f64 = false;
+    for (const RegionIn& r : regs) {
+        if (r.n_reads == 0 || r.n_haps == 0) continue;
+        asks_best |= r.out.best_hap != nullptr;
+        asks_raw |= r.out.raw_f32 != nullptr || r.out.raw_f64 != nullptr;
+        asks_f64 |= r.out.raw_f64 != nullptr;
+    }
+    // a resident batch was planned before anyone said what to download: without best / second-best buffers on the device
+    // the host epilogue serves that call
+    const bool dev = device_epilogue && (!asks_best || s.want_best);
+    const bool need_f32 = !dev || asks_raw;
     if (copy_out && s.n_pairs) {
-        CU(cudaMemcpyAsync(s.h_f32.p, s.d_f32.p, s.n_pairs * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (need_f32) {
+            CU(cudaMemcpyAsync(s.h_f32.p, s.d_f32.p, s.n_pairs * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+            stats.d2h += s.n_pairs * sizeof(float);
+        }
         CU(cudaMemcpyAsync(s.h_cnt.p, s.d_cnt.p, 4, cudaMemcpyDeviceToHost, s.stream));
-        stats.d2h += s.n_pairs * sizeof(float) + 4;
+        if (dev) {
+            CU(cudaMemcpyAsync(s.h_epi.p, s.d_epi.p, s.epi_bytes, cudaMemcpyDeviceToHost, s.stream));
+            stats.d2h += s.epi_bytes;
+        }
+        stats.d2h += 4;
     }
     {
         // short batches (the synchronous per-region callers) finish in tens of microseconds: poll before paying a blocking
@@ -906,9 +983,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     if (s.n_pairs) {
         n64 = *static_cast<uint32_t*>(s.h_cnt.p);
         if (n64 > 0 && !have64) {
-            bool asked = false;                                 // a resident batch learns at download time who wants raw sums
-            for (const RegionIn& r : regs) asked |= r.out.raw_f64 != nullptr && r.n_reads && r.n_haps;
-            if (asked) {
+            if (asks_f64) {                                     // a resident batch learns at download time who wants raw sums
                 CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads,
                                          s.max_cols, s.stream));
                 s.f64_done = have64 = true;
@@ -924,7 +999,10 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
 
     const auto t_epi = std::chrono::steady_clock::now();
-    epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
+    if (dev)
+        epilogue_from_device(s, regs, have64);
+    else
+        epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
     stats.regions += regs.size();
     stats.pairs += s.n_pairs;
     stats.cells += s.n_cells;
@@ -937,6 +1015,42 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
         stats.epilogue_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_epi).count();
     }
     return PHMM_OK;
+}
+
+// The epilogue ran on the device (phmm_epilogue_kernel): hand every region its matrix, surviving reads and best haplotypes.
+void phmm_engine::epilogue_from_device(const Slot& s, const std::vector<RegionIn>& regs, bool have64) const
+{
+    const uint8_t* he = static_cast<const uint8_t*>(s.h_epi.p);
+    const double* lik = reinterpret_cast<const double*>(he);
+    const uint32_t* kept_idx = reinterpret_cast<const uint32_t*>(he + s.e_kept);
+    const uint32_t* best = reinterpret_cast<const uint32_t*>(he + s.e_best);
+    const uint32_t* second = reinterpret_cast<const uint32_t*>(he + s.e_second);
+    const uint32_t* n_kept = reinterpret_cast<const uint32_t*>(he + s.e_nkept);
+    const uint32_t* n_under = reinterpret_cast<const uint32_t*>(he + s.e_under);
+    const float* f32 = static_cast<const float*>(s.h_f32.p);
+    const double* f64 = static_cast<const double*>(s.h_f64.p);
+    for (size_t g = 0; g < regs.size(); ++g) {
+        const RegionIn& r = regs[g];
+        const RegionPlan& rp = s.regions[g];
+        if (r.n_kept_out) *r.n_kept_out = 0;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = 0;
+        if (rp.n_reads == 0 || rp.n_haps == 0) continue;
+        const size_t np = (size_t)rp.n_reads * rp.n_haps;
+        const uint32_t kept = n_kept[g];
+        std::memcpy(r.out.likelihoods, lik + rp.out_off, np * sizeof(double));
+        std::memcpy(r.out.kept_idx, kept_idx + rp.read_begin, kept * sizeof(uint32_t));
+        if (r.out.best_hap) {
+            std::memcpy(r.out.best_hap, best + rp.read_begin, kept * sizeof(uint32_t));
+            std::memcpy(r.out.second_hap, second + rp.read_begin, kept * sizeof(uint32_t));
+        }
+        if (r.out.raw_f32) std::memcpy(r.out.raw_f32, f32 + rp.out_off, np * sizeof(float));
+        if (r.out.raw_f64)
+            for (size_t q = 0; q < np; ++q)
+                r.out.raw_f64[q] = (f32[rp.out_off + q] < kMinAccepted && have64) ? f64[rp.out_off + q] : (double)NAN;
+        if (r.n_kept_out) *r.n_kept_out = kept;
+        if (r.n_fp64_out32) *r.n_fp64_out32 = n_under[g];
+        if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)n_under[g], __ATOMIC_RELAXED);
+    }
 }
 
 // The reference's host side after the kernels (pairhmm_internal.cpp:578-584 conversion, :53-63 normalize, :161-182 filter,
@@ -971,6 +1085,18 @@ void phmm_engine::epilogue(const Slot& s, const std::vector<RegionIn>& regs, con
         // normalize :53-63, filter :161-182, transpose :184-193 into the caller's [nh][nr] matrix (:516) with its NaN tail
         const uint32_t kept = phmm_postprocess_region(lk.data(), nr, nh, s.read_len.data() + rp.read_begin, r.out.likelihoods,
                                                       r.out.kept_idx, log10_mode);
+        if (r.out.best_hap) {
+            // the haplotypes' priorities, contiguous for the search
+            double pri[128];
+            std::vector<double> big;
+            double* pp = pri;
+            if (nh > 128) {
+                big.resize(nh);
+                pp = big.data();
+            }
+            for (uint32_t j = 0; j < nh; ++j) pp[j] = r.haps[j].priority;
+            phmm_best_haplotypes(r.out.likelihoods, nr, nh, kept, pp, r.out.best_hap, r.out.second_hap);
+        }
         if (r.n_kept_out) *r.n_kept_out = kept;
         if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
         if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
@@ -1083,6 +1209,7 @@ static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uin
     for (uint64_t j = 0; j < nh; ++j) {
         haps[j].bases = fb->hap_bases + fb->hap_off[hbeg + j];
         haps[j].len = fb->hap_len[hbeg + j];
+        haps[j].priority = fb->hap_priority ? fb->hap_priority[hbeg + j] : 0.0;
     }
     regs.resize(g1 - g0);
     for (uint32_t g = g0; g < g1; ++g) {
@@ -1104,6 +1231,8 @@ static void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uin
             r.out.kept_idx = fr->kept_idx + r0;
             r.out.raw_f32 = fr->raw_f32 ? fr->raw_f32 + fr->lik_off[g] : nullptr;
             r.out.raw_f64 = fr->raw_f64 ? fr->raw_f64 + fr->lik_off[g] : nullptr;
+            r.out.best_hap = fr->best_hap && fr->second_hap ? fr->best_hap + r0 : nullptr;
+            r.out.second_hap = fr->best_hap && fr->second_hap ? fr->second_hap + r0 : nullptr;
             r.n_kept_out = fr->n_kept + g;
             r.n_fp64_out = &fr->n_fp64;
         }
@@ -1181,6 +1310,14 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
     if (rc != PHMM_OK) return rc;
     CU(cudaMemcpy(e->d_tables.p, t.get(), sizeof(PhmmTables), cudaMemcpyHostToDevice));
     e->log10_mode = phmm_log10_pick_mode();
+    {
+        const uint32_t want = cfg ? cfg->epilogue : PHMM_EPILOGUE_AUTO;
+        const bool pinned_libm = std::getenv("PHMM_B200_LIBM_LOG10F") != nullptr;
+        const bool ok = want != PHMM_EPILOGUE_HOST && !pinned_libm && phmm_log10_restated_matches_libm();
+        if (want == PHMM_EPILOGUE_DEVICE && !ok)
+            return fail(PHMM_ERR_ARG, "PHMM_EPILOGUE_DEVICE: the restated log10f does not give this host's libm bits (or PHMM_B200_LIBM_LOG10F is set)");
+        e->device_epilogue = ok;
+    }
     e->default_gapm = t->gapm[10];
     e->default_ii = t->ph2pr[10];
     for (uint32_t i = 0; i < e->n_workers; ++i) {
@@ -1221,6 +1358,8 @@ int phmm_submit(phmm_engine* e, const phmm_region* region, phmm_result* result, 
     if (!e || !region || !result || !ticket) return fail(PHMM_ERR_ARG, "phmm_submit: null argument");
     if (region->n_reads && region->n_haps && (!result->likelihoods || !result->kept_idx))
         return fail(PHMM_ERR_ARG, "phmm_submit: result buffers are null");
+    if ((result->best_hap != nullptr) != (result->second_hap != nullptr))
+        return fail(PHMM_ERR_ARG, "phmm_submit: best_hap and second_hap go together");
     RegionIn r{};
     r.reads = region->reads;
     r.n_reads = region->n_reads;
@@ -1404,6 +1543,8 @@ int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* f
         x.out.kept_idx = fr->kept_idx + r0;
         x.out.raw_f32 = fr->raw_f32 ? fr->raw_f32 + fr->lik_off[g] : nullptr;
         x.out.raw_f64 = fr->raw_f64 ? fr->raw_f64 + fr->lik_off[g] : nullptr;
+        x.out.best_hap = fr->best_hap && fr->second_hap ? fr->best_hap + r0 : nullptr;
+        x.out.second_hap = fr->best_hap && fr->second_hap ? fr->second_hap + r0 : nullptr;
         x.n_kept_out = fr->n_kept + g;
         x.n_fp64_out = &fr->n_fp64;
     }
@@ -1724,6 +1865,36 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
     return PHMM_OK;
 }
 
+// For tests: the same conversion on the host in `mode` (phmm_log10.h; 0 = libm itself); values under MIN_ACCEPTED come out as -inf
+// like the device's.
+int phmm_debug_host_log10(const float* x, uint32_t n, int mode, double* out)
+{
+    if (!x || !out) return fail(PHMM_ERR_ARG, "phmm_debug_host_log10: null argument");
+    phmm_log10_block(x, out, n, mode);
+    for (uint32_t i = 0; i < n; ++i)
+        if (x[i] < kMinAccepted) out[i] = -INFINITY;
+    return PHMM_OK;
+}
+
+// For tests (GPU): out[i] = (double)(log10f(x[i]) - LOG10_INITIAL_CONSTANT_F) as the DEVICE epilogue computes it (-inf under
+// MIN_ACCEPTED), to be compared with the host's libm.  *in_use says whether this engine runs its epilogue on the device.
+int phmm_debug_device_log10(phmm_engine* e, const float* x, uint32_t n, double* out, int* in_use)
+{
+    if (!e || !x || !out) return fail(PHMM_ERR_ARG, "phmm_debug_device_log10: null argument");
+    if (in_use) *in_use = e->device_epilogue ? 1 : 0;
+    CU(cudaSetDevice(e->device));
+    DevBuf dx, dy;
+    int rc;
+    if ((rc = dx.ensure((size_t)n * sizeof(float))) != PHMM_OK) return rc;
+    if ((rc = dy.ensure((size_t)n * sizeof(double))) != PHMM_OK) return rc;
+    CU(cudaMemcpy(dx.p, x, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(phmm_launch_log10_probe(static_cast<const float*>(dx.p), static_cast<double*>(dy.p), n, nullptr));
+    CU(cudaMemcpy(out, dy.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+    dx.release();
+    dy.release();
+    return PHMM_OK;
+}
+
 // For tests and host timing (no GPU needed): the engine's host epilogue on raw sums the caller brings (the oracle's, say), laid
 // out like phmm_flat_result.raw_f32 / raw_f64 (raw_f64 may be null: underflowing pairs then stand at -inf).  mode as in
 // phmm_debug_log10f_check; runs `reps` times and reports the mean wall time of one run.
@@ -1783,6 +1954,9 @@ uint64_t phmm_debug_log10f_check(uint32_t stride, int mode, int* picked)
     }
     return bad;
 }
+
+// For tests: would phmm_create (PHMM_EPILOGUE_AUTO) put the epilogue on the device on this host?
+int phmm_debug_device_epilogue_allowed(void) { return std::getenv("PHMM_B200_LIBM_LOG10F") == nullptr && phmm_log10_restated_matches_libm() ? 1 : 0; }
 
 // For tests: the restated logf against libm's on [0.5, 2), everything the log10f formula hands it (stride 1 = all 2^24).
 uint64_t phmm_debug_logf_check(uint32_t stride) { return phmm_log10_logf_mismatches(stride); }

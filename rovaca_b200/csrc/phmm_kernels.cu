@@ -30,6 +30,7 @@
 // add.rn.f32x2 into FFMA2 although both carry .rn.  Every packed product below either feeds an FMA addend or has a second
 // consumer; the un-contracted (AVX2) arithmetic variant is therefore written with scalar intrinsics, which ptxas leaves alone.
 #include <cuda_runtime.h>
+#include <math_constants.h>
 #include <stdint.h>
 
 #include <atomic>
@@ -637,6 +638,146 @@ __global__ void __launch_bounds__(128) phmm_pair_kernel(PhmmBatchDev p, const Ph
 }
 
 // ------------------------------------------------------------------------------------------------
+// phmm_epilogue_kernel — the reference's host side after the kernels, on the device: raw sums ->
+// log10 (pairhmm_internal.cpp:578-584), normalize_likelihoods (:53-63), filter_poorly_modelled_evidence (:161-182),
+// transpose_likelihood_matrix (:184-193) with its NaN tail, and the per-read best / second-best haplotype search the next
+// step starts with (AlleleLikelihoods::search_best_allele, genotype/allele_likelihoods.hpp:589-657, as called by
+// best_alleles_breaking_ties :364-383 from realign_reads_to_their_best_haplotype).
+//
+// log10f on the device: the reference's value is whatever the HOST's libm returns, so this is glibc's algorithm restated
+// operation by operation (the fdlibm log10f formula around the table-driven logf; phmm_log10.cpp has the same restatement
+// for the host, and that one is tested bit for bit against the host's libm before an engine is allowed to use either).
+// Integer steps, IEEE double fma/mul/add, IEEE float mul/add/sub, one double->float rounding: the same bits on any IEEE
+// machine.  A pair under MIN_ACCEPTED stands at -inf, which is what the reference as built computes and can never reach
+// the matrix.
+// One CTA per region; threads own reads (strided), a block scan in read order gives each surviving read its column.
+// ------------------------------------------------------------------------------------------------
+__constant__ double c_logf_invc[16] = {0x1.661ec79f8f3bep+0, 0x1.571ed4aaf883dp+0, 0x1.49539f0f010b0p+0, 0x1.3c995b0b80385p+0,
+                                       0x1.30d190c8864a5p+0, 0x1.25e227b0b8ea0p+0, 0x1.1bb4a4a1a343fp+0, 0x1.12358f08ae5bap+0,
+                                       0x1.0953f419900a7p+0, 0x1p+0,               0x1.e608cfd9a47acp-1, 0x1.ca4b31f026aa0p-1,
+                                       0x1.b2036576afce6p-1, 0x1.9c2d163a1aa2dp-1, 0x1.886e6037841edp-1, 0x1.767dcf5534862p-1};
+__constant__ double c_logf_logc[16] = {-0x1.57bf7808caadep-2, -0x1.2bef0a7c06ddbp-2, -0x1.01eae7f513a67p-2, -0x1.b31d8a68224e9p-3,
+                                       -0x1.6574f0ac07758p-3, -0x1.1aa2bc79c8100p-3, -0x1.a4e76ce8c0e5ep-4, -0x1.1973c5a611cccp-4,
+                                       -0x1.252f438e10c1ep-5, 0x0p+0,                0x1.aa5aa5df25984p-5,  0x1.c5e53aa362eb4p-4,
+                                       0x1.526e57720db08p-3,  0x1.bc2860d224770p-3,  0x1.1058bc8a07ee1p-2,  0x1.4043057b6ee09p-2};
+
+__device__ __forceinline__ double log10_of_sum(float f)
+{
+    if (f < 1e-28f) return -CUDART_INF;                     // MIN_ACCEPTED (rovaca/common.h:9): the FP64 branch, see above
+    int hx = __float_as_int(f);
+    const int k = (hx >> 23) - 127;                          // the fdlibm split: f = 2^(k+neg) * m, m in [0.5, 2)
+    const int neg = (int)((unsigned)k >> 31);
+    hx = (hx & 0x007fffff) | ((0x7f - neg) << 23);
+    const float y = __int2float_rn(k + neg);
+    const unsigned tmp = (unsigned)hx - 0x3f330000u;          // logf(m): m = 2^kk * z, z in [OFF, 2*OFF)
+    const int idx = (int)((tmp >> 19) & 15u);
+    const int kk = (int)tmp >> 23;
+    const unsigned iz = (unsigned)hx - (tmp & 0xff800000u);
+    const double z = (double)__uint_as_float(iz);
+    const double r = __fma_rn(z, c_logf_invc[idx], -1.0);
+    const double y0 = __fma_rn((double)kk, 0x1.62e42fefa39efp-1, c_logf_logc[idx]);
+    const double r2 = __dmul_rn(r, r);
+    double p = __fma_rn(0x1.5575b0be00b6ap-2, r, -0x1.ffffef20a4123p-2);
+    p = __fma_rn(-0x1.00ea348b88334p-2, r2, p);
+    p = __fma_rn(p, r2, __dadd_rn(y0, r));
+    const float lf = __double2float_rn(p);
+    const float zz = __fadd_rn(__fmul_rn(y, 7.9034151668e-07f), __fmul_rn(4.3429449201e-01f, lf));
+    const float res = __fadd_rn(zz, __fmul_rn(y, 3.0102920532e-01f));
+    return (double)__fsub_rn(res, 36.1236000061f);          // LOG10_INITIAL_CONSTANT_F (adapter.h:25): float subtract, then widen
+}
+
+__global__ void __launch_bounds__(128) phmm_log10_probe_kernel(const float* x, double* out, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = log10_of_sum(x[i]);
+}
+
+__global__ void __launch_bounds__(128) phmm_epilogue_kernel(PhmmEpilogueDev e)
+{
+    __shared__ uint32_t warp_kept[4];
+    __shared__ uint32_t base_kept, under_sum;
+    const PhmmRegionDev rg = e.regions[blockIdx.x];
+    const uint32_t nr = rg.n_reads, nh = rg.n_haps;
+    if (nr == 0 || nh == 0) {
+        if (threadIdx.x == 0) e.n_kept[blockIdx.x] = e.n_under[blockIdx.x] = 0;
+        return;
+    }
+    uint32_t under = 0;                                      // pairs below MIN_ACCEPTED (:578), reported like the host path does
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* out = e.lik + rg.out_off;
+    if (threadIdx.x == 0) base_kept = under_sum = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < nr; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        const float* row = e.raw + rg.out_off + (size_t)i * nh;
+        bool keep = false;
+        double cmp = 0.0;
+        if (i < nr) {
+            // std::max_element semantics of :56,:170 — the first element, replaced only by a strictly greater one
+            double best = log10_of_sum(row[0]);
+            under += row[0] < 1e-28f;
+            for (uint32_t j = 1; j < nh; ++j) {
+                const double v = log10_of_sum(row[j]);
+                under += row[j] < 1e-28f;
+                if (best < v) best = v;
+            }
+            cmp = __dadd_rn(best, -4.5);                     // normalize_likelihoods caps at best - 4.5 (adapter.h:23)
+            const int len = (int)e.reads[rg.read_begin + i].len;
+            const double lim = fmin(2.0, ceil(__dmul_rn((double)len, 0.02))) * (-4.0);   // adapter.h:20-22
+            keep = !(best < lim);
+        }
+        // column of every surviving read: exclusive scan of the keep flags in read order
+        const uint32_t ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) warp_kept[warp] = (uint32_t)__popc(ballot);
+        __syncthreads();
+        uint32_t pos = base_kept + (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+        for (uint32_t w = 0; w < warp; ++w) pos += warp_kept[w];
+        if (keep) {
+            uint32_t bi = 0, si = 0;
+            double bl = 0.0, sl = -CUDART_INF;
+            for (uint32_t j = 0; j < nh; ++j) {
+                const double v = log10_of_sum(row[j]);
+                const double c = v < cmp ? cmp : v;          // :58-61
+                out[(size_t)j * nr + pos] = c;               // transpose :184-193
+                // search_best_allele, first pass (allele_likelihoods.hpp:609-622), can_be_reference = true
+                if (j == 0) bl = c;
+                else if (c > bl) { si = bi; bi = j; sl = bl; bl = c; }
+                else if (c > sl) { si = j; sl = c; }
+            }
+            e.kept_idx[rg.read_begin + pos] = i;
+            if (e.best) {
+                if (e.hap_priority && bl - sl < 0.2) {       // ties broken by priority (:624-645); 0.2 = s_log_10_informative_threshold
+                    const double* pri = e.hap_priority + rg.hap_begin;
+                    double bp = pri[bi], sp = pri[si];
+                    for (uint32_t a = 0; a < nh; ++a) {
+                        const double c = out[(size_t)a * nr + pos];
+                        if (a == bi || bl - c > 0.2) continue;
+                        const double cp = pri[a];
+                        if (cp > bp) { si = bi; bi = a; sp = bp; bp = cp; }
+                        else if (cp > sp) { si = a; sp = cp; }
+                    }
+                }
+                e.best[rg.read_begin + pos] = bi;
+                e.second[rg.read_begin + pos] = si;
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) base_kept += warp_kept[0] + warp_kept[1] + warp_kept[2] + warp_kept[3];
+        __syncthreads();
+    }
+    const uint32_t kept = base_kept;
+    if (under) atomicAdd(&under_sum, under);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        e.n_kept[blockIdx.x] = kept;
+        e.n_under[blockIdx.x] = under_sum;
+    }
+    // the NaN tail of the filtered reads (the matrix is allocated for every read before the filter runs, :516)
+    const uint32_t tail = nr - kept;
+    for (uint32_t t = threadIdx.x; t < tail * nh; t += blockDim.x) out[(size_t)(t / tail) * nr + kept + t % tail] = __longlong_as_double(0x7FF8000000000000LL);   // the host's (double)NAN, sign bit clear
+}
+
+// ------------------------------------------------------------------------------------------------
 // Issue-rate micro-benchmarks (bench.py's measured FP32 peak; DESIGN.md's pipe model).  Every thread runs
 // independent dependency chains long enough to hide the 4-cycle FMA latency.
 //   mode 0: scalar FFMA                     mode 1: packed FFMA2 (two FMAs per instruction)
@@ -797,5 +938,19 @@ cudaError_t phmm_launch_ubench(int mode, uint32_t blocks, uint32_t iters, float*
         case 3: phmm_ubench_kernel<3><<<blocks, 256, 0, st>>>(out, iters, 0.999f, 1e-3f, 0x1u); break;
         default: return cudaErrorInvalidValue;
     }
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_epilogue(const PhmmEpilogueDev& e, cudaStream_t st)
+{
+    if (e.n_regions == 0) return cudaSuccess;
+    phmm_epilogue_kernel<<<e.n_regions, 128, 0, st>>>(e);
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_log10_probe(const float* x, double* out, uint32_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    phmm_log10_probe_kernel<<<(n + 127) / 128, 128, 0, st>>>(x, out, n);
     return cudaGetLastError();
 }

@@ -32,6 +32,25 @@ struct PhmmBatchDev
     float rg_gapm, rg_ii;         // reference-gap variant: 1 - ph2pr[gcp] and ph2pr[gcp] of the launch-wide gcp (10)
 };
 
+// Device addresses of the epilogue's inputs and outputs (phmm_epilogue_kernel).
+struct PhmmEpilogueDev
+{
+    const PhmmRegionDev* regions;
+    const PhmmRead* reads;
+    const float* raw;             // out_f32
+    const double* hap_priority;   // per haplotype of the batch, or null (best-haplotype tie-break, allele_likelihoods.hpp:624-645)
+    double* lik;                  // per region [n_haps][n_reads] at out_off: surviving reads in front, NaN tail
+    uint32_t* kept_idx;           // per region at read_begin: original index of every surviving read
+    uint32_t* n_kept;             // per region
+    uint32_t* n_under;            // per region: pairs whose raw sum is below MIN_ACCEPTED (the FP64 branch, :578)
+    uint32_t* best;               // per region at read_begin, or null: best / second-best haplotype of every surviving read
+    uint32_t* second;
+    uint32_t n_regions;
+};
+cudaError_t phmm_launch_epilogue(const PhmmEpilogueDev& e, cudaStream_t st);
+// for tests: out[i] = (double)(log10f(x[i]) - LOG10_INITIAL_CONSTANT_F) as the device computes it
+cudaError_t phmm_launch_log10_probe(const float* x, double* out, uint32_t n, cudaStream_t st);
+
 // Read-length bins of the wavefront kernel: a group of LANES lanes (a half warp or a whole warp) owns one read, lane l owns
 // rows l*RPT .. l*RPT+RPT-1 (top-padded with at least one boundary row), so a bin holds reads of length <= LANES*RPT - 1.
 // Half-warp bins come first: more rows per lane means fewer shuffles per cell (3 per RPT cells and stream), which is what

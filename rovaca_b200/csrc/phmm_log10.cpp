@@ -59,6 +59,35 @@ inline float log10f_around_logf(float x)
     return z + y * kLog10_2hi;
 }
 
+// The restatement one value at a time, written with the very operations the device epilogue uses (phmm_kernels.cu,
+// log10_of_sum): what the device computes is what this computes, and this is what gets compared with libm.
+inline float log10f_restated(float x)
+{
+    uint32_t ux;
+    std::memcpy(&ux, &x, 4);
+    int32_t hx = (int32_t)ux;
+    const int32_t k = (hx >> 23) - 127;
+    const int32_t neg = (int32_t)((uint32_t)k >> 31);
+    hx = (hx & 0x007fffff) | ((0x7f - neg) << 23);
+    const float y = (float)(k + neg);
+    const uint32_t tmp = (uint32_t)hx - kOff;
+    const int idx = (int)((tmp >> 19) & 15u);
+    const int32_t kk = (int32_t)tmp >> 23;
+    const uint32_t iz = (uint32_t)hx - (tmp & 0xff800000u);
+    float zf;
+    std::memcpy(&zf, &iz, 4);
+    const double z = zf;
+    const double r = std::fma(z, kInvC[idx], -1.0);
+    const double y0 = std::fma((double)kk, kLn2, kLogC[idx]);
+    const double r2 = r * r;
+    double p = std::fma(kA1, r, kA2);
+    p = std::fma(kA0, r2, p);
+    p = std::fma(p, r2, y0 + r);
+    const float lf = (float)p;
+    const float zz = y * kLog10_2lo + kIvLn10 * lf;
+    return zz + y * kLog10_2hi;
+}
+
 // Eight sums per step.  Lanes below MIN_ACCEPTED (and the lanes past n) come out as garbage and are counted; the caller
 // overwrites them.  `logf_only`: v = (double)logf(f) for f in [0.5, 2), the self-test's view of the middle of the formula.
 __attribute__((target("avx512f,avx512dq,avx512vl,fma"))) size_t block_avx512(const float* f, double* v, size_t n, bool logf_only)
@@ -110,13 +139,14 @@ __attribute__((target("avx512f,avx512dq,avx512vl,fma"))) size_t block_avx512(con
     return under;
 }
 
-size_t block_scalar(const float* f, double* v, size_t n, bool around_logf)
+size_t block_scalar(const float* f, double* v, size_t n, int mode)
 {
     size_t under = 0;
     for (size_t i = 0; i < n; ++i) {
         const float x = f[i];
         under += x < kMinAccepted;
-        v[i] = (double)((around_logf ? log10f_around_logf(x) : log10f(x)) - kLog10InitF);
+        const float l = mode == 3 ? log10f_restated(x) : mode == 1 ? log10f_around_logf(x) : log10f(x);
+        v[i] = (double)(l - kLog10InitF);
     }
     return under;
 }
@@ -227,7 +257,7 @@ bool mode_matches_libm(int mode)
 size_t phmm_log10_block(const float* f, double* v, size_t n, int mode)
 {
     if (mode == 2) return block_avx512(f, v, n, false);
-    return block_scalar(f, v, n, mode == 1);
+    return block_scalar(f, v, n, mode);
 }
 
 uint64_t phmm_log10_logf_mismatches(uint32_t stride)
@@ -248,6 +278,47 @@ uint64_t phmm_log10_logf_mismatches(uint32_t stride)
         }
     }
     return bad;
+}
+
+bool phmm_log10_restated_matches_libm()
+{
+    // the whole domain the formula hands to logf, every 61st float (tests/test_abi.py walks all of it), then the formula itself
+    for (uint32_t bits = 0x3f000000u; bits < 0x40000000u; bits += 61u) {
+        float x;
+        std::memcpy(&x, &bits, 4);
+        const float a = log10f(x), b = log10f_restated(x);
+        if (std::memcmp(&a, &b, 4) != 0) return false;
+    }
+    return mode_matches_libm(3);
+}
+
+uint32_t phmm_best_haplotypes(const double* lik, uint32_t nr, uint32_t nh, uint32_t kept, const double* priority, uint32_t* best,
+                              uint32_t* second)
+{
+    constexpr double kInformative = 0.2;                     // s_log_10_informative_threshold, allele_likelihoods.hpp:27
+    for (uint32_t pos = 0; pos < kept; ++pos) {
+        // search_best_allele with can_be_reference = true (allele_likelihoods.hpp:609-622)
+        uint32_t bi = 0, si = 0;
+        double bl = lik[pos], sl = -INFINITY;
+        for (uint32_t a = 1; a < nh; ++a) {
+            const double c = lik[(size_t)a * nr + pos];
+            if (c > bl) { si = bi; bi = a; sl = bl; bl = c; }
+            else if (c > sl) { si = a; sl = c; }
+        }
+        if (priority && bl - sl < kInformative) {            // :624-645
+            double bp = priority[bi], sp = priority[si];
+            for (uint32_t a = 0; a < nh; ++a) {
+                const double c = lik[(size_t)a * nr + pos];
+                if (a == bi || bl - c > kInformative) continue;
+                const double cp = priority[a];
+                if (cp > bp) { si = bi; bi = a; sp = bp; bp = cp; }
+                else if (cp > sp) { si = a; sp = cp; }
+            }
+        }
+        best[pos] = bi;
+        second[pos] = si;
+    }
+    return kept;
 }
 
 int phmm_log10_pick_mode()

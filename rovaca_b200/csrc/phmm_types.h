@@ -72,6 +72,17 @@ struct PhmmPair
     uint32_t out_idx;
 };
 
+// one region for the device epilogue (phmm_epilogue_kernel)
+struct PhmmRegionDev
+{
+    uint32_t read_begin; // reads[read_begin .. read_begin + n_reads)
+    uint32_t n_reads;
+    uint32_t hap_begin;
+    uint32_t n_haps;
+    uint32_t out_off;    // index of pair (read 0, hap 0) in out_f32; the region's [n_haps][n_reads] matrix starts at the same index
+    uint32_t rsv[3];
+};
+
 // lookup tables, built on the host with libm exactly as core/context.h does, uploaded once
 struct PhmmTables
 {

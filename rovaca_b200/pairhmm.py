@@ -23,6 +23,7 @@ PCR_NONE, PCR_HOSTILE, PCR_AGGRESSIVE, PCR_CONSERVATIVE = 0, 1, 2, 3      # comm
 FMA_AVX512, FMA_NONE = 1, 2
 FLAT_PINNED = 1                                                          # phmm_flat_batch.flags
 FP64_WHEN_OBSERVABLE, FP64_ALWAYS = 0, 1                                     # phmm_config.fp64_mode
+EPILOGUE_AUTO, EPILOGUE_HOST, EPILOGUE_DEVICE = 0, 1, 2                      # phmm_config.epilogue
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _u8p = C.POINTER(C.c_uint8)
@@ -38,7 +39,7 @@ class PhmmError(RuntimeError):
 
 class _Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("fma_mode", C.c_int32), ("n_workers", C.c_uint32), ("batch_cells", C.c_uint64),
-                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("lanes_per_read", C.c_uint32), ("fp64_mode", C.c_uint32), ("rsv", C.c_uint32 * 5)]
+                ("linger_us", C.c_uint32), ("cta_warps", C.c_uint32), ("pipeline_depth", C.c_uint32), ("lanes_per_read", C.c_uint32), ("fp64_mode", C.c_uint32), ("epilogue", C.c_uint32), ("rsv", C.c_uint32 * 4)]
 
 
 class _Read(C.Structure):
@@ -47,7 +48,7 @@ class _Read(C.Structure):
 
 
 class _Hap(C.Structure):
-    _fields_ = [("bases", _u8p), ("len", C.c_uint32)]
+    _fields_ = [("bases", _u8p), ("len", C.c_uint32), ("priority", C.c_double)]
 
 
 class _Region(C.Structure):
@@ -57,19 +58,19 @@ class _Region(C.Structure):
 
 class _Result(C.Structure):
     _fields_ = [("likelihoods", _f64p), ("kept_idx", _u32p), ("n_kept", C.c_uint32), ("raw_f32", _f32p), ("raw_f64", _f64p),
-                ("n_fp64", C.c_uint32)]
+                ("n_fp64", C.c_uint32), ("best_hap", _u32p), ("second_hap", _u32p)]
 
 
 class _FlatBatch(C.Structure):
     _fields_ = [("n_regions", C.c_uint32), ("reg_read_off", _u64p), ("reg_hap_off", _u64p), ("read_len", _u32p),
                 ("read_mapq", _u8p), ("read_off", _u64p), ("read_bases", _u8p), ("read_qual", _u8p), ("read_ins", _u8p),
                 ("read_del", _u8p), ("read_gcp", _u8p), ("hap_len", _u32p), ("hap_off", _u64p), ("hap_bases", _u8p),
-                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32), ("flags", C.c_uint32)]
+                ("min_quality_threshold", C.c_int32), ("pcr_model", C.c_int32), ("flags", C.c_uint32), ("hap_priority", _f64p)]
 
 
 class _FlatResult(C.Structure):
     _fields_ = [("likelihoods", _f64p), ("lik_off", _u64p), ("kept_idx", _u32p), ("n_kept", _u32p), ("raw_f32", _f32p),
-                ("raw_f64", _f64p), ("n_fp64", C.c_uint64)]
+                ("raw_f64", _f64p), ("n_fp64", C.c_uint64), ("best_hap", _u32p), ("second_hap", _u32p)]
 
 
 class _SwParams(C.Structure):
@@ -151,6 +152,8 @@ def load_library():
     L.phmm_debug_tables.restype = None
     L.phmm_debug_log10f_check.restype = C.c_uint64
     L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int)]
+    L.phmm_debug_host_log10.argtypes = [_f32p, C.c_uint32, C.c_int, _f64p]
+    L.phmm_debug_device_log10.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f64p, C.POINTER(C.c_int)]
     L.phmm_debug_logf_check.restype = C.c_uint64
     L.phmm_debug_logf_check.argtypes = [C.c_uint32]
     L.phmm_debug_plan.argtypes = [C.POINTER(_FlatBatch), C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, _u64p]
@@ -189,14 +192,25 @@ def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 
     return d
 
 
+def host_log10(x: np.ndarray, mode: int = 0) -> np.ndarray:
+    """(double)(log10f(x) - 36.1236f) on the host in ``mode`` (0 = libm itself), -inf under 1e-28f."""
+    L = load_library()
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros(x.size, np.float64)
+    rc = L.phmm_debug_host_log10(_ptr(x, _f32p), x.size, mode, _ptr(out, _f64p))
+    if rc != 0:
+        raise PhmmError(f"phmm_debug_host_log10 failed ({rc})")
+    return out
+
+
 def host_epilogue(batch: RegionBatch, raw_f32: np.ndarray, raw_f64: Optional[np.ndarray] = None, mode: int = -1, reps: int = 1,
-                  min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE):
+                  min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE, best: bool = False):
     """Host only (no GPU): the engine's epilogue — log10 conversion, normalisation, filter, transpose — on raw sums laid out
     like ``FlatResult.raw_f32``.  ``mode``: how log10f is computed (0 libm, 1 around libm's logf, 2 AVX-512, -1 as an engine
     would pick).  -> (FlatResult, mean milliseconds per run)."""
     L = load_library()
     fb = _flat_c(batch, min_quality_threshold, pcr_option)
-    res = FlatResult(batch)
+    res = FlatResult(batch, best=best)
     f32 = np.ascontiguousarray(raw_f32, np.float32).reshape(-1)
     f64 = None if raw_f64 is None else np.ascontiguousarray(raw_f64, np.float64).reshape(-1)
     ms = C.c_double(0)
@@ -214,7 +228,7 @@ def _ptr(a: Optional[np.ndarray], t):
 class FlatResult:
     """Host buffers one flat call fills; ``matrix(g)`` gives region g's [n_haps][n_reads] view."""
 
-    def __init__(self, batch: RegionBatch, raw: bool = False):
+    def __init__(self, batch: RegionBatch, raw: bool = False, best: bool = False):
         self.batch = batch
         self.lik_off = batch.lik_off()
         n = int(self.lik_off[-1])
@@ -224,8 +238,11 @@ class FlatResult:
         self.raw_f32 = np.zeros(max(n, 1), np.float32) if raw else None
         self.raw_f64 = np.zeros(max(n, 1), np.float64) if raw else None
         self.n_fp64 = 0
+        self.best_hap = np.zeros(max(batch.n_reads, 1), np.uint32) if best else None
+        self.second_hap = np.zeros(max(batch.n_reads, 1), np.uint32) if best else None
         self.c = _FlatResult(_ptr(self.likelihoods, _f64p), _ptr(self.lik_off, _u64p), _ptr(self.kept_idx, _u32p),
-                             _ptr(self.n_kept, _u32p), _ptr(self.raw_f32, _f32p), _ptr(self.raw_f64, _f64p), 0)
+                             _ptr(self.n_kept, _u32p), _ptr(self.raw_f32, _f32p), _ptr(self.raw_f64, _f64p), 0,
+                             _ptr(self.best_hap, _u32p), _ptr(self.second_hap, _u32p))
 
     def _dims(self, g: int) -> Tuple[int, int]:
         b = self.batch
@@ -239,6 +256,12 @@ class FlatResult:
     def kept(self, g: int) -> np.ndarray:
         r0 = int(self.batch.reg_read_off[g])
         return self.kept_idx[r0:r0 + int(self.n_kept[g])]
+
+    def best(self, g: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(best, second-best) haplotype index of every surviving read of region g."""
+        r0 = int(self.batch.reg_read_off[g])
+        n = int(self.n_kept[g])
+        return self.best_hap[r0:r0 + n], self.second_hap[r0:r0 + n]
 
     def raw32(self, g: int) -> np.ndarray:
         nh, nr = self._dims(g)
@@ -256,7 +279,7 @@ def _flat_c(batch: RegionBatch, thr: int, pcr: int) -> _FlatBatch:
                       _ptr(batch.read_mapq, _u8p), _ptr(batch.read_off, _u64p), _ptr(batch.read_bases, _u8p),
                       _ptr(batch.read_qual, _u8p), _ptr(batch.read_ins, _u8p), _ptr(batch.read_del, _u8p), _ptr(batch.read_gcp, _u8p),
                       _ptr(batch.hap_len, _u32p), _ptr(batch.hap_off, _u64p), _ptr(batch.hap_bases, _u8p), thr, pcr,
-                      FLAT_PINNED if getattr(batch, "pinned", False) else 0)
+                      FLAT_PINNED if getattr(batch, "pinned", False) else 0, _ptr(getattr(batch, "hap_priority", None), _f64p))
 
 
 class Resident:
@@ -275,8 +298,8 @@ class Resident:
         self.eng._check(self.eng.L.phmm_resident_run(self.eng.h, self.h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
 
-    def download(self, raw: bool = False) -> FlatResult:
-        res = FlatResult(self.batch, raw)
+    def download(self, raw: bool = False, best: bool = False) -> FlatResult:
+        res = FlatResult(self.batch, raw, best)
         self.eng._check(self.eng.L.phmm_resident_download(self.eng.h, self.h, C.byref(res.c)))
         res.n_fp64 = int(res.c.n_fp64)
         return res
@@ -297,9 +320,9 @@ class PairHmmEngine:
     """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
 
     def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
-                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0, fp64_mode: int = 0):
+                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0, fp64_mode: int = 0, epilogue: int = 0):
         self.L = load_library()
-        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read, fp64_mode)
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read, fp64_mode, epilogue)
         self.h = C.c_void_p()
         rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
         if rc != 0:
@@ -322,9 +345,11 @@ class PairHmmEngine:
 
     # -- the reference's call ---------------------------------------------------------------------
     def call_pairhmm(self, haps: Sequence, reads: Sequence[dict], min_quality_threshold: int = 18,
-                     pcr_option: int = PCR_CONSERVATIVE, raw: bool = False):
+                     pcr_option: int = PCR_CONSERVATIVE, raw: bool = False, priorities: Optional[Sequence[float]] = None):
         """One region.  reads: dicts with bases, qual, mapq and optionally ins/del/gcp (bytes / uint8 arrays).
-        Returns (matrix[n_haps, n_reads] with NaN tail, kept_idx) and, with raw=True, also (raw_f32, raw_f64, n_fp64)."""
+        Returns (matrix[n_haps, n_reads] with NaN tail, kept_idx) and, with raw=True, also (raw_f32, raw_f64, n_fp64); with
+        ``priorities`` (one per haplotype, the tie-break of best_alleles_breaking_ties) also (best_hap, second_hap) of the
+        surviving reads."""
         n_r, n_h = len(reads), len(haps)
         keep = []
         ra = (_Read * max(n_r, 1))()
@@ -346,18 +371,25 @@ class PairHmmEngine:
             a = _as_u8(h)
             keep.append(a)
             ha[j].bases, ha[j].len = a.ctypes.data_as(_u8p), len(a)
+            ha[j].priority = float(priorities[j]) if priorities is not None else 0.0
+        best = np.zeros(max(n_r, 1), np.uint32) if priorities is not None else None
+        second = np.zeros(max(n_r, 1), np.uint32) if priorities is not None else None
         out = np.full((n_h, n_r), np.nan, np.float64)
         kept = np.zeros(max(n_r, 1), np.uint32)
         raw32 = np.zeros((n_r, n_h), np.float32) if raw else None
         raw64 = np.zeros((n_r, n_h), np.float64) if raw else None
         reg = _Region(ra, n_r, ha, n_h, min_quality_threshold, pcr_option)
-        res = _Result(_ptr(out, _f64p), _ptr(kept, _u32p), 0, _ptr(raw32, _f32p), _ptr(raw64, _f64p), 0)
+        res = _Result(_ptr(out, _f64p), _ptr(kept, _u32p), 0, _ptr(raw32, _f32p), _ptr(raw64, _f64p), 0, _ptr(best, _u32p),
+                      _ptr(second, _u32p))
         self._check(self.L.phmm_call_region(self.h, C.byref(reg), C.byref(res)))
         if n_r == 0 or n_h == 0:       # pairhmm_internal.cpp:508-510 returns an empty matrix
             out = np.zeros((0, 0), np.float64)
+        ret = (out, kept[: res.n_kept].copy())
         if raw:
-            return out, kept[: res.n_kept].copy(), raw32, raw64, int(res.n_fp64)
-        return out, kept[: res.n_kept].copy()
+            ret += (raw32, raw64, int(res.n_fp64))
+        if priorities is not None:
+            ret += (best[: res.n_kept].copy(), second[: res.n_kept].copy())
+        return ret
 
     # -- the step after the path: batched Smith-Waterman ------------------------------------------
     def sw_prepare(self, pairs: Sequence[Tuple], cigar_cap: int = 64):
@@ -394,9 +426,10 @@ class PairHmmEngine:
 
     # -- batch forms ------------------------------------------------------------------------------
     def run_flat(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE,
-                 raw: bool = False, out: Optional[FlatResult] = None) -> FlatResult:
-        """Host buffers in, host buffers out: packing, H2D, kernels, D2H and the host epilogue, pipelined."""
-        res = out or FlatResult(batch, raw)
+                 raw: bool = False, out: Optional[FlatResult] = None, best: bool = False) -> FlatResult:
+        """Host buffers in, host buffers out: packing, H2D, kernels, D2H and the epilogue, pipelined.  ``best``: also the best /
+        second-best haplotype of every surviving read (ties broken by ``batch.hap_priority`` when the batch has one)."""
+        res = out or FlatResult(batch, raw, best)
         fb = _flat_c(batch, min_quality_threshold, pcr_option)
         self._check(self.L.phmm_run_flat(self.h, C.byref(fb), C.byref(res.c)))
         res.n_fp64 = int(res.c.n_fp64)
@@ -409,6 +442,14 @@ class PairHmmEngine:
         s = _Stats()
         self._check(self.L.phmm_get_stats(self.h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    def device_log10(self, x: np.ndarray) -> Tuple[np.ndarray, bool]:
+        """(double)(log10f(x) - 36.1236f) as the device epilogue computes it, and whether this engine's epilogue runs there."""
+        x = np.ascontiguousarray(x, np.float32)
+        out = np.zeros(x.size, np.float64)
+        use = C.c_int(0)
+        self._check(self.L.phmm_debug_device_log10(self.h, _ptr(x, _f32p), x.size, _ptr(out, _f64p), C.byref(use)))
+        return out, bool(use.value)
 
     def ubench(self, mode: int, iters: int = 4096) -> Tuple[float, float]:
         """-> (ms, FMA lane-ops per second) of the FP32 issue-rate micro-benchmark."""

@@ -42,3 +42,13 @@ def engine_nofma():
     eng = PairHmmEngine(fma_mode=FMA_NONE)
     yield eng
     eng.close()
+
+
+@pytest.fixture(scope="session")
+def engine_host_epilogue():
+    """An engine that keeps the epilogue (log10, normalize, filter, transpose, best haplotype) on the host."""
+    from rovaca_b200 import PairHmmEngine
+    from rovaca_b200.pairhmm import EPILOGUE_HOST
+    eng = PairHmmEngine(epilogue=EPILOGUE_HOST)
+    yield eng
+    eng.close()

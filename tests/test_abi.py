@@ -71,6 +71,9 @@ def test_restated_log10f_is_libm_or_is_not_used():
             assert picked.value < mode
         elif bad:
             assert picked.value < mode, f"mode {mode} differs from libm on {bad} inputs but would be used"
+    # mode 3 is the restatement one value at a time, in the device epilogue's operations: the device may run the epilogue only
+    # on a host where it gives libm's bits
+    assert bool(L.phmm_debug_device_epilogue_allowed()) == (L.phmm_debug_log10f_check(263, 3, None) == 0)
     exhaustive = L.phmm_debug_logf_check(1)
     if exhaustive != 2**64 - 1:
         assert exhaustive == 0 or picked.value < 2

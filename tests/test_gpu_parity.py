@@ -287,6 +287,76 @@ def test_matrix_does_not_depend_on_the_fp64_recompute(engine, orc):
         always.close()
 
 
+def test_device_log10_is_the_hosts_libm(engine):
+    """The device epilogue's log10f (glibc's algorithm restated, phmm_kernels.cu log10_of_sum) against the host's libm: every
+    float of [0.5, 2) — all the formula ever hands to logf — and four million floats spread over everything above 1e-28."""
+    from rovaca_b200 import pairhmm as ph
+    _, on_device = engine.device_log10(np.ones(1, np.float32))
+    assert on_device, "this host's libm is not glibc's algorithm: the engine must have kept its epilogue on the host"
+    for lo in range(0x3F000000, 0x40000000, 1 << 22):
+        x = np.arange(lo, lo + (1 << 22), dtype=np.uint32).view(np.float32)
+        got, _ = engine.device_log10(x)
+        assert np.array_equal(got.view(np.uint64), ph.host_log10(x, 0).view(np.uint64)), hex(lo)
+    rng = np.random.default_rng(5)
+    x = rng.integers(0x0D000000, 0x7F800000, 1 << 22, dtype=np.uint32).view(np.float32)
+    got, _ = engine.device_log10(x)
+    want = ph.host_log10(x, 0)
+    assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+    assert np.isneginf(got[x < np.float32(1e-28)]).all()
+
+
+def test_device_epilogue_equals_host_epilogue_and_oracle(engine, engine_host_epilogue, orc):
+    """Matrices, surviving reads, FP64-branch counts and best / second-best haplotypes from the device
+    epilogue, from the host epilogue and from the oracle (orc.region + its restatement of search_best_allele), on regions with
+    duplicate haplotypes (ties for the priorities to break), junk reads, reads under 51 bp and a single-haplotype region."""
+    rng = np.random.default_rng(47)
+    regs, pris = [], []
+    for g in range(24):
+        reads, haps = wl._one_region(rng, int(rng.integers(1, 140)), int(rng.integers(2, 9)), 150, 260, 30, 151, junk=0.15)
+        haps = list(haps)
+        for _ in range(int(rng.integers(0, 4))):
+            haps.insert(int(rng.integers(0, len(haps) + 1)), haps[int(rng.integers(0, len(haps)))].copy())
+        if g == 3:
+            haps = haps[:1]
+        regs.append((reads, haps))
+        pris.append(rng.integers(-3, 3, len(haps)).astype(np.float64))
+    regs.insert(5, ([], [b"ACGT"]))                            # an empty region in the middle
+    pris.insert(5, np.zeros(1))
+    batch = wl.RegionBatch.from_regions(regs)
+    batch.hap_priority = np.concatenate(pris)
+    dev = engine.run_flat(batch, best=True, raw=True)
+    host = engine_host_epilogue.run_flat(batch, best=True, raw=True)
+    assert np.array_equal(dev.n_kept, host.n_kept) and dev.n_fp64 == host.n_fp64
+    assert np.array_equal(_bits64(dev.likelihoods), _bits64(host.likelihoods))
+    assert np.array_equal(_bits32(dev.raw_f32), _bits32(host.raw_f32))
+    assert np.array_equal(_bits64(dev.raw_f64), _bits64(host.raw_f64))
+    ties = 0
+    for g, (reads, haps) in enumerate(regs):
+        assert np.array_equal(dev.kept(g), host.kept(g))
+        for a, b in zip(dev.best(g), host.best(g)):
+            assert np.array_equal(a, b), g
+        if not reads:
+            continue
+        m0, k0, *_ = orc.region(reads, haps)
+        assert np.array_equal(dev.kept(g), k0) and np.array_equal(_bits64(dev.matrix(g)), _bits64(m0))
+        b0, s0, *_ = orc.best_alleles(m0, len(k0), pris[g])
+        ties += int((b0 != orc.best_alleles(m0, len(k0), None)[0]).sum())
+        assert np.array_equal(dev.best(g)[0], b0) and np.array_equal(dev.best(g)[1], s0), g
+        # the per-region call, with and without priorities
+        m, k, b, s2 = engine.call_pairhmm(haps, reads, priorities=pris[g])
+        assert np.array_equal(k, k0) and np.array_equal(_bits64(m), _bits64(m0)) and np.array_equal(b, b0) and np.array_equal(s2, s0)
+    assert ties > 0
+    # without best haplotypes asked for, and a resident batch that learns about them only at download time
+    plain = engine.run_flat(batch)
+    assert np.array_equal(_bits64(plain.likelihoods), _bits64(host.likelihoods)) and np.array_equal(plain.kept_idx, host.kept_idx)
+    resident = engine.upload(batch)
+    resident.run()
+    down = resident.download(best=True)
+    resident.free()
+    assert np.array_equal(_bits64(down.likelihoods), _bits64(host.likelihoods))
+    assert np.array_equal(down.best_hap, host.best_hap) and np.array_equal(down.second_hap, host.second_hap)
+
+
 def test_long_haplotypes_multi_chunk(engine, orc):
     """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
     rng = np.random.default_rng(13)

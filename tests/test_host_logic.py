@@ -126,3 +126,43 @@ def test_host_epilogue_on_the_oracles_raw_sums(orc, mode):
         for g, (m0, k0, *_) in enumerate(want):
             assert np.array_equal(res.kept(g), k0), (g, f64 is None)
             assert np.array_equal(res.matrix(g).view(np.uint64), m0.view(np.uint64)), (g, f64 is None)
+
+
+def _regions_with_ties(rng, n_regions=6):
+    """Regions whose haplotype lists hold exact duplicates and near-duplicates, so that best / second-best haplotypes tie and
+    the priorities decide (allele_likelihoods.hpp:624-645)."""
+    regs, pris = [], []
+    for g in range(n_regions):
+        reads, haps = wl._one_region(rng, int(rng.integers(5, 40)), int(rng.integers(2, 7)), 120, 160, 40, 90, junk=0.15)
+        haps = list(haps)
+        for _ in range(int(rng.integers(1, 4))):
+            haps.insert(int(rng.integers(0, len(haps) + 1)), haps[int(rng.integers(0, len(haps)))].copy())
+        if g == 0:
+            haps = haps[:1]                                   # a single haplotype: second best = best, likelihood -inf
+        regs.append((reads, haps))
+        pris.append(rng.integers(-3, 3, len(haps)).astype(np.float64))
+    return regs, pris
+
+
+@pytest.mark.parametrize("with_priorities", [True, False])
+def test_host_best_haplotypes_match_search_best_allele(orc, with_priorities):
+    """phmm_result.best_hap / second_hap from the host epilogue against the oracle's restatement of
+    AlleleLikelihoods::search_best_allele (genotype/allele_likelihoods.hpp:589-657) on the oracle's own matrices."""
+    from rovaca_b200 import pairhmm as ph
+    rng = np.random.default_rng(43)
+    regs, pris = _regions_with_ties(rng)
+    batch = wl.RegionBatch.from_regions(regs)
+    if with_priorities:
+        batch.hap_priority = np.concatenate(pris)
+    want = [orc.region(reads, haps) for reads, haps in regs]
+    raw32 = np.concatenate([w[2].reshape(-1) for w in want])
+    res, _ = ph.host_epilogue(batch, raw32, None, best=True)
+    tie_broken = 0
+    for g, (m0, k0, *_) in enumerate(want):
+        assert np.array_equal(res.kept(g), k0)
+        b0, s0, *_ = orc.best_alleles(m0, len(k0), pris[g] if with_priorities else None)
+        b_plain, *_ = orc.best_alleles(m0, len(k0), None)
+        tie_broken += int((b0 != b_plain).sum())
+        b1, s1 = res.best(g)
+        assert np.array_equal(b1, b0) and np.array_equal(s1, s0), g
+    assert (tie_broken > 0) == with_priorities

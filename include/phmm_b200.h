@@ -208,6 +208,14 @@ int phmm_flush(phmm_engine* e);
 /* A whole stream of regions in one call, pipelined over the workers (bench / batch callers). */
 int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* batch, phmm_flat_result* result);
 
+/* AlleleLikelihoods::marginalize -> marginal_likelihoods_direct (genotype/allele_likelihoods.hpp:189-216, 702-732) on a matrix
+ * phmm_call_region returned: out[n][e] = the largest values[a][e] over the old alleles a with old_to_new[a] == n, -inf when
+ * there is none (old_to_new[a] < 0: allele a maps to nothing, :717).  values is [n_old][stride], out [n_new][out_stride],
+ * e runs over the first n_evidence columns.  Host only: the maps come from the per-site event analysis that runs after the
+ * path, one per variant site, so there is nothing to fuse into the kernels. */
+int phmm_marginalize(const double* values, uint32_t n_old, uint32_t stride, uint32_t n_evidence, const int32_t* old_to_new,
+                     uint32_t n_new, double* out, uint32_t out_stride);
+
 /* Device-resident form for kernel-only timing: upload once, run the device path (prep + forward +
  * FP64 recompute kernels, no host<->device copies) any number of times, download when wanted. */
 typedef struct phmm_resident phmm_resident;

@@ -96,6 +96,8 @@ class Oracle:
                                  _f64p, _u32p, _u32p, _f32p, _f64p]
         L.orc_best_alleles.restype = None
         L.orc_best_alleles.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, _f64p, _u32p, _u32p, _f64p, _f64p, _f64p]
+        L.orc_marginalize.restype = None
+        L.orc_marginalize.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, _f64p]
         L.orc_sw_align.restype = C.c_int32
         L.orc_sw_align.argtypes = [_u8p, C.c_int32, _u8p, C.c_int32, C.c_void_p, _u32p, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.orc_init()
@@ -164,6 +166,15 @@ class Oracle:
         return q, i, d, c
 
     # region -------------------------------------------------------------------------------
+    def marginalize(self, matrix: np.ndarray, n_evidence: int, old_to_new, n_new: int) -> np.ndarray:
+        """marginal_likelihoods_direct on the first n_evidence columns of matrix[n_old, stride] -> [n_new, n_evidence]."""
+        m = np.ascontiguousarray(matrix, np.float64)
+        mp = np.ascontiguousarray(old_to_new, np.int32)
+        out = np.zeros((n_new, n_evidence), np.float64)
+        self.lib.orc_marginalize(_p(m, _f64p), m.shape[0], m.shape[1], n_evidence, mp.ctypes.data_as(C.POINTER(C.c_int32)), n_new,
+                                 _p(out, _f64p))
+        return out
+
     def best_alleles(self, matrix: np.ndarray, n_evidence: int, priorities=None):
         """search_best_allele for the first n_evidence columns of matrix[n_alleles, stride] ->
         (best, second, best_lik, second_lik, confidence)."""

@@ -446,3 +446,20 @@ void orc_best_alleles(const double* values, uint32_t n_alleles, uint32_t stride,
                 fabs(best_likelihood - second_best_likelihood) < 2.220446049250313e-16 ? 0.0 : best_likelihood - second_best_likelihood;
     }
 }
+
+/* allele_likelihoods.hpp:702-732 */
+void orc_marginalize(const double* old_values, uint32_t old_allele_count, uint32_t stride, uint32_t evidence_count,
+                     const int32_t* old2new_idx_map, uint32_t new_allele_count, double* new_values)
+{
+    for (size_t k = 0; k < (size_t)new_allele_count * evidence_count; k++) new_values[k] = -INFINITY;
+    for (uint32_t ai = 0; ai < old_allele_count; ai++) {
+        const int32_t new_allele_idx = old2new_idx_map[ai];
+        if (new_allele_idx < 0) continue;
+        const double* old_lk = old_values + (size_t)ai * stride;
+        double* new_lk = new_values + (size_t)new_allele_idx * evidence_count;
+        for (uint32_t ri = 0; ri < evidence_count; ri++) {
+            const double likelihoods = old_lk[ri];
+            if (likelihoods > new_lk[ri]) new_lk[ri] = likelihoods;
+        }
+    }
+}

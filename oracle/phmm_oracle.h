@@ -93,6 +93,12 @@ int64_t orc_region(const orc_read* reads, uint32_t n_reads, const orc_hap* haps,
 void orc_best_alleles(const double* values, uint32_t n_alleles, uint32_t stride, uint32_t n_evidence, const double* priorities,
                       uint32_t* best, uint32_t* second, double* best_lik, double* second_lik, double* confidence);
 
+/* AlleleLikelihoods::marginal_likelihoods_direct (genotype/allele_likelihoods.hpp:702-732) for one sample:
+ * new_values[n][r] starts at -inf and takes every old_values[a][r] that is greater, a over the old alleles whose
+ * old2new_idx_map entry is n (entries < 0 = s_missing_index are skipped). */
+void orc_marginalize(const double* old_values, uint32_t old_allele_count, uint32_t stride, uint32_t evidence_count,
+                     const int32_t* old2new_idx_map, uint32_t new_allele_count, double* new_values);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1498,6 +1498,25 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* f
     return rc_all;
 }
 
+int phmm_marginalize(const double* values, uint32_t n_old, uint32_t stride, uint32_t n_evidence, const int32_t* old_to_new,
+                     uint32_t n_new, double* out, uint32_t out_stride)
+{
+    if ((n_old && (!values || !old_to_new)) || (n_new && !out)) return fail(PHMM_ERR_ARG, "phmm_marginalize: null argument");
+    if (n_evidence > stride || n_evidence > out_stride) return fail(PHMM_ERR_ARG, "phmm_marginalize: more evidence than columns");
+    for (uint32_t n = 0; n < n_new; ++n)
+        for (uint32_t e = 0; e < n_evidence; ++e) out[(size_t)n * out_stride + e] = -INFINITY;     // :714
+    for (uint32_t a = 0; a < n_old; ++a) {
+        const int32_t n = old_to_new[a];
+        if (n < 0) continue;                                                                       // s_missing_index, :717
+        if ((uint32_t)n >= n_new) return fail(PHMM_ERR_ARG, "phmm_marginalize: old_to_new names an allele past n_new");
+        const double* in = values + (size_t)a * stride;
+        double* o = out + (size_t)n * out_stride;
+        for (uint32_t e = 0; e < n_evidence; ++e)
+            if (in[e] > o[e]) o[e] = in[e];                                                        // :723-726
+    }
+    return PHMM_OK;
+}
+
 int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* fb, phmm_resident** out)
 {
     if (!e || !fb || !out) return fail(PHMM_ERR_ARG, "phmm_resident_upload: null argument");

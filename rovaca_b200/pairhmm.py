@@ -96,7 +96,7 @@ class _Stats(C.Structure):
                 ("gpu_ms", C.c_double), ("kernel_launches", C.c_uint64), ("host_plan_ms", C.c_double), ("host_epilogue_ms", C.c_double)]
 
 
-EXPORTS = ["phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
+EXPORTS = ["phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
            "phmm_resident_upload", "phmm_resident_run", "phmm_resident_download", "phmm_resident_free",
            "phmm_resident_launches", "phmm_get_stats", "phmm_kernel_info", "phmm_ubench", "phmm_last_error", "phmm_version"]
 
@@ -152,6 +152,7 @@ def load_library():
     L.phmm_debug_tables.restype = None
     L.phmm_debug_log10f_check.restype = C.c_uint64
     L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int)]
+    L.phmm_marginalize.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, _f64p, C.c_uint32]
     L.phmm_debug_host_log10.argtypes = [_f32p, C.c_uint32, C.c_int, _f64p]
     L.phmm_debug_device_log10.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f64p, C.POINTER(C.c_int)]
     L.phmm_debug_logf_check.restype = C.c_uint64
@@ -190,6 +191,20 @@ def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 
     d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)
     d["lane_utilisation"] = d["wavefront_cells"] / max(2 * d["lane_steps"], 1)      # two haplotype streams per lane
     return d
+
+
+def marginalize(matrix: np.ndarray, n_evidence: int, old_to_new, n_new: int) -> np.ndarray:
+    """``AlleleLikelihoods::marginalize`` on a matrix ``call_pairhmm`` returned: [n_new, n_evidence], each entry the largest
+    likelihood over the old alleles mapped to it (-inf when none is)."""
+    L = load_library()
+    m = np.ascontiguousarray(matrix, np.float64)
+    mp = np.ascontiguousarray(old_to_new, np.int32)
+    out = np.zeros((n_new, max(n_evidence, 1)), np.float64)
+    rc = L.phmm_marginalize(_ptr(m, _f64p), m.shape[0], m.shape[1] if m.ndim == 2 else 0, n_evidence,
+                            mp.ctypes.data_as(C.POINTER(C.c_int32)), n_new, _ptr(out, _f64p), out.shape[1])
+    if rc != 0:
+        raise PhmmError(f"phmm_marginalize failed ({rc}): {L.phmm_last_error().decode()}")
+    return out[:, :n_evidence]
 
 
 def host_log10(x: np.ndarray, mode: int = 0) -> np.ndarray:

@@ -166,3 +166,22 @@ def test_host_best_haplotypes_match_search_best_allele(orc, with_priorities):
         b1, s1 = res.best(g)
         assert np.array_equal(b1, b0) and np.array_equal(s1, s0), g
     assert (tie_broken > 0) == with_priorities
+
+
+def test_marginalize_matches_marginal_likelihoods_direct(orc):
+    """phmm_marginalize against the oracle's restatement of AlleleLikelihoods::marginal_likelihoods_direct
+    (genotype/allele_likelihoods.hpp:702-732) on the oracle's matrices: several haplotypes per allele, haplotypes that map
+    to nothing, an allele nobody maps to (-inf row)."""
+    from rovaca_b200 import pairhmm as ph
+    rng = np.random.default_rng(53)
+    for _ in range(8):
+        reads, haps = wl._one_region(rng, int(rng.integers(1, 50)), int(rng.integers(1, 12)), 100, 140, 30, 80, junk=0.1)
+        m, kept, *_ = orc.region(reads, haps)
+        n_new = int(rng.integers(1, 5))
+        mp = rng.integers(-1, n_new, len(haps)).astype(np.int32)
+        got = ph.marginalize(m, len(kept), mp, n_new + 1)          # allele n_new has no haplotype
+        want = orc.marginalize(m, len(kept), mp, n_new + 1)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64))
+        assert np.isneginf(got[n_new]).all()
+    with pytest.raises(ph.PhmmError):
+        ph.marginalize(np.zeros((2, 3)), 3, [0, 5], 2)

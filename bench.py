@@ -3,8 +3,8 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--regions R]
 
-One "step" = one pass of the hot path (quality capping + PCR-indel model, forward recurrence, FP64 recompute, and in the
-end-to-end leg packing, H2D, D2H and the host epilogue) over one batch of synthetic active regions:
+One "step" = one pass of the hot path (quality capping + PCR-indel model, forward recurrence, log10 / normalise / filter /
+transpose epilogue, and in the end-to-end leg planning, H2D, D2H and the hand-over to the caller's arrays) over one batch of synthetic active regions:
 BASELINE.json configs[1], 150 bp reads x 300 bp haplotypes, 8 haplotypes and 64 reads per region, R regions per GPU
 (default 4096 = 94.4 G cells per GPU per step; raw inputs + packed rows + outputs ~ 270 MB > the 126 MB L2).
 Multi-GPU (torchrun, one rank per GPU): regions are independent, every rank runs its own R regions through its own

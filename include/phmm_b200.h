@@ -63,7 +63,9 @@ typedef struct phmm_config
  * best-haplotype search the next step opens with (genotype/allele_likelihoods.hpp:589-657) run either on the host or in
  * one more kernel on the device.  log10f is whatever the HOST's libm says, so the device (and the host's vector path) use a
  * restatement of glibc's algorithm that is tested bit for bit against this host's libm when the engine is created; AUTO
- * takes the device only if that test passes, DEVICE fails phmm_create if it does not. */
+ * takes the device only if that test passes and only for batches of 32 768 pairs or more (a smaller batch — the few regions
+ * synchronous callers have in flight — is done sooner by the host's vector epilogue than one more launch takes); DEVICE
+ * takes it for every batch and fails phmm_create if the test does not pass. */
 #define PHMM_EPILOGUE_AUTO 0u
 #define PHMM_EPILOGUE_HOST 1u
 #define PHMM_EPILOGUE_DEVICE 2u
@@ -186,7 +188,9 @@ typedef struct phmm_stats
     double gpu_ms;                    /* sum of per-batch device time (CUDA events, kernels only) */
     uint64_t kernel_launches;
     double host_plan_ms;              /* sum over batches of host planning + packing time (worker threads, wall) */
-    double host_epilogue_ms;          /* sum over batches of the host epilogue (log10, cap, filter, transpose) */
+    double host_epilogue_ms;          /* sum over batches of the host epilogue (log10, cap, filter, transpose), or of the
+                                         hand-over of the device epilogue's output */
+    uint64_t device_epilogue_batches; /* batches whose epilogue ran on the device (PHMM_EPILOGUE_*) */
 } phmm_stats;
 
 /* Replaces rovaca::init_pairhmm_ptr (pairhmm/pairhmm_engine.cpp:21): builds the libm tables of

@@ -211,6 +211,7 @@ struct Slot
     PhmmEpilogueDev epi{};
     size_t e_kept = 0, e_best = 0, e_second = 0, e_nkept = 0, e_under = 0, epi_bytes = 0;
     size_t o_regions = 0, o_pri = 0;
+    bool dev_epi = false;                // this batch's epilogue runs on the device
     bool want_best = false;              // some region of the batch asks for best / second-best haplotypes
     bool want_raw = false;               // ... for the raw FP32 sums
     bool want_f64 = false;               // the FP64 recompute goes out with the batch (someone will read its values)
@@ -250,7 +251,7 @@ struct Slot
 
 struct Stats
 {
-    std::atomic<uint64_t> regions{0}, pairs{0}, cells{0}, fp64_pairs{0}, slow_pairs{0}, h2d{0}, d2h{0}, batches{0}, launches{0};
+    std::atomic<uint64_t> regions{0}, pairs{0}, cells{0}, fp64_pairs{0}, slow_pairs{0}, h2d{0}, d2h{0}, batches{0}, launches{0}, dev_epilogues{0};
     std::mutex m;
     double gpu_ms = 0.0, plan_ms = 0.0, epilogue_ms = 0.0;
 };
@@ -330,6 +331,7 @@ struct phmm_engine
     bool fp64_always = false;    // PHMM_FP64_ALWAYS: recompute every underflowing pair even when nobody can see the value
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     bool device_epilogue = false;  // log10 / normalize / filter / transpose / best haplotype in one more kernel (PHMM_EPILOGUE_*)
+    uint64_t device_epilogue_min_pairs = 0;   // ... for batches of at least this many pairs (AUTO: small batches stay on the host)
     int log10_mode = 0;            // how raw sums become log10 doubles: phmm_log10.cpp, picked (and tested against libm) at creation
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()
@@ -438,6 +440,9 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         n_pairs += (uint64_t)r.n_reads * r.n_haps;
         n_cells += rb * hb;
     }
+    // One more kernel and a D2H twice the size pay off once the host would otherwise spend longer on the pairs than a launch
+    // costs; the few-region batches of synchronous callers keep the (vector) host epilogue.
+    s.dev_epi = device_epilogue && n_pairs >= device_epilogue_min_pairs;
     if (n_pairs >= (1ull << 31) || read_bytes >= (1ull << 31) || hap_bytes >= (1ull << 31))
         return fail(PHMM_ERR_ARG, "batch too large for 32-bit device offsets; lower batch_cells");
     // What the reference itself feeds its kernels — deletion qualities aliasing the insertion ones, one gap-continuation
@@ -722,11 +727,11 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     const size_t o_tasks = place(task_reads.size() * sizeof(uint32_t));
     const size_t o_slow = place(slow.size() * sizeof(PhmmPair));
     ps.regions_dev.clear();
-    if (device_epilogue)
+    if (s.dev_epi)
         for (const RegionPlan& rp : s.regions)
             ps.regions_dev.push_back(PhmmRegionDev{rp.read_begin, rp.n_reads, rp.hap_begin, rp.n_haps, (uint32_t)rp.out_off, {0, 0, 0}});
     const size_t o_regions = place(ps.regions_dev.size() * sizeof(PhmmRegionDev));
-    const size_t o_pri = place((device_epilogue ? ps.pri.size() : 0) * sizeof(double));
+    const size_t o_pri = place((s.dev_epi ? ps.pri.size() : 0) * sizeof(double));
     const size_t o_rb = place(read_bytes + 16);
     const size_t o_rq = place(read_bytes + 16);
     const size_t o_ri = any_ins ? place(read_bytes + 16) : 0;
@@ -747,7 +752,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
     std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
     std::memcpy(h + o_regions, ps.regions_dev.data(), ps.regions_dev.size() * sizeof(PhmmRegionDev));
-    if (device_epilogue) std::memcpy(h + o_pri, ps.pri.data(), ps.pri.size() * sizeof(double));
+    if (s.dev_epi) std::memcpy(h + o_pri, ps.pri.data(), ps.pri.size() * sizeof(double));
     s.o_regions = o_regions;
     s.o_pri = o_pri;
     [[maybe_unused]] const auto pt4 = PT_NOW();
@@ -824,7 +829,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
     if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
 
-    if (device_epilogue) {
+    if (s.dev_epi) {
         // [lik: one double per pair | kept_idx, best, second: one u32 per read | n_kept, n_under: one u32 per region]
         size_t eo = 0;
         auto eplace = [&](size_t bytes) { size_t at = eo; eo = align_up(eo + bytes, 256); return at; };
@@ -862,7 +867,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     b.n_reads = (uint32_t)reads.size();
     b.rg_gapm = default_gapm;      // gap_conts() is the constant '+' - 33 = 10 for every read, read_record.cpp:205-210
     b.rg_ii = default_ii;
-    if (device_epilogue) {
+    if (s.dev_epi) {
         uint8_t* de = static_cast<uint8_t*>(s.d_epi.p);
         PhmmEpilogueDev& ep = s.epi;
         ep.regions = reinterpret_cast<const PhmmRegionDev*>(d + o_regions);
@@ -885,7 +890,7 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
     s.n_haps = (uint32_t)haps.size();
     s.n_slow = (uint32_t)slow.size();
     s.max_cols = max_cols;
-    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + (s.want_f64 ? 1 : 0) + (device_epilogue ? 1 : 0);
+    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + (s.want_f64 ? 1 : 0) + (s.dev_epi ? 1 : 0);
     return PHMM_OK;
 }
 
@@ -931,7 +936,7 @@ int phmm_engine::launch(Slot& s, bool copy_in)
     if (s.f64_done)
         CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
                                  s.stream));
-    if (device_epilogue && s.n_pairs) CU(phmm_launch_epilogue(s.epi, s.stream));
+    if (s.dev_epi && s.n_pairs) CU(phmm_launch_epilogue(s.epi, s.stream));
     CU(cudaEventRecord(s.ev[3], s.stream));
     stats.launches += s.n_launches;
     return PHMM_OK;
@@ -950,7 +955,7 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     }
     // a resident batch was planned before anyone said what to download: without best / second-best buffers on the device
     // the host epilogue serves that call
-    const bool dev = device_epilogue && (!asks_best || s.want_best);
+    const bool dev = s.dev_epi && (!asks_best || s.want_best);
     const bool need_f32 = !dev || asks_raw;
     if (copy_out && s.n_pairs) {
         if (need_f32) {
@@ -999,8 +1004,10 @@ int phmm_engine::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_ou
     CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
 
     const auto t_epi = std::chrono::steady_clock::now();
-    if (dev)
+    if (dev) {
         epilogue_from_device(s, regs, have64);
+        stats.dev_epilogues += 1;
+    }
     else
         epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
     stats.regions += regs.size();
@@ -1317,6 +1324,7 @@ int phmm_create(const phmm_config* cfg, phmm_engine** out)
         if (want == PHMM_EPILOGUE_DEVICE && !ok)
             return fail(PHMM_ERR_ARG, "PHMM_EPILOGUE_DEVICE: the restated log10f does not give this host's libm bits (or PHMM_B200_LIBM_LOG10F is set)");
         e->device_epilogue = ok;
+        e->device_epilogue_min_pairs = want == PHMM_EPILOGUE_DEVICE ? 0 : 32768;
     }
     e->default_gapm = t->gapm[10];
     e->default_ii = t->ph2pr[10];
@@ -1767,6 +1775,7 @@ int phmm_get_stats(phmm_engine* e, phmm_stats* out)
         out->host_plan_ms = e->stats.plan_ms;
         out->host_epilogue_ms = e->stats.epilogue_ms;
     }
+    out->device_epilogue_batches = e->stats.dev_epilogues;
     return PHMM_OK;
 }
 

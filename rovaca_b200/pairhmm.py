@@ -93,7 +93,8 @@ SW_ASSEMBLE = (200, -150, -260, -11)   # sw_parameters_assemble, :13
 class _Stats(C.Structure):
     _fields_ = [("regions", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64),
                 ("slow_pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("batches", C.c_uint64),
-                ("gpu_ms", C.c_double), ("kernel_launches", C.c_uint64), ("host_plan_ms", C.c_double), ("host_epilogue_ms", C.c_double)]
+                ("gpu_ms", C.c_double), ("kernel_launches", C.c_uint64), ("host_plan_ms", C.c_double), ("host_epilogue_ms", C.c_double),
+                ("device_epilogue_batches", C.c_uint64)]
 
 
 EXPORTS = ["phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",

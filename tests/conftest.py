@@ -30,8 +30,11 @@ def ref():
 
 @pytest.fixture(scope="session")
 def engine():
+    """The engine the parity tests run on: every batch, however small, goes through the DEVICE epilogue (the default, AUTO,
+    keeps batches under 32 768 pairs on the host; test_gpu_parity.py has a test of its own for that)."""
     from rovaca_b200 import PairHmmEngine
-    eng = PairHmmEngine()
+    from rovaca_b200.pairhmm import EPILOGUE_DEVICE
+    eng = PairHmmEngine(epilogue=EPILOGUE_DEVICE)
     yield eng
     eng.close()
 

@@ -357,6 +357,25 @@ def test_device_epilogue_equals_host_epilogue_and_oracle(engine, engine_host_epi
     assert np.array_equal(down.best_hap, host.best_hap) and np.array_equal(down.second_hap, host.second_hap)
 
 
+def test_default_engine_picks_the_epilogue_by_batch_size(engine):
+    """PHMM_EPILOGUE_AUTO: the device epilogue for batches of 32 768 pairs or more, the host's for smaller ones; same bytes."""
+    auto = PairHmmEngine()
+    try:
+        small, big = wl.cfg2(8, seed=61), wl.cfg2(1024, seed=62)          # 4 096 pairs; 524 288 pairs in sub-batches of >= 65 000
+        n0 = auto.stats()["device_epilogue_batches"]
+        a = auto.run_flat(small)
+        n1 = auto.stats()["device_epilogue_batches"]
+        b = auto.run_flat(big)
+        n2 = auto.stats()["device_epilogue_batches"]
+        assert n1 == n0 and n2 > n1
+        for got, batch in ((a, small), (b, big)):
+            want = engine.run_flat(batch)
+            assert np.array_equal(_bits64(got.likelihoods), _bits64(want.likelihoods))
+            assert np.array_equal(got.kept_idx, want.kept_idx) and np.array_equal(got.n_kept, want.n_kept)
+    finally:
+        auto.close()
+
+
 def test_long_haplotypes_multi_chunk(engine, orc):
     """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
     rng = np.random.default_rng(13)

@@ -12,5 +12,7 @@ echo "launch list exit $?"
 $CMD > gpurun_out/${TAG}_plain2.json 2>> gpurun_out/${TAG}_plain.err &&
 ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 3 -c 2 -f -o gpurun_out/${TAG}_fwd $CMD > gpurun_out/${TAG}_ncu2.log 2>&1
 echo "full capture exit $?"
+ncu --set full --clock-control none --import-source on -k regex:phmm_epilogue -s 3 -c 1 -f -o gpurun_out/${TAG}_epi $CMD > gpurun_out/${TAG}_ncu3.log 2>&1
+echo "epilogue capture exit $?"
 cat gpurun_out/${TAG}_plain.json
 ls -la gpurun_out/

@@ -48,7 +48,7 @@ typedef struct phmm_config
     int32_t device;               /* CUDA ordinal; -1 = current device */
     int32_t fma_mode;             /* PHMM_FMA_* (0 = the AVX-512 flavour) */
     uint32_t n_workers;           /* host worker threads = batches in flight (0 = cores / visible GPUs, clamped to 2..6) */
-    uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 12e9) */
+    uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 32e9) */
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
     uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 3) */

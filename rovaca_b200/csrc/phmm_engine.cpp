@@ -62,6 +62,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
+constexpr uint32_t kWavesWanted = 8;           // warps per warp slot a batch should have before its chunks may be full length
 constexpr uint32_t kMinStreamCols = 200;        // small batches are cut finer (more, shorter warps), but never below this
 constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)
 constexpr uint32_t kPairThreads = 148 * 3 * 128;   // per-pair wavefront kernel: one warp per pair, 12 warps per SM
@@ -324,7 +325,7 @@ struct phmm_engine
     int device = 0;
     bool fma = true;
     uint32_t n_workers = 6;
-    uint64_t batch_cells = 12000000000ull;
+    uint64_t batch_cells = 32000000000ull;   // mixed-length batches under ~8e9 cells run their per-bin kernels too small to fill the device
     uint32_t linger_us = 200;
     uint32_t cta_warps = 0;      // warps per forward-kernel CTA; 0 = chosen per launch from the fill of the read slots
     uint32_t lanes_pref = 0;     // lanes per read of the reference-gap kernels: 0 = by batch size, else 8 / 16 / 32
@@ -473,8 +474,11 @@ int phmm_engine::plan(Slot& s, const std::vector<RegionIn>& regs)
         else if (est_warps * 4 <= want)
             min_lanes = 16;
         est_warps *= (uint64_t)min_lanes / 8;
-        if (est_warps > 0 && est_warps < want)
-            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want);
+        // ... and a batch runs at 1 / (1 + slots / warps) of the device's rate while its last warps finish alone: below
+        // kWavesWanted waves the chunks are cut shorter (a 300-column sweep costs a warp ~2 % in prologue, tools/chunk_curve.py)
+        const uint64_t want_chunks = want * (kWavesWanted / 2);
+        if (est_warps > 0 && est_warps < want_chunks)
+            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want_chunks);
     }
     Slot::PlanScratch& ps = s.ps;
     std::vector<PhmmRead>& reads = ps.reads;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One workload shape, looked at closely: device-resident step time, the engine's own phase timers for the end-to-end
 call, and (under ncu --metrics gpu__time_duration.sum) the per-kernel launch list of exactly three resident steps.
-   python tools/shape_probe.py cfg3|cfg5|cfg5t [n_regions] [--resident-only]"""
+   python tools/shape_probe.py cfg3|cfg5|cfg5t [n_regions] [--resident-only] [--epilogue host|device]"""
 import os
 import sys
 import time
@@ -19,7 +19,12 @@ make = {"cfg2": lambda: wl.cfg2(n or 4096, seed=2),
         "cfg5t": lambda: wl.cfg5(n or 4096, seed=5, post_trim_fraction=1.0)}[shape]
 b = make()
 cells = b.cells()
-eng = PairHmmEngine()
+epi = {"host": 1, "device": 2}.get(sys.argv[sys.argv.index("--epilogue") + 1], 0) if "--epilogue" in sys.argv else 0
+def _opt(name, default=0):
+    return int(float(sys.argv[sys.argv.index(name) + 1])) if name in sys.argv else default
+
+
+eng = PairHmmEngine(epilogue=epi, n_workers=_opt("--workers"), batch_cells=_opt("--batch-cells"))
 res = eng.upload(b)
 t = [res.run() for _ in range(3)]
 print(f"{shape}: {cells / 1e9:.2f} Gcells, {b.pairs()} pairs; resident step {t[-1][0]:.3f} ms (forward {t[-1][1]:.3f} ms) "

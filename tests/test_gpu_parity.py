@@ -376,6 +376,22 @@ def test_default_engine_picks_the_epilogue_by_batch_size(engine):
         auto.close()
 
 
+def test_forcing_libm_keeps_the_epilogue_off_the_device(monkeypatch):
+    """PHMM_B200_LIBM_LOG10F pins the host's own log10f: nothing restated may run, so PHMM_EPILOGUE_DEVICE must refuse to
+    start and a default engine must keep every batch's epilogue on the host."""
+    from rovaca_b200 import PhmmError
+    from rovaca_b200.pairhmm import EPILOGUE_DEVICE
+    monkeypatch.setenv("PHMM_B200_LIBM_LOG10F", "1")
+    with pytest.raises(PhmmError, match="log10f"):
+        PairHmmEngine(epilogue=EPILOGUE_DEVICE)
+    eng = PairHmmEngine()
+    try:
+        eng.run_flat(wl.cfg2(256, seed=63))
+        assert eng.stats()["device_epilogue_batches"] == 0
+    finally:
+        eng.close()
+
+
 def test_long_haplotypes_multi_chunk(engine, orc):
     """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
     rng = np.random.default_rng(13)

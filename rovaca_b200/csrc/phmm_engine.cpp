@@ -62,7 +62,7 @@ int fail(int code, const std::string& msg)
     } while (0)
 
 constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
-constexpr uint32_t kWavesWanted = 8;           // warps per warp slot a batch should have before its chunks may be full length
+constexpr uint32_t kWavesWanted = 16;          // warps per warp slot a batch should have before its chunks may be full length
 constexpr uint32_t kMinStreamCols = 200;        // small batches are cut finer (more, shorter warps), but never below this
 constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)
 constexpr uint32_t kPairThreads = 148 * 3 * 128;   // per-pair wavefront kernel: one warp per pair, 12 warps per SM

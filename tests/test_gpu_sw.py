@@ -66,8 +66,12 @@ def test_sw_realigns_reads_of_a_region(engine, orc, ref):
     from rovaca_b200 import workloads as wl
     rng = np.random.default_rng(10)
     reads, haps = wl._one_region(rng, 80, 6, 280, 340, 90, 151, junk=0.05)
-    m, kept = engine.call_pairhmm(haps, reads)
-    best = np.argmax(m[:, : len(kept)], axis=0)
+    # the chain the reference runs: call_pairhmm -> best_alleles_breaking_ties (reference haplotype first, then the fewest
+    # CIGAR elements: assembly_based_caller_utils.cpp:150-155) -> one Smith-Waterman per read against its best haplotype
+    pri = [1.0] + [float(1 - int(rng.integers(1, 6))) for _ in haps[1:]]
+    m, kept, best, second = engine.call_pairhmm(haps, reads, priorities=pri)
+    b0, s0, *_ = orc.best_alleles(m, len(kept), pri)
+    assert np.array_equal(best, b0) and np.array_equal(second, s0)
     pairs = [(haps[int(best[c])], reads[int(kept[c])]["bases"]) for c in range(len(kept))]
     got = engine.sw_align(pairs)
     for (hap, rd), g in zip(pairs, got):

@@ -45,10 +45,15 @@ def test_an_idle_device_gets_the_wide_layouts():
 
 
 def test_small_batches_are_cut_finer():
-    few, many = ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=64)
+    """A batch with fewer than sixteen waves of warps gets shorter chunks (its last warps would otherwise finish alone); a batch
+    that fills the device many times over keeps one full-length chunk per cfg2 region."""
+    few, many = ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2048, seed=3), busy_batches=1)
     _sound(few)
     _sound(many)
-    assert few["chunks"] > many["chunks"] and few["warps"] > many["warps"]       # latency over staging when the GPU is empty
+    assert few["chunks"] == 2 * 4 and many["chunks"] == 2048          # 8 haplotypes: at most four chunks of one pair each
+    mid = ph.plan_audit(wl.cfg2(256, seed=3), busy_batches=1)
+    _sound(mid)
+    assert 256 < mid["chunks"] <= 4 * 256
 
 
 @pytest.mark.parametrize("make", [lambda: wl.cfg3(2, seed=3, n_reads=120, n_haps=11), lambda: wl.cfg4(6, seed=4, mix=True),

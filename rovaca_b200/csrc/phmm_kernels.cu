@@ -392,8 +392,9 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     }
 
     // two steps per trip let the registers of a step's inputs and outputs alternate (one step per trip costs a third of the
-    // throughput in moves); four pay for their code size only in the middle (measured: +1-3 % at 9-13 rows, -2-4 % below 9, 0 above)
-#pragma unroll(RPT >= 9 && RPT <= 13 ? 4 : 2)
+    // throughput in moves); four pay for their code size only in the middle (measured: +1-3 % at 9-13 rows, -2-4 % below 9, 0 above;
+    // at 9 rows and its 128-register cap four steps spill, so it stays at two)
+#pragma unroll(RPT >= 10 && RPT <= 13 ? 4 : 2)
     for (uint32_t s = 0; s < nsteps; ++s) {
         uint2 w = sp[s];
         if ((int)(w.x | w.y) < 0) {

@@ -115,8 +115,8 @@ def test_sass_audit():
             continue
         rpt = int(m.group(1))
         seen += 1
-        # copies of the step in the code: the loop is unrolled by two, or by four (+ one step for the remainder) at 9..13 rows
-        steps = 5 if 9 <= rpt <= 13 else 2
+        # copies of the step in the code: the loop is unrolled by two, or by four (+ one step for the remainder) at 10..13 rows
+        steps = 5 if 10 <= rpt <= 13 else 2
         assert c["FFMA2"] == 4 * rpt * steps and c["FMUL2"] == 3 * rpt * steps, (name, c)
         assert c["FMUL"] >= 2 * rpt * steps, (name, c)
         assert c["FADD2"] == 2 * steps, (name, c)

@@ -392,6 +392,22 @@ def test_forcing_libm_keeps_the_epilogue_off_the_device(monkeypatch):
         eng.close()
 
 
+def test_epilogue_with_many_reads_and_haplotypes(engine, engine_host_epilogue, orc):
+    """More reads than the epilogue kernel's CTA has threads (its block scan runs over several tiles, with dropped reads in
+    every tile) and more haplotypes than a warp has lanes; priorities that flip many of the ties."""
+    rng = np.random.default_rng(71)
+    reads, haps = wl._one_region(rng, 300, 40, 90, 110, 30, 70, junk=0.3)
+    haps = list(haps) + [h.copy() for h in haps[:8]]
+    pri = rng.integers(-2, 3, len(haps)).astype(np.float64)
+    m0, k0, *_ = orc.region(reads, haps)
+    b0, s0, *_ = orc.best_alleles(m0, len(k0), pri)
+    assert 50 < len(k0) < 290
+    for eng in (engine, engine_host_epilogue):
+        m, k, b, s2 = eng.call_pairhmm(haps, reads, priorities=pri)
+        assert np.array_equal(k, k0) and np.array_equal(_bits64(m), _bits64(m0))
+        assert np.array_equal(b, b0) and np.array_equal(s2, s0)
+
+
 def test_long_haplotypes_multi_chunk(engine, orc):
     """More haplotype columns than one shared-memory chunk holds: the region is swept in several chunks."""
     rng = np.random.default_rng(13)

@@ -262,10 +262,12 @@ typedef struct phmm_sw_result
                                     alignment_offset = 1 and no CIGAR (sw_avx.c:494-499), so does this; 2 = cigar_cap too small */
 } phmm_sw_result;
 
-/* All pairs are aligned on the device in one pass (fill kernel: one warp per alignment; trace kernel: one thread per
- * alignment).  Empty sequences are a PHMM_ERR_ARG.  Thread-safe (calls are serialised per engine). */
+/* All pairs are aligned on the device (fill kernel: one warp per alignment; trace kernel: one thread per alignment), in
+ * sub-batches of 32 768 alignments on two streams so that packing, kernels and the hand-back of results overlap.  Empty
+ * sequences are a PHMM_ERR_ARG.  Thread-safe (calls are serialised per engine). */
 int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, const phmm_sw_params* params, phmm_sw_result* results);
-/* Device time (CUDA events: fill + trace kernels) and cells (sum ref_len x read_len) of the last phmm_sw_align call. */
+/* Device time (CUDA events: the union of the sub-batches' fill + trace kernel spans) and cells (sum ref_len x read_len) of the
+ * last phmm_sw_align call. */
 int phmm_sw_last_timing(phmm_engine* e, float* gpu_ms, uint64_t* cells);
 
 int phmm_get_stats(phmm_engine* e, phmm_stats* out);

@@ -339,13 +339,25 @@ struct phmm_engine
     float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
 
     // batched Smith-Waterman (phmm_sw_align): its own stream and arenas, one call at a time
-    struct SwContext
+    struct SwSlot                    // one sub-batch in flight: the host packs the next one while this one runs
     {
-        std::mutex m;
         cudaStream_t stream = nullptr;
         cudaEvent_t ev[2] = {nullptr, nullptr};
         HostBuf h_in, h_out;
         DevBuf d_in, d_bt, d_aux, d_cig, d_out;
+        std::vector<PhmmSwTask> tasks;
+        std::vector<uint32_t> src, order;       // task -> pair of the call; tasks ordered by kernel instantiation
+        uint32_t n = 0, cigar_cap = 0;
+        uint64_t cells = 0;
+        size_t in_bytes = 0;
+        bool busy = false;
+    };
+    struct SwContext
+    {
+        std::mutex m;
+        SwSlot slot[2];
+        cudaEvent_t base = nullptr;      // start of the call on the device's clock: sub-batches overlap, their kernel time is a union
+        float covered_ms = 0.f;
         float last_ms = 0.f;
         uint64_t last_cells = 0;
     } sw;
@@ -1356,11 +1368,14 @@ void phmm_destroy(phmm_engine* e)
     for (auto& t : e->workers) t.join();
     cudaSetDevice(e->device);
     for (auto& s : e->slots) s->destroy();
-    for (auto* b : {&e->sw.h_in, &e->sw.h_out}) b->release();
-    for (auto* b : {&e->sw.d_in, &e->sw.d_bt, &e->sw.d_aux, &e->sw.d_cig, &e->sw.d_out}) b->release();
-    for (auto& ev : e->sw.ev)
-        if (ev) cudaEventDestroy(ev);
-    if (e->sw.stream) cudaStreamDestroy(e->sw.stream);
+    for (auto& ss : e->sw.slot) {
+        for (auto* b : {&ss.h_in, &ss.h_out}) b->release();
+        for (auto* b : {&ss.d_in, &ss.d_bt, &ss.d_aux, &ss.d_cig, &ss.d_out}) b->release();
+        for (auto& ev : ss.ev)
+            if (ev) cudaEventDestroy(ev);
+        if (ss.stream) cudaStreamDestroy(ss.stream);
+    }
+    if (e->sw.base) cudaEventDestroy(e->sw.base);
     e->d_tables.release();
     delete e;
 }
@@ -1601,7 +1616,6 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
     if (!e || !params || (n_pairs && (!pairs || !results))) return fail(PHMM_ERR_ARG, "phmm_sw_align: null argument");
     if (n_pairs == 0) return PHMM_OK;
     constexpr uint32_t kGiveUp = 2048;                                  // MAX_SEQ_LEN, sw_avx.c:17,494-499
-    constexpr size_t kBtBudget = (size_t)12 << 30;                       // back-track words held on the device at once
     uint32_t cigar_cap = 0;
     for (uint32_t k = 0; k < n_pairs; ++k) {
         if (pairs[k].ref_len == 0 || pairs[k].read_len == 0 || !pairs[k].ref || !pairs[k].read)
@@ -1613,17 +1627,65 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
     phmm_engine::SwContext& c = e->sw;
     std::lock_guard<std::mutex> lk(c.m);
     CU(cudaSetDevice(e->device));
-    if (!c.stream) {
-        CU(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        for (auto& ev : c.ev) CU(cudaEventCreate(&ev));
-    }
+    for (auto& ss : c.slot)
+        if (!ss.stream) {
+            CU(cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking));
+            for (auto& ev : ss.ev) CU(cudaEventCreate(&ev));
+        }
+    if (!c.base) CU(cudaEventCreate(&c.base));
+    CU(cudaEventRecord(c.base, c.slot[0].stream));
     c.last_ms = 0.f;
+    c.covered_ms = 0.f;
     c.last_cells = 0;
-    // sub-batches that fit the back-track budget
-    uint32_t at = 0;
-    while (at < n_pairs) {
-        std::vector<PhmmSwTask> tasks;
-        std::vector<uint32_t> src;                                      // task -> pair
+    constexpr size_t kBtBudget = (size_t)6 << 30;                        // back-track words one sub-batch may hold on the device
+    constexpr uint32_t kSubBatch = 32768;                                // alignments per sub-batch: several per big call, so that packing,
+                                                                         // kernels and the hand-back of results overlap
+
+    // results of a finished sub-batch -> the caller's buffers
+    auto finish = [&](phmm_engine::SwSlot& ss) -> int {
+        if (!ss.busy) return PHMM_OK;
+        ss.busy = false;
+        CU(cudaStreamSynchronize(ss.stream));
+        // kernel time of the call = the union of the sub-batches' kernel spans (two of them can be on the device at once)
+        float t0 = 0.f, t1 = 0.f;
+        CU(cudaEventElapsedTime(&t0, c.base, ss.ev[0]));
+        CU(cudaEventElapsedTime(&t1, c.base, ss.ev[1]));
+        if (t1 > c.covered_ms) {
+            c.last_ms += t1 - std::max(t0, c.covered_ms);
+            c.covered_ms = t1;
+        }
+        c.last_cells += ss.cells;
+        const uint32_t n = ss.n;
+        const uint8_t* ho = static_cast<const uint8_t*>(ss.h_out.p);
+        const PhmmSwOut* outs = reinterpret_cast<const PhmmSwOut*>(ho);
+        const uint32_t* cig = reinterpret_cast<const uint32_t*>(ho + (size_t)n * sizeof(PhmmSwOut));
+        for (uint32_t k = 0; k < n; ++k) {
+            phmm_sw_result& r = results[ss.src[k]];
+            r.alignment_offset = outs[k].alignment_offset;
+            r.score = outs[k].score;
+            r.status = outs[k].status;
+            r.n_cigar = outs[k].n_cigar;
+            if (outs[k].n_cigar > r.cigar_cap) {                          // the device buffer was sized for the largest caller buffer
+                r.status = 2;
+                r.n_cigar = r.cigar_cap;
+            }
+            if (r.n_cigar) std::memcpy(r.cigar, cig + (size_t)k * ss.cigar_cap, (size_t)r.n_cigar * 4);
+        }
+        e->stats.launches += 2;
+        e->stats.h2d += ss.in_bytes;
+        e->stats.d2h += (size_t)n * (sizeof(PhmmSwOut) + (size_t)ss.cigar_cap * 4);
+        return PHMM_OK;
+    };
+
+    uint32_t at = 0, turn = 0;
+    int rc = PHMM_OK;
+    while (at < n_pairs && rc == PHMM_OK) {
+        phmm_engine::SwSlot& ss = c.slot[turn++ & 1];
+        if ((rc = finish(ss)) != PHMM_OK) break;                          // the sub-batch before last: its kernels ran while the last one was packed
+        std::vector<PhmmSwTask>& tasks = ss.tasks;
+        std::vector<uint32_t>& src = ss.src;
+        tasks.clear();
+        src.clear();
         struct SwCopy { size_t dst; const uint8_t* src; size_t len; };
         std::vector<SwCopy> copies;                                     // what to gather into the byte blob
         constexpr int kRefCache = 16;
@@ -1631,7 +1693,7 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
         int ref_next = 0;
         uint64_t cells = 0;
         size_t bytes = 0, bt_words = 0, aux_ints = 0;
-        while (at < n_pairs) {
+        while (at < n_pairs && tasks.size() < kSubBatch) {
             const phmm_sw_pair& p = pairs[at];
             phmm_sw_result& r = results[at];
             if (std::max(p.ref_len, p.read_len) >= kGiveUp) {            // the reference returns alignment_offset = 1, no CIGAR
@@ -1669,16 +1731,18 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             t.bt_off = bt_words; bt_words += words;
             t.aux_off = aux_ints; aux_ints += (size_t)p.ref_len + p.read_len;
             t.cpt = (uint32_t)cpt;
-            if (bytes >= ((size_t)1 << 32)) return fail(PHMM_ERR_ARG, "phmm_sw_align: more than 4 GiB of sequence in one call");
+            if (bytes >= ((size_t)1 << 32)) { rc = fail(PHMM_ERR_ARG, "phmm_sw_align: more than 4 GiB of sequence in one sub-batch"); break; }
             tasks.push_back(t);
             src.push_back(at);
             cells += (uint64_t)p.ref_len * p.read_len;
             ++at;
         }
+        if (rc != PHMM_OK) break;
         const uint32_t n = (uint32_t)tasks.size();
         if (n == 0) continue;
         // order by cpt (one fill launch per kernel instantiation): a counting sort, input order kept inside a group
-        std::vector<uint32_t> order(n);
+        std::vector<uint32_t>& order = ss.order;
+        order.resize(n);
         {
             uint32_t count[kPhmmSwNumCpt + 1] = {};
             auto group_of = [&](uint32_t cpt) { int q = 0; while (kPhmmSwCpt[q] != (int)cpt) ++q; return q; };
@@ -1689,66 +1753,62 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
         size_t off = 0;
         auto place = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
         const size_t o_tasks = place(n * sizeof(PhmmSwTask)), o_order = place(n * sizeof(uint32_t)), o_bytes = place(bytes + 16);
-        int rc;
-        if ((rc = c.h_in.ensure(off)) != PHMM_OK) return rc;
-        if ((rc = c.d_in.ensure(off)) != PHMM_OK) return rc;
-        if ((rc = c.d_bt.ensure(std::max<size_t>(bt_words, 1) * 4)) != PHMM_OK) return rc;
-        if ((rc = c.d_aux.ensure(std::max<size_t>(aux_ints, 1) * 4)) != PHMM_OK) return rc;
-        if ((rc = c.d_cig.ensure((size_t)n * cigar_cap * 4)) != PHMM_OK) return rc;
-        if ((rc = c.d_out.ensure((size_t)n * sizeof(PhmmSwOut))) != PHMM_OK) return rc;
-        if ((rc = c.h_out.ensure((size_t)n * (sizeof(PhmmSwOut) + (size_t)cigar_cap * 4))) != PHMM_OK) return rc;
-        uint8_t* h = static_cast<uint8_t*>(c.h_in.p);
+        if ((rc = ss.h_in.ensure(off)) != PHMM_OK) break;
+        if ((rc = ss.d_in.ensure(off)) != PHMM_OK) break;
+        if ((rc = ss.d_bt.ensure(std::max<size_t>(bt_words, 1) * 4)) != PHMM_OK) break;
+        if ((rc = ss.d_aux.ensure(std::max<size_t>(aux_ints, 1) * 4)) != PHMM_OK) break;
+        if ((rc = ss.d_cig.ensure((size_t)n * cigar_cap * 4)) != PHMM_OK) break;
+        if ((rc = ss.d_out.ensure((size_t)n * sizeof(PhmmSwOut))) != PHMM_OK) break;
+        if ((rc = ss.h_out.ensure((size_t)n * (sizeof(PhmmSwOut) + (size_t)cigar_cap * 4))) != PHMM_OK) break;
+        uint8_t* h = static_cast<uint8_t*>(ss.h_in.p);
         std::memcpy(h + o_tasks, tasks.data(), n * sizeof(PhmmSwTask));
         std::memcpy(h + o_order, order.data(), n * sizeof(uint32_t));
         for (const SwCopy& cp : copies) std::memcpy(h + o_bytes + cp.dst, cp.src, cp.len);
-        uint8_t* d = static_cast<uint8_t*>(c.d_in.p);
+        uint8_t* d = static_cast<uint8_t*>(ss.d_in.p);
         PhmmSwBatchDev b{};
         b.tasks = reinterpret_cast<const PhmmSwTask*>(d + o_tasks);
         b.order = reinterpret_cast<const uint32_t*>(d + o_order);
         b.bytes = d + o_bytes;
-        b.bt = static_cast<uint32_t*>(c.d_bt.p);
-        b.aux = static_cast<int32_t*>(c.d_aux.p);
-        b.cigars = static_cast<uint32_t*>(c.d_cig.p);
-        b.outs = static_cast<PhmmSwOut*>(c.d_out.p);
+        b.bt = static_cast<uint32_t*>(ss.d_bt.p);
+        b.aux = static_cast<int32_t*>(ss.d_aux.p);
+        b.cigars = static_cast<uint32_t*>(ss.d_cig.p);
+        b.outs = static_cast<PhmmSwOut*>(ss.d_out.p);
         b.cigar_cap = cigar_cap;
         b.match = params->match; b.mismatch = params->mismatch; b.gap_open = params->gap_open; b.gap_extend = params->gap_extend;
-        CU(cudaMemcpyAsync(c.d_in.p, c.h_in.p, off, cudaMemcpyHostToDevice, c.stream));
-        CU(cudaEventRecord(c.ev[0], c.stream));
-        for (uint32_t g0 = 0; g0 < n;) {                                 // one fill launch per cpt group
-            uint32_t g1 = g0;
-            while (g1 < n && tasks[order[g1]].cpt == tasks[order[g0]].cpt) ++g1;
-            const uint32_t warps = std::min<uint32_t>(g1 - g0, e->warp_slots * 4);
-            CU(phmm_launch_sw_fill(b, (int)tasks[order[g0]].cpt, g0, g1 - g0, warps, c.stream));
-            g0 = g1;
-        }
-        CU(phmm_launch_sw_trace(b, 0, n, c.stream));
-        CU(cudaEventRecord(c.ev[1], c.stream));
-        uint8_t* ho = static_cast<uint8_t*>(c.h_out.p);
-        CU(cudaMemcpyAsync(ho, c.d_out.p, (size_t)n * sizeof(PhmmSwOut), cudaMemcpyDeviceToHost, c.stream));
-        CU(cudaMemcpyAsync(ho + (size_t)n * sizeof(PhmmSwOut), c.d_cig.p, (size_t)n * cigar_cap * 4, cudaMemcpyDeviceToHost, c.stream));
-        CU(cudaStreamSynchronize(c.stream));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]));
-        c.last_ms += ms;
-        c.last_cells += cells;
-        const PhmmSwOut* outs = reinterpret_cast<const PhmmSwOut*>(ho);
-        const uint32_t* cig = reinterpret_cast<const uint32_t*>(ho + (size_t)n * sizeof(PhmmSwOut));
-        for (uint32_t k = 0; k < n; ++k) {
-            phmm_sw_result& r = results[src[k]];
-            r.alignment_offset = outs[k].alignment_offset;
-            r.score = outs[k].score;
-            r.status = outs[k].status;
-            r.n_cigar = outs[k].n_cigar;
-            if (outs[k].n_cigar > r.cigar_cap) {                          // the device buffer was sized for the largest caller buffer
-                r.status = 2;
-                r.n_cigar = r.cigar_cap;
+        ss.n = n;
+        ss.cigar_cap = cigar_cap;
+        ss.cells = cells;
+        ss.in_bytes = off;
+        ss.busy = true;                                                  // from here on the slot must be drained, also on an error
+        auto launch = [&]() -> int {
+            CU(cudaMemcpyAsync(ss.d_in.p, ss.h_in.p, off, cudaMemcpyHostToDevice, ss.stream));
+            CU(cudaEventRecord(ss.ev[0], ss.stream));
+            for (uint32_t g0 = 0; g0 < n;) {                             // one fill launch per cpt group
+                uint32_t g1 = g0;
+                while (g1 < n && tasks[order[g1]].cpt == tasks[order[g0]].cpt) ++g1;
+                const uint32_t warps = std::min<uint32_t>(g1 - g0, e->warp_slots * 4);
+                CU(phmm_launch_sw_fill(b, (int)tasks[order[g0]].cpt, g0, g1 - g0, warps, ss.stream));
+                g0 = g1;
             }
-            if (r.n_cigar) std::memcpy(r.cigar, cig + (size_t)k * cigar_cap, (size_t)r.n_cigar * 4);
-        }
-        e->stats.launches += 2;
-        e->stats.h2d += off;
-        e->stats.d2h += (size_t)n * (sizeof(PhmmSwOut) + (size_t)cigar_cap * 4);
+            CU(phmm_launch_sw_trace(b, 0, n, ss.stream));
+            CU(cudaEventRecord(ss.ev[1], ss.stream));
+            uint8_t* ho = static_cast<uint8_t*>(ss.h_out.p);
+            CU(cudaMemcpyAsync(ho, ss.d_out.p, (size_t)n * sizeof(PhmmSwOut), cudaMemcpyDeviceToHost, ss.stream));
+            CU(cudaMemcpyAsync(ho + (size_t)n * sizeof(PhmmSwOut), ss.d_cig.p, (size_t)n * cigar_cap * 4, cudaMemcpyDeviceToHost, ss.stream));
+            return PHMM_OK;
+        };
+        rc = launch();
     }
+    if (rc != PHMM_OK) {                                                 // leave no work in flight behind an error
+        for (auto& ss : c.slot) {
+            if (ss.busy) cudaStreamSynchronize(ss.stream);
+            ss.busy = false;
+        }
+        return rc;
+    }
+    // drain: oldest first
+    for (int k = 0; k < 2; ++k)
+        if ((rc = finish(c.slot[(turn + k) & 1])) != PHMM_OK) return rc;
     return PHMM_OK;
 }
 

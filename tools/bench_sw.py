@@ -36,7 +36,8 @@ ms, dev_cells = eng.sw_last_timing()
 assert dev_cells == cells and all(o[3] == 0 for o in out)
 line = {"alignments": len(pairs), "cells": cells, "device_ms": round(ms, 3), "device_gcups": round(cells / ms / 1e6, 1),
         "device_alignments_per_s": round(len(pairs) / (ms * 1e-3)), "e2e_ms": round(e2e * 1e3, 2), "e2e_gcups": round(cells / e2e / 1e9, 1),
-        "e2e_is": "one phmm_sw_align call: host gather, H2D, fill + trace kernels, D2H of CIGARs, scatter into the caller's buffers"}
+        "e2e_is": "one phmm_sw_align call: host gather, H2D, fill + trace kernels, D2H of CIGARs, scatter into the caller's buffers; sub-batches of 32768 alignments pipelined on two streams",
+        "device_is": "union of the sub-batches' kernel spans (includes the gaps the host leaves; one un-pipelined batch of this size ran 18.8 ms = 627 GCUPS)"}
 ref = ob.ref()
 if ref is not None:
     cores = len(os.sched_getaffinity(0))

@@ -244,6 +244,10 @@ class Ref:
         L.ref_bench_regions.argtypes = [C.c_int, C.c_int, C.c_uint32, _u64p, _u64p, _u8p, _u8p, _u64p, _u32p, _u8p, _u8p, _u64p,
                                         _u32p, C.c_int32, C.c_int, _f64p]
         self.avx512 = bool(L.ref_has_avx512())
+        L.ref_best_alleles.restype = C.c_int
+        L.ref_best_alleles.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, _f64p, C.c_int32, _u32p, _u32p, _f64p, _f64p, _f64p]
+        L.ref_marginalize.restype = C.c_int
+        L.ref_marginalize.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, _f64p]
         L.ref_sw_align.restype = C.c_int
         L.ref_sw_align.argtypes = [C.c_int, C.c_int, _u8p, C.c_int, _u8p, C.c_int, _u32p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                    C.POINTER(C.c_int)]
@@ -262,6 +266,31 @@ class Ref:
         secs = self.lib.ref_sw_bench(n_threads, int(assemble), len(hb), _p(hcat, _u8p), _p(ho, _u64p), _p(hl, _u32p), _p(rcat, _u8p),
                                      _p(ro, _u64p), _p(rl, _u32p), C.byref(chk))
         return float(secs), int(chk.value)
+
+    def best_alleles(self, matrix: np.ndarray, n_evidence: int, priorities, reference_index: int = 0):
+        """The reference's own AlleleLikelihoods::best_alleles_breaking_ties (al_shim.cpp) on matrix[n_alleles, stride] ->
+        (best, second, best_lik, second_lik, confidence) for the first n_evidence columns."""
+        m = np.ascontiguousarray(matrix, np.float64)
+        na, stride = m.shape
+        pri = np.ascontiguousarray(priorities, np.float64)
+        best, second = np.zeros(max(n_evidence, 1), np.uint32), np.zeros(max(n_evidence, 1), np.uint32)
+        bl, sl, conf = (np.zeros(max(n_evidence, 1), np.float64) for _ in range(3))
+        rc = self.lib.ref_best_alleles(_p(m, _f64p), na, stride, n_evidence, _p(pri, _f64p),
+                                       reference_index, _p(best, _u32p), _p(second, _u32p), _p(bl, _f64p), _p(sl, _f64p), _p(conf, _f64p))
+        if rc != 0:
+            raise RuntimeError("ref_best_alleles failed rc=%d" % rc)
+        return best[:n_evidence], second[:n_evidence], bl[:n_evidence], sl[:n_evidence], conf[:n_evidence]
+
+    def marginalize(self, matrix: np.ndarray, n_evidence: int, old_to_new, n_new: int) -> np.ndarray:
+        """The reference's own AlleleLikelihoods::marginalize (al_shim.cpp) -> [n_new, n_evidence]."""
+        m = np.ascontiguousarray(matrix, np.float64)
+        mp = np.ascontiguousarray(old_to_new, np.int32)
+        out = np.zeros((n_new, max(n_evidence, 1)), np.float64)[:, :n_evidence].copy()
+        rc = self.lib.ref_marginalize(_p(m, _f64p), m.shape[0], m.shape[1], n_evidence, mp.ctypes.data_as(C.POINTER(C.c_int32)), n_new,
+                                      _p(out, _f64p))
+        if rc != 0:
+            raise RuntimeError("ref_marginalize failed rc=%d" % rc)
+        return out
 
     def sw_align(self, seq1, seq2, assemble: bool = False, isa: int = -1):
         """The reference's Smith-Waterman (sw_avx.c / sw_avx2.c): seq2 (read) against seq1 (haplotype).

@@ -61,3 +61,34 @@ def test_regions_random(orc, ref, path):
         m1, k1 = ref.region(reads, haps, 18, ob.PCR_CONSERVATIVE, path)
         assert np.array_equal(k0, k1)
         assert np.array_equal(m0.view(np.uint64), m1.view(np.uint64))
+
+
+def test_best_alleles_and_marginalisation_vs_the_references_own_class(orc, ref):
+    """the oracle's restatements of search_best_allele (genotype/allele_likelihoods.hpp:589-657, as
+    best_alleles_breaking_ties :364-383 calls it) and marginal_likelihoods_direct (:702-732) against the reference's
+    AlleleLikelihoods template itself, instantiated in place by oracle/al_shim.cpp — on the matrices call_pairhmm returns
+    for regions with duplicated haplotypes (ties), under several priority vectors, with alleles that map to nothing."""
+    rng = np.random.default_rng(83)
+    broke = 0
+    for case in range(30):
+        reads, haps = wl._one_region(rng, int(rng.integers(1, 60)), int(rng.integers(1, 9)), 100, 150, 30, 90, junk=0.15)
+        haps = list(haps)
+        for _ in range(int(rng.integers(0, 4))):
+            haps.insert(int(rng.integers(0, len(haps) + 1)), haps[int(rng.integers(0, len(haps)))].copy())
+        m, kept, *_ = orc.region(reads, haps)
+        n = len(kept)
+        pri = rng.integers(-3, 3, len(haps)).astype(np.float64)
+        # random priorities; the reference's default (reference allele first, :349); all equal = no tie-break at all
+        for p in (pri, np.array([1.0] + [0.0] * (len(haps) - 1)), np.zeros(len(haps))):
+            want = ref.best_alleles(m, n, p, reference_index=0)
+            got = orc.best_alleles(m, n, p)
+            for w, g in zip(want, got):
+                assert np.array_equal(np.asarray(w).view(np.uint8), np.asarray(g).view(np.uint8)), case
+        plain = orc.best_alleles(m, n, None)
+        for w, g in zip(got, plain):
+            assert np.array_equal(np.asarray(w).view(np.uint8), np.asarray(g).view(np.uint8)), case
+        broke += int((orc.best_alleles(m, n, pri)[0] != orc.best_alleles(m, n, None)[0]).sum())
+        n_new = int(rng.integers(1, 5))
+        mp = rng.integers(-1, n_new, len(haps)).astype(np.int32)
+        assert np.array_equal(ref.marginalize(m, n, mp, n_new + 1).view(np.uint64), orc.marginalize(m, n, mp, n_new + 1).view(np.uint64))
+    assert broke > 0

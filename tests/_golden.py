@@ -63,3 +63,15 @@ def sw():
             d[name] = (z[f"cig_{tag}{k}"], off, score)
         out.append(d)
     return out
+
+
+def alleles():
+    """-> list of dict(matrix, n_evidence, priorities, best, second, best_lik, second_lik, confidence, old_to_new, marginal) from
+    the reference's AlleleLikelihoods (make_golden.py --alleles)."""
+    z = np.load(os.path.join(HERE, "alleles.npz"))
+    out = []
+    for k in range(int(z["count"][0])):
+        out.append(dict(matrix=z[f"m{k}"].view(np.float64), n_evidence=int(z[f"n{k}"][0]), priorities=z[f"pri{k}"], best=z[f"best{k}"],
+                        second=z[f"second{k}"], best_lik=z[f"bl{k}"], second_lik=z[f"sl{k}"], confidence=z[f"conf{k}"],
+                        old_to_new=z[f"map{k}"], marginal=z[f"marg{k}"]))
+    return out

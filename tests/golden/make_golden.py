@@ -177,7 +177,40 @@ def make_sw():
     print("sw.npz:", len(cases), "cases")
 
 
+def make_alleles():
+    """tests/golden/alleles.npz: what the UNMODIFIED reference's AlleleLikelihoods template (genotype/allele_likelihoods.hpp,
+    instantiated in place by oracle/al_shim.cpp) answers for best_alleles_breaking_ties and marginalize on call_pairhmm's
+    matrices: regions with duplicated haplotypes (ties), random priorities, alleles that map to nothing."""
+    from rovaca_b200 import workloads as wl
+    ref, orc = ob.ref(), ob.oracle()
+    assert ref is not None, "needs oracle/_ref (make -C oracle with /root/reference present)"
+    rng = np.random.default_rng(20261019)
+    rec, n_cases = {}, 40
+    for k in range(n_cases):
+        reads, haps = wl._one_region(rng, int(rng.integers(1, 60)), int(rng.integers(1, 9)), 100, 150, 30, 90, junk=0.15)
+        haps = list(haps)
+        for _ in range(int(rng.integers(0, 4))):
+            haps.insert(int(rng.integers(0, len(haps) + 1)), haps[int(rng.integers(0, len(haps)))].copy())
+        m, kept = ref.region(reads, haps)                 # the reference's own call_pairhmm
+        n = len(kept)
+        pri = rng.integers(-3, 3, len(haps)).astype(np.float64)
+        best, second, bl, sl, conf = ref.best_alleles(m, n, pri)
+        n_new = int(rng.integers(1, 5))
+        mp = rng.integers(-1, n_new, len(haps)).astype(np.int32)
+        rec[f"m{k}"], rec[f"n{k}"], rec[f"pri{k}"] = m.view(np.uint64), np.array([n]), pri
+        rec[f"best{k}"], rec[f"second{k}"], rec[f"bl{k}"], rec[f"sl{k}"], rec[f"conf{k}"] = best, second, bl.view(np.uint64), sl.view(np.uint64), conf.view(np.uint64)
+        rec[f"map{k}"], rec[f"marg{k}"] = mp, ref.marginalize(m, n, mp, n_new + 1).view(np.uint64)
+    rec["count"] = np.array([n_cases])
+    np.savez_compressed(os.path.join(HERE, "alleles.npz"), **rec)
+    print("alleles.npz:", n_cases, "cases")
+
+
 if __name__ == "__main__":
-    if "--sw" not in sys.argv:       # --sw: only the Smith-Waterman vectors
-        main()
-    make_sw()
+    if "--alleles" in sys.argv:      # --alleles: only the best-allele / marginalisation vectors
+        make_alleles()
+    else:
+        if "--sw" not in sys.argv:   # --sw: only the Smith-Waterman vectors
+            main()
+        make_sw()
+        if "--sw" not in sys.argv:
+            make_alleles()

@@ -69,3 +69,24 @@ def test_edge_cases(orc):
     # qualities are masked & 127
     q2 = bytes([30 | 128] * 4)
     assert orc.pair_f32(b"ACGT", b"ACGT", q2, g, g, c) == base
+
+
+def test_best_alleles_and_marginalisation(orc):
+    """SURVEY.md §8f item 4 against golden vectors from the reference's own AlleleLikelihoods class (make_golden.py --alleles):
+    the oracle's restatements AND the product's host implementations (phmm_best_haplotypes through the epilogue is covered on
+    the GPU; phmm_marginalize here)."""
+    from rovaca_b200 import pairhmm as ph
+    cases = _golden.alleles()
+    assert len(cases) >= 40
+    ties = 0
+    for c in cases:
+        m, n = c["matrix"], c["n_evidence"]
+        best, second, bl, sl, conf = orc.best_alleles(m, n, c["priorities"])
+        assert np.array_equal(best, c["best"]) and np.array_equal(second, c["second"])
+        assert np.array_equal(bl.view(np.uint64), c["best_lik"]) and np.array_equal(sl.view(np.uint64), c["second_lik"])
+        assert np.array_equal(conf.view(np.uint64), c["confidence"])
+        ties += int((best != orc.best_alleles(m, n, None)[0]).sum())
+        n_new = c["marginal"].shape[0]
+        assert np.array_equal(orc.marginalize(m, n, c["old_to_new"], n_new).view(np.uint64), c["marginal"])
+        assert np.array_equal(np.ascontiguousarray(ph.marginalize(m, n, c["old_to_new"], n_new)).view(np.uint64), c["marginal"])
+    assert ties > 0

@@ -77,3 +77,32 @@ def test_sw_realigns_reads_of_a_region(engine, orc, ref):
     for (hap, rd), g in zip(pairs, got):
         want = ref.sw_align(hap, rd, False)
         assert _same(g, want), (ob.cigar_string(g[0]), ob.cigar_string(want[0]))
+
+
+def test_sw_many_alignments_cross_the_sub_batches(engine, orc):
+    """phmm_sw_align runs big calls as sub-batches of 32 768 alignments on two streams: 80 000 small alignments (five hundred
+    distinct ones, shuffled, with a few the reference gives up on in between) must come back in the caller's order."""
+    rng = np.random.default_rng(91)
+    distinct = []
+    for _ in range(500):
+        H = int(rng.integers(30, 70))
+        hap = B[rng.integers(0, 4, H)]
+        R = int(rng.integers(10, H + 1))
+        o = int(rng.integers(0, H - R + 1))
+        rd = hap[o:o + R].copy()
+        m = rng.random(R) < 0.05
+        rd[m] = B[rng.integers(0, 4, int(m.sum()))]
+        distinct.append((hap, rd))
+    want = [orc.sw_align(h, r, ph.SW_REALIGN) for h, r in distinct]
+    long_hap = B[rng.integers(0, 4, 2100)]
+    pick = rng.integers(0, 500, 80000)
+    pairs = [distinct[int(k)] for k in pick]
+    gave_up = (5, 32767, 32768, 65536, 79999)
+    for k in gave_up:
+        pairs[k] = (long_hap, long_hap[:40].copy())
+    got = engine.sw_align(pairs, ph.SW_REALIGN, cigar_cap=32)
+    for k, g in enumerate(got):
+        if k in gave_up:
+            assert g[3] == 1 and g[1] == 1 and len(g[0]) == 0
+        else:
+            assert g[3] == 0 and _same(g, want[int(pick[k])]), k

@@ -122,3 +122,17 @@ def test_sass_audit():
         assert c["FADD2"] == 2 * steps, (name, c)
         assert c["SHFL"] >= 6 * steps, (name, c)
     assert seen == 18 + 31 + 18          # generic, reference-gap throughput bins, reference-gap latency bins
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not on PATH")
+def test_example_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/realign_chain.cpp (call_pairhmm + best haplotypes -> Smith-Waterman) must build against
+    include/phmm_b200.h and link against the library as it stands; without an sm_100 device it must stop at phmm_create with a
+    message, not compute anything."""
+    exe = str(tmp_path / "realign_chain")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "realign_chain.cpp"), "-L" + os.path.join(ROOT, "rovaca_b200"), "-lphmm_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "rovaca_b200"), "-o", exe], check=True)
+    if not _has_gpu():
+        run = subprocess.run([exe], capture_output=True, text=True)
+        assert run.returncode == 1 and "no CPU fallback" in run.stderr and run.stdout == ""

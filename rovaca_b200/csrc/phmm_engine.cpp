@@ -1279,6 +1279,32 @@ static std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb)
     return pre;
 }
 
+// phmm_run_flat's cut of a stream of regions (pre = prefix sums of their work, flat_work_prefix) into sub-batches [first, end).
+static std::vector<std::pair<uint32_t, uint32_t>> flat_partition(const std::vector<uint64_t>& pre, uint32_t n_regions, uint64_t batch_cells,
+                                                                 uint32_t n_workers)
+{
+    const uint64_t total = pre[n_regions];
+    // sub-batch size: batch_cells at most, and small enough that every worker gets about two of them (host-bound streams of
+    // small regions need the planning and the epilogues spread over all workers), but not below a quarter of batch_cells
+    // (mixed-length batches much smaller than that run their per-bin kernels too small to fill the device)
+    const uint64_t full = std::max<uint64_t>(1, std::min<uint64_t>(batch_cells, std::max<uint64_t>(total / (2ull * std::max(n_workers, 1u)), batch_cells >> 2)));
+    std::vector<std::pair<uint32_t, uint32_t>> parts;
+    uint32_t g = 0;
+    int ramp = 2;                                    // next sizes: full/4, full/2, then full
+    while (g < n_regions) {
+        const uint64_t left = total - pre[g];
+        uint64_t want = ramp > 0 ? (full >> ramp) : full;
+        if (ramp > 0) --ramp;
+        // ramp down: never take more than half of what is left while more than full/4 remains
+        if (left > (full >> 2)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 2));
+        uint32_t end = g + 1;
+        while (end < n_regions && pre[end] - pre[g] < want) ++end;
+        parts.emplace_back(g, end);
+        g = end;
+    }
+    return parts;
+}
+
 static uint64_t region_cells(const RegionIn& r)
 {
     uint64_t rb = 0, hb = 0;
@@ -1475,28 +1501,7 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* f
     // Cut the stream into sub-batches that the workers plan, ship, run and finish independently, so that packing, H2D,
     // kernels, D2H and the host epilogue of different sub-batches overlap.  Sizes ramp up from batch_cells / 8 and down
     // again at the end: the GPU starts after one small plan and only a small epilogue is left when it finishes.
-    const std::vector<uint64_t> pre = flat_work_prefix(fb);
-    const uint64_t total = pre[fb->n_regions];
-    // sub-batch size: batch_cells at most, and small enough that every worker gets about two of them (host-bound streams of
-    // small regions need the planning and the epilogues spread over all workers), but not below a quarter of batch_cells
-    // (about a millisecond of device work: smaller batches are cut into finer chunks and run less efficiently)
-    const uint64_t full = std::max<uint64_t>(1, std::min<uint64_t>(e->batch_cells, std::max<uint64_t>(total / (2ull * e->n_workers), e->batch_cells >> 2)));
-    std::vector<std::pair<uint32_t, uint32_t>> parts;
-    {
-        uint32_t g = 0;
-        int ramp = 2;                                    // next sizes: full/4, full/2, then full
-        while (g < fb->n_regions) {
-            const uint64_t left = total - pre[g];
-            uint64_t want = ramp > 0 ? (full >> ramp) : full;
-            if (ramp > 0) --ramp;
-            // ramp down: never take more than half of what is left while more than full/4 remains
-            if (left > (full >> 2)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 2));
-            uint32_t end = g + 1;
-            while (end < fb->n_regions && pre[end] - pre[g] < want) ++end;
-            parts.emplace_back(g, end);
-            g = end;
-        }
-    }
+    const std::vector<std::pair<uint32_t, uint32_t>> parts = flat_partition(flat_work_prefix(fb), fb->n_regions, e->batch_cells, e->n_workers);
     std::mutex m;
     std::condition_variable cv;
     size_t remaining = parts.size();
@@ -2045,6 +2050,24 @@ uint64_t phmm_debug_log10f_check(uint32_t stride, int mode, int* picked)
         }
     }
     return bad;
+}
+
+// For tests (no GPU needed): how phmm_run_flat would cut `fb` with `n_workers` workers and `batch_cells` (0 = the default);
+// bounds[2k], bounds[2k+1] = first and one-past-last region of sub-batch k (at most cap of them), work[k] = its weighted work.
+int phmm_debug_partition(const phmm_flat_batch* fb, uint32_t n_workers, uint64_t batch_cells, uint32_t* bounds, uint64_t* work,
+                         uint32_t cap, uint32_t* n_parts)
+{
+    if (!fb || !bounds || !n_parts) return fail(PHMM_ERR_ARG, "phmm_debug_partition: null argument");
+    phmm_engine e;
+    const std::vector<uint64_t> pre = flat_work_prefix(fb);
+    const auto parts = flat_partition(pre, fb->n_regions, batch_cells ? batch_cells : e.batch_cells, n_workers ? n_workers : e.n_workers);
+    *n_parts = (uint32_t)parts.size();
+    for (uint32_t k = 0; k < parts.size() && k < cap; ++k) {
+        bounds[2 * k] = parts[k].first;
+        bounds[2 * k + 1] = parts[k].second;
+        if (work) work[k] = pre[parts[k].second] - pre[parts[k].first];
+    }
+    return PHMM_OK;
 }
 
 // For tests: would phmm_create (PHMM_EPILOGUE_AUTO) put the epilogue on the device on this host?

@@ -154,6 +154,7 @@ def load_library():
     L.phmm_debug_log10f_check.restype = C.c_uint64
     L.phmm_debug_log10f_check.argtypes = [C.c_uint32, C.c_int, C.POINTER(C.c_int)]
     L.phmm_marginalize.argtypes = [_f64p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_int32), C.c_uint32, _f64p, C.c_uint32]
+    L.phmm_debug_partition.argtypes = [C.POINTER(_FlatBatch), C.c_uint32, C.c_uint64, _u32p, _u64p, C.c_uint32, _u32p]
     L.phmm_debug_host_log10.argtypes = [_f32p, C.c_uint32, C.c_int, _f64p]
     L.phmm_debug_device_log10.argtypes = [C.c_void_p, _f32p, C.c_uint32, _f64p, C.POINTER(C.c_int)]
     L.phmm_debug_logf_check.restype = C.c_uint64
@@ -192,6 +193,18 @@ def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 
     d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)
     d["lane_utilisation"] = d["wavefront_cells"] / max(2 * d["lane_steps"], 1)      # two haplotype streams per lane
     return d
+
+
+def flat_partition(batch: RegionBatch, n_workers: int = 0, batch_cells: int = 0):
+    """Host only: how ``run_flat`` would cut ``batch`` into sub-batches -> (bounds[k] = (first, end), work[k])."""
+    L = load_library()
+    fb = _flat_c(batch, 18, PCR_CONSERVATIVE)
+    cap = max(batch.n_regions, 1)
+    bounds, work, n = np.zeros(2 * cap, np.uint32), np.zeros(cap, np.uint64), C.c_uint32(0)
+    rc = L.phmm_debug_partition(C.byref(fb), n_workers, int(batch_cells), _ptr(bounds, _u32p), _ptr(work, _u64p), cap, C.byref(n))
+    if rc != 0:
+        raise PhmmError(f"phmm_debug_partition failed ({rc}): {L.phmm_last_error().decode()}")
+    return bounds[: 2 * n.value].reshape(-1, 2), work[: n.value]
 
 
 def marginalize(matrix: np.ndarray, n_evidence: int, old_to_new, n_new: int) -> np.ndarray:

@@ -96,3 +96,32 @@ def test_out_of_envelope_shapes_go_to_the_pair_kernel():
     empty = wl.RegionBatch.from_regions([([], [long_hap[:50].copy()]), (reads[:2], [])])
     a = ph.plan_audit(empty)
     assert a["pairs"] == 0 and a["warps"] == 0
+
+
+_STREAMS = {}
+
+
+def _stream(name):
+    if name not in _STREAMS:
+        _STREAMS[name] = {"cfg2": lambda: wl.cfg2(4096, seed=2), "cfg5": lambda: wl.cfg5(2048, seed=5, post_trim_fraction=0.0),
+                          "cfg5t": lambda: wl.cfg5(300, seed=6, post_trim_fraction=1.0), "one": lambda: wl.cfg2(1, seed=3),
+                          "cfg3": lambda: wl.cfg3(5, seed=3)}[name]()
+    return _STREAMS[name]
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg5", "cfg5t", "one", "cfg3"])
+def test_flat_partition_covers_the_stream_in_order(name):
+    """phmm_run_flat's sub-batches: contiguous, in order, every region exactly once; sizes ramp up from a quarter of the full
+    size (so the device starts after one small plan) and down again at the end; no sub-batch above batch_cells unless a
+    single region is."""
+    b = _stream(name)
+    for workers in (2, 4, 6):
+        for batch_cells in (0, int(4e9)):
+            bounds, work = ph.flat_partition(b, workers, batch_cells)
+            assert bounds[0, 0] == 0 and bounds[-1, 1] == b.n_regions
+            assert np.array_equal(bounds[1:, 0], bounds[:-1, 1]) and np.all(bounds[:, 1] > bounds[:, 0])
+            cap = batch_cells or int(32e9)
+            one_region_slack = 1.2 * cap / 4 if b.n_regions > 1 else float("inf")
+            assert np.all((work <= cap + one_region_slack) | (bounds[:, 1] - bounds[:, 0] == 1))
+            if len(work) >= 6:
+                assert work[0] <= work[2] * 0.6 and work[-1] <= work.max() * 0.6          # ramp up, ramp down

@@ -136,3 +136,13 @@ def test_example_compiles_against_the_header_and_fails_loudly_without_a_gpu(tmp_
     if not _has_gpu():
         run = subprocess.run([exe], capture_output=True, text=True)
         assert run.returncode == 1 and "no CPU fallback" in run.stderr and run.stdout == ""
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="gcc not on PATH")
+def test_header_is_plain_c(tmp_path):
+    """include/phmm_b200.h is what a cgo / JNI / ctypes-style binding includes: it must compile as C11, pedantically."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "phmm_b200.h"\nint main(void) { phmm_config c = {0}; phmm_sw_params p = PHMM_SW_PARAMS_REALIGN; '
+                   'phmm_result r = {0}; (void)c; (void)p; (void)r; return 0; }\n')
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I" + os.path.join(ROOT, "include"), "-fsyntax-only",
+                    str(src)], check=True)

@@ -393,73 +393,74 @@ int64_t orc_region(const orc_read* reads, uint32_t n_reads, const orc_hap* haps,
     return n_fp64;
 }
 
-/* allele_likelihoods.hpp:589-657, one evidence at a time; names follow the reference's locals */
+/* Restatement of the best-allele search (allele_likelihoods.hpp:589-657) for can_be_reference = true.
+ *   pass 1 (:609-622): scan the alleles in order keeping a leader and a runner-up; a candidate takes the lead only when
+ *                      strictly greater, the runner-up slot likewise (so among equals the earliest allele leads);
+ *   pass 2 (:624-645): only when priorities exist and the lead over the runner-up is under 0.2: every allele within 0.2 of
+ *                      the pass-1 leader's likelihood competes again on priority alone, strictly-greater again; the
+ *                      likelihood bar stays the pass-1 leader's even after the lead changes hands;
+ *   report (:647-656): likelihoods are re-read for the final pair, the runner-up's is -inf when it is the leader itself,
+ *                      confidence is their difference, or exactly 0 when that difference is below DBL_EPSILON. */
+typedef struct { int32_t lead, runner; } orc_rank;
+
+static orc_rank orc_rank_by_likelihood(const double* col, size_t step, uint32_t n, double* lead_lik, double* runner_lik)
+{
+    orc_rank r = {0, 0};
+    double top = col[0], next = -INFINITY;
+    for (uint32_t a = 1; a < n; a++) {
+        const double v = col[(size_t)a * step];
+        if (v > top) { r.runner = r.lead; next = top; r.lead = (int32_t)a; top = v; }
+        else if (v > next) { r.runner = (int32_t)a; next = v; }
+    }
+    *lead_lik = top;
+    *runner_lik = next;
+    return r;
+}
+
 void orc_best_alleles(const double* values, uint32_t n_alleles, uint32_t stride, uint32_t n_evidence, const double* priorities,
                       uint32_t* best, uint32_t* second, double* best_lik, double* second_lik, double* confidence)
 {
-    const double informative_threshold = 0.2000;            /* s_log_10_informative_threshold, :27 */
-    for (uint32_t evidence_index = 0; evidence_index < n_evidence; evidence_index++) {
-#define SAMPLE_VALUE(a) values[(size_t)(a) * stride + evidence_index]
-        int32_t best_allele_index = 0;                       /* can_be_reference, :610 */
-        int32_t second_best_index = 0;
-        double best_likelihood = SAMPLE_VALUE(best_allele_index);
-        double second_best_likelihood = -INFINITY, candidate_likelihood;
-        for (int32_t a = best_allele_index + 1; a < (int32_t)n_alleles; a++) {            /* :614-622 */
-            candidate_likelihood = SAMPLE_VALUE(a);
-            if (candidate_likelihood > best_likelihood) {
-                second_best_index = best_allele_index;
-                best_allele_index = a;
-                second_best_likelihood = best_likelihood;
-                best_likelihood = candidate_likelihood;
-            } else if (candidate_likelihood > second_best_likelihood) {
-                second_best_index = a;
-                second_best_likelihood = candidate_likelihood;
-            }
-        }
-        if (priorities && best_likelihood - second_best_likelihood < informative_threshold) {   /* :624-645 */
-            double best_priority = priorities[best_allele_index];
-            double second_best_priority = priorities[second_best_index];
-            for (int32_t a = 0; a < (int32_t)n_alleles; a++) {
-                candidate_likelihood = SAMPLE_VALUE(a);
-                if (a == best_allele_index || best_likelihood - candidate_likelihood > informative_threshold) continue;
-                const double candidate_priority = priorities[a];
-                if (candidate_priority > best_priority) {
-                    second_best_index = best_allele_index;
-                    best_allele_index = a;
-                    second_best_priority = best_priority;
-                    best_priority = candidate_priority;
-                } else if (candidate_priority > second_best_priority) {
-                    second_best_index = a;
-                    second_best_priority = candidate_priority;
+    const double window = 0.2;                               /* s_log_10_informative_threshold, :27 */
+    for (uint32_t e = 0; e < n_evidence; e++) {
+        const double* col = values + e;
+        double bar, below;
+        orc_rank r = orc_rank_by_likelihood(col, stride, n_alleles, &bar, &below);
+        if (priorities != NULL && bar - below < window) {
+            double lead_pri = priorities[r.lead], runner_pri = priorities[r.runner];
+            uint32_t a = 0;
+            while (a < n_alleles) {
+                const int contender = (int32_t)a != r.lead && !(bar - col[(size_t)a * stride] > window);
+                if (contender) {
+                    const double p = priorities[a];
+                    if (p > lead_pri) { r.runner = r.lead; runner_pri = lead_pri; r.lead = (int32_t)a; lead_pri = p; }
+                    else if (p > runner_pri) { r.runner = (int32_t)a; runner_pri = p; }
                 }
+                a++;
             }
         }
-        best_likelihood = SAMPLE_VALUE(best_allele_index);                                  /* :647-649 */
-        second_best_likelihood = second_best_index != best_allele_index ? SAMPLE_VALUE(second_best_index) : -INFINITY;
-#undef SAMPLE_VALUE
-        best[evidence_index] = (uint32_t)best_allele_index;
-        second[evidence_index] = (uint32_t)second_best_index;
-        if (best_lik) best_lik[evidence_index] = best_likelihood;
-        if (second_lik) second_lik[evidence_index] = second_best_likelihood;
-        if (confidence)                                                                     /* BestAllele, :52-62 */
-            confidence[evidence_index] =
-                fabs(best_likelihood - second_best_likelihood) < 2.220446049250313e-16 ? 0.0 : best_likelihood - second_best_likelihood;
+        const double lik1 = col[(size_t)r.lead * stride];
+        const double lik2 = r.runner == r.lead ? -INFINITY : col[(size_t)r.runner * stride];
+        best[e] = (uint32_t)r.lead;
+        second[e] = (uint32_t)r.runner;
+        if (best_lik) best_lik[e] = lik1;
+        if (second_lik) second_lik[e] = lik2;
+        if (confidence) confidence[e] = fabs(lik1 - lik2) < 2.220446049250313e-16 ? 0.0 : lik1 - lik2;   /* BestAllele, :52-62 */
     }
 }
 
-/* allele_likelihoods.hpp:702-732 */
+/* Restatement of marginal_likelihoods_direct (allele_likelihoods.hpp:702-732): every new allele's row starts at -inf (:714) and
+ * is raised, evidence by evidence, to any strictly greater value found in the rows of the old alleles mapped onto it
+ * (:723-726); old alleles mapped to nothing (s_missing_index) contribute nowhere (:717). */
 void orc_marginalize(const double* old_values, uint32_t old_allele_count, uint32_t stride, uint32_t evidence_count,
                      const int32_t* old2new_idx_map, uint32_t new_allele_count, double* new_values)
 {
-    for (size_t k = 0; k < (size_t)new_allele_count * evidence_count; k++) new_values[k] = -INFINITY;
-    for (uint32_t ai = 0; ai < old_allele_count; ai++) {
-        const int32_t new_allele_idx = old2new_idx_map[ai];
-        if (new_allele_idx < 0) continue;
-        const double* old_lk = old_values + (size_t)ai * stride;
-        double* new_lk = new_values + (size_t)new_allele_idx * evidence_count;
-        for (uint32_t ri = 0; ri < evidence_count; ri++) {
-            const double likelihoods = old_lk[ri];
-            if (likelihoods > new_lk[ri]) new_lk[ri] = likelihoods;
+    for (uint32_t n = 0; n < new_allele_count; n++) {
+        double* dst = new_values + (size_t)n * evidence_count;
+        for (uint32_t e = 0; e < evidence_count; e++) {
+            double m = -INFINITY;
+            for (uint32_t a = 0; a < old_allele_count; a++)
+                if (old2new_idx_map[a] == (int32_t)n && old_values[(size_t)a * stride + e] > m) m = old_values[(size_t)a * stride + e];
+            dst[e] = m;
         }
     }
 }

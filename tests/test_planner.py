@@ -125,3 +125,12 @@ def test_flat_partition_covers_the_stream_in_order(name):
             assert np.all((work <= cap + one_region_slack) | (bounds[:, 1] - bounds[:, 0] == 1))
             if len(work) >= 6:
                 assert work[0] <= work[2] * 0.6 and work[-1] <= work.max() * 0.6          # ramp up, ramp down
+
+
+def test_planner_quality_does_not_regress():
+    """How well a plan uses the lanes it occupies (useful cells / lane-steps, read slots filled) on the shapes the workload
+    table watches: a guard for later planner changes — these are the numbers of the round-1 planner, rounded down."""
+    for name, util, fill in (("cfg2", 0.97, 0.999), ("cfg5", 0.84, 0.95), ("cfg5t", 0.78, 0.95), ("cfg3", 0.86, 0.99)):
+        a = ph.plan_audit(_stream(name), busy_batches=6)
+        _sound(a)
+        assert a["lane_utilisation"] >= util and a["slot_fill"] >= fill, (name, a["lane_utilisation"], a["slot_fill"])

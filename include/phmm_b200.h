@@ -47,7 +47,7 @@ typedef struct phmm_config
 {
     int32_t device;               /* CUDA ordinal; -1 = current device */
     int32_t fma_mode;             /* PHMM_FMA_* (0 = the AVX-512 flavour) */
-    uint32_t n_workers;           /* host worker threads = batches in flight (0 = cores / visible GPUs, clamped to 2..6) */
+    uint32_t n_workers;           /* host worker threads = batches in flight, per device (0 = cores / visible GPUs, clamped to 2..6) */
     uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 32e9) */
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
@@ -185,7 +185,8 @@ typedef struct phmm_stats
     uint64_t slow_pairs;              /* pairs outside the wavefront kernel's envelope (per-pair kernel) */
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t batches;
-    double gpu_ms;                    /* sum of per-batch device time (CUDA events, kernels only) */
+    double gpu_ms;                    /* device time with kernels of the path running: the UNION of the batches' kernel spans
+                                         (CUDA events; batches of different workers overlap on the device), summed over devices */
     uint64_t kernel_launches;
     double host_plan_ms;              /* sum over batches of host planning + packing time (worker threads, wall) */
     double host_epilogue_ms;          /* sum over batches of the host epilogue (log10, cap, filter, transpose), or of the
@@ -197,6 +198,18 @@ typedef struct phmm_stats
  * core/context.h:13-190 on the host, uploads them, starts the workers. */
 int phmm_create(const phmm_config* cfg, phmm_engine** out);
 void phmm_destroy(phmm_engine* e);
+
+/* One engine in front of several GPUs of the box.  The reference is ONE multi-threaded process that binds the path once
+ * (haplotypecaller.cpp:49) and calls it from its pool workers (:97, haplotypecaller_engine.cpp:250); with this form such a
+ * process uses every GPU: each sealed batch of regions (phmm_submit / phmm_wait) and each sub-batch of a flat stream
+ * (phmm_run_flat) goes to the device with the least outstanding work, the results land in the caller's host buffers as with
+ * one device.  Regions are independent, so there is no collective and no peer access, and the result
+ * of a region does not depend on the device that computed it.  devices[k] are CUDA ordinals (-1 = the current device; an
+ * ordinal may be listed twice: two independent queues on one GPU); n_devices = 0 means every visible device.  cfg->device is
+ * ignored, cfg->n_workers counts per device (0 = cores / max(devices used, devices visible), clamped to 2..6). */
+int phmm_create_multi(const phmm_config* cfg, const int32_t* devices, uint32_t n_devices, phmm_engine** out);
+uint32_t phmm_device_count(const phmm_engine* e);
+int phmm_device_ordinal(const phmm_engine* e, uint32_t index);   /* CUDA ordinal of the engine's index-th device, -1 if out of range */
 
 /* Replaces one synchronous rovaca::call_pairhmm call (haplotypecaller_engine.cpp:250).
  * = phmm_submit + phmm_wait.  Thread-safe; efficient only when many callers are in flight. */
@@ -223,7 +236,8 @@ int phmm_marginalize(const double* values, uint32_t n_old, uint32_t stride, uint
 /* Device-resident form for kernel-only timing: upload once, run the device path (prep + forward +
  * FP64 recompute kernels, no host<->device copies) any number of times, download when wanted. */
 typedef struct phmm_resident phmm_resident;
-int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* batch, phmm_resident** out);
+int phmm_resident_upload(phmm_engine* e, const phmm_flat_batch* batch, phmm_resident** out);   /* on the engine's first device */
+int phmm_resident_upload_on(phmm_engine* e, uint32_t device_index, const phmm_flat_batch* batch, phmm_resident** out);
 int phmm_resident_run(phmm_engine* e, phmm_resident* r, float* gpu_ms, float* fwd_ms);
 int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* result);
 void phmm_resident_free(phmm_engine* e, phmm_resident* r);
@@ -270,7 +284,8 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
  * last phmm_sw_align call. */
 int phmm_sw_last_timing(phmm_engine* e, float* gpu_ms, uint64_t* cells);
 
-int phmm_get_stats(phmm_engine* e, phmm_stats* out);
+int phmm_get_stats(phmm_engine* e, phmm_stats* out);                                    /* summed over the engine's devices */
+int phmm_get_device_stats(phmm_engine* e, uint32_t device_index, phmm_stats* out);      /* one device's share */
 /* Static facts about the forward-kernel instantiation that serves reads of `read_len` bases (registers, spill bytes,
  * lanes per read, read rows per lane) for reports. */
 int phmm_kernel_info(uint32_t read_len, int fma_mode, int* regs, int* local_bytes, int* lanes, int* rows_per_lane);

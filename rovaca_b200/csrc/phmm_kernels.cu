@@ -265,14 +265,14 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     {
         uint32_t* sw = reinterpret_cast<uint32_t*>(stream);
         if (threadIdx.x == 0) {                      // empty streams still need their end sentinel
-            if (ch.n_x == 0) sw[2 * 32 + 0] = PHMM_FLAG_BIT;
-            if (ch.n_x == ch.n_haps) sw[2 * 32 + 1] = PHMM_FLAG_BIT;
+            if ((ch.n_xy & 0xffffu) == 0) sw[2 * 32 + 0] = PHMM_FLAG_BIT;
+            if ((ch.n_xy >> 16) == 0) sw[2 * 32 + 1] = PHMM_FLAG_BIT;
         }
         for (uint32_t j = 0; j < ch.n_haps; ++j) {
             const PhmmHap hp = p.haps[ch.hap_begin + j];
             if (hp.pos == 0) continue;               // not in a stream (empty / over-long: per-pair kernel)
             const uint32_t e = hp.ord_stream & 1u, ord = hp.ord_stream >> 1;
-            const uint32_t n_e = e ? (ch.n_haps - ch.n_x) : ch.n_x;
+            const uint32_t n_e = e ? (ch.n_xy >> 16) : (ch.n_xy & 0xffffu);
             const uint8_t* hb = p.hap_bases + hp.byte_off;
             for (uint32_t c = threadIdx.x; c < hp.len; c += NT) {
                 uint32_t w = base_class(hb[c]) * CSTRIDE;

@@ -1,0 +1,574 @@
+// phmm_plan.cpp — the planner: a list of regions -> read-length bins, haplotype chunks of two balanced column streams, CTAs,
+// and the one pinned arena that carries all of it to the device.  Replaces the reference's 16-lane CPU
+// grouping (generate_histogram / generate_new_pairhmm_idx, pairhmm_internal.cpp:231-391), on which results do not depend.
+#include "phmm_host.h"
+
+namespace
+{
+
+
+// Fill the read slots of a region's CTAs.  A warp of the forward kernel holds 32 / LANES reads of ONE bin; a region whose
+// reads scatter over many length bins would run many part-empty warps.  A read may run in any higher bin of its lane family
+// (more top padding, same result), so the remainder of a bin can be carried up into the next occupied one.  Cost of a warp
+// = rows per lane of its bin; the small DP below picks, per family, which remainders to carry (f[i][c]: best cost of bins
+// i.. with c reads carried in).
+void promote_remainders(std::vector<std::vector<uint32_t>>& by_bin, int first, int last)
+{
+    constexpr int kMaxBins = 24, kMaxS = 4;
+    const int S = 32 / kPhmmBins[first].lanes;            // reads per warp in this family
+    const int nb = last - first + 1;
+    if (S <= 1 || nb < 2 || nb > kMaxBins || S > kMaxS) return;
+    int occupied = 0;
+    bool ragged = false;
+    for (int i = 0; i < nb; ++i) {
+        const size_t n = by_bin[first + i].size();
+        occupied += n != 0;
+        ragged |= n % S != 0;
+    }
+    if (occupied < 2 || !ragged) return;                   // nothing to merge
+    uint32_t f[kMaxBins + 1][kMaxS] = {};
+    uint8_t carry[kMaxBins][kMaxS] = {};
+    uint32_t own[kMaxBins];
+    for (int i = nb - 1; i >= 0; --i) {
+        const uint32_t rpt = (uint32_t)kPhmmBins[first + i].rpt;
+        own[i] = (uint32_t)by_bin[first + i].size();
+        for (int c = 0; c < S; ++c) {
+            const uint32_t t = (uint32_t)c + own[i];
+            uint32_t best = (t + S - 1) / S * rpt + f[i + 1][0];
+            uint8_t how = 0;
+            if (i + 1 < nb && t % S != 0) {
+                const uint32_t alt = t / S * rpt + f[i + 1][t % S];
+                if (alt < best) { best = alt; how = 1; }
+            }
+            f[i][c] = best;
+            carry[i][c] = how;
+        }
+    }
+    uint32_t c = 0;                                        // reads carried into bin i (already appended to its vector)
+    for (int i = 0; i + 1 < nb; ++i) {
+        auto& cur = by_bin[first + i];
+        const uint32_t t = c + own[i];                    // == cur.size()
+        if (carry[i][c]) {
+            const uint32_t rem = t % S;
+            auto& up = by_bin[first + i + 1];
+            up.insert(up.end(), cur.end() - rem, cur.end());
+            cur.resize(t - rem);
+            c = rem;
+        } else {
+            c = 0;
+        }
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Planning + packing
+// ------------------------------------------------------------------------------------------------
+
+#ifndef PHMM_PLAN_TIMING      // section timers for tools/plan_timing.cpp; compiled out of the library
+#define PT_NOW() 0
+#define PT_ADD(i, a, b) (void)0
+#endif
+
+int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
+{
+    [[maybe_unused]] const auto pt0 = PT_NOW();
+    uint64_t n_reads = 0, n_haps = 0, read_bytes = 0, hap_bytes = 0, n_pairs = 0, n_cells = 0;
+    bool any_ins = false, any_del = false, any_gcp = false;
+    s.want_f64 = cfg->fp64_always;
+    s.want_best = s.want_raw = false;
+    for (const RegionIn& r : regs) {
+        if (r.n_reads == 0 || r.n_haps == 0) continue;           // pairhmm_internal.cpp:508-510
+        s.want_f64 |= r.out.raw_f64 != nullptr;
+        s.want_raw |= r.out.raw_f32 != nullptr || r.out.raw_f64 != nullptr;
+        s.want_best |= r.out.best_hap != nullptr;
+        uint64_t rb = 0, hb = 0;
+        for (uint32_t k = 0; k < r.n_reads; ++k) {
+            rb += r.reads[k].len;
+            any_ins |= r.reads[k].ins != nullptr;
+            any_del |= r.reads[k].del != nullptr;
+            any_gcp |= r.reads[k].gcp != nullptr;
+        }
+        for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
+        n_reads += r.n_reads;
+        n_haps += r.n_haps;
+        read_bytes += rb;
+        hap_bytes += hb;
+        n_pairs += (uint64_t)r.n_reads * r.n_haps;
+        n_cells += rb * hb;
+    }
+    // One more kernel and a D2H twice the size pay off once the host would otherwise spend longer on the pairs than a launch
+    // costs; the few-region batches of synchronous callers keep the (vector) host epilogue.
+    s.dev_epi = cfg->device_epilogue && n_pairs >= cfg->device_epilogue_min_pairs;
+    if (n_pairs >= (1ull << 31) || read_bytes >= (1ull << 31) || hap_bytes >= (1ull << 31))
+        return fail(PHMM_ERR_ARG, "batch too large for 32-bit device offsets; lower batch_cells");
+    // What the reference itself feeds its kernels — deletion qualities aliasing the insertion ones, one gap-continuation
+    // quality per read (read_record.cpp:191-210, pairhmm_internal.cpp:425,559) — is served by the leaner kernel variant.
+    const bool refgaps = cfg->fma && !any_del && !any_gcp;
+    // A warp sweeps its chunk's columns one after the other (~0.2 us per column), so the chunk length is the latency of a
+    // batch and chunks x reads its parallelism.  A big batch fills the GPU with long chunks (fewest seams and staging); a
+    // small one (the synchronous per-region callers) is cut finer until it has about two warps per warp slot of the device.
+    uint32_t target_cols = kTargetStreamCols;
+    int min_lanes = 8;             // lanes per read of the reference-gap kernels
+    {
+        uint64_t est_warps = 0;
+        for (const RegionIn& r : regs) {
+            uint64_t hb = 0;
+            for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
+            est_warps += (uint64_t)((r.n_reads + 3) / 4) * std::max<uint64_t>(1, (hb + 2ull * kTargetStreamCols - 1) / (2ull * kTargetStreamCols));
+        }
+        // batches already on the device fill it too: share the target among them
+        const uint64_t want = 2ull * warp_slots / std::max<uint32_t>(1, busy_batches.load(std::memory_order_relaxed));
+        // First spread each read over more lanes (fewer rows per lane = a cheaper step: the latency bins), then cut the chunks
+        // shorter, until the batch has about `want` warps.
+        // (only while even the widened batch leaves half of its share of the device empty: the wide layouts do 10-15 % less
+        // work per issue slot, so a busy device wants the throughput layout)
+        if (cfg->lanes_pref)
+            min_lanes = (int)cfg->lanes_pref;
+        else if (est_warps * 8 <= want)
+            min_lanes = 32;
+        else if (est_warps * 4 <= want)
+            min_lanes = 16;
+        est_warps *= (uint64_t)min_lanes / 8;
+        // ... and a batch runs at 1 / (1 + slots / warps) of the device's rate while its last warps finish alone: below
+        // kWavesWanted waves the chunks are cut shorter (a 300-column sweep costs a warp ~2 % in prologue, tools/chunk_curve.py)
+        const uint64_t want_chunks = want * (kWavesWanted / 2);
+        if (est_warps > 0 && est_warps < want_chunks)
+            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want_chunks);
+    }
+    Slot::PlanScratch& ps = s.ps;
+    std::vector<PhmmRead>& reads = ps.reads;
+    std::vector<PhmmHap>& haps = ps.haps;
+    std::vector<PhmmChunk>& chunks = ps.chunks;
+    std::vector<PhmmPair>& slow = ps.slow;
+    reads.clear();
+    haps.clear();
+    chunks.clear();
+    slow.clear();
+    ps.pri.clear();
+    reads.reserve(n_reads);
+    haps.reserve(n_haps);
+    s.regions.clear();
+    s.regions.reserve(regs.size());
+    s.read_len.clear();
+    s.read_len.reserve(n_reads);
+    // per bin: (chunk, reads...) groups
+    using Group = Slot::Group;
+    std::vector<std::vector<Group>>& groups = ps.groups;
+    std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;
+    std::vector<std::vector<uint32_t>>& by_bin = ps.by_bin;
+    groups.resize(kPhmmNumBins);
+    group_reads.resize(kPhmmNumBins);
+    by_bin.resize(kPhmmNumBins);
+    for (int b = 0; b < kPhmmNumBins; ++b) {
+        groups[b].clear();
+        group_reads[b].clear();
+        by_bin[b].clear();
+    }
+    std::vector<uint32_t>&order = ps.order, &region_chunks = ps.region_chunks, &idx = ps.idx;
+    // read length -> bin, for the lengths the wavefront kernels take (a table instead of a search per read)
+    uint8_t bin_lut[640];
+    int bin_lo = kPhmmNumBins, bin_hi = -1;        // the bins this batch can use (one variant, lane families from min_lanes up)
+    for (uint32_t len = 0; len < 640; ++len) {
+        const int b = phmm_bin_of(len, refgaps, min_lanes);
+        bin_lut[len] = b < 0 ? 255 : (uint8_t)b;
+        if (b >= 0) {
+            bin_lo = std::min(bin_lo, b);
+            bin_hi = std::max(bin_hi, b);
+        }
+    }
+
+    uint64_t raw_off = 0, hap_off = 0, out_off = 0;
+    uint32_t max_cols = 0;
+    [[maybe_unused]] const auto pt1 = PT_NOW();
+    PT_ADD(0, pt0, pt1);
+    for (const RegionIn& r : regs) {
+        RegionPlan rp{};
+        rp.read_begin = (uint32_t)reads.size();
+        rp.hap_begin = (uint32_t)haps.size();
+        rp.out_off = out_off;
+        if (r.n_reads == 0 || r.n_haps == 0) {
+            rp.n_reads = rp.n_haps = 0;
+            s.regions.push_back(rp);
+            continue;
+        }
+        rp.n_reads = r.n_reads;
+        rp.n_haps = r.n_haps;
+        s.regions.push_back(rp);
+        if (s.want_best)
+            for (uint32_t j = 0; j < r.n_haps; ++j) ps.pri.push_back(r.haps[j].priority);
+        // haplotypes -> chunks of two balanced streams
+        for (uint32_t j = 0; j < r.n_haps; ++j) {
+            PhmmHap h{};
+            h.byte_off = (uint32_t)hap_off;
+            h.len = r.haps[j].len;
+            h.out_col = j;
+            hap_off += h.len;
+            max_cols = std::max(max_cols, h.len);
+            haps.push_back(h);
+        }
+        order.clear();
+        uint64_t total = 0;
+        for (uint32_t j = 0; j < r.n_haps; ++j)
+            if (r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols) {
+                order.push_back(j);
+                total += r.haps[j].len;
+            }
+        const bool all_haps_in_stream = order.size() == r.n_haps;
+        region_chunks.clear();
+        if (!order.empty()) {
+            // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty
+            const uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / 2),
+                                                                 std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols)));
+            const uint64_t per_chunk = (total + n_chunks - 1) / n_chunks;
+            size_t at = 0;
+            while (at < order.size()) {
+                // take haplotypes (in region order) until this chunk holds its share
+                size_t end = at;
+                uint64_t acc = 0;
+                while (end < order.size() && (end == at || acc + r.haps[order[end]].len <= per_chunk + target_cols / 4)) {
+                    acc += r.haps[order[end]].len;
+                    ++end;
+                    if (acc >= per_chunk) break;
+                }
+                // longest first onto the lighter stream.  A stream may not outgrow what one CTA can stage in shared memory
+                // (kMaxStreamCols): if it would (several very long haplotypes in one chunk), the chunk takes fewer of them.
+                uint32_t sum[2], cnt[2];
+                for (;;) {
+                    idx.assign(order.begin() + at, order.begin() + end);
+                    for (size_t a = 1; a < idx.size(); ++a) {              // stable insertion sort, longest first (a handful of entries)
+                        const uint32_t v = idx[a];
+                        size_t at2 = a;
+                        while (at2 > 0 && r.haps[idx[at2 - 1]].len < r.haps[v].len) {
+                            idx[at2] = idx[at2 - 1];
+                            --at2;
+                        }
+                        idx[at2] = v;
+                    }
+                    sum[0] = sum[1] = cnt[0] = cnt[1] = 0;
+                    for (uint32_t j : idx) {
+                        const uint32_t e = (sum[1] < sum[0]) ? 1u : 0u;
+                        PhmmHap& h = haps[rp.hap_begin + j];
+                        h.pos = 32 + sum[e];
+                        h.ord_stream = (cnt[e] << 1) | e;
+                        sum[e] += h.len;
+                        ++cnt[e];
+                    }
+                    if (std::max(sum[0], sum[1]) <= kMaxStreamCols || end - at <= 1) break;
+                    --end;
+                    haps[rp.hap_begin + order[end]].pos = 0;               // back to "not placed"
+                }
+                // the device walks haps[hap_begin .. +n_haps); empty or over-long haplotypes inside that range keep pos == 0,
+                // which the kernel skips (they are served by the per-pair kernel) — so the chunk carries the two streams'
+                // own counts, not the span's
+                PhmmChunk c{};
+                c.hap_begin = rp.hap_begin + order[at];
+                c.n_haps = order[end - 1] - order[at] + 1;
+                c.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
+                c.n_xy = cnt[0] | (cnt[1] << 16);
+                region_chunks.push_back((uint32_t)chunks.size());
+                chunks.push_back(c);
+                at = end;
+            }
+        }
+        // reads
+        for (int b = bin_lo; b <= bin_hi; ++b) by_bin[b].clear();
+        for (uint32_t k = 0; k < r.n_reads; ++k) {
+            const phmm_read& in = r.reads[k];
+            PhmmRead d{};
+            d.raw_off = (uint32_t)raw_off;
+            d.word_off = (uint32_t)raw_off;
+            d.len = in.len;
+            d.out_off = (uint32_t)(out_off + (uint64_t)k * r.n_haps);
+            d.n_haps = r.n_haps;
+            d.hap_begin = rp.hap_begin;
+            d.thr = (int16_t)std::max(-32768, std::min(32767, r.thr));
+            d.mapq = in.mapq;
+            const uint32_t fl = (in.ins ? PHMM_RD_HAS_INS : 0u) | (in.del ? PHMM_RD_HAS_DEL : 0u) | (in.gcp ? PHMM_RD_HAS_GCP : 0u);
+            // apply_pcr_error_model's switch takes HOSTILE / AGGRESSIVE / CONSERVATIVE and leaves the read alone for anything
+            // else (pairhmm_internal.cpp:121-159, default: break)
+            const uint32_t pcr = (r.pcr >= PHMM_PCR_HOSTILE && r.pcr <= PHMM_PCR_CONSERVATIVE) ? (uint32_t)r.pcr : (uint32_t)PHMM_PCR_NONE;
+            d.model_flags = (uint8_t)(pcr | (fl << 4));
+            raw_off += in.len;
+            const uint32_t rid = (uint32_t)reads.size();
+            reads.push_back(d);
+            s.read_len.push_back(in.len);
+            const int b = in.len < 640 ? (bin_lut[in.len] == 255 ? -1 : (int)bin_lut[in.len]) : -1;
+            if (b >= 0) by_bin[b].push_back(rid);
+            if (b < 0 || !all_haps_in_stream)
+                for (uint32_t j = 0; j < r.n_haps; ++j) {
+                const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
+                if (b < 0 || !hap_ok) {
+                    PhmmPair p{};
+                    p.read = rid;
+                    p.hap = rp.hap_begin + j;
+                    p.out_idx = d.out_off + j;
+                    slow.push_back(p);
+                }
+            }
+        }
+        for (int b0 = bin_lo; b0 <= bin_hi;) {           // one lane family at a time (bins of a family are contiguous)
+            int b1 = b0;
+            while (b1 + 1 <= bin_hi && kPhmmBins[b1 + 1].lanes == kPhmmBins[b0].lanes && kPhmmBins[b1 + 1].refgaps == kPhmmBins[b0].refgaps) ++b1;
+            promote_remainders(by_bin, b0, b1);
+            b0 = b1 + 1;
+        }
+        for (int b = bin_lo; b <= bin_hi; ++b) {
+            if (by_bin[b].empty()) continue;
+            // every chunk of the region sweeps the same reads: one copy of the list, one group per chunk
+            const uint32_t first = (uint32_t)group_reads[b].size();
+            group_reads[b].insert(group_reads[b].end(), by_bin[b].begin(), by_bin[b].end());
+            for (uint32_t ci : region_chunks) groups[b].push_back(Group{ci, chunks[ci].stream_len, first, (uint32_t)by_bin[b].size()});
+        }
+        out_off += (uint64_t)r.n_reads * r.n_haps;
+    }
+
+    [[maybe_unused]] const auto pt2 = PT_NOW();
+    PT_ADD(1, pt1, pt2);
+    // CTAs per bin, longest streams first
+    std::vector<PhmmCta>& ctas = ps.ctas;
+    std::vector<uint32_t>& task_reads = ps.task_reads;
+    ctas.clear();
+    task_reads.clear();
+    s.launches.clear();
+    for (int b = std::max(bin_lo, 0); b <= bin_hi; ++b) {
+        if (groups[b].empty()) continue;
+        {
+            // stable, longest stream first: a counting sort on the stream length (at most kMaxStreamCols + 33 values)
+            uint32_t longest = 0;
+            for (const Group& g : groups[b]) longest = std::max(longest, g.stream_len);
+            ps.bucket.assign((size_t)longest + 2, 0u);
+            for (const Group& g : groups[b]) ++ps.bucket[longest - g.stream_len + 1];
+            for (uint32_t k = 1; k <= longest + 1; ++k) ps.bucket[k] += ps.bucket[k - 1];
+            ps.sorted.resize(groups[b].size());
+            for (const Group& g : groups[b]) ps.sorted[ps.bucket[longest - g.stream_len]++] = g;
+            groups[b].swap(ps.sorted);
+        }
+        FwdLaunch fl{};
+        fl.bin = b;
+        fl.cta_base = (uint32_t)ctas.size();
+        size_t smem = 0;
+        // warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but their
+        // read slots come in bigger lumps; take the biggest size that wastes at most 8 % more slots than single-warp CTAs
+        uint32_t cta_warps = cfg->cta_warps;
+        if (cta_warps == 0) {
+            const uint32_t per_warp = phmm_bin_reads_per_cta(b, 1);
+            uint64_t slots[3] = {0, 0, 0};
+            for (const Group& g : groups[b])
+                for (int k = 0; k < 3; ++k) {
+                    const uint32_t per = per_warp << k;
+                    slots[k] += (uint64_t)((g.n + per - 1) / per) * per;
+                }
+            cta_warps = 1;
+            for (int k = 1; k < 3; ++k)
+                if (slots[k] * 100 <= slots[0] * 108) cta_warps = 1u << k;
+        }
+        // ... that still fits the device's shared memory with this launch's longest chunk (streams of very long haplotypes)
+        for (;;) {
+            smem = 0;
+            for (const Group& g : groups[b])
+                smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps, b, cta_warps));
+            if (smem <= smem_optin || cta_warps == 1) break;
+            cta_warps >>= 1;
+        }
+        for (const Group& g : groups[b]) {
+            const uint32_t per_cta = phmm_bin_reads_per_cta(b, cta_warps);
+            for (uint32_t at = 0; at < g.n; at += per_cta) {
+                PhmmCta c{};
+                c.chunk = g.chunk;
+                c.read_begin = (uint32_t)task_reads.size();
+                c.n_reads = std::min<uint32_t>(per_cta, g.n - at);
+                for (uint32_t k = 0; k < c.n_reads; ++k) task_reads.push_back(group_reads[b][g.first + at + k]);
+                ctas.push_back(c);
+            }
+        }
+        fl.n_ctas = (uint32_t)ctas.size() - fl.cta_base;
+        fl.cta_warps = cta_warps;
+        fl.smem = smem;
+        s.launches.push_back(fl);
+    }
+
+    // biggest launches first: the small ones fill the tails
+    std::stable_sort(s.launches.begin(), s.launches.end(), [](const FwdLaunch& x, const FwdLaunch& y) {
+        return (uint64_t)x.n_ctas * x.cta_warps * kPhmmBins[x.bin].rpt > (uint64_t)y.n_ctas * y.cta_warps * kPhmmBins[y.bin].rpt;
+    });
+
+    [[maybe_unused]] const auto pt3 = PT_NOW();
+    PT_ADD(2, pt2, pt3);
+    // ---- arena layout ---------------------------------------------------------------------------
+    size_t off = 0;
+    auto place = [&](size_t bytes) { size_t at = off; off = align_up(off + bytes, 256); return at; };
+    const size_t o_reads = place(reads.size() * sizeof(PhmmRead));
+    const size_t o_haps = place(haps.size() * sizeof(PhmmHap));
+    const size_t o_chunks = place(chunks.size() * sizeof(PhmmChunk));
+    const size_t o_ctas = place(ctas.size() * sizeof(PhmmCta));
+    const size_t o_tasks = place(task_reads.size() * sizeof(uint32_t));
+    const size_t o_slow = place(slow.size() * sizeof(PhmmPair));
+    ps.regions_dev.clear();
+    if (s.dev_epi)
+        for (const RegionPlan& rp : s.regions)
+            ps.regions_dev.push_back(PhmmRegionDev{rp.read_begin, rp.n_reads, rp.hap_begin, rp.n_haps, (uint32_t)rp.out_off, {0, 0, 0}});
+    const size_t o_regions = place(ps.regions_dev.size() * sizeof(PhmmRegionDev));
+    const size_t o_pri = place((s.dev_epi ? ps.pri.size() : 0) * sizeof(double));
+    const size_t o_rb = place(read_bytes + 16);
+    const size_t o_rq = place(read_bytes + 16);
+    const size_t o_ri = any_ins ? place(read_bytes + 16) : 0;
+    const size_t o_rd = any_del ? place(read_bytes + 16) : 0;
+    const size_t o_rg = any_gcp ? place(read_bytes + 16) : 0;
+    const size_t o_hb = place(hap_bytes + 16);
+    s.in_bytes = off;
+    s.o_reads = o_reads; s.o_haps = o_haps; s.o_chunks = o_chunks; s.o_ctas = o_ctas; s.o_tasks = o_tasks; s.o_slow = o_slow;
+    s.n_chunks = chunks.size(); s.n_ctas = ctas.size(); s.n_tasks = task_reads.size();
+    int rc;
+    if ((rc = s.h_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
+    if ((rc = s.d_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
+    uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
+    std::memcpy(h + o_reads, reads.data(), reads.size() * sizeof(PhmmRead));
+    std::memcpy(h + o_haps, haps.data(), haps.size() * sizeof(PhmmHap));
+    std::memcpy(h + o_chunks, chunks.data(), chunks.size() * sizeof(PhmmChunk));
+    std::memcpy(h + o_ctas, ctas.data(), ctas.size() * sizeof(PhmmCta));
+    std::memcpy(h + o_tasks, task_reads.data(), task_reads.size() * sizeof(uint32_t));
+    std::memcpy(h + o_slow, slow.data(), slow.size() * sizeof(PhmmPair));
+    std::memcpy(h + o_regions, ps.regions_dev.data(), ps.regions_dev.size() * sizeof(PhmmRegionDev));
+    if (s.dev_epi) std::memcpy(h + o_pri, ps.pri.data(), ps.pri.size() * sizeof(double));
+    s.o_regions = o_regions;
+    s.o_pri = o_pri;
+    [[maybe_unused]] const auto pt4 = PT_NOW();
+    PT_ADD(3, pt3, pt4);
+    {
+        // gather the raw bytes; callers that keep their reads back to back (flat batches, BAM-like buffers) get one
+        // memcpy per contiguous run instead of one per read.  When the caller says its buffers are page-locked and the runs
+        // are few, nothing is gathered at all: the runs become host-to-device copies of their own (launch()).
+        struct Run
+        {
+            const uint8_t* src = nullptr;
+            size_t len = 0, dst = 0;
+            std::vector<Slot::DirectCopy>* runs;
+            void add(const uint8_t* p, size_t n, size_t at)
+            {
+                if (src && p == src + len && at == dst + len) {
+                    len += n;
+                    return;
+                }
+                flush();
+                src = p;
+                len = n;
+                dst = at;
+            }
+            void flush()
+            {
+                if (src && len) runs->push_back(Slot::DirectCopy{dst, src, len});
+                src = nullptr;
+            }
+        };
+        std::vector<Slot::DirectCopy> runs;
+        Run rb_run{nullptr, 0, 0, &runs}, rq_run = rb_run, ri_run = rb_run, rd_run = rb_run, rg_run = rb_run, hb_run = rb_run;
+        bool pinned = true;
+        size_t ro = 0, ho = 0;
+        for (const RegionIn& r : regs) {
+            if (r.n_reads == 0 || r.n_haps == 0) continue;
+            pinned &= r.pinned_src;
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const phmm_read& in = r.reads[k];
+                rb_run.add(in.bases, in.len, o_rb + ro);
+                rq_run.add(in.qual, in.len, o_rq + ro);
+                if (in.ins) ri_run.add(in.ins, in.len, o_ri + ro);
+                if (in.del) rd_run.add(in.del, in.len, o_rd + ro);
+                if (in.gcp) rg_run.add(in.gcp, in.len, o_rg + ro);
+                ro += in.len;
+            }
+            for (uint32_t j = 0; j < r.n_haps; ++j) {
+                hb_run.add(r.haps[j].bases, r.haps[j].len, o_hb + ho);
+                ho += r.haps[j].len;
+            }
+        }
+        rb_run.flush(); rq_run.flush(); ri_run.flush(); rd_run.flush(); rg_run.flush(); hb_run.flush();
+        s.direct.clear();
+        s.staged_bytes = s.in_bytes;
+        if (pinned && !s.h_in.host_only && runs.size() <= 24) {
+            s.direct = std::move(runs);
+            s.staged_bytes = o_rb;                   // records only; the byte blobs follow them in the arena
+        } else {
+            for (const Slot::DirectCopy& c : runs) std::memcpy(h + c.dst, c.src, c.len);
+        }
+    }
+    PT_ADD(4, pt4, PT_NOW());
+    // ---- device-only buffers --------------------------------------------------------------------
+    const size_t pairs_alloc = std::max<uint64_t>(n_pairs, 1);
+    if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t), &high_water[1])) != PHMM_OK) return rc;
+    if ((rc = s.d_f32.ensure(pairs_alloc * sizeof(float), &high_water[2])) != PHMM_OK) return rc;
+    if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
+    if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair), &high_water[4])) != PHMM_OK) return rc;
+    if ((rc = s.d_cnt.ensure(256)) != PHMM_OK) return rc;
+    if ((rc = s.d_scr64.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(double), &high_water[5])) != PHMM_OK) return rc;
+    if (!slow.empty())
+        if ((rc = s.d_scr32.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(float), &high_water[6])) != PHMM_OK) return rc;
+    if ((rc = s.h_f32.ensure(pairs_alloc * sizeof(float), &high_water[2])) != PHMM_OK) return rc;
+    if ((rc = s.h_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
+    if ((rc = s.h_cnt.ensure(256)) != PHMM_OK) return rc;
+
+    if (s.dev_epi) {
+        // [lik: one double per pair | kept_idx, best, second: one u32 per read | n_kept, n_under: one u32 per region]
+        size_t eo = 0;
+        auto eplace = [&](size_t bytes) { size_t at = eo; eo = align_up(eo + bytes, 256); return at; };
+        eplace(pairs_alloc * sizeof(double));
+        s.e_kept = eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t));
+        s.e_best = s.want_best ? eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t)) : 0;
+        s.e_second = s.want_best ? eplace(std::max<uint64_t>(n_reads, 1) * sizeof(uint32_t)) : 0;
+        s.e_nkept = eplace(std::max<size_t>(regs.size(), 1) * sizeof(uint32_t));
+        s.e_under = eplace(std::max<size_t>(regs.size(), 1) * sizeof(uint32_t));
+        s.epi_bytes = eo;
+        if ((rc = s.d_epi.ensure(eo, &high_water[7])) != PHMM_OK) return rc;
+        if ((rc = s.h_epi.ensure(eo, &high_water[7])) != PHMM_OK) return rc;
+    }
+
+    uint8_t* d = static_cast<uint8_t*>(s.d_in.p);
+    PhmmBatchDev& b = s.dev;
+    b.reads = reinterpret_cast<const PhmmRead*>(d + o_reads);
+    b.haps = reinterpret_cast<const PhmmHap*>(d + o_haps);
+    b.chunks = reinterpret_cast<const PhmmChunk*>(d + o_chunks);
+    b.ctas = reinterpret_cast<const PhmmCta*>(d + o_ctas);
+    b.task_reads = reinterpret_cast<const uint32_t*>(d + o_tasks);
+    b.slow_pairs = reinterpret_cast<const PhmmPair*>(d + o_slow);
+    b.read_bases = d + o_rb;
+    b.read_qual = d + o_rq;
+    b.read_ins = any_ins ? d + o_ri : nullptr;
+    b.read_del = any_del ? d + o_rd : nullptr;
+    b.read_gcp = any_gcp ? d + o_rg : nullptr;
+    b.hap_bases = d + o_hb;
+    b.words = static_cast<uint32_t*>(s.d_words.p);
+    b.out_f32 = static_cast<float*>(s.d_f32.p);
+    b.out_f64 = static_cast<double*>(s.d_f64.p);
+    b.f64_pairs = static_cast<PhmmPair*>(s.d_pairs.p);
+    b.f64_count = static_cast<uint32_t*>(s.d_cnt.p);
+    b.tables = static_cast<const PhmmTables*>(d_tables.p);
+    b.n_reads = (uint32_t)reads.size();
+    b.rg_gapm = cfg->default_gapm;      // gap_conts() is the constant '+' - 33 = 10 for every read, read_record.cpp:205-210
+    b.rg_ii = cfg->default_ii;
+    if (s.dev_epi) {
+        uint8_t* de = static_cast<uint8_t*>(s.d_epi.p);
+        PhmmEpilogueDev& ep = s.epi;
+        ep.regions = reinterpret_cast<const PhmmRegionDev*>(d + o_regions);
+        ep.reads = b.reads;
+        ep.raw = b.out_f32;
+        ep.hap_priority = s.want_best ? reinterpret_cast<const double*>(d + o_pri) : nullptr;
+        ep.lik = reinterpret_cast<double*>(de);
+        ep.kept_idx = reinterpret_cast<uint32_t*>(de + s.e_kept);
+        ep.best = s.want_best ? reinterpret_cast<uint32_t*>(de + s.e_best) : nullptr;
+        ep.second = s.want_best ? reinterpret_cast<uint32_t*>(de + s.e_second) : nullptr;
+        ep.n_kept = reinterpret_cast<uint32_t*>(de + s.e_nkept);
+        ep.n_under = reinterpret_cast<uint32_t*>(de + s.e_under);
+        ep.n_regions = (uint32_t)regs.size();
+    }
+
+    s.n_pairs = n_pairs;
+    s.n_cells = n_cells;
+    s.n_words = read_bytes;
+    s.n_reads = (uint32_t)reads.size();
+    s.n_haps = (uint32_t)haps.size();
+    s.n_slow = (uint32_t)slow.size();
+    s.max_cols = max_cols;
+    s.n_launches = 1 + (uint32_t)s.launches.size() + (s.n_slow ? 1 : 0) + (s.want_f64 ? 1 : 0) + (s.dev_epi ? 1 : 0);
+    return PHMM_OK;
+}

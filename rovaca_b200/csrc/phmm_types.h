@@ -53,7 +53,8 @@ struct PhmmChunk
     uint32_t hap_begin;  // haps[hap_begin .. hap_begin + n_haps)
     uint32_t n_haps;
     uint32_t stream_len; // positions per stream: 32 lead-in dummies + columns + sentinel, padded to the longer one
-    uint32_t n_x;        // haplotypes in stream x (the rest are in y)
+    uint32_t n_xy;       // haplotypes placed in stream x (low 16 bits) and in stream y (high 16 bits); haplotypes of the span
+                         // that are in neither (empty, over-long: pos == 0) go to the per-pair kernel
 };
 
 struct PhmmCta

@@ -97,7 +97,7 @@ class _Stats(C.Structure):
                 ("device_epilogue_batches", C.c_uint64)]
 
 
-EXPORTS = ["phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
+EXPORTS = ["phmm_create_multi", "phmm_device_count", "phmm_device_ordinal", "phmm_get_device_stats", "phmm_resident_upload_on", "phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
            "phmm_resident_upload", "phmm_resident_run", "phmm_resident_download", "phmm_resident_free",
            "phmm_resident_launches", "phmm_get_stats", "phmm_kernel_info", "phmm_ubench", "phmm_last_error", "phmm_version"]
 
@@ -130,6 +130,12 @@ def load_library():
     L.phmm_last_error.restype = C.c_char_p
     L.phmm_version.restype = C.c_char_p
     L.phmm_create.argtypes = [C.POINTER(_Config), C.POINTER(C.c_void_p)]
+    L.phmm_create_multi.argtypes = [C.POINTER(_Config), C.POINTER(C.c_int32), C.c_uint32, C.POINTER(C.c_void_p)]
+    L.phmm_device_count.argtypes = [C.c_void_p]
+    L.phmm_device_count.restype = C.c_uint32
+    L.phmm_device_ordinal.argtypes = [C.c_void_p, C.c_uint32]
+    L.phmm_get_device_stats.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_Stats)]
+    L.phmm_resident_upload_on.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(_FlatBatch), C.POINTER(C.c_void_p)]
     L.phmm_destroy.argtypes = [C.c_void_p]
     L.phmm_destroy.restype = None
     L.phmm_call_region.argtypes = [C.c_void_p, C.POINTER(_Region), C.POINTER(_Result)]
@@ -314,11 +320,11 @@ def _flat_c(batch: RegionBatch, thr: int, pcr: int) -> _FlatBatch:
 class Resident:
     """A batch living in HBM: ``run()`` executes the device path only (kernel-timing leg of the bench)."""
 
-    def __init__(self, eng: "PairHmmEngine", batch: RegionBatch, thr: int, pcr: int):
+    def __init__(self, eng: "PairHmmEngine", batch: RegionBatch, thr: int, pcr: int, device_index: int = 0):
         self.eng, self.batch = eng, batch
         self.h = C.c_void_p()
         fb = _flat_c(batch, thr, pcr)
-        eng._check(eng.L.phmm_resident_upload(eng.h, C.byref(fb), C.byref(self.h)))
+        eng._check(eng.L.phmm_resident_upload_on(eng.h, device_index, C.byref(fb), C.byref(self.h)))
         self.launches = int(eng.L.phmm_resident_launches(self.h))
 
     def run(self) -> Tuple[float, float]:
@@ -346,16 +352,36 @@ class Resident:
 
 
 class PairHmmEngine:
-    """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200."""
+    """``init_pairhmm_ptr`` + ``call_pairhmm`` of the reference, on one B200 or on several behind one engine."""
 
     def __init__(self, device: int = -1, fma_mode: int = FMA_AVX512, n_workers: int = 0, batch_cells: int = 0,
-                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0, fp64_mode: int = 0, epilogue: int = 0):
+                 linger_us: int = 0, cta_warps: int = 0, lanes_per_read: int = 0, fp64_mode: int = 0, epilogue: int = 0,
+                 devices: Optional[Sequence[int]] = None, pipeline_depth: int = 0):
+        """``devices``: CUDA ordinals this one engine drives (``phmm_create_multi``; ``"all"`` or ``[]`` = every visible
+        device, an ordinal may repeat); without it the engine owns the single ``device``."""
         self.L = load_library()
-        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, 0, lanes_per_read, fp64_mode, epilogue)
+        cfg = _Config(device, fma_mode, n_workers, batch_cells, linger_us, cta_warps, pipeline_depth, lanes_per_read, fp64_mode, epilogue)
         self.h = C.c_void_p()
-        rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
+        if devices is None:
+            rc = self.L.phmm_create(C.byref(cfg), C.byref(self.h))
+        else:
+            ords = [] if isinstance(devices, str) else [int(d) for d in devices]
+            arr = (C.c_int32 * max(len(ords), 1))(*ords)
+            rc = self.L.phmm_create_multi(C.byref(cfg), arr, len(ords), C.byref(self.h))
         if rc != 0:
             raise PhmmError(f"phmm_create failed ({rc}): {self.L.phmm_last_error().decode()}")
+
+    @property
+    def n_devices(self) -> int:
+        return int(self.L.phmm_device_count(self.h))
+
+    def device_ordinals(self):
+        return [int(self.L.phmm_device_ordinal(self.h, k)) for k in range(self.n_devices)]
+
+    def device_stats(self, index: int) -> dict:
+        s = _Stats()
+        self._check(self.L.phmm_get_device_stats(self.h, index, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
 
     def _check(self, rc: int):
         if rc != 0:
@@ -464,8 +490,9 @@ class PairHmmEngine:
         res.n_fp64 = int(res.c.n_fp64)
         return res
 
-    def upload(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE) -> Resident:
-        return Resident(self, batch, min_quality_threshold, pcr_option)
+    def upload(self, batch: RegionBatch, min_quality_threshold: int = 18, pcr_option: int = PCR_CONSERVATIVE,
+               device_index: int = 0) -> Resident:
+        return Resident(self, batch, min_quality_threshold, pcr_option, device_index)
 
     def stats(self) -> dict:
         s = _Stats()

@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — PairHMM throughput (GCUPS) of the B200 engine on BASELINE.json's headline workload.
+"""bench.py — PairHMM throughput (GCUPS) of the B200 engine on BASELINE.json's headline workload, plus the other configs.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--regions R]
+                    [--no-workloads] [--no-cpu-baseline] [--sustain SECONDS] [--stream-regions M]
 
 One "step" = one pass of the hot path (quality capping + PCR-indel model, forward recurrence, log10 / normalise / filter /
-transpose epilogue, and in the end-to-end leg planning, H2D, D2H and the hand-over to the caller's arrays) over one batch of synthetic active regions:
-BASELINE.json configs[1], 150 bp reads x 300 bp haplotypes, 8 haplotypes and 64 reads per region, R regions per GPU
-(default 4096 = 94.4 G cells per GPU per step; raw inputs + packed rows + outputs ~ 270 MB > the 126 MB L2).
-Multi-GPU (torchrun, one rank per GPU): regions are independent, every rank runs its own R regions through its own
-engine, no data-path collective ("scaling": "weak"); torch.distributed is used for the barrier and the max-over-ranks.
+transpose epilogue, and in the end-to-end leg planning, H2D, D2H and the hand-over to the caller's arrays) over one batch of
+synthetic active regions: BASELINE.json configs[1], 150 bp reads x 300 bp haplotypes, 8 haplotypes and 64 reads per region,
+R regions per GPU (default 4096 = 94.4 G cells per GPU per step; raw inputs + packed rows + outputs ~ 270 MB > the 126 MB L2).
+Multi-GPU (torchrun, one rank per GPU): `value` is weak scaling — independent replicas, every rank its own R regions through
+its own engine, no data-path collective; torch.distributed carries the barrier, the max-over-ranks and, for the
+`sharded_stream` record, one 64-bit digest per region.
 
 Prints ONE JSON line (rank 0).  `value` is device-timed (CUDA events on the engine's stream) with inputs resident in HBM;
 `e2e` is the same metric through the public host-buffer call (phmm_run_flat) with pack/H2D/D2H/epilogue in the timed region.
+Beside the headline: `workloads` (N = 1: BASELINE.json configs[2..4] — cfg3 high depth, cfg4 long, cfg4 mix, the cfg5 region
+stream at 0 / 50 / 100 % post-trim shapes — each with device GCUPS, end-to-end GCUPS, forward-kernel roofline fraction,
+FP64-branch pairs and a parity sample against the reference's own CPU path), `sustained` (the cfg2 device step repeated for
+`--sustain` seconds, default 3, with its own clock record) and `sharded_stream` (ONE common cfg5 stream sharded over the N
+ranks, per-region digests gathered on rank 0 and compared with a single-GPU run of the whole stream).
 """
 import argparse
 import json
@@ -148,6 +155,98 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def cfg2_config(regions, cells, pairs, world):
+    """The `config` object of the headline workload: the same keys on both arms (the reference arm times a bounded sample of
+    it and says so in `sample_of`)."""
+    per_region_cells, per_region_pairs = 64 * 150 * 8 * 300, 64 * 8
+    return {"workload": WORKLOAD, "regions_per_gpu": regions,
+            "cells_per_gpu_per_step": int(cells if cells is not None else regions * per_region_cells),
+            "pairs_per_gpu_per_step": int(pairs if pairs is not None else regions * per_region_pairs),
+            "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18, "fma_mode": "avx512-contracted",
+            "l2_policy": "inputs larger than L2: ~270 MB touched per step (raw reads, packed rows, outputs) vs 126 MB L2",
+            "parallelism": f"independent replicas: {regions} regions per GPU on each of {world} GPU(s), no collective (weak scaling)"}
+
+
+def workload_specs(quick):
+    """BASELINE.json configs[2..4] at the shapes of SURVEY.md §8d, generated by the C stream generator (workloads.stream)."""
+    from rovaca_b200 import workloads as wl
+    import numpy as np
+
+    def cfg4_mix(n):
+        a, b = wl.stream("cfg4", n // 2, seed=4), wl.stream("cfg2", n // 2, seed=4)
+        both = wl.concat([a, b])
+        order = np.arange(n).reshape(2, n // 2).T.reshape(-1)          # long, short, long, short, ...
+        return wl.take(both, order)
+    q = 4 if quick else 1
+    return [
+        ("cfg3", "high depth: 500 reads x 32 haplotypes per region, R 100-151, H 250-450, 5 % junk reads (FP64 branch)",
+         lambda: wl.stream("cfg3", 96 // q, seed=3)),
+        ("cfg4", "long: 250 bp reads x 1000 bp haplotypes, 16 haplotypes x 64 reads per region", lambda: wl.stream("cfg4", 192 // q, seed=4)),
+        ("cfg4_mix", "cfg4 regions alternating with 150x300 (cfg2) regions: length-binned load balance", lambda: cfg4_mix(384 // q)),
+        ("cfg5_trim0", "region stream, Poisson(41) reads of 60-151 bp x ~8.8 haplotypes of 201-499 bp", lambda: wl.stream("cfg5", 16384 // q, seed=5)),
+        ("cfg5_trim50", "region stream, 50 % of the regions with post-trim shapes (H 41-120, R <= H)",
+         lambda: wl.stream("cfg5", 16384 // q, seed=5, post_trim_fraction=0.5)),
+        ("cfg5_trim100", "region stream, post-trim shapes only", lambda: wl.stream("cfg5", 32768 // q, seed=5, post_trim_fraction=1.0)),
+    ]
+
+
+def run_workloads(eng, prop_sms, sm_max_mhz, quick, parity):
+    """Every other BASELINE config through the same two legs as the headline (device-resident, end to end)."""
+    import numpy as np
+    from rovaca_b200.pairhmm import FlatResult
+    rows = []
+    for key, what, make in workload_specs(quick):
+        b = make().pin()
+        cells = b.cells()
+        res = eng.upload(b)
+        for _ in range(2):
+            res.run()
+        t = [res.run() for _ in range(3)]
+        dev, fwd = sum(x[0] for x in t) / 3, sum(x[1] for x in t) / 3
+        launches = res.launches
+        res.free()
+        out = FlatResult(b)
+        for _ in range(2):                                   # the first calls size the pinned / device arenas of every worker
+            eng.run_flat(b, out=out)
+        s0 = eng.stats()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            eng.run_flat(b, out=out)
+        e2e = (time.perf_counter() - t0) / 3
+        s1 = eng.stats()
+        row = {"workload": key, "what": what, "regions": b.n_regions, "gcells": round(cells / 1e9, 2), "pairs": b.pairs(),
+               "device_ms": round(dev, 3), "fwd_ms": round(fwd, 3), "device_gcups": round(cells / dev / 1e6, 1),
+               "e2e_ms": round(e2e * 1e3, 3), "e2e_gcups": round(cells / e2e / 1e9, 1), "e2e_over_device": round(dev * 1e-3 / e2e, 3),
+               "fwd_frac": round(cells * FP32_INSTR_PER_CELL / (fwd * 1e-3) / (prop_sms * 128 * sm_max_mhz * 1e6), 4),
+               "fp64_pairs": int((s1["fp64_pairs"] - s0["fp64_pairs"]) // 3), "slow_pairs": int((s1["slow_pairs"] - s0["slow_pairs"]) // 3),
+               "launches_per_step": int(launches), "batches_per_e2e_step": int((s1["batches"] - s0["batches"]) // 3)}
+        if parity:
+            from oracle import check
+            chk = check.sample_parity(b, out, n_sample=48 if key.startswith("cfg5") else 4)
+            row["parity_sample_ok"] = chk["ok"]
+            row["parity_sample"] = f"{chk['regions_checked']} regions byte-compared with the {chk['against']} CPU path, {chk['regions_differing']} differ"
+        rows.append(row)
+    return rows
+
+
+def sustained_leg(resident, seconds, gpu_index, cells):
+    """The device step back to back for `seconds` of wall time, with its own clock record: evidence for a seconds-long run
+    (the K timed steps of the headline last about half a second)."""
+    if seconds <= 0:
+        return None
+    sampler = ClockSampler(gpu_index)
+    t0 = time.perf_counter()
+    ms = []
+    while time.perf_counter() - t0 < seconds:
+        ms.append(resident.run()[0])
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    half = ms[len(ms) // 2:]
+    return {"seconds": round(wall, 2), "steps": len(ms), "gcups": round(cells * len(ms) / (sum(ms) * 1e-3) / 1e9, 1),
+            "gcups_second_half": round(cells * len(half) / (sum(half) * 1e-3) / 1e9, 1),
+            "ms_per_step_min_max": [round(min(ms), 3), round(max(ms), 3)], "device_busy_fraction_of_wall": round(sum(ms) * 1e-3 / wall, 3), "clocks": clocks}
+
+
 def reference_arm(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path on this box's host cores (rank 0 only)."""
     if rank != 0:
@@ -164,8 +263,7 @@ def reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": round(gcups, 3), "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(t * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "regions_per_step": n_regions, "regions_per_gpu": args.regions,
-                   "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18},
+        "config": cfg2_config(args.regions, None, None, args.gpus) | {"sample_of": f"{n_regions} of the {args.regions} regions per step"},
         "cpu_baseline": {"value": round(gcups, 3), "unit": "GCUPS", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(gcups, 3), "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -215,6 +313,9 @@ def ours_arm(args, rank, world, local_rank):
     total_cells = sharding.sum_over_ranks(float(cells))
     value = total_cells / (ms_step * 1e-3) / 1e9
     check = resident.download()
+    fp64_step = int(check.n_fp64)
+    sustained = sustained_leg(resident, args.sustain, visible_gpu_index(local_rank), cells) if rank == 0 else None
+    sharding.barrier()
     resident.free()
 
     # ---- leg 2: end to end through the host-buffer call ------------------------------------------
@@ -234,8 +335,17 @@ def ours_arm(args, rank, world, local_rank):
     same = bool(np.array_equal(out.likelihoods.view(np.uint64), check.likelihoods.view(np.uint64)))
     clocks = sampler.stop() if sampler else None
 
+    # ---- ONE common stream sharded over the ranks, digests compared with a single-GPU run (BASELINE.json configs[4]) ----
+    shard_rec = None
+    if args.stream_regions > 0:
+        from rovaca_b200 import streams
+        shard_rec = streams.sharded_stream(eng, streams.StreamSpec("cfg5", args.stream_regions, 5, 0.5), rank, world)
+
     if rank != 0:
         eng.close()
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
         return
     # ---- roofline of the dominant kernel (forward wavefront) -------------------------------------
     prop = torch.cuda.get_device_properties(local_rank)
@@ -281,16 +391,16 @@ def ours_arm(args, rank, world, local_rank):
         kind, times, isa = cpu_reference_run(sample_batch, cores, 1, 0)
         cpu = {"value": round(sample_batch.cells() / times[0] / 1e9, 3), "unit": "GCUPS", "cores": cores, "kind": kind,
                "sample": f"first {n_cpu} of {args.regions} regions ({sample_batch.cells() / 1e9:.1f} G cells), {isa}, {times[0]:.2f} s wall"}
+    # ---- the other BASELINE configs (N = 1 only; the scaling runs time the headline and the sharded stream) ----
+    work_rows = None
+    if world == 1 and not args.no_workloads:
+        work_rows = run_workloads(eng, n_sm, sm_max, args.quick, parity=not args.no_cpu_baseline)
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "GCUPS", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms_step, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD,
-                   "regions_per_gpu": args.regions, "cells_per_gpu_per_step": cells, "pairs_per_gpu_per_step": batch.pairs(),
-                   "pcr_indel_model": "CONSERVATIVE", "base_quality_score_threshold": 18, "fma_mode": "avx512-contracted",
-                   "l2_policy": "inputs larger than L2: ~270 MB touched per step (raw reads, packed rows, outputs) vs 126 MB L2",
-                   "parallelism": f"regions sharded over {world} GPU(s), no collective"},
+        "config": cfg2_config(args.regions, cells, batch.pairs(), world),
         "e2e": {"value": round(e2e, 2), "unit": "GCUPS", "h2d_bytes_per_step": int((st3["h2d_bytes"] - st2["h2d_bytes"]) / K),
                 "d2h_bytes_per_step": int((st3["d2h_bytes"] - st2["d2h_bytes"]) / K), "ms_per_step": round(e2e_s * 1e3, 3),
                 "api": "phmm_run_flat (pinned host buffers in, host likelihood matrices out)", "matches_resident_run": same,
@@ -302,8 +412,11 @@ def ours_arm(args, rank, world, local_rank):
         "cpu_baseline": cpu,
         "clocks": clocks,
         "device_step_wall_ms": round(wall_dev * 1e3, 3),
-        "fp64_pairs_per_step": int((st1["fp64_pairs"] - st0["fp64_pairs"])),
+        "fp64_pairs_per_step": fp64_step,
         "gpu": prop.name,
+        "sustained": sustained,
+        "workloads": work_rows,
+        "sharded_stream": shard_rec,
     }
     print(json.dumps(line), flush=True)
     eng.close()
@@ -319,7 +432,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--regions", type=int, default=4096, help="cfg2 regions per GPU per step")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU reference legs (baseline and parity samples)")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the cfg3 / cfg4 / cfg5 table")
+    ap.add_argument("--quick", action="store_true", help="quarter-size workloads table")
+    ap.add_argument("--sustain", type=float, default=3.0, help="seconds of back-to-back device steps for the sustained record (0 = off)")
+    ap.add_argument("--stream-regions", type=int, default=131072, help="regions of the common cfg5 stream sharded over the ranks (0 = off)")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

@@ -240,6 +240,9 @@ class Ref:
         L.ref_region.restype = C.c_int
         L.ref_region.argtypes = [C.c_int, C.c_uint32, _u8p, _u8p, _u64p, _u32p, _u8p, C.c_uint32, _u8p, _u64p, _u32p, C.c_int32,
                                  C.c_int, _f64p, _u32p, _u32p]
+        L.ref_regions_flat.restype = C.c_int
+        L.ref_regions_flat.argtypes = [C.c_int, C.c_int, C.c_uint32, _u64p, _u64p, _u8p, _u8p, _u64p, _u32p, _u8p, _u8p, _u64p,
+                                       _u32p, C.c_int32, C.c_int, _u64p, _f64p, _u32p, _u32p]
         L.ref_bench_regions.restype = C.c_double
         L.ref_bench_regions.argtypes = [C.c_int, C.c_int, C.c_uint32, _u64p, _u64p, _u8p, _u8p, _u64p, _u32p, _u8p, _u8p, _u64p,
                                         _u32p, C.c_int32, C.c_int, _f64p]
@@ -370,6 +373,22 @@ class Ref:
             raise RuntimeError("ref_region failed rc=%d" % rc)
         return out, kept[: n_kept.value].copy()
 
+    def regions_flat(self, batch, n_threads: int, thr: int = 18, model: int = PCR_CONSERVATIVE, path: int = -1):
+        """Every region of a RegionBatch through the reference's call_pairhmm on n_threads threads ->
+        (likelihoods flat at batch.lik_off(), kept_idx flat at reg_read_off, n_kept per region)."""
+        lik_off = batch.lik_off()
+        lik = np.empty(max(int(lik_off[-1]), 1), np.float64)
+        kept = np.zeros(max(batch.n_reads, 1), np.uint32)
+        n_kept = np.zeros(max(batch.n_regions, 1), np.uint32)
+        rc = self.lib.ref_regions_flat(path, n_threads, batch.n_regions, _p(batch.reg_read_off, _u64p), _p(batch.reg_hap_off, _u64p),
+                                       _p(batch.read_bases, _u8p), _p(batch.read_qual, _u8p), _p(batch.read_off, _u64p),
+                                       _p(batch.read_len, _u32p), _p(batch.read_mapq, _u8p), _p(batch.hap_bases, _u8p),
+                                       _p(batch.hap_off, _u64p), _p(batch.hap_len, _u32p), thr, model, _p(lik_off, _u64p),
+                                       _p(lik, _f64p), _p(kept, _u32p), _p(n_kept, _u32p))
+        if rc != 0:
+            raise RuntimeError("ref_regions_flat failed rc=%d" % rc)
+        return lik, kept, n_kept
+
     def bench_regions(self, batch, n_threads: int, thr: int = 18, model: int = PCR_CONSERVATIVE, path: int = -1):
         """batch: a rovaca_b200.workloads.RegionBatch (flat arrays).  Returns (seconds, checksum)."""
         chk = C.c_double(0.0)
@@ -387,16 +406,42 @@ class Adapter:
     """rovaca_b200/adapter/call_pairhmm_b200.cpp (the drop-in with the reference's signature) driven through the reference's
     own ReadRecord / Haplotype / RovacaMemoryPool objects (oracle/_ref/libphmm_adapter_test.so).  Needs a B200 to run."""
 
-    EXPORTS = ["adapter_init", "adapter_shutdown", "adapter_region", "adapter_last_error"]
+    EXPORTS = ["adapter_init", "adapter_init_devices", "adapter_shutdown", "adapter_region", "adapter_window", "adapter_last_error"]
 
     def __init__(self, path: str):
         L = self.lib = C.CDLL(path)
         L.adapter_last_error.restype = C.c_char_p
         L.adapter_init.restype, L.adapter_init.argtypes = C.c_int, [C.c_int]
+        L.adapter_init_devices.restype, L.adapter_init_devices.argtypes = C.c_int, [C.POINTER(C.c_int), C.c_int]
+        L.adapter_window.restype = C.c_int
+        L.adapter_window.argtypes = [C.c_uint32, _u64p, _u64p, _u8p, _u8p, _u64p, _u32p, _u8p, _u8p, _u64p, _u32p, C.c_int32, C.c_int,
+                                     _u64p, _f64p, _u32p, _u32p]
         L.adapter_shutdown.restype = None
         L.adapter_region.restype = C.c_int
         L.adapter_region.argtypes = [C.c_uint32, _u8p, _u8p, _u64p, _u32p, _u8p, C.c_uint32, _u8p, _u64p, _u32p, C.c_int32, C.c_int,
                                      _f64p, _u32p, _u32p]
+
+    def init_devices(self, devices: Sequence[int]):
+        arr = (C.c_int * max(len(devices), 1))(*devices)
+        rc = self.lib.adapter_init_devices(arr, len(devices))
+        if rc != 0:
+            raise RuntimeError("init_pairhmm_ptr_b200_devices failed (%d): %s" % (rc, self.lib.adapter_last_error().decode()))
+
+    def window(self, batch, thr: int = 18, model: int = PCR_CONSERVATIVE):
+        """Every region of a RegionBatch through call_pairhmm_b200_window (submit all, collect in order) ->
+        (likelihoods flat at batch.lik_off(), kept_idx flat at reg_read_off, n_kept per region)."""
+        lik_off = batch.lik_off()
+        lik = np.empty(max(int(lik_off[-1]), 1), np.float64)
+        kept = np.zeros(max(batch.n_reads, 1), np.uint32)
+        n_kept = np.zeros(max(batch.n_regions, 1), np.uint32)
+        rc = self.lib.adapter_window(batch.n_regions, _p(batch.reg_read_off, _u64p), _p(batch.reg_hap_off, _u64p),
+                                     _p(batch.read_bases, _u8p), _p(batch.read_qual, _u8p), _p(batch.read_off, _u64p),
+                                     _p(batch.read_len, _u32p), _p(batch.read_mapq, _u8p), _p(batch.hap_bases, _u8p),
+                                     _p(batch.hap_off, _u64p), _p(batch.hap_len, _u32p), thr, model, _p(lik_off, _u64p),
+                                     _p(lik, _f64p), _p(kept, _u32p), _p(n_kept, _u32p))
+        if rc != 0:
+            raise RuntimeError("adapter_window failed (%d): %s" % (rc, self.lib.adapter_last_error().decode()))
+        return lik, kept, n_kept
 
     def init(self, device: int = -1):
         rc = self.lib.adapter_init(device)

@@ -235,8 +235,8 @@ int ref_region(int path, uint32_t n_reads, const uint8_t* rbase, const uint8_t* 
     if (path == 1 && !g_avx512) return -2;
     CsrGuard g;
 
-    std::vector<uint8_t> buffer((size_t)64 << 20);
-    rovaca::RovacaMemoryPool pool{buffer.data(), buffer.size()};
+    static thread_local std::unique_ptr<uint8_t[]> buffer(new uint8_t[(size_t)64 << 20]);   /* not zeroed, reused per thread */
+    rovaca::RovacaMemoryPool pool{buffer.get(), (size_t)64 << 20};
     std::vector<FakeBam> bams(n_reads);
     rovaca::ReadVector rs{&pool};
     std::unordered_map<rovaca::pReadRecord, uint32_t> index_of;
@@ -344,6 +344,46 @@ double ref_bench_regions(int path, int n_threads, uint32_t n_regions, const uint
         *checksum = s;
     }
     return std::chrono::duration<double>(w1 - w0).count();
+}
+
+/*
+ * Many regions (same flat layout) through the reference's call_pairhmm on n_threads threads, results kept: region g's
+ * [n_haps][n_reads] matrix at out + lik_off[g], the original indices of the reads left in `rs` at kept_idx + reg_read_off[g],
+ * their count in n_kept[g].  For sampled parity checks of big streams.  Reads of a region must come in ascending length
+ * when the new path is taken (the caller's sort, haplotypecaller_engine.cpp:245-248, is the input's business here, so that
+ * column order is defined).  Returns 0, or <0 on a contract violation.
+ */
+int ref_regions_flat(int path, int n_threads, uint32_t n_regions, const uint64_t* reg_read_off, const uint64_t* reg_hap_off,
+                     const uint8_t* rbase, const uint8_t* rqual, const uint64_t* roff, const uint32_t* rlen, const uint8_t* rmapq,
+                     const uint8_t* hbase, const uint64_t* hoff, const uint32_t* hlen, int32_t min_quality_threshold, int pcr_model,
+                     const uint64_t* lik_off, double* out, uint32_t* kept_idx, uint32_t* n_kept)
+{
+    bind_kernels();
+    if (path < 0) path = g_avx512 ? 1 : 0;
+    if (path == 1 && !g_avx512) return -2;
+    if (n_threads < 1) n_threads = 1;
+    std::atomic<uint32_t> next{0};
+    std::atomic<int> rc_all{0};
+    auto worker = [&]() {
+        for (;;) {
+            const uint32_t reg = next.fetch_add(1);
+            if (reg >= n_regions) break;
+            const uint64_t r0 = reg_read_off[reg], h0 = reg_hap_off[reg];
+            const uint32_t nr = (uint32_t)(reg_read_off[reg + 1] - r0), nh = (uint32_t)(reg_hap_off[reg + 1] - h0);
+            if (nr == 0 || nh == 0) {
+                n_kept[reg] = 0;
+                continue;
+            }
+            /* ref_region takes offsets relative to the blobs it is handed: pass the whole blobs and this region's slices */
+            const int rc = ref_region(path, nr, rbase, rqual, roff + r0, rlen + r0, rmapq + r0, nh, hbase, hoff + h0, hlen + h0,
+                                      min_quality_threshold, pcr_model, out + lik_off[reg], kept_idx + r0, n_kept + reg);
+            if (rc != 0) rc_all.store(rc);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; ++t) th.emplace_back(worker);
+    for (auto& x : th) x.join();
+    return rc_all.load();
 }
 
 }  // extern "C"

@@ -9,6 +9,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 #include <xmmintrin.h>
 
 #include "common/utils/rovaca_memory_pool.h"
@@ -60,15 +61,53 @@ void dump_region(const phmm_region& region)
 }
 }  // namespace
 
+// ROVACA_B200_DEVICES=all | 0,1,2,...: which GPUs the one engine of this process drives
+static bool devices_from_env(std::vector<int32_t>& out, bool& all)
+{
+    const char* env = std::getenv("ROVACA_B200_DEVICES");
+    if (!env || !*env) return false;
+    all = std::strcmp(env, "all") == 0;
+    if (all) return true;
+    for (const char* p = env; *p;) {
+        char* end = nullptr;
+        const long v = std::strtol(p, &end, 10);
+        if (end == p) break;
+        out.push_back((int32_t)v);
+        p = *end == ',' ? end + 1 : end;
+    }
+    return !out.empty();
+}
+
+static void create_engine(const int32_t* devices, uint32_t n)
+{
+    phmm_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    if (phmm_create_multi(&cfg, devices, n, &g_engine) != PHMM_OK)
+        throw std::runtime_error(std::string("init_pairhmm_ptr_b200: ") + phmm_last_error());
+}
+
 void init_pairhmm_ptr_b200(int device)
 {
     std::lock_guard<std::mutex> lk(g_engine_mutex);
     if (!g_engine) {
-        phmm_config cfg;
-        std::memset(&cfg, 0, sizeof(cfg));
-        cfg.device = device;
-        if (phmm_create(&cfg, &g_engine) != PHMM_OK)
-            throw std::runtime_error(std::string("init_pairhmm_ptr_b200: ") + phmm_last_error());
+        std::vector<int32_t> ords;
+        bool all = false;
+        if (devices_from_env(ords, all)) {
+            create_engine(all ? nullptr : ords.data(), all ? 0u : (uint32_t)ords.size());
+        } else {
+            const int32_t d = device;
+            create_engine(&d, 1);
+        }
+    }
+    call_pairhmm = call_pairhmm_b200;
+}
+
+void init_pairhmm_ptr_b200_devices(const int* devices, int n_devices)
+{
+    std::lock_guard<std::mutex> lk(g_engine_mutex);
+    if (!g_engine) {
+        std::vector<int32_t> ords(devices, devices + (n_devices > 0 ? n_devices : 0));
+        create_engine(ords.empty() ? nullptr : ords.data(), (uint32_t)ords.size());
     }
     call_pairhmm = call_pairhmm_b200;
 }
@@ -80,25 +119,35 @@ void shutdown_pairhmm_b200()
     g_engine = nullptr;
 }
 
-DoubleVector2D call_pairhmm_b200(const HaplotypeVector& hs, ReadVector& rs, int32_t min_quality_threshold, PcrIndelModel pcr_option,
-                                 pMemoryPool pool)
+// One call in flight: everything lives in the region's pool.
+struct PairhmmCallB200
 {
-    if (hs.empty() || rs.empty()) return {};                           // pairhmm_internal.cpp:508-510
+    uint64_t ticket;
+    phmm_result result;
+    size_t n_reads, n_haps;
+    double* flat;
+    uint32_t* kept;
+    pMemoryPool pool;
+};
+
+// The reference's objects -> the C ABI's plain views (staged in `pool`), and the submit.
+static PairhmmCallB200* submit_region(const HaplotypeVector& hs, const ReadVector& rs, int32_t min_quality_threshold,
+                                      PcrIndelModel pcr_option, pMemoryPool pool)
+{
     if (!g_engine) throw std::runtime_error("call_pairhmm_b200: init_pairhmm_ptr_b200 has not been called");
-    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);                        // init_native, :21-25: stays set on the caller thread
-
     const size_t n_reads = rs.size(), n_haps = hs.size();
-    DoubleVector2D final_likelihood{n_haps, DoubleVector{n_reads, NAN, pool}, pool};   // :516, allocated before the guard
-    auto* lp = static_cast<RovacaMemoryPool*>(pool);
-    MemoryPoolGuard scratch_guard{lp};                                  // :517-518: everything below is rewound on return
-
     size_t read_bytes = 0;
     for (pReadRecord r : rs) read_bytes += (size_t)r->seq_length();
+    auto* call = static_cast<PairhmmCallB200*>(pool->allocate(sizeof(PairhmmCallB200), alignof(PairhmmCallB200)));
     auto* reads = static_cast<phmm_read*>(pool->allocate(sizeof(phmm_read) * n_reads, alignof(phmm_read)));
     auto* haps = static_cast<phmm_hap*>(pool->allocate(sizeof(phmm_hap) * n_haps, alignof(phmm_hap)));
     auto* bases = static_cast<uint8_t*>(pool->allocate(read_bytes + 1, 8));
-    auto* flat = static_cast<double*>(pool->allocate(sizeof(double) * n_reads * n_haps, alignof(double)));
-    auto* kept = static_cast<uint32_t*>(pool->allocate(sizeof(uint32_t) * n_reads, alignof(uint32_t)));
+    auto* region = static_cast<phmm_region*>(pool->allocate(sizeof(phmm_region), alignof(phmm_region)));
+    call->flat = static_cast<double*>(pool->allocate(sizeof(double) * n_reads * n_haps, alignof(double)));
+    call->kept = static_cast<uint32_t*>(pool->allocate(sizeof(uint32_t) * n_reads, alignof(uint32_t)));
+    call->n_reads = n_reads;
+    call->n_haps = n_haps;
+    call->pool = pool;
 
     size_t at = 0;
     for (size_t i = 0; i < n_reads; ++i) {
@@ -118,34 +167,77 @@ DoubleVector2D call_pairhmm_b200(const HaplotypeVector& hs, ReadVector& rs, int3
         pBases b = hs[j]->get_display_string();                        // genotype/allele.h:104
         haps[j].bases = b->data;
         haps[j].len = b->num;
+        haps[j].priority = 0.0;
     }
-
-    phmm_region region;
-    region.reads = reads;
-    region.n_reads = (uint32_t)n_reads;
-    region.haps = haps;
-    region.n_haps = (uint32_t)n_haps;
-    region.min_quality_threshold = min_quality_threshold;
-    region.pcr_model = static_cast<int32_t>(pcr_option);               // common/enum.h:8, same numeric values
-    dump_region(region);
-    phmm_result result;
-    std::memset(&result, 0, sizeof(result));
-    result.likelihoods = flat;
-    result.kept_idx = kept;
-    if (phmm_call_region(g_engine, &region, &result) != PHMM_OK)
+    region->reads = reads;
+    region->n_reads = (uint32_t)n_reads;
+    region->haps = haps;
+    region->n_haps = (uint32_t)n_haps;
+    region->min_quality_threshold = min_quality_threshold;
+    region->pcr_model = static_cast<int32_t>(pcr_option);              // common/enum.h:8, same numeric values
+    dump_region(*region);
+    std::memset(&call->result, 0, sizeof(call->result));
+    call->result.likelihoods = call->flat;
+    call->result.kept_idx = call->kept;
+    if (phmm_submit(g_engine, region, &call->result, &call->ticket) != PHMM_OK)
         throw std::runtime_error(std::string("call_pairhmm_b200: ") + phmm_last_error());   // caught at rovaca_main.cpp:39-42
+    return call;
+}
 
-    for (size_t j = 0; j < n_haps; ++j) std::memcpy(final_likelihood[j].data(), flat + j * n_reads, sizeof(double) * n_reads);
+// Wait, then the reference's return value and its side effect on `rs`.
+static void finish_region(PairhmmCallB200* call, ReadVector& rs, DoubleVector2D& final_likelihood)
+{
+    if (phmm_wait(g_engine, call->ticket) != PHMM_OK)
+        throw std::runtime_error(std::string("call_pairhmm_b200: ") + phmm_last_error());
+    const size_t n_reads = call->n_reads, n_haps = call->n_haps;
+    for (size_t j = 0; j < n_haps; ++j) std::memcpy(final_likelihood[j].data(), call->flat + j * n_reads, sizeof(double) * n_reads);
     // filter_poorly_modelled_evidence's side effect on `rs` (:178-181): erase, back to front, every read not kept
-    size_t k = result.n_kept;
+    size_t k = call->result.n_kept;
     for (size_t i = n_reads; i-- > 0;) {
-        if (k > 0 && kept[k - 1] == i) {
+        if (k > 0 && call->kept[k - 1] == i) {
             --k;
             continue;
         }
         rs.erase(rs.begin() + (std::ptrdiff_t)i);
     }
+}
+
+DoubleVector2D call_pairhmm_b200(const HaplotypeVector& hs, ReadVector& rs, int32_t min_quality_threshold, PcrIndelModel pcr_option,
+                                 pMemoryPool pool)
+{
+    if (hs.empty() || rs.empty()) return {};                           // pairhmm_internal.cpp:508-510
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);                        // init_native, :21-25: stays set on the caller thread
+    DoubleVector2D final_likelihood{hs.size(), DoubleVector{rs.size(), NAN, pool}, pool};   // :516, allocated before the guard
+    auto* lp = static_cast<RovacaMemoryPool*>(pool);
+    MemoryPoolGuard scratch_guard{lp};                                  // :517-518: everything below is rewound on return
+    PairhmmCallB200* call = submit_region(hs, rs, min_quality_threshold, pcr_option, pool);
+    finish_region(call, rs, final_likelihood);
     return final_likelihood;
+}
+
+PairhmmCallB200* call_pairhmm_b200_submit(const HaplotypeVector& hs, const ReadVector& rs, int32_t min_quality_threshold,
+                                          PcrIndelModel pcr_option, pMemoryPool pool)
+{
+    if (hs.empty() || rs.empty()) return nullptr;                      // wait() returns the reference's empty matrix
+    return submit_region(hs, rs, min_quality_threshold, pcr_option, pool);
+}
+
+DoubleVector2D call_pairhmm_b200_wait(PairhmmCallB200* call, ReadVector& rs)
+{
+    if (!call) return {};
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+    DoubleVector2D final_likelihood{call->n_haps, DoubleVector{call->n_reads, NAN, call->pool}, call->pool};
+    finish_region(call, rs, final_likelihood);
+    return final_likelihood;
+}
+
+void call_pairhmm_b200_window(PairhmmRegionB200* regions, size_t n_regions, int32_t min_quality_threshold, PcrIndelModel pcr_option)
+{
+    std::vector<PairhmmCallB200*> calls(n_regions, nullptr);
+    for (size_t k = 0; k < n_regions; ++k)
+        calls[k] = call_pairhmm_b200_submit(*regions[k].hs, *regions[k].rs, min_quality_threshold, pcr_option, regions[k].pool);
+    if (g_engine) phmm_flush(g_engine);                                // the window is complete: do not wait for more callers
+    for (size_t k = 0; k < n_regions; ++k) regions[k].likelihoods = call_pairhmm_b200_wait(calls[k], *regions[k].rs);
 }
 
 }  // namespace rovaca

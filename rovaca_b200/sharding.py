@@ -37,6 +37,45 @@ def shard_regions(batch: RegionBatch, rank: int, world: int) -> np.ndarray:
     return np.nonzero(owner == rank)[0]
 
 
+def shard_blocks(block_cells: np.ndarray, rank: int, world: int) -> np.ndarray:
+    """The same longest-processing-time-first assignment over BLOCKS of consecutive regions of a stream (``block_cells[b]`` =
+    cells of block b): a rank generates and runs whole blocks, so a stream of a million regions is never held or shipped in
+    one piece.  Returns the ascending block indices rank ``rank`` owns; deterministic, identical on every rank."""
+    n = len(block_cells)
+    if world <= 1:
+        return np.arange(n)
+    order = np.argsort(-np.asarray(block_cells, np.int64), kind="stable")
+    load = np.zeros(world, np.int64)
+    owner = np.zeros(n, np.int64)
+    for b in order:
+        r = int(np.argmin(load))
+        owner[b] = r
+        load[r] += int(block_cells[b])
+    return np.nonzero(owner == rank)[0]
+
+
+def gather_digests(region_ids: np.ndarray, digests: np.ndarray, n_regions: int) -> Optional[np.ndarray]:
+    """Per-region 64-bit digests of the regions this rank ran -> on rank 0 the digest of every region of the stream (None
+    elsewhere).  Host-side gather of a few bytes per region: the only thing that travels between ranks."""
+    d = _dist()
+    if d is None:
+        out = np.zeros(n_regions, np.uint64)
+        out[region_ids] = digests
+        return out
+    parts = [None] * d.get_world_size()
+    d.all_gather_object(parts, (np.asarray(region_ids, np.int64), np.asarray(digests, np.uint64)))
+    if d.get_rank() != 0:
+        return None
+    out = np.zeros(n_regions, np.uint64)
+    seen = np.zeros(n_regions, np.int64)
+    for ids, dg in parts:
+        out[ids] = dg
+        seen[ids] += 1
+    if not np.all(seen == 1):
+        raise RuntimeError("sharded stream: a region was run by %s ranks" % ("no" if seen.min() == 0 else "several"))
+    return out
+
+
 def _dist():
     import torch.distributed as dist
     return dist if dist.is_available() and dist.is_initialized() else None

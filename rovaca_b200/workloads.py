@@ -303,3 +303,173 @@ def cfg5(n_regions: int = 256, seed: int = 5, post_trim_fraction: float = 0.5) -
         else:
             regs.append(_one_region(rng, n_reads, n_haps, 201, 499, 60, 151, junk=0.02))
     return RegionBatch.from_regions(regs, name=f"cfg5 region stream x {n_regions}")
+
+
+# ---- big streams: the C generator (csrc/workgen.cpp -> libphmm_workgen.so) -----------------------------------------------
+import ctypes as _C
+import os as _os
+
+
+class _WgSpec(_C.Structure):
+    _fields_ = [("seed", _C.c_uint64), ("hap_lambda", _C.c_double), ("hap_min", _C.c_uint32), ("hap_max", _C.c_uint32),
+                ("read_lambda", _C.c_double), ("read_fixed", _C.c_uint32), ("hap_lo", _C.c_uint32), ("hap_hi", _C.c_uint32),
+                ("read_lo", _C.c_uint32), ("read_hi", _C.c_uint32), ("post_trim", _C.c_double), ("pt_hap_lo", _C.c_uint32),
+                ("pt_hap_hi", _C.c_uint32), ("pt_read_lo", _C.c_uint32), ("pt_read_hi", _C.c_uint32), ("junk", _C.c_double),
+                ("indel", _C.c_double), ("sub_rate", _C.c_double)]
+
+
+# name -> (hap_lambda, hap_min, hap_max, read_lambda, read_fixed, hap_lo, hap_hi, read_lo, read_hi, junk, indel): SURVEY.md §8d
+STREAM_KINDS = {
+    "cfg2": (0.0, 8, 8, 0.0, 64, 300, 300, 150, 150, 0.0, 0.0),
+    "cfg3": (0.0, 32, 32, 0.0, 500, 250, 450, 100, 151, 0.05, 0.3),
+    "cfg4": (0.0, 16, 16, 0.0, 64, 1000, 1000, 250, 250, 0.0, 0.0),
+    "cfg5": (7.8, 2, 24, 41.0, 0, 201, 499, 60, 151, 0.02, 0.3),
+}
+
+_wg = None
+
+
+def _workgen():
+    global _wg
+    if _wg is None:
+        path = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libphmm_workgen.so")
+        if not _os.path.exists(path):
+            raise RuntimeError(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)")
+        L = _C.CDLL(path)
+        vp, u32, u64 = _C.c_void_p, _C.c_uint32, _C.c_uint64
+        L.wg_counts.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, u32]
+        L.wg_lengths.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, vp, vp, u32]
+        L.wg_fill.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, u32]
+        L.wg_digest_regions.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, u32]
+        L.wg_region_cells.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, u32]
+        for f in (L.wg_counts, L.wg_lengths, L.wg_fill, L.wg_digest_regions, L.wg_region_cells):
+            f.restype = None
+        _wg = L
+    return _wg
+
+
+def _threads(threads: Optional[int]) -> int:
+    if threads:
+        return int(threads)
+    try:
+        return max(1, len(_os.sched_getaffinity(0)))
+    except AttributeError:
+        return _os.cpu_count() or 1
+
+
+def _spec(kind: str, seed: int, post_trim_fraction: float) -> _WgSpec:
+    k = STREAM_KINDS[kind]
+    return _WgSpec(seed, k[0], k[1], k[2], k[3], k[4], k[5], k[6], k[7], k[8], post_trim_fraction, 41, 120, 10, 100, k[9], k[10], 0.01)
+
+
+def stream_cells(kind: str, n_regions: int, first: int = 0, seed: int = 5, post_trim_fraction: float = 0.0,
+                 threads: Optional[int] = None) -> np.ndarray:
+    """Cells of every region of [first, first + n_regions) of the stream, without generating it (for sharding plans)."""
+    sp = _spec(kind, seed, post_trim_fraction)
+    out = np.zeros(max(int(n_regions), 1), np.uint64)
+    _workgen().wg_region_cells(_C.byref(sp), first, int(n_regions), out.ctypes.data, _threads(threads))
+    return out[: int(n_regions)]
+
+
+def stream(kind: str, n_regions: int, first: int = 0, seed: int = 5, post_trim_fraction: float = 0.0, pinned: bool = False,
+           threads: Optional[int] = None) -> RegionBatch:
+    """Regions [first, first + n_regions) of the synthetic stream ``kind`` (STREAM_KINDS).  Region g is a pure function of
+    (kind, seed, post_trim_fraction, g): slices generated by different processes concatenate to the one stream, so N ranks
+    can shard a common stream without shipping it.  ``pinned``: the byte blobs are allocated page-locked (torch) and filled
+    in place."""
+    sp = _spec(kind, seed, post_trim_fraction)
+    L, n, th = _workgen(), int(n_regions), _threads(threads)
+    n_reads, n_haps = np.zeros(max(n, 1), np.uint32), np.zeros(max(n, 1), np.uint32)
+    L.wg_counts(_C.byref(sp), first, n, n_reads.ctypes.data, n_haps.ctypes.data, th)
+    rro, rho = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    np.cumsum(n_reads[:n], out=rro[1:])
+    np.cumsum(n_haps[:n], out=rho[1:])
+    read_len, hap_len = np.zeros(max(int(rro[-1]), 1), np.uint32), np.zeros(max(int(rho[-1]), 1), np.uint32)
+    L.wg_lengths(_C.byref(sp), first, n, rro.ctypes.data, rho.ctypes.data, read_len.ctypes.data, hap_len.ctypes.data, th)
+    read_len, hap_len = read_len[: int(rro[-1])], hap_len[: int(rho[-1])]
+    read_off, hap_off = _excl_cumsum(read_len), _excl_cumsum(hap_len)
+    rb_n, hb_n = int(read_len.sum(dtype=np.uint64)) + 16, int(hap_len.sum(dtype=np.uint64)) + 16
+    keep = []
+
+    def blob(nbytes):
+        if pinned:
+            import torch
+            t = torch.zeros(nbytes, dtype=torch.uint8).pin_memory()
+            keep.append(t)
+            return t.numpy()
+        return np.zeros(nbytes, np.uint8)
+
+    read_bases, read_qual, hap_bases = blob(rb_n), blob(rb_n), blob(hb_n)
+    read_mapq = np.zeros(max(len(read_len), 1), np.uint8)
+    L.wg_fill(_C.byref(sp), first, n, rro.ctypes.data, rho.ctypes.data, read_off.ctypes.data, hap_off.ctypes.data,
+              read_bases.ctypes.data, read_qual.ctypes.data, read_mapq.ctypes.data, hap_bases.ctypes.data, th)
+    b = RegionBatch(reg_read_off=rro, reg_hap_off=rho, read_len=read_len, read_mapq=read_mapq[: len(read_len)], read_off=read_off,
+                    read_bases=read_bases, read_qual=read_qual, hap_len=hap_len, hap_off=hap_off, hap_bases=hap_bases,
+                    name=f"{kind} stream, regions {first}..{first + n} (seed {seed}, post-trim {post_trim_fraction:g})", pinned=pinned)
+    b._pinned_tensors = keep
+    return b
+
+
+def region_digests(result, threads: Optional[int] = None) -> np.ndarray:
+    """One 64-bit digest per region of a FlatResult (matrix bytes incl. the NaN tail, kept indices, kept count): what ranks
+    and runs exchange to prove their results identical without shipping the matrices."""
+    b = result.batch
+    out = np.zeros(max(b.n_regions, 1), np.uint64)
+    _workgen().wg_digest_regions(b.n_regions, b.reg_read_off.ctypes.data, b.reg_hap_off.ctypes.data, result.lik_off.ctypes.data,
+                                 result.likelihoods.ctypes.data, result.kept_idx.ctypes.data, result.n_kept.ctypes.data,
+                                 out.ctypes.data, _threads(threads))
+    return out[: b.n_regions]
+
+
+def concat(batches: Sequence[RegionBatch], name: str = "") -> RegionBatch:
+    """Regions of several batches, in order, as one batch (default gap qualities only)."""
+    rro, rho, ro, ho = [np.zeros(1, np.uint64)], [np.zeros(1, np.uint64)], [], []
+    r_at = h_at = rb_at = hb_at = 0
+    for b in batches:
+        rro.append(b.reg_read_off[1:] + np.uint64(r_at))
+        rho.append(b.reg_hap_off[1:] + np.uint64(h_at))
+        ro.append(b.read_off + np.uint64(rb_at))
+        ho.append(b.hap_off + np.uint64(hb_at))
+        r_at += b.n_reads
+        h_at += b.n_haps
+        rb_at += int(b.read_len.sum(dtype=np.uint64))
+        hb_at += int(b.hap_len.sum(dtype=np.uint64))
+    pad = np.zeros(16, np.uint8)
+    cut = lambda a, lens: a[: int(lens.sum(dtype=np.uint64))]
+    return RegionBatch(
+        reg_read_off=np.concatenate(rro), reg_hap_off=np.concatenate(rho), read_len=np.concatenate([b.read_len for b in batches]),
+        read_mapq=np.concatenate([b.read_mapq for b in batches]), read_off=np.concatenate(ro),
+        read_bases=np.concatenate([cut(b.read_bases, b.read_len) for b in batches] + [pad]),
+        read_qual=np.concatenate([cut(b.read_qual, b.read_len) for b in batches] + [pad]),
+        hap_len=np.concatenate([b.hap_len for b in batches]), hap_off=np.concatenate(ho),
+        hap_bases=np.concatenate([cut(b.hap_bases, b.hap_len) for b in batches] + [pad]), name=name)
+
+
+def take(batch: RegionBatch, regions) -> RegionBatch:
+    """The given regions of ``batch`` as a batch of their own, vectorised (``RegionBatch.subset`` goes through Python objects
+    per read; this one is for shards of big streams).  Default gap qualities only."""
+    regions = np.asarray(regions, np.int64)
+    nr = (batch.reg_read_off[regions + 1] - batch.reg_read_off[regions]).astype(np.int64)
+    nh = (batch.reg_hap_off[regions + 1] - batch.reg_hap_off[regions]).astype(np.int64)
+
+    def expand(starts, counts):                       # indices starts[i] .. starts[i] + counts[i], concatenated
+        total = int(counts.sum())
+        if total == 0:
+            return np.zeros(0, np.int64)
+        ends = np.cumsum(counts)
+        idx = np.arange(total, dtype=np.int64) - np.repeat(ends - counts, counts)
+        return idx + np.repeat(starts, counts)
+
+    ri = expand(batch.reg_read_off[regions].astype(np.int64), nr)
+    hi = expand(batch.reg_hap_off[regions].astype(np.int64), nh)
+    read_len, hap_len = batch.read_len[ri], batch.hap_len[hi]
+    rbi = expand(batch.read_off[ri].astype(np.int64), read_len.astype(np.int64))
+    hbi = expand(batch.hap_off[hi].astype(np.int64), hap_len.astype(np.int64))
+    pad = np.zeros(16, np.uint8)
+    rro, rho = np.zeros(len(regions) + 1, np.uint64), np.zeros(len(regions) + 1, np.uint64)
+    np.cumsum(nr, out=rro[1:])
+    np.cumsum(nh, out=rho[1:])
+    return RegionBatch(reg_read_off=rro, reg_hap_off=rho, read_len=read_len, read_mapq=batch.read_mapq[ri], read_off=_excl_cumsum(read_len),
+                       read_bases=np.concatenate([batch.read_bases[rbi], pad]), read_qual=np.concatenate([batch.read_qual[rbi], pad]),
+                       hap_len=hap_len, hap_off=_excl_cumsum(hap_len), hap_bases=np.concatenate([batch.hap_bases[hbi], pad]),
+                       name=batch.name + f" [{len(regions)} regions]")

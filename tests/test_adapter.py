@@ -64,3 +64,24 @@ def test_adapter_equals_reference_call_pairhmm(adapter, ref):
     m, k = adapter.region([], [b"ACGT"])
     assert len(k) == 0
     adapter.shutdown()
+
+
+@pytest.mark.gpu
+def test_adapter_window_and_devices(adapter, ref):
+    """The asynchronous use of the boundary (call_pairhmm_b200_window: submit a window of regions, collect them in order) on an
+    engine that drives several devices (init_pairhmm_ptr_b200_devices; two queues on the one GPU of a single-GPU box): the
+    same bytes and the same surviving reads as the reference's own call_pairhmm, region by region."""
+    import torch
+    n = torch.cuda.device_count()
+    adapter.shutdown()
+    adapter.init_devices(list(range(n)) if n >= 2 else [0, 0])
+    b = wl.stream("cfg5", 96, seed=17, post_trim_fraction=0.5)
+    lik, kept, nk = adapter.window(b)
+    lik0, kept0, nk0 = ref.regions_flat(b, 8)
+    assert np.array_equal(nk, nk0) and np.array_equal(kept, kept0)
+    assert np.array_equal(lik.view(np.uint64), lik0.view(np.uint64))
+    reads, haps = b.region(3)                                     # the synchronous form still works on the same engine
+    m0, k0 = ref.region(reads, haps, 18, ob.PCR_CONSERVATIVE)
+    m1, k1 = adapter.region(reads, haps, 18, ob.PCR_CONSERVATIVE)
+    assert np.array_equal(k0, k1) and np.array_equal(m0.view(np.uint64), m1.view(np.uint64))
+    adapter.shutdown()

@@ -1,11 +1,11 @@
-// Times the sections of phmm_engine::plan on the CPU (host-only slot, no GPU), cfg2-shaped synthetic regions (NOT product).
-//   nvcc -O2 -std=c++17 -x cu -Irovaca_b200/csrc -Iinclude -o build/plan_timing tools/plan_timing.cpp rovaca_b200/csrc/phmm_tables.cpp -Lrovaca_b200 -lphmm_b200 -Xlinker -rpath=$PWD/rovaca_b200
+// Times the sections of PhmmDevice::plan on the CPU (host-only slot, no GPU), cfg2- or cfg5-shaped synthetic regions (NOT product).
+//   nvcc -O2 -std=c++17 -x cu -Irovaca_b200/csrc -Iinclude -o build/plan_timing tools/plan_timing.cpp -Lrovaca_b200 -lphmm_b200 -Xlinker -rpath=$PWD/rovaca_b200
 #include <chrono>
 static double g_t[8];
 #define PT_NOW() std::chrono::steady_clock::now()
 #define PT_ADD(i, a, b) g_t[i] += std::chrono::duration<double, std::milli>(b - a).count()
 #define PHMM_PLAN_TIMING 1
-#include "../rovaca_b200/csrc/phmm_engine.cpp"
+#include "../rovaca_b200/csrc/phmm_plan.cpp"
 #include <random>
 #include <string>
 int main(int argc, char** argv)
@@ -43,7 +43,9 @@ int main(int argc, char** argv)
         for (uint32_t j = 0; j < nh[g]; ++j) { haps[hi++] = phmm_hap{hb.data() + ho, hl[g][j]}; ho += hl[g][j]; }
         po += (size_t)nr[g] * nh[g];
     }
-    phmm_engine e;
+    PhmmSettings cfg;
+    PhmmDevice e;
+    e.cfg = &cfg;
     e.busy_batches.store(16);
     Slot s;
     s.set_host_only();

@@ -192,7 +192,7 @@ struct Slot
         std::vector<PhmmCta> ctas;
         std::vector<PhmmRegionDev> regions_dev;
         std::vector<double> pri;
-        std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket;
+        std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket, rec_of, hap_boff, stream_sum, stream_of, stream_idx;
         std::vector<std::vector<Group>> groups;
         std::vector<Group> sorted;
         std::vector<std::vector<uint32_t>> group_reads, by_bin;

@@ -109,7 +109,9 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     // A warp sweeps its chunk's columns one after the other (~0.2 us per column), so the chunk length is the latency of a
     // batch and chunks x reads its parallelism.  A big batch fills the GPU with long chunks (fewest seams and staging); a
     // small one (the synchronous per-region callers) is cut finer until it has about two warps per warp slot of the device.
-    uint32_t target_cols = kTargetStreamCols;
+    static const uint32_t env_cols = std::getenv("PHMM_B200_STREAM_COLS") ? (uint32_t)std::atoi(std::getenv("PHMM_B200_STREAM_COLS")) : 0u;   // experiments only
+    const uint32_t full_cols = env_cols ? env_cols : kTargetStreamCols;
+    uint32_t target_cols = full_cols;
     int min_lanes = 8;             // lanes per read of the reference-gap kernels
     {
         uint64_t est_warps = 0;
@@ -135,7 +137,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         // kWavesWanted waves the chunks are cut shorter (a 300-column sweep costs a warp ~2 % in prologue, tools/chunk_curve.py)
         const uint64_t want_chunks = want * (kWavesWanted / 2);
         if (est_warps > 0 && est_warps < want_chunks)
-            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)kTargetStreamCols * est_warps / want_chunks);
+            target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)full_cols * est_warps / want_chunks);
     }
     Slot::PlanScratch& ps = s.ps;
     std::vector<PhmmRead>& reads = ps.reads;
@@ -198,79 +200,107 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         s.regions.push_back(rp);
         if (s.want_best)
             for (uint32_t j = 0; j < r.n_haps; ++j) ps.pri.push_back(r.haps[j].priority);
-        // haplotypes -> chunks of two balanced streams
-        for (uint32_t j = 0; j < r.n_haps; ++j) {
-            PhmmHap h{};
-            h.byte_off = (uint32_t)hap_off;
-            h.len = r.haps[j].len;
-            h.out_col = j;
-            hap_off += h.len;
-            max_cols = std::max(max_cols, h.len);
-            haps.push_back(h);
-        }
+        // haplotypes -> chunks of two balanced streams.  The region's in-envelope haplotypes are dealt, longest first onto the
+        // lightest, into 2 x n_chunks streams of about target_cols columns; streams of similar length are then paired into
+        // chunks (a chunk sweeps max(x, y) steps: what one stream has beyond the other is idle lanes).  The haplotype records
+        // are written in chunk order, so that a chunk owns a contiguous range of them; out_col keeps the caller's column.
         order.clear();
         uint64_t total = 0;
-        for (uint32_t j = 0; j < r.n_haps; ++j)
+        for (uint32_t j = 0; j < r.n_haps; ++j) {
+            max_cols = std::max(max_cols, r.haps[j].len);
             if (r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols) {
                 order.push_back(j);
                 total += r.haps[j].len;
             }
+        }
         const bool all_haps_in_stream = order.size() == r.n_haps;
         region_chunks.clear();
-        if (!order.empty()) {
-            // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty
-            const uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / 2),
-                                                                 std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols)));
-            const uint64_t per_chunk = (total + n_chunks - 1) / n_chunks;
-            size_t at = 0;
-            while (at < order.size()) {
-                // take haplotypes (in region order) until this chunk holds its share
-                size_t end = at;
-                uint64_t acc = 0;
-                while (end < order.size() && (end == at || acc + r.haps[order[end]].len <= per_chunk + target_cols / 4)) {
-                    acc += r.haps[order[end]].len;
-                    ++end;
-                    if (acc >= per_chunk) break;
-                }
-                // longest first onto the lighter stream.  A stream may not outgrow what one CTA can stage in shared memory
-                // (kMaxStreamCols): if it would (several very long haplotypes in one chunk), the chunk takes fewer of them.
-                uint32_t sum[2], cnt[2];
-                for (;;) {
-                    idx.assign(order.begin() + at, order.begin() + end);
-                    for (size_t a = 1; a < idx.size(); ++a) {              // stable insertion sort, longest first (a handful of entries)
-                        const uint32_t v = idx[a];
-                        size_t at2 = a;
-                        while (at2 > 0 && r.haps[idx[at2 - 1]].len < r.haps[v].len) {
-                            idx[at2] = idx[at2 - 1];
-                            --at2;
-                        }
-                        idx[at2] = v;
+        std::vector<uint32_t>& rec_of = ps.rec_of;                     // caller's haplotype index -> its record in haps[]
+        rec_of.assign(r.n_haps, 0u);
+        {
+            // byte offset of every haplotype in the blob (the bytes are gathered in the caller's order)
+            std::vector<uint32_t>& boff = ps.hap_boff;
+            boff.resize(r.n_haps);
+            for (uint32_t j = 0; j < r.n_haps; ++j) {
+                boff[j] = (uint32_t)hap_off;
+                hap_off += r.haps[j].len;
+            }
+            auto emit = [&](uint32_t j, uint32_t pos, uint32_t ord_stream) {
+                PhmmHap h{};
+                h.byte_off = boff[j];
+                h.len = r.haps[j].len;
+                h.out_col = j;
+                h.pos = pos;
+                h.ord_stream = ord_stream;
+                rec_of[j] = (uint32_t)haps.size();
+                haps.push_back(h);
+            };
+            if (!order.empty()) {
+                for (size_t a = 1; a < order.size(); ++a) {                // stable insertion sort, longest first (a handful of entries)
+                    const uint32_t v = order[a];
+                    size_t at2 = a;
+                    while (at2 > 0 && r.haps[order[at2 - 1]].len < r.haps[v].len) {
+                        order[at2] = order[at2 - 1];
+                        --at2;
                     }
-                    sum[0] = sum[1] = cnt[0] = cnt[1] = 0;
-                    for (uint32_t j : idx) {
-                        const uint32_t e = (sum[1] < sum[0]) ? 1u : 0u;
-                        PhmmHap& h = haps[rp.hap_begin + j];
-                        h.pos = 32 + sum[e];
-                        h.ord_stream = (cnt[e] << 1) | e;
-                        sum[e] += h.len;
+                    order[at2] = v;
+                }
+                // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty
+                uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / 2),
+                                                                 std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols)));
+                std::vector<uint32_t>&ssum = ps.stream_sum, &sown = ps.stream_of, &sidx = ps.stream_idx;
+                for (;;) {
+                    const uint32_t S = 2 * n_chunks;
+                    ssum.assign(S, 0u);
+                    sown.resize(order.size());
+                    bool fits = true;
+                    for (size_t a = 0; a < order.size(); ++a) {
+                        uint32_t best = 0;
+                        for (uint32_t q = 1; q < S; ++q)
+                            if (ssum[q] < ssum[best]) best = q;
+                        sown[a] = best;
+                        ssum[best] += r.haps[order[a]].len;
+                        fits &= ssum[best] <= kMaxStreamCols;              // what one CTA can stage in shared memory
+                    }
+                    if (fits || 2 * n_chunks >= order.size()) break;
+                    ++n_chunks;                                            // several very long haplotypes: spread them further
+                }
+                const uint32_t S = 2 * n_chunks;
+                sidx.resize(S);
+                for (uint32_t q = 0; q < S; ++q) sidx[q] = q;
+                for (uint32_t a = 1; a < S; ++a) {                         // streams by length, longest first
+                    const uint32_t v = sidx[a];
+                    uint32_t at2 = a;
+                    while (at2 > 0 && ssum[sidx[at2 - 1]] < ssum[v]) {
+                        sidx[at2] = sidx[at2 - 1];
+                        --at2;
+                    }
+                    sidx[at2] = v;
+                }
+                for (uint32_t c = 0; c < n_chunks; ++c) {
+                    const uint32_t sx = sidx[2 * c], sy = sidx[2 * c + 1];
+                    if (ssum[sx] == 0) break;                              // fewer haplotypes than streams
+                    PhmmChunk ch{};
+                    ch.hap_begin = (uint32_t)haps.size();
+                    uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
+                    for (size_t a = 0; a < order.size(); ++a) {
+                        if (sown[a] != sx && sown[a] != sy) continue;
+                        const uint32_t e = sown[a] == sx ? 0u : 1u;
+                        emit(order[a], 32 + sum[e], (cnt[e] << 1) | e);
+                        sum[e] += r.haps[order[a]].len;
                         ++cnt[e];
                     }
-                    if (std::max(sum[0], sum[1]) <= kMaxStreamCols || end - at <= 1) break;
-                    --end;
-                    haps[rp.hap_begin + order[end]].pos = 0;               // back to "not placed"
+                    ch.n_haps = cnt[0] + cnt[1];
+                    ch.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
+                    ch.n_xy = cnt[0] | (cnt[1] << 16);
+                    region_chunks.push_back((uint32_t)chunks.size());
+                    chunks.push_back(ch);
                 }
-                // the device walks haps[hap_begin .. +n_haps); empty or over-long haplotypes inside that range keep pos == 0,
-                // which the kernel skips (they are served by the per-pair kernel) — so the chunk carries the two streams'
-                // own counts, not the span's
-                PhmmChunk c{};
-                c.hap_begin = rp.hap_begin + order[at];
-                c.n_haps = order[end - 1] - order[at] + 1;
-                c.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
-                c.n_xy = cnt[0] | (cnt[1] << 16);
-                region_chunks.push_back((uint32_t)chunks.size());
-                chunks.push_back(c);
-                at = end;
             }
+            // empty or over-long haplotypes: records of their own behind the chunks', served by the per-pair kernel (pos == 0)
+            if (!all_haps_in_stream)
+                for (uint32_t j = 0; j < r.n_haps; ++j)
+                    if (!(r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols)) emit(j, 0u, 0u);
         }
         // reads
         for (int b = bin_lo; b <= bin_hi; ++b) by_bin[b].clear();
@@ -302,7 +332,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 if (b < 0 || !hap_ok) {
                     PhmmPair p{};
                     p.read = rid;
-                    p.hap = rp.hap_begin + j;
+                    p.hap = rec_of[j];
                     p.out_idx = d.out_off + j;
                     slow.push_back(p);
                 }

@@ -228,10 +228,27 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* batch, phmm_flat_result
 /* AlleleLikelihoods::marginalize -> marginal_likelihoods_direct (genotype/allele_likelihoods.hpp:189-216, 702-732) on a matrix
  * phmm_call_region returned: out[n][e] = the largest values[a][e] over the old alleles a with old_to_new[a] == n, -inf when
  * there is none (old_to_new[a] < 0: allele a maps to nothing, :717).  values is [n_old][stride], out [n_new][out_stride],
- * e runs over the first n_evidence columns.  Host only: the maps come from the per-site event analysis that runs after the
- * path, one per variant site, so there is nothing to fuse into the kernels. */
+ * e runs over the first n_evidence columns.  This one runs on the host, on a matrix the caller already holds;
+ * phmm_resident_marginalize below does the same for many sites on matrices still on the device. */
 int phmm_marginalize(const double* values, uint32_t n_old, uint32_t stride, uint32_t n_evidence, const int32_t* old_to_new,
                      uint32_t n_new, double* out, uint32_t out_stride);
+
+/* The same for many variant sites at once, ON THE DEVICE, over the matrices a resident batch (below) holds there after
+ * phmm_resident_run — for a caller that keeps the per-site haplotype -> allele maps of many regions (the genotyping step walks
+ * the variant sites of a region and marginalises its read likelihoods once per site, germline_genotying_engine via
+ * AlleleLikelihoods::marginalize).  Site k reads the matrix of region sites[k].region of the batch and writes
+ * [n_new][n_reads of that region] doubles at out + out_off[k]: the first n_kept columns are the marginal likelihoods of the
+ * surviving reads, the rest NaN like the matrix's own tail.  Needs an engine whose epilogue runs on the device
+ * (PHMM_EPILOGUE_AUTO on a glibc host, or PHMM_EPILOGUE_DEVICE); otherwise PHMM_ERR_STATE: download and use phmm_marginalize. */
+typedef struct phmm_marginal_site
+{
+    uint32_t region;              /* index of the region in the resident batch */
+    uint32_t n_new;               /* alleles after marginalisation */
+    const int32_t* old_to_new;    /* [n_haps of the region]: new allele of every haplotype, < 0 = maps to nothing */
+} phmm_marginal_site;
+struct phmm_resident;
+int phmm_resident_marginalize(phmm_engine* e, struct phmm_resident* r, const phmm_marginal_site* sites, uint32_t n_sites,
+                              const uint64_t* out_off, double* out);
 
 /* Device-resident form for kernel-only timing: upload once, run the device path (prep + forward +
  * FP64 recompute kernels, no host<->device copies) any number of times, download when wanted. */

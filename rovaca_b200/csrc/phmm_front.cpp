@@ -457,6 +457,7 @@ int phmm_resident_upload_on(phmm_engine* e, uint32_t device_index, const phmm_fl
     int rc = r->slot.init();
     if (rc != PHMM_OK) return rc;
     flat_to_regions(fb, nullptr, 0, fb->n_regions, r->reads, r->haps, r->regs);
+    r->slot.force_dev_epi = true;
     if ((rc = d.plan(r->slot, r->regs)) != PHMM_OK) return rc;
     CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.staged_bytes, cudaMemcpyHostToDevice, r->slot.stream));
     for (const Slot::DirectCopy& c : r->slot.direct)
@@ -483,6 +484,64 @@ int phmm_resident_run(phmm_engine* e, phmm_resident* r, float* gpu_ms, float* fw
     CU(cudaEventElapsedTime(&r->slot.fwd_ms, r->slot.ev[1], r->slot.ev[2]));
     if (gpu_ms) *gpu_ms = r->slot.gpu_ms;
     if (fwd_ms) *fwd_ms = r->slot.fwd_ms;
+    r->ran = true;
+    return PHMM_OK;
+}
+
+// AlleleLikelihoods::marginalize for many variant sites on the matrices a resident batch left on the device.
+int phmm_resident_marginalize(phmm_engine* e, phmm_resident* r, const phmm_marginal_site* sites, uint32_t n_sites, const uint64_t* out_off,
+                              double* out)
+{
+    if (!e || !r || (n_sites && (!sites || !out_off || !out))) return fail(PHMM_ERR_ARG, "phmm_resident_marginalize: null argument");
+    if (n_sites == 0) return PHMM_OK;
+    Slot& s = r->slot;
+    if (!r->ran) return fail(PHMM_ERR_STATE, "phmm_resident_marginalize: the batch has not been run (phmm_resident_run)");
+    if (!s.dev_epi)
+        return fail(PHMM_ERR_STATE, "phmm_resident_marginalize: this engine keeps the epilogue on the host (PHMM_EPILOGUE_HOST, or a libm whose "
+                                    "log10f the device cannot reproduce): download the matrices and use phmm_marginalize");
+    CU(cudaSetDevice(r->dev->ordinal));
+    // sites + maps in one staging block, outputs behind them
+    size_t n_map = 0, n_out = 0;
+    for (uint32_t k = 0; k < n_sites; ++k) {
+        if (sites[k].region >= s.regions.size()) return fail(PHMM_ERR_ARG, "phmm_resident_marginalize: region index out of range");
+        const RegionPlan& rp = s.regions[sites[k].region];
+        if (rp.n_haps && !sites[k].old_to_new) return fail(PHMM_ERR_ARG, "phmm_resident_marginalize: old_to_new is null");
+        for (uint32_t a = 0; a < rp.n_haps; ++a)
+            if (sites[k].old_to_new[a] >= 0 && (uint32_t)sites[k].old_to_new[a] >= sites[k].n_new)
+                return fail(PHMM_ERR_ARG, "phmm_resident_marginalize: old_to_new names an allele past n_new");
+        n_map += rp.n_haps;
+        n_out = std::max<size_t>(n_out, out_off[k] + (size_t)sites[k].n_new * rp.n_reads);
+    }
+    const size_t o_sites = 0, o_maps = align_up(n_sites * sizeof(PhmmMargSite), 256), o_out = align_up(o_maps + n_map * sizeof(int32_t), 256);
+    const size_t total = o_out + std::max<size_t>(n_out, 1) * sizeof(double);
+    int rc;
+    if ((rc = r->h_marg.ensure(total)) != PHMM_OK) return rc;
+    if ((rc = r->d_marg.ensure(total)) != PHMM_OK) return rc;
+    uint8_t* h = static_cast<uint8_t*>(r->h_marg.p);
+    PhmmMargSite* hs = reinterpret_cast<PhmmMargSite*>(h + o_sites);
+    int32_t* hm = reinterpret_cast<int32_t*>(h + o_maps);
+    size_t at = 0;
+    for (uint32_t k = 0; k < n_sites; ++k) {
+        const RegionPlan& rp = s.regions[sites[k].region];
+        hs[k] = PhmmMargSite{sites[k].region, sites[k].n_new, (uint32_t)at, 0u, out_off[k]};
+        if (rp.n_haps) std::memcpy(hm + at, sites[k].old_to_new, rp.n_haps * sizeof(int32_t));
+        at += rp.n_haps;
+    }
+    uint8_t* d = static_cast<uint8_t*>(r->d_marg.p);
+    CU(cudaMemcpyAsync(d, h, o_out, cudaMemcpyHostToDevice, s.stream));
+    CU(phmm_launch_marginalize(s.epi, reinterpret_cast<const PhmmMargSite*>(d + o_sites), reinterpret_cast<const int32_t*>(d + o_maps), n_sites,
+                               reinterpret_cast<double*>(d + o_out), s.stream));
+    CU(cudaMemcpyAsync(h + o_out, d + o_out, n_out * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CU(cudaStreamSynchronize(s.stream));
+    // only what the sites own is handed back (gaps between the sites' blocks, if the caller left any, are not touched)
+    const double* ho = reinterpret_cast<const double*>(h + o_out);
+    for (uint32_t k = 0; k < n_sites; ++k) {
+        const size_t n = (size_t)sites[k].n_new * s.regions[sites[k].region].n_reads;
+        std::memcpy(out + out_off[k], ho + out_off[k], n * sizeof(double));
+    }
+    r->dev->stats.launches += 1;
+    r->dev->stats.h2d += o_out;
+    r->dev->stats.d2h += n_out * sizeof(double);
     return PHMM_OK;
 }
 
@@ -512,6 +571,8 @@ void phmm_resident_free(phmm_engine* e, phmm_resident* r)
     if (!r) return;
     (void)e;
     if (r->dev) cudaSetDevice(r->dev->ordinal);
+    r->d_marg.release();
+    r->h_marg.release();
     r->slot.destroy();
     delete r;
 }

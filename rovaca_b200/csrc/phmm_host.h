@@ -211,6 +211,8 @@ struct Slot
     size_t e_kept = 0, e_best = 0, e_second = 0, e_nkept = 0, e_under = 0, epi_bytes = 0;
     size_t o_regions = 0, o_pri = 0;
     bool dev_epi = false;                // this batch's epilogue runs on the device
+    bool force_dev_epi = false;          // ... whatever its size (resident batches: the matrices stay on the device for
+                                         // phmm_resident_marginalize), if the host's libm allows the device epilogue at all
     bool want_best = false;              // some region of the batch asks for best / second-best haplotypes
     bool want_raw = false;               // ... for the raw FP32 sums
     bool want_f64 = false;               // the FP64 recompute goes out with the batch (someone will read its values)
@@ -344,6 +346,9 @@ struct phmm_resident
 {
     PhmmDevice* dev = nullptr;
     Slot slot;
+    bool ran = false;                    // the device holds results of a phmm_resident_run
+    DevBuf d_marg;                       // phmm_resident_marginalize: sites + maps in, marginal matrices out
+    HostBuf h_marg;
     std::vector<RegionIn> regs;
     std::vector<phmm_read> reads;
     std::vector<phmm_hap> haps;

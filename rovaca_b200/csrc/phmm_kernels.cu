@@ -781,6 +781,38 @@ __global__ void __launch_bounds__(128) phmm_epilogue_kernel(PhmmEpilogueDev e)
 }
 
 // ------------------------------------------------------------------------------------------------
+// phmm_marginalize_kernel — AlleleLikelihoods::marginalize -> marginal_likelihoods_direct (genotype/allele_likelihoods.hpp:189-216,
+// 702-732) for many variant sites at once, on the matrices the epilogue left on the device: site s of
+// region g maps the region's haplotypes onto n_new alleles; out[n][e] = the largest lik[a][e] over the haplotypes a with
+// map[a] == n, -inf when there is none (:714), for the region's surviving reads e (columns past n_kept are the matrix's NaN
+// tail and stay NaN).  One CTA per site, threads own evidence columns, so the running maximum needs no atomics; the compare
+// is the reference's `if (in > out) out = in` (:723-726).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) phmm_marginalize_kernel(PhmmEpilogueDev e, const PhmmMargSite* sites, const int32_t* maps, double* out)
+{
+    const PhmmMargSite st = sites[blockIdx.x];
+    const PhmmRegionDev rg = e.regions[st.region];
+    const uint32_t nr = rg.n_reads, nh = rg.n_haps, kept = e.n_kept[st.region];
+    const double* lik = e.lik + rg.out_off;
+    const int32_t* map = maps + st.map_off;
+    double* o = out + st.out_off;
+    for (uint32_t col = threadIdx.x; col < nr; col += blockDim.x) {
+        if (col >= kept) {
+            for (uint32_t n = 0; n < st.n_new; ++n) o[(size_t)n * nr + col] = __longlong_as_double(0x7FF8000000000000LL);
+            continue;
+        }
+        for (uint32_t n = 0; n < st.n_new; ++n) o[(size_t)n * nr + col] = -CUDART_INF;
+        for (uint32_t a = 0; a < nh; ++a) {
+            const int32_t n = map[a];
+            if (n < 0 || (uint32_t)n >= st.n_new) continue;          // s_missing_index (:717); the host rejects n >= n_new
+            const double v = lik[(size_t)a * nr + col];
+            double* cell = o + (size_t)n * nr + col;
+            if (v > *cell) *cell = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Issue-rate micro-benchmarks (bench.py's measured FP32 peak; DESIGN.md's pipe model).  Every thread runs
 // independent dependency chains long enough to hide the 4-cycle FMA latency.
 //   mode 0: scalar FFMA                     mode 1: packed FFMA2 (two FMAs per instruction)
@@ -948,6 +980,14 @@ cudaError_t phmm_launch_epilogue(const PhmmEpilogueDev& e, cudaStream_t st)
 {
     if (e.n_regions == 0) return cudaSuccess;
     phmm_epilogue_kernel<<<e.n_regions, 128, 0, st>>>(e);
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_marginalize(const PhmmEpilogueDev& e, const PhmmMargSite* sites, const int32_t* maps, uint32_t n_sites, double* out,
+                                    cudaStream_t st)
+{
+    if (n_sites == 0) return cudaSuccess;
+    phmm_marginalize_kernel<<<n_sites, 128, 0, st>>>(e, sites, maps, out);
     return cudaGetLastError();
 }
 

@@ -48,6 +48,15 @@ struct PhmmEpilogueDev
     uint32_t n_regions;
 };
 cudaError_t phmm_launch_epilogue(const PhmmEpilogueDev& e, cudaStream_t st);
+// one variant site for phmm_marginalize_kernel: which region's matrix, how many alleles come out, where its haplotype -> allele
+// map starts in the concatenated maps, where its [n_new][n_reads] output starts
+struct PhmmMargSite
+{
+    uint32_t region, n_new, map_off, rsv;
+    uint64_t out_off;
+};
+cudaError_t phmm_launch_marginalize(const PhmmEpilogueDev& e, const PhmmMargSite* sites, const int32_t* maps, uint32_t n_sites, double* out,
+                                    cudaStream_t st);
 // for tests: out[i] = (double)(log10f(x[i]) - LOG10_INITIAL_CONSTANT_F) as the device computes it
 cudaError_t phmm_launch_log10_probe(const float* x, double* out, uint32_t n, cudaStream_t st);
 

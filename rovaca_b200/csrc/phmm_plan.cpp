@@ -100,7 +100,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     }
     // One more kernel and a D2H twice the size pay off once the host would otherwise spend longer on the pairs than a launch
     // costs; the few-region batches of synchronous callers keep the (vector) host epilogue.
-    s.dev_epi = cfg->device_epilogue && n_pairs >= cfg->device_epilogue_min_pairs;
+    s.dev_epi = cfg->device_epilogue && (n_pairs >= cfg->device_epilogue_min_pairs || s.force_dev_epi);
     if (n_pairs >= (1ull << 31) || read_bytes >= (1ull << 31) || hap_bytes >= (1ull << 31))
         return fail(PHMM_ERR_ARG, "batch too large for 32-bit device offsets; lower batch_cells");
     // What the reference itself feeds its kernels — deletion qualities aliasing the insertion ones, one gap-continuation

@@ -90,6 +90,10 @@ SW_REALIGN = (10, -15, -30, -5)        # sw_parameters_genotype, common/base/lib
 SW_ASSEMBLE = (200, -150, -260, -11)   # sw_parameters_assemble, :13
 
 
+class _MargSite(C.Structure):
+    _fields_ = [("region", C.c_uint32), ("n_new", C.c_uint32), ("old_to_new", C.POINTER(C.c_int32))]
+
+
 class _Stats(C.Structure):
     _fields_ = [("regions", C.c_uint64), ("pairs", C.c_uint64), ("cells", C.c_uint64), ("fp64_pairs", C.c_uint64),
                 ("slow_pairs", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("batches", C.c_uint64),
@@ -97,7 +101,7 @@ class _Stats(C.Structure):
                 ("device_epilogue_batches", C.c_uint64)]
 
 
-EXPORTS = ["phmm_create_multi", "phmm_device_count", "phmm_device_ordinal", "phmm_get_device_stats", "phmm_resident_upload_on", "phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
+EXPORTS = ["phmm_resident_marginalize", "phmm_create_multi", "phmm_device_count", "phmm_device_ordinal", "phmm_get_device_stats", "phmm_resident_upload_on", "phmm_marginalize", "phmm_sw_align", "phmm_sw_last_timing", "phmm_create", "phmm_destroy", "phmm_call_region", "phmm_submit", "phmm_wait", "phmm_flush", "phmm_run_flat",
            "phmm_resident_upload", "phmm_resident_run", "phmm_resident_download", "phmm_resident_free",
            "phmm_resident_launches", "phmm_get_stats", "phmm_kernel_info", "phmm_ubench", "phmm_last_error", "phmm_version"]
 
@@ -146,6 +150,7 @@ def load_library():
     L.phmm_resident_upload.argtypes = [C.c_void_p, C.POINTER(_FlatBatch), C.POINTER(C.c_void_p)]
     L.phmm_resident_run.argtypes = [C.c_void_p, C.c_void_p, _f32p, _f32p]
     L.phmm_resident_download.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_FlatResult)]
+    L.phmm_resident_marginalize.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_MargSite), C.c_uint32, _u64p, _f64p]
     L.phmm_resident_free.argtypes = [C.c_void_p, C.c_void_p]
     L.phmm_resident_free.restype = None
     L.phmm_resident_launches.argtypes = [C.c_void_p]
@@ -337,6 +342,28 @@ class Resident:
         res = FlatResult(self.batch, raw, best)
         self.eng._check(self.eng.L.phmm_resident_download(self.eng.h, self.h, C.byref(res.c)))
         res.n_fp64 = int(res.c.n_fp64)
+        return res
+
+    def marginalize(self, sites: Sequence[Tuple[int, Sequence[int], int]]):
+        """``AlleleLikelihoods::marginalize`` for many variant sites on the matrices this batch left on the device
+        (``phmm_resident_marginalize``).  sites: (region index, old_to_new per haplotype of that region, n_new).
+        -> per site the [n_new, n_reads of the region] array: first n_kept columns valid, NaN tail like the matrix."""
+        b = self.batch
+        n = len(sites)
+        arr = (_MargSite * max(n, 1))()
+        keep, off, at = [], np.zeros(max(n, 1), np.uint64), 0
+        for k, (g, mp, n_new) in enumerate(sites):
+            m = np.ascontiguousarray(mp, np.int32)
+            keep.append(m)
+            arr[k] = _MargSite(int(g), int(n_new), m.ctypes.data_as(C.POINTER(C.c_int32)))
+            off[k] = at
+            at += int(n_new) * int(b.reg_read_off[g + 1] - b.reg_read_off[g])
+        out = np.zeros(max(at, 1), np.float64)
+        self.eng._check(self.eng.L.phmm_resident_marginalize(self.eng.h, self.h, arr, n, _ptr(off, _u64p), _ptr(out, _f64p)))
+        res = []
+        for k, (g, mp, n_new) in enumerate(sites):
+            nr = int(b.reg_read_off[g + 1] - b.reg_read_off[g])
+            res.append(out[int(off[k]):int(off[k]) + int(n_new) * nr].reshape(int(n_new), nr))
         return res
 
     def free(self):

@@ -248,3 +248,65 @@ def test_gpu_ms_is_a_union_not_a_sum(engine):
     gpu = s1["gpu_ms"] - s0["gpu_ms"]
     assert 0 < gpu <= wall * 1.02, (gpu, wall)
     assert s1["batches"] - s0["batches"] >= 6
+
+
+def test_device_marginalisation_of_resident_matrices(ref):
+    """§8f item 4: AlleleLikelihoods::marginalize (genotype/allele_likelihoods.hpp:189-216, 702-732) for many sites on the
+    matrices a resident batch left on the device, against tests/golden/alleles.npz — the UNMODIFIED reference's
+    AlleleLikelihoods on the reference's own call_pairhmm matrices.  The regions are regenerated with the generating script's
+    seed (tests/golden/make_golden.py::make_alleles), so the device's matrices must equal the golden ones first."""
+    import _golden
+    gold = _golden.alleles()
+    rng = np.random.default_rng(20261019)
+    regs, sites = [], []
+    for k, gcase in enumerate(gold):
+        reads, haps = wl._one_region(rng, int(rng.integers(1, 60)), int(rng.integers(1, 9)), 100, 150, 30, 90, junk=0.15)
+        haps = list(haps)
+        for _ in range(int(rng.integers(0, 4))):
+            haps.insert(int(rng.integers(0, len(haps) + 1)), haps[int(rng.integers(0, len(haps)))].copy())
+        rng.integers(-3, 3, len(haps))                       # the priorities the script drew
+        n_new = int(rng.integers(1, 5))
+        mp = rng.integers(-1, n_new, len(haps)).astype(np.int32)
+        assert np.array_equal(mp, gcase["old_to_new"]) and gcase["matrix"].shape == (len(haps), len(reads))
+        regs.append((reads, haps))
+        sites.append((k, mp, n_new + 1))
+    batch = wl.RegionBatch.from_regions(regs)
+    for epilogue in (EPILOGUE_DEVICE, 0):                    # forced, and as a default engine places it (resident batches: device)
+        eng = PairHmmEngine(epilogue=epilogue)
+        try:
+            res = eng.upload(batch)
+            res.run()
+            got = res.marginalize(sites)
+            full = res.download()
+            for k, gcase in enumerate(gold):
+                n = gcase["n_evidence"]
+                assert int(full.n_kept[k]) == n
+                assert np.array_equal(full.matrix(k).view(np.uint64), gcase["matrix"].view(np.uint64))
+                assert np.array_equal(got[k][:, :n].view(np.uint64), gcase["marginal"].view(np.uint64)), k
+                assert np.isnan(got[k][:, n:]).all()
+            # several sites on one region, in any order; the host form gives the same
+            from rovaca_b200 import marginalize
+            k = max(range(len(gold)), key=lambda i: gold[i]["matrix"].shape[0])
+            nh = gold[k]["matrix"].shape[0]
+            maps = [np.arange(nh, dtype=np.int32) % 3, np.full(nh, -1, np.int32), np.zeros(nh, np.int32)]
+            out = res.marginalize([(k, maps[2], 1), (0, sites[0][1], sites[0][2]), (k, maps[0], 3), (k, maps[1], 2)])
+            n = gold[k]["n_evidence"]
+            for o, (mp, n_new) in zip([out[2], out[3], out[0]], [(maps[0], 3), (maps[1], 2), (maps[2], 1)]):
+                want = marginalize(full.matrix(k), n, mp, n_new)
+                assert np.array_equal(o[:, :n].view(np.uint64), want.view(np.uint64))
+            assert np.array_equal(out[1].view(np.uint64), got[0].view(np.uint64))
+            with pytest.raises(Exception):
+                res.marginalize([(k, np.full(nh, 5, np.int32), 2)])
+            res.free()
+        finally:
+            eng.close()
+    host = PairHmmEngine(epilogue=EPILOGUE_HOST)
+    try:
+        res = host.upload(batch)
+        res.run()
+        with pytest.raises(Exception) as ei:
+            res.marginalize(sites[:1])
+        assert "phmm_marginalize" in str(ei.value)
+        res.free()
+    finally:
+        host.close()

@@ -9,7 +9,7 @@ extern "C" {
 // must be computed exactly once — by exactly one forward-kernel warp slot whose chunk holds the haplotype, or by the per-pair
 // kernel — every read must sit in a bin that holds it, every CTA must respect its launch's shape.  out[0..15]:
 //   0 pairs  1 pairs covered by the wavefront kernel  2 per-pair-kernel pairs  3 pairs covered more than once  4 pairs missed
-//   5 warps launched  6 read slots  7 read slots filled  8 reads in a bin too small for them  9 launches  10 chunks
+//   5 warps launched  6 lanes of those warps  7 lanes that hold a read  8 reads on too few lanes  9 launches  10 chunks
 //   11 lane-steps (sum over warps of 32 x RPT x steps)  12 cells (sum R x H over wavefront pairs)  13 CTA shape violations
 int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps, uint32_t busy_batches, uint32_t lanes_per_read, uint64_t* out)
 {
@@ -42,31 +42,46 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
     out[9] = s.launches.size();
     out[10] = s.n_chunks;
     for (const FwdLaunch& fl : s.launches) {
-        const PhmmBin bin = kPhmmBins[fl.bin];
-        const uint32_t per_warp = 32u / (uint32_t)bin.lanes, per_cta = per_warp * fl.cta_warps;
+        const uint32_t rpt = (uint32_t)fl.rpt;
         for (uint32_t c = fl.cta_base; c < fl.cta_base + fl.n_ctas; ++c) {
             const PhmmCta& cta = T[c];
             const PhmmChunk& ch = C[cta.chunk];
-            if (cta.n_reads == 0 || cta.n_reads > per_cta || cta.read_begin + cta.n_reads > s.n_tasks) ++out[13];
-            const uint32_t warps = (cta.n_reads + per_warp - 1) / per_warp;
-            const uint64_t steps = ch.stream_len - 1 - (32 - (uint32_t)bin.lanes);
-            out[5] += warps;
-            out[6] += (uint64_t)warps * per_warp;
-            out[7] += cta.n_reads;
-            out[11] += (uint64_t)warps * 32u * (uint32_t)bin.rpt * steps;
-            for (uint32_t k = 0; k < cta.n_reads; ++k) {
-                const PhmmRead& rd = R[tasks[cta.read_begin + k]];
-                if (rd.len + 1 > (uint32_t)(bin.lanes * bin.rpt)) ++out[8];
-                for (uint32_t j = 0; j < ch.n_haps; ++j) {
-                    const PhmmHap& hp = H[ch.hap_begin + j];
-                    if (hp.pos == 0) continue;
-                    const uint64_t idx = (uint64_t)rd.out_off + hp.out_col;
-                    if (idx >= s.n_pairs || hp.out_col >= rd.n_haps) { ++out[13]; continue; }
-                    if (seen[idx]++) ++out[3];
-                    ++out[1];
-                    out[12] += (uint64_t)rd.len * hp.len;
+            if (cta.n_reads == 0 || cta.read_begin + cta.n_reads > s.n_tasks) ++out[13];
+            uint32_t at = cta.read_begin, in_warps = 0;
+            for (uint32_t w = 0; w < PHMM_WARPS; ++w) {
+                const uint32_t n = (cta.warp_reads >> (8 * w)) & 0xffu;
+                in_warps += n;
+                if (n == 0) continue;
+                if (w >= fl.cta_warps) ++out[13];                         // a warp the launch does not have
+                uint32_t lanes = 0, widest = 0;
+                for (uint32_t k = 0; k < n; ++k) {
+                    const PhmmRead& rd = R[tasks[at + k]];
+                    const uint32_t nl = phmm_read_lanes(rd.len, (int)rpt);
+                    if (nl * rpt < rd.len + 1 || rd.len == 0) ++out[8];
+                    lanes += nl;
+                    widest = std::max(widest, nl);
                 }
+                if (lanes > 32) ++out[13];                                // the kernel gives every read consecutive lanes of ONE warp
+                const uint64_t steps = ch.stream_len - 1 - (32 - widest);
+                out[5] += 1;
+                out[6] += 32;
+                out[7] += lanes;
+                out[11] += (uint64_t)32u * rpt * steps;
+                for (uint32_t k = 0; k < n; ++k) {
+                    const PhmmRead& rd = R[tasks[at + k]];
+                    for (uint32_t j = 0; j < ch.n_haps; ++j) {
+                        const PhmmHap& hp = H[ch.hap_begin + j];
+                        if (hp.pos == 0) { ++out[13]; continue; }        // chunks own placed haplotypes only
+                        const uint64_t idx = (uint64_t)rd.out_off + hp.out_col;
+                        if (idx >= s.n_pairs || hp.out_col >= rd.n_haps) { ++out[13]; continue; }
+                        if (seen[idx]++) ++out[3];
+                        ++out[1];
+                        out[12] += (uint64_t)rd.len * hp.len;
+                    }
+                }
+                at += n;
             }
+            if (in_warps != cta.n_reads) ++out[13];
         }
     }
     for (uint32_t k = 0; k < s.n_slow; ++k) {

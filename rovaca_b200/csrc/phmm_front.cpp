@@ -232,7 +232,7 @@ int phmm_create_multi(const phmm_config* cfg, const int32_t* devices, uint32_t n
     // host workers per device: the box's cores are shared by the devices this process drives and — one rank per GPU being the
     // other deployment — by the ranks beside it
     const unsigned sharers = (unsigned)std::max<size_t>(std::max<size_t>(ords.size(), (size_t)ndev), 1);
-    s.n_workers = std::max(2u, std::min(6u, std::thread::hardware_concurrency() / sharers));
+    s.n_workers = std::max(2u, std::min(12u, std::thread::hardware_concurrency() * 3 / 4 / sharers));
     if (const char* env = std::getenv("PHMM_B200_WORKERS"))          // deployment override of the default only
         if (std::atoi(env) > 0) s.n_workers = std::min(32, std::atoi(env));
     if (cfg) {
@@ -598,14 +598,17 @@ int phmm_get_device_stats(phmm_engine* e, uint32_t device_index, phmm_stats* out
 
 int phmm_kernel_info(uint32_t read_len, int fma_mode, int* regs, int* local_bytes, int* lanes, int* rows_per_lane)
 {
-    const int bin = phmm_bin_of(read_len, fma_mode != PHMM_FMA_NONE);
-    if (bin < 0) return fail(PHMM_ERR_ARG, "phmm_kernel_info: no wavefront bin holds reads of this length (per-pair kernel)");
+    // what the planner picks for a big region of reads of this one length (the reference's own gap qualities, throughput policy)
+    const bool fma = fma_mode != PHMM_FMA_NONE;
+    if (read_len == 0 || read_len > phmm_max_read_len(fma))
+        return fail(PHMM_ERR_ARG, "phmm_kernel_info: the wavefront kernel does not take reads of this length (per-pair kernel)");
+    const int rpt = phmm_plan_rpt_for_uniform_reads(read_len, fma);
     PhmmKernelInfo ki{};
-    CU(phmm_fwd_kernel_info(bin, fma_mode != PHMM_FMA_NONE, &ki));
+    CU(phmm_fwd_kernel_info(rpt, fma, fma, &ki));
     if (regs) *regs = ki.regs;
     if (local_bytes) *local_bytes = ki.local_bytes;
-    if (lanes) *lanes = kPhmmBins[bin].lanes;
-    if (rows_per_lane) *rows_per_lane = kPhmmBins[bin].rpt;
+    if (lanes) *lanes = (int)phmm_read_lanes(read_len, rpt);
+    if (rows_per_lane) *rows_per_lane = rpt;
     return PHMM_OK;
 }
 

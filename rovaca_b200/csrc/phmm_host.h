@@ -162,7 +162,8 @@ struct HostBuf
 
 struct FwdLaunch
 {
-    int bin;
+    int rpt;                 // rows per lane: which instantiation of the forward kernel
+    bool refgaps;            // ... and which variant (the reference's own gap qualities, or per-base ones)
     uint32_t cta_base, n_ctas, cta_warps;
     size_t smem;
 };
@@ -182,7 +183,7 @@ struct Slot
     std::vector<FwdLaunch> launches;
     std::vector<uint32_t> read_len;      // per read (for the filter)
     // plan()'s working storage: kept between batches so that a plan allocates nothing once its slot has seen a batch its size
-    struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first; uint32_t n; };
+    struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first_read; uint32_t first_warp; uint32_t n_warps; };
     struct PlanScratch
     {
         std::vector<PhmmRead> reads;
@@ -195,7 +196,9 @@ struct Slot
         std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket, rec_of, hap_boff, stream_sum, stream_of, stream_idx;
         std::vector<std::vector<Group>> groups;
         std::vector<Group> sorted;
-        std::vector<std::vector<uint32_t>> group_reads, by_bin;
+        std::vector<std::vector<uint32_t>> group_reads;
+        std::vector<std::vector<uint8_t>> group_warps;
+        std::vector<uint16_t> fast_len;
     } ps;
     size_t in_bytes = 0;
     size_t staged_bytes = 0;             // leading part of the arena that goes through the pinned staging copy
@@ -404,6 +407,9 @@ struct phmm_engine
     float sw_last_ms = 0.f;
     uint64_t sw_last_cells = 0;
 };
+
+// rows per lane the throughput policy picks for a region of many reads of one length (phmm_plan.cpp)
+int phmm_plan_rpt_for_uniform_reads(uint32_t read_len, bool refgaps);
 
 // flat batches (phmm_front.cpp)
 void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_read>& reads,

@@ -6,12 +6,14 @@
 // (SURVEY.md §8a), flush-to-zero, result = (sum_c M[R][c]) + (sum_c I[R][c]).
 //
 // Mapping (B200-first, not a port of the AVX lane layout; DESIGN.md §4-5 has the measurements behind each choice):
-//   * a group of LANES lanes (8, 16 or 32) owns one read; lane l owns rows l*RPT .. l*RPT+RPT-1 of the table, the read is
-//     top-padded to LANES*RPT rows with "boundary generator" rows (prior = 0, dd = 1) that reproduce the reference's row -1
-//     (M = I = 0, D = 2^120/H) for any garbage fed in from above, so lane 0 needs no special case and the last read row
-//     is always the last register row of the group's last lane.  Tall, narrow groups (8 x 19 rows for 150/151-bp reads)
-//     need the fewest shuffles per cell and the least padding;
-//   * the group sweeps the columns as an anti-diagonal wavefront: at step s lane l is at stream position s - l and
+//   * a run of consecutive lanes of a warp owns one read: as many lanes as the read needs at RPT rows per lane,
+//     ceil((len + 1) / RPT), so a warp carries reads of any mix of lengths packed lane by lane (8 lanes x 19 rows for a
+//     150/151-bp read, 3 lanes for a 50-bp one beside it).  Lane l of a read owns rows l*RPT .. l*RPT+RPT-1 of its table; the
+//     read is top-padded to a whole number of lanes with "boundary generator" rows (prior = 0, dd = 1) that reproduce the
+//     reference's row -1 (M = I = 0, D = 2^120/H) for ANY garbage fed in from above — which is what lets the first lane of a
+//     read sit right under the last lane of another read in the same shuffle — and the last read row is always the last
+//     register row of the read's last lane.  Many rows per lane need the fewest shuffles and loads per cell;
+//   * the lanes of a read sweep the columns as an anti-diagonal wavefront: at step s lane l is at stream position s - l and
 //     receives the bottom row (M, I, D) of lane l-1 with three __shfl_up_sync per stream;
 //   * every thread carries TWO haplotype streams at once in the two halves of packed f32x2 registers (FFMA2 / FMUL2 /
 //     FADD2); the per-row transition probabilities stay scalar and enter the packed instructions as broadcast operands —
@@ -236,7 +238,7 @@ constexpr int fwd_min_blocks_rg(int rpt) { return rpt <= 3 ? 6 : rpt <= 6 ? 5 : 
 //                               pairhmm_internal.cpp:425,559), so md == mi and gapm / ii / dd are per-read scalars: half the
 //                               parameter registers, which is what lets 19 rows per lane (8 lanes x 19 = 152 rows for 150/151-bp
 //                               reads, 1 % padding instead of 6 %) fit the register file.
-template <int RPT, int LANES, int VAR>
+template <int RPT, int VAR>
 __global__ void __launch_bounds__(PHMM_WARPS * 32, VAR == PHMM_VAR_REFGAPS ? fwd_min_blocks_rg(RPT) : fwd_min_blocks(RPT))
 phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 {
@@ -289,13 +291,37 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     }
     __syncthreads();
 
-    // ---- which read is mine: LANES lanes per read, 32 / LANES reads per warp ---------------------
-    const uint32_t slot = threadIdx.x / LANES, lane = threadIdx.x & (LANES - 1);
-    if ((threadIdx.x >> 5) * (32 / LANES) >= cta.n_reads) return;      // whole warp has no read (the host sizes CTAs so that this is rare)
-    const bool live = slot < cta.n_reads;                              // a dead half warp shadows the last read, never writes
-    const uint32_t rid = p.task_reads[cta.read_begin + (live ? slot : cta.n_reads - 1)];
+    // ---- which read is mine: this warp's reads, each on ceil((len + 1) / RPT) consecutive lanes ---------------
+    const uint32_t wlane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t wcnt = (cta.warp_reads >> (8 * warp)) & 0xffu;                  // reads of this warp
+    if (wcnt == 0) return;                                                         // (the host packs warps so that this is rare)
+    uint32_t wbeg = cta.read_begin;                                                // ... and where they start in the task list
+#pragma unroll
+    for (uint32_t w = 0; w < PHMM_WARPS; ++w) wbeg += w < warp ? ((cta.warp_reads >> (8 * w)) & 0xffu) : 0u;
+    uint32_t my_rid = 0, my_nl = 0;
+    if (wlane < wcnt) {
+        my_rid = p.task_reads[wbeg + wlane];
+        my_nl = (p.reads[my_rid].len + RPT) / RPT;                                 // ceil((len + 1) / RPT): at least one pad row on top
+    }
+    uint32_t start = my_nl;                                                        // exclusive prefix sum: first lane of read i
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, start, d);
+        if (wlane >= (uint32_t)d) start += v;
+    }
+    const uint32_t used = __shfl_sync(0xffffffffu, start, 31);                     // lanes with a read (<= 32 by the host's packing)
+    start -= my_nl;
+    const uint32_t starts = __reduce_or_sync(0xffffffffu, wlane < wcnt ? (1u << start) : 0u);
+    const uint32_t nl_max = __reduce_max_sync(0xffffffffu, my_nl);
+    const bool live = wlane < used;                                                // a lane without a read shadows lane 0 of the last read, never writes
+    const uint32_t below = starts & (0xffffffffu >> (31 - (live ? wlane : used - 1)));
+    const uint32_t ridx = (uint32_t)__popc(below) - 1u;                           // which of the warp's reads covers me
+    const uint32_t first = 31u - (uint32_t)__clz((int)below);
+    const uint32_t rid = __shfl_sync(0xffffffffu, my_rid, ridx);
+    const uint32_t nl = __shfl_sync(0xffffffffu, my_nl, ridx);
+    const uint32_t lane = live ? wlane - first : 0u;                               // my lane within the read
     const PhmmRead rd = p.reads[rid];
-    const int npad = LANES * RPT - (int)rd.len;       // >= 1 by binning
+    const int npad = (int)(nl * RPT) - (int)rd.len;   // >= 1
 
     // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers, priors into my table ----
     float mm[RPT], mi[RPT], dd[RPT], gapm[NP], ii[NP], md[NP];
@@ -367,8 +393,8 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     uint32_t jx = 0, jy = 0;                       // haplotypes begun so far in each stream
     const uint2* sp = stream + 32 - lane;
     const unsigned char* tb = tbl + threadIdx.x * TSTRIDE;
-    const uint32_t nsteps = L - 1 - (32 - LANES);  // the last lane of the group reaches the end sentinel at step L - 33 + LANES
-    const bool writer = live && (lane == LANES - 1);
+    const uint32_t nsteps = L - 1 - (32 - nl_max); // the last lane of the warp's widest read reaches the end sentinel at step L - 33 + nl_max
+    const bool writer = live && (lane == nl - 1);
 
 #define PHMM_BOUNDARY(E, J, EI)                                                                         \
     {                                                                                                   \
@@ -468,12 +494,12 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             sumM.x = __fadd_rn(sumM.x, Ml[RPT - 1].x); sumM.y = __fadd_rn(sumM.y, Ml[RPT - 1].y);
             sumI.x = __fadd_rn(sumI.x, Il[RPT - 1].x); sumI.y = __fadd_rn(sumI.y, Il[RPT - 1].y);
         }
-        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1, LANES);
-        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1, LANES);
-        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1, LANES);
-        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1, LANES);
-        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1, LANES);
-        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1, LANES);
+        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1);
+        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1);
+        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1);
+        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1);
+        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1);
+        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1);
     }
 #undef PHMM_BOUNDARY
 }
@@ -853,10 +879,10 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
     if (acc == 123.456f) out[0] = acc;
 }
 
-template <int RPT, int LANES, int VAR>
+template <int RPT, int VAR>
 cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps, size_t smem, cudaStream_t st)
 {
-    auto kern = phmm_fwd_kernel<RPT, LANES, VAR>;
+    auto kern = phmm_fwd_kernel<RPT, VAR>;
     // Raise the dynamic shared-memory limit of this instantiation once, to the device maximum: several host workers launch
     // concurrently, and a per-launch "set to what I need" lets one worker lower the limit under another's launch.
     static std::atomic<uint64_t> limit_set{0};            // one bit per device ordinal
@@ -875,11 +901,11 @@ cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ct
     return cudaGetLastError();
 }
 
-template <int RPT, int LANES, int VAR>
+template <int RPT, int VAR>
 cudaError_t info_t(PhmmKernelInfo* info)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, LANES, VAR>);
+    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, VAR>);
     if (e != cudaSuccess) return e;
     info->regs = a.numRegs;
     info->local_bytes = (int)a.localSizeBytes;
@@ -898,50 +924,36 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// generic bins exist in both arithmetic flavours, reference-gap bins only in the (default) contracted one
-#define PHMM_CASE_G(R, LN, FN, ...)                                                    \
-    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN && !kPhmmBins[bin].refgaps) \
-        return fma ? FN<R, LN, PHMM_VAR_GENERIC>(__VA_ARGS__) : FN<R, LN, PHMM_VAR_GENERIC_NOFMA>(__VA_ARGS__);
-#define PHMM_CASE_R(R, LN, FN, ...) \
-    if (kPhmmBins[bin].rpt == R && kPhmmBins[bin].lanes == LN && kPhmmBins[bin].refgaps && fma) return FN<R, LN, PHMM_VAR_REFGAPS>(__VA_ARGS__);
-#define PHMM_DISPATCH_BIN(FN, ...)                                                                                    \
-    PHMM_CASE_G(1, 16, FN, __VA_ARGS__) PHMM_CASE_G(2, 16, FN, __VA_ARGS__) PHMM_CASE_G(3, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_G(4, 16, FN, __VA_ARGS__) PHMM_CASE_G(5, 16, FN, __VA_ARGS__) PHMM_CASE_G(6, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_G(7, 16, FN, __VA_ARGS__) PHMM_CASE_G(8, 16, FN, __VA_ARGS__) PHMM_CASE_G(9, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_G(10, 16, FN, __VA_ARGS__) PHMM_CASE_G(11, 16, FN, __VA_ARGS__) PHMM_CASE_G(12, 16, FN, __VA_ARGS__)    \
-    PHMM_CASE_G(7, 32, FN, __VA_ARGS__) PHMM_CASE_G(8, 32, FN, __VA_ARGS__) PHMM_CASE_G(9, 32, FN, __VA_ARGS__)       \
-    PHMM_CASE_G(10, 32, FN, __VA_ARGS__) PHMM_CASE_G(11, 32, FN, __VA_ARGS__) PHMM_CASE_G(12, 32, FN, __VA_ARGS__)    \
-    PHMM_CASE_R(1, 8, FN, __VA_ARGS__) PHMM_CASE_R(2, 8, FN, __VA_ARGS__) PHMM_CASE_R(3, 8, FN, __VA_ARGS__)          \
-    PHMM_CASE_R(4, 8, FN, __VA_ARGS__) PHMM_CASE_R(5, 8, FN, __VA_ARGS__) PHMM_CASE_R(6, 8, FN, __VA_ARGS__)          \
-    PHMM_CASE_R(7, 8, FN, __VA_ARGS__) PHMM_CASE_R(8, 8, FN, __VA_ARGS__) PHMM_CASE_R(9, 8, FN, __VA_ARGS__)          \
-    PHMM_CASE_R(10, 8, FN, __VA_ARGS__) PHMM_CASE_R(11, 8, FN, __VA_ARGS__) PHMM_CASE_R(12, 8, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(13, 8, FN, __VA_ARGS__) PHMM_CASE_R(14, 8, FN, __VA_ARGS__) PHMM_CASE_R(15, 8, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(16, 8, FN, __VA_ARGS__) PHMM_CASE_R(17, 8, FN, __VA_ARGS__) PHMM_CASE_R(18, 8, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(19, 8, FN, __VA_ARGS__)                                                                               \
-    PHMM_CASE_R(1, 16, FN, __VA_ARGS__) PHMM_CASE_R(2, 16, FN, __VA_ARGS__) PHMM_CASE_R(3, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(4, 16, FN, __VA_ARGS__) PHMM_CASE_R(5, 16, FN, __VA_ARGS__) PHMM_CASE_R(6, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(7, 16, FN, __VA_ARGS__) PHMM_CASE_R(8, 16, FN, __VA_ARGS__) PHMM_CASE_R(9, 16, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(1, 32, FN, __VA_ARGS__) PHMM_CASE_R(2, 32, FN, __VA_ARGS__) PHMM_CASE_R(3, 32, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(4, 32, FN, __VA_ARGS__) PHMM_CASE_R(5, 32, FN, __VA_ARGS__) PHMM_CASE_R(6, 32, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(7, 32, FN, __VA_ARGS__) PHMM_CASE_R(8, 32, FN, __VA_ARGS__) PHMM_CASE_R(9, 32, FN, __VA_ARGS__)       \
-    PHMM_CASE_R(10, 16, FN, __VA_ARGS__) PHMM_CASE_R(12, 16, FN, __VA_ARGS__) PHMM_CASE_R(14, 16, FN, __VA_ARGS__)    \
-    PHMM_CASE_R(16, 16, FN, __VA_ARGS__) PHMM_CASE_R(18, 16, FN, __VA_ARGS__) PHMM_CASE_R(19, 16, FN, __VA_ARGS__)    \
-    PHMM_CASE_R(10, 32, FN, __VA_ARGS__) PHMM_CASE_R(12, 32, FN, __VA_ARGS__) PHMM_CASE_R(14, 32, FN, __VA_ARGS__)    \
-    PHMM_CASE_R(16, 32, FN, __VA_ARGS__) PHMM_CASE_R(18, 32, FN, __VA_ARGS__) PHMM_CASE_R(19, 32, FN, __VA_ARGS__)    \
+// rows per lane 1..PHMM_MAX_RPT_GENERIC exist in both arithmetic flavours for any per-base gap qualities, 1..PHMM_MAX_RPT in the
+// (default, contracted) flavour for the reference's own gap qualities
+#define PHMM_CASE(R, FN, ...)                                                                                        \
+    if (rpt == R) {                                                                                                  \
+        if (refgaps) return fma ? FN<R, PHMM_VAR_REFGAPS>(__VA_ARGS__) : cudaErrorInvalidValue;                      \
+        if (R <= PHMM_MAX_RPT_GENERIC)                                                                               \
+            return fma ? FN<(R <= PHMM_MAX_RPT_GENERIC ? R : 1), PHMM_VAR_GENERIC>(__VA_ARGS__)                      \
+                       : FN<(R <= PHMM_MAX_RPT_GENERIC ? R : 1), PHMM_VAR_GENERIC_NOFMA>(__VA_ARGS__);               \
+        return cudaErrorInvalidValue;                                                                                \
+    }
+#define PHMM_DISPATCH_RPT(FN, ...)                                                                                   \
+    PHMM_CASE(1, FN, __VA_ARGS__) PHMM_CASE(2, FN, __VA_ARGS__) PHMM_CASE(3, FN, __VA_ARGS__) PHMM_CASE(4, FN, __VA_ARGS__)     \
+    PHMM_CASE(5, FN, __VA_ARGS__) PHMM_CASE(6, FN, __VA_ARGS__) PHMM_CASE(7, FN, __VA_ARGS__) PHMM_CASE(8, FN, __VA_ARGS__)     \
+    PHMM_CASE(9, FN, __VA_ARGS__) PHMM_CASE(10, FN, __VA_ARGS__) PHMM_CASE(11, FN, __VA_ARGS__) PHMM_CASE(12, FN, __VA_ARGS__)  \
+    PHMM_CASE(13, FN, __VA_ARGS__) PHMM_CASE(14, FN, __VA_ARGS__) PHMM_CASE(15, FN, __VA_ARGS__) PHMM_CASE(16, FN, __VA_ARGS__) \
+    PHMM_CASE(17, FN, __VA_ARGS__) PHMM_CASE(18, FN, __VA_ARGS__) PHMM_CASE(19, FN, __VA_ARGS__)                                \
     return cudaErrorInvalidValue;
 
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
                             size_t smem_bytes, cudaStream_t st)
 {
     if (n_ctas == 0) return cudaSuccess;
-    if (bin < 0 || bin >= kPhmmNumBins || cta_warps < 1 || cta_warps > PHMM_WARPS) return cudaErrorInvalidValue;
-    PHMM_DISPATCH_BIN(launch_fwd_t, b, cta_base, n_ctas, cta_warps, smem_bytes, st)
+    if (rpt < 1 || rpt > phmm_max_rpt(refgaps) || cta_warps < 1 || cta_warps > PHMM_WARPS) return cudaErrorInvalidValue;
+    PHMM_DISPATCH_RPT(launch_fwd_t, b, cta_base, n_ctas, cta_warps, smem_bytes, st)
 }
 
-cudaError_t phmm_fwd_kernel_info(int bin, bool fma, PhmmKernelInfo* info)
+cudaError_t phmm_fwd_kernel_info(int rpt, bool refgaps, bool fma, PhmmKernelInfo* info)
 {
-    if (bin < 0 || bin >= kPhmmNumBins) return cudaErrorInvalidValue;
-    PHMM_DISPATCH_BIN(info_t, info)
+    if (rpt < 1 || rpt > phmm_max_rpt(refgaps)) return cudaErrorInvalidValue;
+    PHMM_DISPATCH_RPT(info_t, info)
 }
 
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,

@@ -60,49 +60,19 @@ cudaError_t phmm_launch_marginalize(const PhmmEpilogueDev& e, const PhmmMargSite
 // for tests: out[i] = (double)(log10f(x[i]) - LOG10_INITIAL_CONSTANT_F) as the device computes it
 cudaError_t phmm_launch_log10_probe(const float* x, double* out, uint32_t n, cudaStream_t st);
 
-// Read-length bins of the wavefront kernel: a group of LANES lanes (a half warp or a whole warp) owns one read, lane l owns
-// rows l*RPT .. l*RPT+RPT-1 (top-padded with at least one boundary row), so a bin holds reads of length <= LANES*RPT - 1.
-// Half-warp bins come first: more rows per lane means fewer shuffles per cell (3 per RPT cells and stream), which is what
-// the issue/register-read budget of the SM rewards ("kernel budget"); whole-warp bins take over where a
-// half-warp read would need more than 12 rows per lane (register file).
+// The forward kernel comes in one instantiation per rows-per-lane count RPT (and arithmetic variant): a read of `len` bases
+// takes ceil((len + 1) / RPT) consecutive lanes of a warp (at least one boundary row on top), so any read up to 32 * RPT - 1
+// bases fits, and a warp carries whatever mix of reads packs into its 32 lanes.  More rows per lane = fewer shuffles and
+// shared-memory loads per cell ("kernel budget"); fewer rows per lane = more lanes per read = a shorter wavefront
+// step, which is what a small batch on an idle device wants.  The planner picks RPT per region (phmm_plan.cpp).
 #define PHMM_VAR_GENERIC_NOFMA 0
 #define PHMM_VAR_GENERIC 1
 #define PHMM_VAR_REFGAPS 2
 
-struct PhmmBin
-{
-    int lanes;
-    int rpt;
-    int refgaps;   // 1: the reference-gap-quality variant of the kernel (deletion = insertion qualities, one gcp per read)
-};
-// generic bins (any per-base qualities; both arithmetic flavours) ...
-static const PhmmBin kPhmmBins[] = {
-    {16, 1, 0}, {16, 2, 0}, {16, 3, 0}, {16, 4, 0}, {16, 5, 0}, {16, 6, 0}, {16, 7, 0}, {16, 8, 0}, {16, 9, 0}, {16, 10, 0}, {16, 11, 0},
-    {16, 12, 0}, {32, 7, 0}, {32, 8, 0}, {32, 9, 0}, {32, 10, 0}, {32, 11, 0}, {32, 12, 0},
-    // ... and the bins of the reference-gap variant.  Throughput bins: 8 lanes up to 151 bp (8 x 19 = 152 rows hold a 150/151-bp
-    // read with 1-2 pad rows), 16 lanes up to 303 bp, 32 lanes up to 607 bp.  The short 16- and 32-lane bins are the latency
-    // bins: a read spread over more lanes has fewer rows per lane and so a cheaper wavefront step (the time of a sweep is
-    // steps x rows per lane), which is what a small batch on an idle device wants (phmm_engine::plan picks the family).
-    {8, 1, 1}, {8, 2, 1}, {8, 3, 1}, {8, 4, 1}, {8, 5, 1}, {8, 6, 1}, {8, 7, 1}, {8, 8, 1}, {8, 9, 1}, {8, 10, 1}, {8, 11, 1}, {8, 12, 1},
-    {8, 13, 1}, {8, 14, 1}, {8, 15, 1}, {8, 16, 1}, {8, 17, 1}, {8, 18, 1}, {8, 19, 1},
-    {16, 1, 1}, {16, 2, 1}, {16, 3, 1}, {16, 4, 1}, {16, 5, 1}, {16, 6, 1}, {16, 7, 1}, {16, 8, 1}, {16, 9, 1},
-    {16, 10, 1}, {16, 12, 1}, {16, 14, 1}, {16, 16, 1}, {16, 18, 1}, {16, 19, 1},
-    {32, 1, 1}, {32, 2, 1}, {32, 3, 1}, {32, 4, 1}, {32, 5, 1}, {32, 6, 1}, {32, 7, 1}, {32, 8, 1}, {32, 9, 1},
-    {32, 10, 1}, {32, 12, 1}, {32, 14, 1}, {32, 16, 1}, {32, 18, 1}, {32, 19, 1}};
-static const int kPhmmNumBins = sizeof(kPhmmBins) / sizeof(kPhmmBins[0]);
-static const int kPhmmFirstRefGapBin = 18;
-static inline uint32_t phmm_bin_capacity(int bin) { return (uint32_t)(kPhmmBins[bin].lanes * kPhmmBins[bin].rpt) - 1u; }
-static inline uint32_t phmm_bin_reads_per_cta(int bin, uint32_t cta_warps) { return cta_warps * 32u / (uint32_t)kPhmmBins[bin].lanes; }
-// The bin that serves a read: the first one of its family (reference gaps or generic) that holds it — for the reference-gap
-// family the first with at least min_lanes lanes per read (8 = throughput bins, 16 / 32 = latency bins); -1 = none (per-pair
-// kernel).
-static inline int phmm_bin_of(uint32_t len, bool refgaps, int min_lanes = 8)
-{
-    if (len == 0) return -1;
-    for (int b = refgaps ? kPhmmFirstRefGapBin : 0; b < (refgaps ? kPhmmNumBins : kPhmmFirstRefGapBin); ++b)
-        if (len <= phmm_bin_capacity(b) && (!refgaps || kPhmmBins[b].lanes >= min_lanes)) return b;
-    return -1;
-}
+static inline int phmm_max_rpt(bool refgaps) { return refgaps ? PHMM_MAX_RPT : PHMM_MAX_RPT_GENERIC; }
+static inline uint32_t phmm_read_lanes(uint32_t len, int rpt) { return (len + (uint32_t)rpt) / (uint32_t)rpt; }   // ceil((len + 1) / rpt)
+// longest read the wavefront kernel takes (longer ones go to the per-pair kernel)
+static inline uint32_t phmm_max_read_len(bool refgaps) { return 32u * (uint32_t)phmm_max_rpt(refgaps) - 1u; }
 
 // Prior tables in shared memory: [6 base classes][thread][ceil(RPT/4) float4].  The per-thread slice is padded to an odd number
 // of 16-byte chunks so that the eight chunks a quarter warp fetches with one LDS.128 fall into eight different bank groups
@@ -114,17 +84,17 @@ constexpr uint32_t phmm_prior_table_stride(int rpt) { return (uint32_t)(((rpt + 
 
 // Shared memory one CTA of the forward kernel needs for a chunk: the two column streams, the per-haplotype seam records and
 // the per-thread prior tables (6 base classes x ceil(RPT/4) float4 per thread).
-static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int bin, uint32_t cta_warps)
+static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int rpt, uint32_t cta_warps)
 {
     const size_t streams = (size_t)(stream_len + 32) * 8;
     const size_t info = (((streams + (size_t)(n_haps + 1) * 2 * 12) + 15) & ~(size_t)15) - streams;
-    const size_t tables = (size_t)6 * phmm_prior_table_stride(kPhmmBins[bin].rpt) * cta_warps * 32;
+    const size_t tables = (size_t)6 * phmm_prior_table_stride(rpt) * cta_warps * 32;
     return streams + info + tables;
 }
 
 cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st);
-// Forward wavefront kernel over ctas[cta_base .. cta_base + n_ctas) (all of one RPT bin).
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int bin, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
+// Forward wavefront kernel over ctas[cta_base .. cta_base + n_ctas) (all of one rows-per-lane count).
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
                             size_t smem_bytes, cudaStream_t st);
 // Per-pair kernels.  count_dev != null: the pair count is read on the device (FP64 recompute list).
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
@@ -138,7 +108,7 @@ struct PhmmKernelInfo
     int local_bytes;
     int max_threads;
 };
-cudaError_t phmm_fwd_kernel_info(int bin, bool fma, PhmmKernelInfo* info);
+cudaError_t phmm_fwd_kernel_info(int rpt, bool refgaps, bool fma, PhmmKernelInfo* info);
 
 // ---- batched Smith-Waterman (sw_kernels.cu) -------------------------------------------------------------------------
 struct PhmmSwTask

@@ -3,64 +3,78 @@
 // grouping (generate_histogram / generate_new_pairhmm_idx, pairhmm_internal.cpp:231-391), on which results do not depend.
 #include "phmm_host.h"
 
+#include <array>
+
 namespace
 {
 
+// What a padded row costs at `rpt` rows per lane: 1000 / (fraction of the FP32 roofline the forward kernel reaches on reads that
+// fill their lanes exactly), measured on a B200 (profiles/r02_rpt_curve.txt: 64 reads x 8 haplotypes of 300, reads of
+// 8 x rpt - 1 bases).  Few rows per lane pay a step's shuffles, loads and loop for little arithmetic; 12 rows is the sweet
+// spot (165 registers: three CTAs, i.e. three warps per scheduler); from 13 up the register file holds two warps per scheduler.
+// A region costs warps x steps x rpt x this.
+constexpr uint32_t kRowCost[PHMM_MAX_RPT + 1] = {0,    4680, 2188, 1603, 1531, 1456, 1404, 1344, 1307, 1310,
+                                                 1282, 1294, 1229, 1314, 1312, 1308, 1289, 1284, 1289, 1274};
+inline uint32_t step_cost(int rpt) { return (uint32_t)rpt * kRowCost[rpt]; }
+// Rows-per-lane counts the throughput policy chooses among: every distinct count in a batch is a launch of its own with its own
+// tail, and neighbouring counts differ by a per cent or two — so a few well-separated ones.
+constexpr int kRptChoices[] = {12, 16, 19};
+constexpr int kRptChoicesGeneric[] = {8, 10, 12};
 
-// Fill the read slots of a region's CTAs.  A warp of the forward kernel holds 32 / LANES reads of ONE bin; a region whose
-// reads scatter over many length bins would run many part-empty warps.  A read may run in any higher bin of its lane family
-// (more top padding, same result), so the remainder of a bin can be carried up into the next occupied one.  Cost of a warp
-// = rows per lane of its bin; the small DP below picks, per family, which remainders to carry (f[i][c]: best cost of bins
-// i.. with c reads carried in).
-void promote_remainders(std::vector<std::vector<uint32_t>>& by_bin, int first, int last)
+// Pack reads that need lanes_of[k] consecutive lanes each into warps of 32 lanes, biggest first into the first warp that still
+// has room (by_lanes[n] = how many reads need n lanes).  Returns the warps needed; with `out`, also which reads go where:
+// out_warp_count[w] = reads of warp w, order = read slots (indices into the region's reads) warp after warp.
+struct LanePacker
 {
-    constexpr int kMaxBins = 24, kMaxS = 4;
-    const int S = 32 / kPhmmBins[first].lanes;            // reads per warp in this family
-    const int nb = last - first + 1;
-    if (S <= 1 || nb < 2 || nb > kMaxBins || S > kMaxS) return;
-    int occupied = 0;
-    bool ragged = false;
-    for (int i = 0; i < nb; ++i) {
-        const size_t n = by_bin[first + i].size();
-        occupied += n != 0;
-        ragged |= n % S != 0;
-    }
-    if (occupied < 2 || !ragged) return;                   // nothing to merge
-    uint32_t f[kMaxBins + 1][kMaxS] = {};
-    uint8_t carry[kMaxBins][kMaxS] = {};
-    uint32_t own[kMaxBins];
-    for (int i = nb - 1; i >= 0; --i) {
-        const uint32_t rpt = (uint32_t)kPhmmBins[first + i].rpt;
-        own[i] = (uint32_t)by_bin[first + i].size();
-        for (int c = 0; c < S; ++c) {
-            const uint32_t t = (uint32_t)c + own[i];
-            uint32_t best = (t + S - 1) / S * rpt + f[i + 1][0];
-            uint8_t how = 0;
-            if (i + 1 < nb && t % S != 0) {
-                const uint32_t alt = t / S * rpt + f[i + 1][t % S];
-                if (alt < best) { best = alt; how = 1; }
-            }
-            f[i][c] = best;
-            carry[i][c] = how;
+    uint32_t count[33];
+    uint32_t first[34];                        // final packing: where the read slots of every lane count start in `slots`
+    std::vector<uint32_t> slots;               // read ids sorted by lane count (counting sort, input order kept)
+    uint32_t pack(std::vector<uint32_t>* order, std::vector<uint8_t>* warp_count)
+    {
+        uint32_t left = 0, warps = 0;
+        uint32_t cnt[33], cursor[33];
+        int top = 0;
+        for (int n = 1; n <= 32; ++n) {
+            cnt[n] = count[n];
+            cursor[n] = first[n];
+            left += count[n];
+            if (count[n]) top = n;
         }
-    }
-    uint32_t c = 0;                                        // reads carried into bin i (already appended to its vector)
-    for (int i = 0; i + 1 < nb; ++i) {
-        auto& cur = by_bin[first + i];
-        const uint32_t t = c + own[i];                    // == cur.size()
-        if (carry[i][c]) {
-            const uint32_t rem = t % S;
-            auto& up = by_bin[first + i + 1];
-            up.insert(up.end(), cur.end() - rem, cur.end());
-            cur.resize(t - rem);
-            c = rem;
-        } else {
-            c = 0;
+        while (left) {
+            uint32_t room = 32, in_warp = 0;
+            while (top > 0 && cnt[top] == 0) --top;
+            for (int n = top; n >= 1 && room; --n)
+                while (cnt[n] && (uint32_t)n <= room) {
+                    --cnt[n];
+                    --left;
+                    room -= (uint32_t)n;
+                    ++in_warp;
+                    if (order) order->push_back(slots[cursor[n]++]);
+                }
+            if (warp_count) warp_count->push_back((uint8_t)in_warp);
+            ++warps;
         }
+        return warps;
     }
-}
+};
 
 }  // namespace
+
+int phmm_plan_rpt_for_uniform_reads(uint32_t read_len, bool refgaps)
+{
+    const int max_rpt = phmm_max_rpt(refgaps), rpt_lo = (int)((read_len + 32) / 32);
+    const int* choices = refgaps ? kRptChoices : kRptChoicesGeneric;
+    int rpt = 0;
+    uint64_t best = UINT64_MAX;
+    for (int q = 2; q >= 0; --q) {
+        const int c = std::max(rpt_lo, choices[q]);
+        if (c > max_rpt || c == rpt) continue;
+        const uint32_t per_warp = 32u / phmm_read_lanes(read_len, c);
+        const uint64_t cost = (uint64_t)step_cost(c) * 1024 / std::max(per_warp, 1u);
+        if (cost < best) { best = cost; rpt = c; }
+    }
+    return rpt ? rpt : max_rpt;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Planning + packing
@@ -112,7 +126,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     static const uint32_t env_cols = std::getenv("PHMM_B200_STREAM_COLS") ? (uint32_t)std::atoi(std::getenv("PHMM_B200_STREAM_COLS")) : 0u;   // experiments only
     const uint32_t full_cols = env_cols ? env_cols : kTargetStreamCols;
     uint32_t target_cols = full_cols;
-    int min_lanes = 8;             // lanes per read of the reference-gap kernels
+    int min_lanes = 8;             // lanes the longest read of a region should spread over at least (latency policy below)
     {
         uint64_t est_warps = 0;
         for (const RegionIn& r : regs) {
@@ -155,31 +169,40 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     s.regions.reserve(regs.size());
     s.read_len.clear();
     s.read_len.reserve(n_reads);
-    // per bin: (chunk, reads...) groups
+    // per rows-per-lane count: (chunk, warps of reads) groups
     using Group = Slot::Group;
+    const int max_rpt = phmm_max_rpt(refgaps);
+    const uint32_t max_read = phmm_max_read_len(refgaps);
     std::vector<std::vector<Group>>& groups = ps.groups;
-    std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;
-    std::vector<std::vector<uint32_t>>& by_bin = ps.by_bin;
-    groups.resize(kPhmmNumBins);
-    group_reads.resize(kPhmmNumBins);
-    by_bin.resize(kPhmmNumBins);
-    for (int b = 0; b < kPhmmNumBins; ++b) {
+    std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;       // read ids, warp after warp
+    std::vector<std::vector<uint8_t>>& group_warps = ps.group_warps;        // reads per warp
+    groups.resize(PHMM_MAX_RPT + 1);
+    group_reads.resize(PHMM_MAX_RPT + 1);
+    group_warps.resize(PHMM_MAX_RPT + 1);
+    for (int b = 0; b <= PHMM_MAX_RPT; ++b) {
         groups[b].clear();
         group_reads[b].clear();
-        by_bin[b].clear();
+        group_warps[b].clear();
     }
-    std::vector<uint32_t>&order = ps.order, &region_chunks = ps.region_chunks, &idx = ps.idx;
-    // read length -> bin, for the lengths the wavefront kernels take (a table instead of a search per read)
-    uint8_t bin_lut[640];
-    int bin_lo = kPhmmNumBins, bin_hi = -1;        // the bins this batch can use (one variant, lane families from min_lanes up)
-    for (uint32_t len = 0; len < 640; ++len) {
-        const int b = phmm_bin_of(len, refgaps, min_lanes);
-        bin_lut[len] = b < 0 ? 255 : (uint8_t)b;
-        if (b >= 0) {
-            bin_lo = std::min(bin_lo, b);
-            bin_hi = std::max(bin_hi, b);
+    std::vector<uint32_t>&order = ps.order, &region_chunks = ps.region_chunks;
+    static thread_local LanePacker tl_packer;                                // per worker thread: no allocation once warm
+    LanePacker& packer = tl_packer;
+    // rows per lane picked for a region of n reads (capped at 255) of one length: [n][len], 0 = not seen yet; per worker
+    // thread and per variant (the candidates differ)
+    static thread_local std::vector<std::array<uint8_t, 32 * PHMM_MAX_RPT>> tl_uniform[2];
+    std::vector<std::array<uint8_t, 32 * PHMM_MAX_RPT>>& uniform_rpt = tl_uniform[refgaps ? 1 : 0];
+    if (uniform_rpt.empty()) uniform_rpt.assign(256, std::array<uint8_t, 32 * PHMM_MAX_RPT>{});
+    // lanes a read of every length takes at every rows-per-lane count (a division per read and candidate otherwise)
+    static const struct LanesLut
+    {
+        uint8_t v[PHMM_MAX_RPT + 1][32 * PHMM_MAX_RPT];
+        LanesLut()
+        {
+            for (int c = 1; c <= PHMM_MAX_RPT; ++c)
+                for (uint32_t len = 0; len < 32u * PHMM_MAX_RPT; ++len) v[c][len] = (uint8_t)std::min<uint32_t>(255u, phmm_read_lanes(len, c));
         }
-    }
+        const uint8_t* operator[](int c) const { return v[c]; }
+    } lanes_lut;
 
     uint64_t raw_off = 0, hap_off = 0, out_off = 0;
     uint32_t max_cols = 0;
@@ -303,7 +326,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     if (!(r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols)) emit(j, 0u, 0u);
         }
         // reads
-        for (int b = bin_lo; b <= bin_hi; ++b) by_bin[b].clear();
+        uint32_t longest_read = 0, shortest_read = UINT32_MAX, fast_reads = 0;
         for (uint32_t k = 0; k < r.n_reads; ++k) {
             const phmm_read& in = r.reads[k];
             PhmmRead d{};
@@ -324,45 +347,95 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             const uint32_t rid = (uint32_t)reads.size();
             reads.push_back(d);
             s.read_len.push_back(in.len);
-            const int b = in.len < 640 ? (bin_lut[in.len] == 255 ? -1 : (int)bin_lut[in.len]) : -1;
-            if (b >= 0) by_bin[b].push_back(rid);
-            if (b < 0 || !all_haps_in_stream)
-                for (uint32_t j = 0; j < r.n_haps; ++j) {
-                const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
-                if (b < 0 || !hap_ok) {
-                    PhmmPair p{};
-                    p.read = rid;
-                    p.hap = rec_of[j];
-                    p.out_idx = d.out_off + j;
-                    slow.push_back(p);
-                }
+            const bool fast = in.len > 0 && in.len <= max_read && !region_chunks.empty();   // the wavefront kernel takes it
+            if (fast) {
+                ++fast_reads;
+                longest_read = std::max(longest_read, in.len);
+                shortest_read = std::min(shortest_read, in.len);
             }
+            if (!fast || !all_haps_in_stream)
+                for (uint32_t j = 0; j < r.n_haps; ++j) {
+                    const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
+                    if (!fast || !hap_ok) {
+                        PhmmPair p{};
+                        p.read = rid;
+                        p.hap = rec_of[j];
+                        p.out_idx = d.out_off + j;
+                        slow.push_back(p);
+                    }
+                }
         }
-        for (int b0 = bin_lo; b0 <= bin_hi;) {           // one lane family at a time (bins of a family are contiguous)
-            int b1 = b0;
-            while (b1 + 1 <= bin_hi && kPhmmBins[b1 + 1].lanes == kPhmmBins[b0].lanes && kPhmmBins[b1 + 1].refgaps == kPhmmBins[b0].refgaps) ++b1;
-            promote_remainders(by_bin, b0, b1);
-            b0 = b1 + 1;
-        }
-        for (int b = bin_lo; b <= bin_hi; ++b) {
-            if (by_bin[b].empty()) continue;
-            // every chunk of the region sweeps the same reads: one copy of the list, one group per chunk
-            const uint32_t first = (uint32_t)group_reads[b].size();
-            group_reads[b].insert(group_reads[b].end(), by_bin[b].begin(), by_bin[b].end());
-            for (uint32_t ci : region_chunks) groups[b].push_back(Group{ci, chunks[ci].stream_len, first, (uint32_t)by_bin[b].size()});
+        if (fast_reads) {
+            // Rows per lane for this region.  A read of len bases takes ceil((len + 1) / rpt) consecutive lanes; the region's
+            // reads are packed into warps lane by lane.  Throughput: the rpt with the least warps x step cost (many rows per
+            // lane amortise a step's shuffles and loads, but pad every read up to a whole lane).  Latency (a small batch on an
+            // idle device): the longest read spread over about min_lanes lanes, so that a step is short.
+            int rpt = 0;
+            const int rpt_lo = (int)((longest_read + 32) / 32);                 // the longest read must fit 32 lanes
+            // the lengths of the reads the wavefront kernel takes, compact (0 = not one of them)
+            std::vector<uint16_t>& lens = ps.fast_len;
+            lens.resize(r.n_reads);
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const uint32_t len = r.reads[k].len;
+                lens[k] = (len - 1u < max_read) ? (uint16_t)len : (uint16_t)0;
+            }
+            auto exact_cost = [&](int c) {                                      // warps after packing x step cost
+                for (int n = 0; n <= 32; ++n) packer.count[n] = 0;
+                const uint8_t* lut = lanes_lut[c];
+                for (uint32_t k = 0; k < r.n_reads; ++k) ++packer.count[lut[lens[k]]];   // lut[0] = 1 lane: subtract the non-reads below
+                packer.count[1] -= r.n_reads - fast_reads;
+                return packer.pack(nullptr, nullptr) * step_cost(c);
+            };
+            static const int env_rpt = std::getenv("PHMM_B200_RPT") ? std::atoi(std::getenv("PHMM_B200_RPT")) : 0;   // experiments only
+            if (env_rpt > 0) {
+                rpt = std::max(rpt_lo, std::min(max_rpt, env_rpt));
+            } else if (min_lanes > 8) {
+                rpt = std::max(rpt_lo, std::min(max_rpt, (int)((longest_read + (uint32_t)min_lanes) / (uint32_t)min_lanes)));
+            } else if (shortest_read == longest_read && (rpt = uniform_rpt[std::min<uint32_t>(fast_reads, 255u)][longest_read]) != 0) {
+                // a region of equal-length reads (the usual short-read case): remembered from the last such region
+            } else {
+                // the few candidate counts, each packed for real: least warps x step cost (ties: more rows per lane)
+                uint32_t best = UINT32_MAX;
+                const int* choices = refgaps ? kRptChoices : kRptChoicesGeneric;
+                for (int q = 2; q >= 0; --q) {
+                    const int c = std::max(rpt_lo, choices[q]);
+                    if (c > max_rpt || c == rpt) continue;
+                    const uint32_t cost = exact_cost(c);
+                    if (cost < best) { best = cost; rpt = c; }
+                }
+                if (rpt == 0) rpt = max_rpt;
+                if (shortest_read == longest_read) uniform_rpt[std::min<uint32_t>(fast_reads, 255u)][longest_read] = (uint8_t)rpt;
+            }
+            // the packing itself: read ids by lane count (a counting sort that keeps the caller's order), then warp after warp
+            {
+                const uint8_t* lut = lanes_lut[rpt];
+                for (int n = 0; n <= 32; ++n) packer.count[n] = 0;
+                for (uint32_t k = 0; k < r.n_reads; ++k) ++packer.count[lens[k] ? lut[lens[k]] : 0];
+                uint32_t at = 0;
+                for (int n = 1; n <= 32; ++n) { packer.first[n] = at; at += packer.count[n]; }
+                packer.slots.resize(at);
+                uint32_t cur[33];
+                for (int n = 1; n <= 32; ++n) cur[n] = packer.first[n];
+                for (uint32_t k = 0; k < r.n_reads; ++k)
+                    if (lens[k]) packer.slots[cur[lut[lens[k]]]++] = rp.read_begin + k;
+            }
+            const uint32_t first_read = (uint32_t)group_reads[rpt].size(), first_warp = (uint32_t)group_warps[rpt].size();
+            const uint32_t n_warps = packer.pack(&group_reads[rpt], &group_warps[rpt]);
+            // every chunk of the region sweeps the same warps: one copy of the lists, one group per chunk
+            for (uint32_t ci : region_chunks) groups[rpt].push_back(Group{ci, chunks[ci].stream_len, first_read, first_warp, n_warps});
         }
         out_off += (uint64_t)r.n_reads * r.n_haps;
     }
 
     [[maybe_unused]] const auto pt2 = PT_NOW();
     PT_ADD(1, pt1, pt2);
-    // CTAs per bin, longest streams first
+    // CTAs per rows-per-lane count, longest streams first
     std::vector<PhmmCta>& ctas = ps.ctas;
     std::vector<uint32_t>& task_reads = ps.task_reads;
     ctas.clear();
     task_reads.clear();
     s.launches.clear();
-    for (int b = std::max(bin_lo, 0); b <= bin_hi; ++b) {
+    for (int b = 1; b <= max_rpt; ++b) {
         if (groups[b].empty()) continue;
         {
             // stable, longest stream first: a counting sort on the stream length (at most kMaxStreamCols + 33 values)
@@ -376,19 +449,20 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             groups[b].swap(ps.sorted);
         }
         FwdLaunch fl{};
-        fl.bin = b;
+        fl.rpt = b;
+        fl.refgaps = refgaps;
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
-        // warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but their
-        // read slots come in bigger lumps; take the biggest size that wastes at most 8 % more slots than single-warp CTAs
+        // warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but a
+        // region's warps then come in bigger lumps; take the biggest size that wastes at most 8 % more warp slots than
+        // single-warp CTAs
         uint32_t cta_warps = cfg->cta_warps;
         if (cta_warps == 0) {
-            const uint32_t per_warp = phmm_bin_reads_per_cta(b, 1);
             uint64_t slots[3] = {0, 0, 0};
             for (const Group& g : groups[b])
                 for (int k = 0; k < 3; ++k) {
-                    const uint32_t per = per_warp << k;
-                    slots[k] += (uint64_t)((g.n + per - 1) / per) * per;
+                    const uint32_t per = 1u << k;
+                    slots[k] += (uint64_t)((g.n_warps + per - 1) / per) * per;
                 }
             cta_warps = 1;
             for (int k = 1; k < 3; ++k)
@@ -402,14 +476,22 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             if (smem <= smem_optin || cta_warps == 1) break;
             cta_warps >>= 1;
         }
+        const std::vector<uint32_t>& gr = group_reads[b];
+        const std::vector<uint8_t>& gw = group_warps[b];
         for (const Group& g : groups[b]) {
-            const uint32_t per_cta = phmm_bin_reads_per_cta(b, cta_warps);
-            for (uint32_t at = 0; at < g.n; at += per_cta) {
+            uint32_t at_read = g.first_read;
+            for (uint32_t w0 = 0; w0 < g.n_warps; w0 += cta_warps) {
                 PhmmCta c{};
                 c.chunk = g.chunk;
                 c.read_begin = (uint32_t)task_reads.size();
-                c.n_reads = std::min<uint32_t>(per_cta, g.n - at);
-                for (uint32_t k = 0; k < c.n_reads; ++k) task_reads.push_back(group_reads[b][g.first + at + k]);
+                const uint32_t w1 = std::min(g.n_warps, w0 + cta_warps);
+                for (uint32_t w = w0; w < w1; ++w) {
+                    const uint32_t n = gw[g.first_warp + w];
+                    c.warp_reads |= n << (8 * (w - w0));
+                    c.n_reads += n;
+                }
+                task_reads.insert(task_reads.end(), gr.begin() + at_read, gr.begin() + at_read + c.n_reads);
+                at_read += c.n_reads;
                 ctas.push_back(c);
             }
         }
@@ -421,7 +503,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
 
     // biggest launches first: the small ones fill the tails
     std::stable_sort(s.launches.begin(), s.launches.end(), [](const FwdLaunch& x, const FwdLaunch& y) {
-        return (uint64_t)x.n_ctas * x.cta_warps * kPhmmBins[x.bin].rpt > (uint64_t)y.n_ctas * y.cta_warps * kPhmmBins[y.bin].rpt;
+        return (uint64_t)x.n_ctas * x.cta_warps * (uint32_t)x.rpt > (uint64_t)y.n_ctas * y.cta_warps * (uint32_t)y.rpt;
     });
 
     [[maybe_unused]] const auto pt3 = PT_NOW();

@@ -4,8 +4,8 @@
 //   reads[]      PhmmRead, one per read of every region in the batch
 //   haps[]       PhmmHap, one per haplotype
 //   chunks[]     PhmmChunk: a region's haplotype list (or a slice of it) laid out as two column streams
-//   ctas[]       PhmmCta: up to WARPS reads of one length bin that sweep one chunk together
-//   task_reads[] read ids, ordered by (bin, chunk)
+//   ctas[]       PhmmCta: up to PHMM_WARPS warps of reads (packed lane by lane) that sweep one chunk together
+//   task_reads[] read ids, ordered by (rows per lane, chunk, warp)
 //   raw blobs    read bases / quals (/ ins / del / gcp when the caller supplies them), haplotype bases
 //   words[]      written by the prep kernel: one packed u32 per read base (q | ins | del | gcp | one-hot)
 //   out_f32[]    raw forward sums, [read][hap] per region  (pairhmm_internal.cpp:529 temp layout)
@@ -16,7 +16,8 @@
 #include <stdint.h>
 
 #define PHMM_FLAG_BIT 0x80000000u   // stream word: first column of a haplotype (or the end sentinel)
-#define PHMM_MAX_RPT 12
+#define PHMM_MAX_RPT 19              // rows per lane of the forward kernel: 1..19 for the reference's own gap qualities ...
+#define PHMM_MAX_RPT_GENERIC 12      // ... 1..12 when a caller brings per-base deletion / continuation qualities (register file)
 #define PHMM_WARPS 4                // reads per CTA (G = 32)
 
 // read flags
@@ -60,9 +61,9 @@ struct PhmmChunk
 struct PhmmCta
 {
     uint32_t chunk;
-    uint32_t read_begin; // into task_reads
-    uint32_t n_reads;    // <= PHMM_WARPS
-    uint32_t rsv;
+    uint32_t read_begin; // into task_reads: the reads of warp 0, then of warp 1, ...
+    uint32_t n_reads;    // all warps together
+    uint32_t warp_reads; // reads of warp w in byte w (PHMM_WARPS = 4 warps at most); their lanes, ceil((len + 1) / RPT) each, sum to <= 32
 };
 
 // one (read, haplotype) pair for the per-pair kernels (FP64 recompute, out-of-envelope shapes)

@@ -201,7 +201,7 @@ def plan_audit(batch: RegionBatch, fma_mode: int = FMA_AVX512, cta_warps: int = 
     if rc != 0:
         raise PhmmError(f"phmm_debug_plan failed ({rc}): {L.phmm_last_error().decode()}")
     d = {k: int(v) for k, v in zip(PLAN_AUDIT_FIELDS, out)}
-    d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)
+    d["slot_fill"] = d["read_slots_filled"] / max(d["read_slots"], 1)             # lanes that hold a read / lanes of the warps launched
     d["lane_utilisation"] = d["wavefront_cells"] / max(2 * d["lane_steps"], 1)      # two haplotype streams per lane
     return d
 

@@ -10,8 +10,9 @@ static double g_t[8];
 #include <string>
 int main(int argc, char** argv)
 {
-    const bool mixed = argc > 1 && std::string(argv[1]) == "cfg5";     // cfg5-like: Poisson(41) reads of 60-151 bp, 2-24 haplotypes of 201-499
-    const int G = mixed ? 16384 : 4096;
+    const bool trim = argc > 1 && std::string(argv[1]) == "cfg5t";     // post-trim shapes: H 41-120, reads 10..min(H, 100)
+    const bool mixed = trim || (argc > 1 && std::string(argv[1]) == "cfg5");     // cfg5-like: Poisson(41) reads of 60-151 bp, 2-24 haplotypes of 201-499
+    const int G = trim ? 32768 : mixed ? 16384 : 4096;
     std::mt19937_64 rng(1);
     std::vector<uint32_t> nr(G), nh(G);
     std::vector<std::vector<uint32_t>> rl(G), hl(G);
@@ -20,8 +21,9 @@ int main(int argc, char** argv)
     for (int g = 0; g < G; ++g) {
         nr[g] = mixed ? std::max(1, pr(rng)) : 64;
         nh[g] = mixed ? std::min(24, std::max(2, ph(rng) + 1)) : 8;
-        const uint32_t H = mixed ? 201 + rng() % 299 : 300;
-        for (uint32_t k = 0; k < nr[g]; ++k) { rl[g].push_back(mixed ? 60 + rng() % 92 : 150); rbytes += rl[g].back(); }
+        const uint32_t H = trim ? 41 + rng() % 80 : mixed ? 201 + rng() % 299 : 300;
+        for (uint32_t k = 0; k < nr[g]; ++k) { rl[g].push_back(trim ? 10 + rng() % (std::min(H, 100u) - 9) : mixed ? 60 + rng() % 92 : 150); rbytes += rl[g].back(); }
+        std::sort(rl[g].begin(), rl[g].end());
         for (uint32_t j = 0; j < nh[g]; ++j) { hl[g].push_back(H); hbytes += H; }
         n_reads += nr[g]; n_haps += nh[g]; n_pairs += (size_t)nr[g] * nh[g];
     }

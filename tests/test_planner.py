@@ -71,16 +71,16 @@ def test_mixed_workloads_cover_every_pair_once(make, fma):
 
 
 def test_reads_of_any_length_mix_share_warps():
-    """A region whose reads scatter over many lengths: every read takes the lanes it needs (4 to 8 at 19 rows per lane) and the
-    warps are packed lane by lane — one launch, no warp per length class."""
+    """A region whose reads scatter over many lengths: every read takes the lanes it needs and the warps are packed lane by
+    lane — one launch, no warp per length class."""
     rng = np.random.default_rng(7)
     hap = B[rng.integers(0, 4, 300)]
     reads = [dict(bases=B[rng.integers(0, 4, n)], qual=np.full(n, 30, np.uint8), mapq=60) for n in range(60, 152, 3)]   # 31 reads, 31 lengths
     b = wl.RegionBatch.from_regions([(reads, [hap, hap[::-1].copy()])] * 20)
     a = ph.plan_audit(b, cta_warps=1, busy_batches=64)   # a busy device: one chunk per region
     _sound(a)
-    assert a["slot_fill"] > 0.95, a                   # 187 lanes in 6 warps
-    assert a["chunks"] == 20 and a["warps"] == 20 * 6 and a["launches"] == 1
+    assert a["slot_fill"] > 0.9, a                    # at 12 rows per lane: 6 to 13 lanes per read, 7 warps per region
+    assert a["chunks"] == 20 and a["warps"] <= 20 * 7 and a["launches"] == 1
 
 
 def test_out_of_envelope_shapes_go_to_the_pair_kernel():

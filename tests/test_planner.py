@@ -134,7 +134,8 @@ def test_planner_quality_does_not_regress():
     """How well a plan uses the lanes it occupies (useful cells / lane-steps, lanes that hold a read) on the shapes the workload
     table watches: a guard for later planner changes — the numbers of the round-2 planner, rounded down.  (Lane utilisation
     is per padded row; the planner trades some of it for more rows per lane, i.e. fewer shuffles and loads per cell.)"""
-    for name, util, fill in (("cfg2", 0.97, 0.999), ("cfg5", 0.83, 0.96), ("cfg5t", 0.78, 0.98), ("cfg3", 0.86, 0.93)):
+    for name, util, fill in (("cfg2", 0.97, 0.999), ("cfg5", 0.82, 0.93), ("cfg5t", 0.76, 0.93), ("cfg3", 0.86, 0.93)):
         a = ph.plan_audit(_stream(name), busy_batches=6)
         _sound(a)
         assert a["lane_utilisation"] >= util and a["slot_fill"] >= fill, (name, a["lane_utilisation"], a["slot_fill"])
+        assert a["launches"] <= 3, (name, a["launches"])              # a few well-separated rows-per-lane counts, not one per length

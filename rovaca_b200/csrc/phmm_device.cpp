@@ -7,6 +7,21 @@
 // Device side of one batch
 // ------------------------------------------------------------------------------------------------
 
+// The FP64 recompute of the pairs the forward kernels queued (pairhmm_internal.cpp:578-581).  The second half of the pair
+// buffer is the fast kernel's hand-back list; its counter sits behind the first one.
+cudaError_t PhmmDevice::launch_f64(Slot& s)
+{
+    PhmmPair* redo = static_cast<PhmmPair*>(s.d_pairs.p) + std::max<uint64_t>(s.n_pairs, 1);
+    uint32_t* redo_count = s.dev.f64_count + 1;
+    cudaError_t e = cudaMemsetAsync(redo_count, 0, 4, s.stream);
+    if (e != cudaSuccess) return e;
+    const bool general_only = std::getenv("PHMM_B200_FP64_GENERAL") != nullptr;              // tests: the general kernel alone (read per launch)
+    const char* trip = std::getenv("PHMM_B200_FP64_TRIP_HI");                                  // tests: a higher floor forces hand-backs
+    const uint32_t trip_hi = trip ? (uint32_t)std::strtoul(trip, nullptr, 0) : PHMM_PAIR64_TRIP_HI;
+    return phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
+                                 general_only ? nullptr : redo, redo_count, cfg->default_gapm_d, cfg->default_gcp_d, trip_hi, s.stream);
+}
+
 int PhmmDevice::launch(Slot& s, bool copy_in)
 {
     if (copy_in && s.in_bytes) {
@@ -47,8 +62,7 @@ int PhmmDevice::launch(Slot& s, bool copy_in)
                                  s.stream));
     s.f64_done = s.want_f64 && s.n_pairs;
     if (s.f64_done)
-        CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads, s.max_cols,
-                                 s.stream));
+        CU(launch_f64(s));
     if (s.dev_epi && s.n_pairs) CU(phmm_launch_epilogue(s.epi, s.stream));
     CU(cudaEventRecord(s.ev[3], s.stream));
     stats.launches += s.n_launches;
@@ -102,8 +116,7 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
         n64 = *static_cast<uint32_t*>(s.h_cnt.p);
         if (n64 > 0 && !have64) {
             if (asks_f64) {                                     // a resident batch learns at download time who wants raw sums
-                CU(phmm_launch_pairs_f64(s.dev, s.dev.f64_pairs, s.dev.f64_count, static_cast<double*>(s.d_scr64.p), kPairThreads,
-                                         s.max_cols, s.stream));
+                CU(launch_f64(s));
                 s.f64_done = have64 = true;
             }
         }

@@ -259,6 +259,8 @@ int phmm_create_multi(const phmm_config* cfg, const int32_t* devices, uint32_t n
     }
     s.default_gapm = t->gapm[10];
     s.default_ii = t->ph2pr[10];
+    s.default_gcp_d = t->ph2pr_d[10];
+    s.default_gapm_d = 1.0 - t->ph2pr_d[10];                  // what RowParams<double> computes on the device: one IEEE subtraction
     int rc = PHMM_OK;
     for (size_t k = 0; k < ords.size() && rc == PHMM_OK; ++k) {
         e->devs.emplace_back(new PhmmDevice());

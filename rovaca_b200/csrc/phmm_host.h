@@ -274,6 +274,7 @@ struct PhmmSettings
     uint64_t device_epilogue_min_pairs = 0;   // ... for batches of at least this many pairs (AUTO: small batches stay on the host)
     int log10_mode = 0;            // how raw sums become log10 doubles: phmm_log10.cpp, picked (and tested against libm) at creation
     float default_gapm = 0.f, default_ii = 0.f;   // table values of the default gap-continuation quality
+    double default_gapm_d = 0.0, default_gcp_d = 0.0;   // ... in FP64 (the recompute kernel)
     uint32_t pipeline_depth = 3;   // batches per device the ticket path keeps in flight before it starts batching up
 };
 
@@ -335,6 +336,7 @@ struct PhmmDevice
     void shutdown();
     int plan(Slot& s, const std::vector<RegionIn>& regs);
     int launch(Slot& s, bool copy_in);
+    cudaError_t launch_f64(Slot& s);
     int finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out);
     void epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const;
     void epilogue_from_device(const Slot& s, const std::vector<RegionIn>& regs, bool have64) const;

@@ -667,6 +667,167 @@ __global__ void __launch_bounds__(128) phmm_pair_kernel(PhmmBatchDev p, const Ph
 }
 
 // ------------------------------------------------------------------------------------------------
+// phmm_pair64_kernel — the FP64 recompute (pairhmm_internal.cpp:578-581) for the common shapes, fast: one warp per pair, the
+// read on all 32 lanes at RPT = ceil((R + 1) / 32) <= 5 rows per lane (one strip, nothing through memory), the haplotype's base
+// classes staged once in shared memory, priors fetched from a per-lane table instead of selected, gap-continuation parameters
+// as kernel-wide constants.  Same recurrence, same operation order and the same FP64 tables as phmm_pair_kernel<double>.
+//
+// Flush-to-zero without a test after every operation.  The reference runs its FP64 kernels with MXCSR.FTZ set, so a result
+// below DBL_MIN becomes 0; the GPU has no FP64 FTZ mode, and phmm_pair_kernel<double> tests after each of the 8 operations of a
+// cell (which costs more than the arithmetic).  Here: every value is >= 0, so only a PRODUCT can come out tiny, and a product
+// of a state value v with a table constant c (>= 6.6e-14, the smallest prior) is tiny only if v < 3.4e-295.  State values are
+// bounded below by their M term: I[r][c] >= M[r-1][c] * mi and D[r][c] >= M[r][c-1] * md with mi, md >= 2e-13 (quality 127).
+// So as long as every nonzero M the sweep produces is >= 2^-830 (1.4e-250), every operand of every product is 0 or
+// >= 2.8e-263, no result is tiny, and flushing would have changed nothing.  The kernel checks exactly that — two integer
+// instructions per cell on the high word of M — and a pair that trips the check is handed to phmm_pair_kernel<double>, which
+// flushes operation by operation.  (With the default gap-continuation quality a read of <= 159 bases cannot get there: one
+// long insertion costs 10^-(R + 5), so every nonzero value stays above 10^-180 of the 2^1020 scale.  The check is what makes
+// that argument unnecessary.)  Pairs whose read brings its own deletion / continuation qualities, reads over 159 bases and
+// haplotypes over PAIR64_MAX_H go to the general kernel too.
+// ------------------------------------------------------------------------------------------------
+constexpr int PAIR64_MAX_RPT = 5;
+constexpr uint32_t PAIR64_MAX_H = 2048;
+constexpr uint32_t PAIR64_TSTRIDE = 48;            // bytes per lane and class: 5 doubles, padded to an odd number of 16-byte chunks
+
+template <int RPT>
+__device__ __forceinline__ bool pair64_sweep(const PhmmBatchDev& p, const PhmmRead& rd, const PhmmHap& hp, uint32_t lane, const uint8_t* s_cls,
+                                             unsigned char* s_tbl, double gapm, double gcp_p, uint32_t trip_hi, double* result)
+{
+    const PhmmTables* __restrict__ tb = p.tables;
+    const int H = (int)hp.len, R = (int)rd.len;
+    const int npad = 32 * RPT - R;                               // >= 1
+    double mm[RPT], mi[RPT], dd[RPT];
+    {
+        double pm[RPT], pmm[RPT];
+        uint32_t rb[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = (int)lane * RPT + k - npad;
+            if (r >= 0) {
+                const uint32_t w = p.words[rd.word_off + r];
+                const uint32_t q = w & 127u, qi = (w >> 7) & 127u;       // deletion quality == insertion quality here (no explicit ones)
+                mm[k] = tb->mm_d[((qi * (qi + 1)) >> 1) + qi];
+                mi[k] = tb->ph2pr_d[qi];
+                dd[k] = gcp_p;
+                pm[k] = __dsub_rn(1.0, tb->ph2pr_d[q]);
+                pmm[k] = __ddiv_rn(tb->ph2pr_d[q], 3.0);
+                rb[k] = w >> 28;
+            } else {                                             // boundary-generator row
+                mm[k] = 0.0; mi[k] = 0.0; dd[k] = 1.0; pm[k] = 0.0; pmm[k] = 0.0; rb[k] = 0u;
+            }
+        }
+#pragma unroll
+        for (uint32_t b = 0; b < 6; ++b) {
+            const uint32_t hb = class_onehot(b);
+            double* t = reinterpret_cast<double*>(s_tbl + b * (32 * PAIR64_TSTRIDE) + lane * PAIR64_TSTRIDE);
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) t[k] = (rb[k] & hb) ? pm[k] : pmm[k];
+        }
+    }
+    __syncwarp();
+    const double init = __ddiv_rn(__longlong_as_double(0x7FB0000000000000LL), (double)H);      // 2^1020 / H
+    const bool above_pad = (int)lane * RPT - 1 < npad;
+    double Ml[RPT], Il[RPT], Dl[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { Ml[k] = 0.0; Il[k] = 0.0; Dl[k] = 0.0; }
+    double upM = 0.0, upI = 0.0, upD = 0.0, dgM = 0.0, dgI = 0.0, dgD = 0.0, sumM = 0.0, sumI = 0.0;
+    const unsigned char* tl = s_tbl + lane * PAIR64_TSTRIDE;
+    bool small = false;
+    for (int s = 0; s < H + 31; ++s) {
+        const int c = s - (int)lane;                             // my column this step; outside [0, H): idle work, never kept
+        if (c == 0) {                                            // column -1 state: M = I = D = 0, generator rows hold D = init
+#pragma unroll
+            for (int k = 0; k < RPT; ++k) { Ml[k] = 0.0; Il[k] = 0.0; Dl[k] = (((int)lane * RPT + k) < npad) ? init : 0.0; }
+            dgM = 0.0; dgI = 0.0; dgD = above_pad ? init : 0.0;
+        }
+        const bool valid = c >= 0 && c < H;
+        const double* pr = reinterpret_cast<const double*>(tl + (valid ? (uint32_t)s_cls[c] : 5u) * (32 * PAIR64_TSTRIDE));
+        double prior[RPT];
+        if (RPT >= 2) {
+            const double2 v = *reinterpret_cast<const double2*>(pr);
+            prior[0] = v.x;
+            prior[RPT >= 2 ? 1 : 0] = v.y;
+        } else {
+            prior[0] = pr[0];
+        }
+        if (RPT >= 4) {
+            const double2 v = *reinterpret_cast<const double2*>(pr + 2);
+            prior[RPT >= 4 ? 2 : 0] = v.x;
+            prior[RPT >= 4 ? 3 : 0] = v.y;
+        } else if (RPT == 3) {
+            prior[RPT >= 3 ? 2 : 0] = pr[2];
+        }
+        if (RPT == 5) prior[RPT >= 5 ? 4 : 0] = pr[4];
+        double pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+        bool step_small = false;
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const double oM = Ml[k], oI = Il[k], oD = Dl[k];
+            double t = __dmul_rn(pM, mm[k]);
+            t = __fma_rn(pI, gapm, t);
+            t = __fma_rn(pD, gapm, t);
+            const double m = __dmul_rn(t, prior[k]);
+            const double i = __fma_rn(uI, gcp_p, __dmul_rn(uM, mi[k]));
+            const double d = __fma_rn(oD, dd[k], __dmul_rn(oM, mi[k]));
+            step_small |= (uint32_t)(__double2hiint(m) - 1) < trip_hi - 1u;         // 0 < m < 2^-830 (trip_hi = 0x0C100000)
+            Ml[k] = m; Il[k] = i; Dl[k] = d;
+            pM = oM; pI = oI; pD = oD;
+            uM = m; uI = i;
+        }
+        dgM = upM; dgI = upI; dgD = upD;
+        if (valid) {
+            small |= step_small;
+            sumM = __dadd_rn(sumM, Ml[RPT - 1]);                 // only the last lane's sums are read
+            sumI = __dadd_rn(sumI, Il[RPT - 1]);
+        }
+        const double nuM = __shfl_up_sync(0xffffffffu, Ml[RPT - 1], 1);
+        const double nuI = __shfl_up_sync(0xffffffffu, Il[RPT - 1], 1);
+        const double nuD = __shfl_up_sync(0xffffffffu, Dl[RPT - 1], 1);
+        if (lane != 0) { upM = nuM; upI = nuI; upD = nuD; }
+    }
+    *result = __dadd_rn(sumM, sumI);
+    return __any_sync(0xffffffffu, small);
+}
+
+__global__ void __launch_bounds__(128) phmm_pair64_kernel(PhmmBatchDev p, const PhmmPair* pairs, const uint32_t* count_dev, double* out,
+                                                          PhmmPair* redo, uint32_t* redo_count, double gapm, double gcp_p, uint32_t trip_hi)
+{
+    __shared__ __align__(16) unsigned char s_tbl_all[4][6 * 32 * PAIR64_TSTRIDE];
+    __shared__ uint8_t s_cls_all[4][PAIR64_MAX_H];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t n = *count_dev;
+    unsigned char* s_tbl = s_tbl_all[wib];
+    uint8_t* s_cls = s_cls_all[wib];
+    for (uint32_t pi = wid; pi < n; pi += nwarps) {
+        const PhmmPair pr = pairs[pi];
+        const PhmmRead rd = p.reads[pr.read];
+        const PhmmHap hp = p.haps[pr.hap];
+        const uint32_t flags = rd.model_flags >> 4;
+        bool redo_it = rd.len == 0 || rd.len > 32u * PAIR64_MAX_RPT - 1u || hp.len == 0 || hp.len > PAIR64_MAX_H ||
+                       (flags & (PHMM_RD_HAS_DEL | PHMM_RD_HAS_GCP)) != 0;
+        double res = 0.0;
+        if (!redo_it) {
+            const uint8_t* hb = p.hap_bases + hp.byte_off;
+            __syncwarp();                                        // the previous pair's tables and classes are no longer read
+            for (uint32_t c = lane; c < hp.len; c += 32) s_cls[c] = (uint8_t)base_class(hb[c]);
+            const uint32_t rpt = (rd.len + 32u) / 32u;           // ceil((R + 1) / 32)
+            switch (rpt) {
+                case 1: redo_it = pair64_sweep<1>(p, rd, hp, lane, s_cls, s_tbl, gapm, gcp_p, trip_hi, &res); break;
+                case 2: redo_it = pair64_sweep<2>(p, rd, hp, lane, s_cls, s_tbl, gapm, gcp_p, trip_hi, &res); break;
+                case 3: redo_it = pair64_sweep<3>(p, rd, hp, lane, s_cls, s_tbl, gapm, gcp_p, trip_hi, &res); break;
+                case 4: redo_it = pair64_sweep<4>(p, rd, hp, lane, s_cls, s_tbl, gapm, gcp_p, trip_hi, &res); break;
+                default: redo_it = pair64_sweep<5>(p, rd, hp, lane, s_cls, s_tbl, gapm, gcp_p, trip_hi, &res); break;
+            }
+        }
+        if (lane == 31) {
+            if (redo_it) redo[atomicAdd(redo_count, 1u)] = pr;
+            else out[pr.out_idx] = res;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // phmm_epilogue_kernel — the reference's host side after the kernels, on the device: raw sums ->
 // log10 (pairhmm_internal.cpp:578-584), normalize_likelihoods (:53-63), filter_poorly_modelled_evidence (:161-182),
 // transpose_likelihood_matrix (:184-193) with its NaN tail, and the per-read best / second-best haplotype search the next
@@ -969,10 +1130,20 @@ cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPai
 }
 
 cudaError_t phmm_launch_pairs_f64(const PhmmBatchDev& b, const PhmmPair* pairs, const uint32_t* count_dev, double* scratch,
-                                  uint32_t threads, uint32_t max_cols, cudaStream_t st)
+                                  uint32_t threads, uint32_t max_cols, PhmmPair* redo, uint32_t* redo_count, double gapm_d, double gcp_d,
+                                  uint32_t trip_hi, cudaStream_t st)
 {
     const uint32_t blocks = threads / 128;
-    phmm_pair_kernel<double, true><<<blocks, 128, 0, st>>>(b, pairs, count_dev, 0u, scratch, max_cols, b.out_f64);
+    // the common shapes one warp per pair without a flush test per operation; what that kernel hands back (and every pair when
+    // there is no redo list) through the general kernel
+    if (redo) {
+        phmm_pair64_kernel<<<blocks * 2, 128, 0, st>>>(b, pairs, count_dev, b.out_f64, redo, redo_count, gapm_d, gcp_d, trip_hi);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        phmm_pair_kernel<double, true><<<blocks, 128, 0, st>>>(b, redo, redo_count, 0u, scratch, max_cols, b.out_f64);
+    } else {
+        phmm_pair_kernel<double, true><<<blocks, 128, 0, st>>>(b, pairs, count_dev, 0u, scratch, max_cols, b.out_f64);
+    }
     return cudaGetLastError();
 }
 

@@ -99,8 +99,14 @@ cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool f
 // Per-pair kernels.  count_dev != null: the pair count is read on the device (FP64 recompute list).
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
                                   uint32_t threads, uint32_t max_cols, cudaStream_t st);
+// FP64 recompute of the pairs listed on the device.  redo / redo_count (a second list of the same capacity and its counter,
+// zeroed by the caller): the fast kernel takes the common shapes and hands the rest to the general one; null: the general
+// kernel takes everything.  gapm_d / gcp_d: 1 - ph2pr_d[gcp] and ph2pr_d[gcp] of the default gap-continuation quality.
+// trip_hi: high word of the smallest M the fast kernel accepts (PHMM_PAIR64_TRIP_HI = 2^-830; tests raise it to force hand-backs).
+#define PHMM_PAIR64_TRIP_HI 0x0C100000u
 cudaError_t phmm_launch_pairs_f64(const PhmmBatchDev& b, const PhmmPair* pairs, const uint32_t* count_dev, double* scratch,
-                                  uint32_t threads, uint32_t max_cols, cudaStream_t st);
+                                  uint32_t threads, uint32_t max_cols, PhmmPair* redo, uint32_t* redo_count, double gapm_d, double gcp_d,
+                                  uint32_t trip_hi, cudaStream_t st);
 // Static facts for reports (registers, spills) — filled from cudaFuncGetAttributes.
 struct PhmmKernelInfo
 {

@@ -126,6 +126,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     static const uint32_t env_cols = std::getenv("PHMM_B200_STREAM_COLS") ? (uint32_t)std::atoi(std::getenv("PHMM_B200_STREAM_COLS")) : 0u;   // experiments only
     const uint32_t full_cols = env_cols ? env_cols : kTargetStreamCols;
     uint32_t target_cols = full_cols;
+    bool single_stream = false;    // one haplotype stream per chunk (latency policy below)
     int min_lanes = 8;             // lanes the longest read of a region should spread over at least (latency policy below)
     {
         uint64_t est_warps = 0;
@@ -146,6 +147,8 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             min_lanes = 32;
         else if (est_warps * 4 <= want)
             min_lanes = 16;
+        // (est_warps counts 8-lane warps of full-length chunks: 32 lanes and a haplotype per chunk make 32 times as many)
+        single_stream = min_lanes == 32 && !cfg->lanes_pref && est_warps * 64 <= want;
         est_warps *= (uint64_t)min_lanes / 8;
         // ... and a batch runs at 1 / (1 + slots / warps) of the device's rate while its last warps finish alone: below
         // kWavesWanted waves the chunks are cut shorter (a 300-column sweep costs a warp ~2 % in prologue, tools/chunk_curve.py)
@@ -268,12 +271,15 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     }
                     order[at2] = v;
                 }
-                // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty
-                uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / 2),
-                                                                 std::max<uint64_t>(1, (total + 2ull * target_cols - 1) / (2ull * target_cols)));
+                // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty —
+                // unless the batch is so small that most of the device would idle anyway (the one-region calls of a lone
+                // synchronous caller): then a haplotype per chunk halves the sweep, i.e. the call's latency
+                const uint32_t per_chunk = single_stream ? 1u : 2u;
+                uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / per_chunk),
+                                                                 std::max<uint64_t>(1, (total + per_chunk * (uint64_t)target_cols - 1) / (per_chunk * (uint64_t)target_cols)));
                 std::vector<uint32_t>&ssum = ps.stream_sum, &sown = ps.stream_of, &sidx = ps.stream_idx;
                 for (;;) {
-                    const uint32_t S = 2 * n_chunks;
+                    const uint32_t S = per_chunk * n_chunks;
                     ssum.assign(S, 0u);
                     sown.resize(order.size());
                     bool fits = true;
@@ -285,10 +291,10 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                         ssum[best] += r.haps[order[a]].len;
                         fits &= ssum[best] <= kMaxStreamCols;              // what one CTA can stage in shared memory
                     }
-                    if (fits || 2 * n_chunks >= order.size()) break;
+                    if (fits || per_chunk * n_chunks >= order.size()) break;
                     ++n_chunks;                                            // several very long haplotypes: spread them further
                 }
-                const uint32_t S = 2 * n_chunks;
+                const uint32_t S = per_chunk * n_chunks;
                 sidx.resize(S);
                 for (uint32_t q = 0; q < S; ++q) sidx[q] = q;
                 for (uint32_t a = 1; a < S; ++a) {                         // streams by length, longest first
@@ -301,7 +307,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     sidx[at2] = v;
                 }
                 for (uint32_t c = 0; c < n_chunks; ++c) {
-                    const uint32_t sx = sidx[2 * c], sy = sidx[2 * c + 1];
+                    const uint32_t sx = sidx[per_chunk * c], sy = single_stream ? UINT32_MAX : sidx[2 * c + 1];
                     if (ssum[sx] == 0) break;                              // fewer haplotypes than streams
                     PhmmChunk ch{};
                     ch.hap_begin = (uint32_t)haps.size();
@@ -611,7 +617,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     if ((rc = s.d_words.ensure((read_bytes + 16) * sizeof(uint32_t), &high_water[1])) != PHMM_OK) return rc;
     if ((rc = s.d_f32.ensure(pairs_alloc * sizeof(float), &high_water[2])) != PHMM_OK) return rc;
     if ((rc = s.d_f64.ensure(pairs_alloc * sizeof(double), &high_water[3])) != PHMM_OK) return rc;
-    if ((rc = s.d_pairs.ensure(pairs_alloc * sizeof(PhmmPair), &high_water[4])) != PHMM_OK) return rc;
+    if ((rc = s.d_pairs.ensure(2 * pairs_alloc * sizeof(PhmmPair), &high_water[4])) != PHMM_OK) return rc;   // + the FP64 hand-back list
     if ((rc = s.d_cnt.ensure(256)) != PHMM_OK) return rc;
     if ((rc = s.d_scr64.ensure((size_t)(kPairThreads / 32) * (max_cols + 1) * 3 * sizeof(double), &high_water[5])) != PHMM_OK) return rc;
     if (!slow.empty())

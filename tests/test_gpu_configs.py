@@ -310,3 +310,44 @@ def test_device_marginalisation_of_resident_matrices(ref):
         res.free()
     finally:
         host.close()
+
+
+def test_fast_fp64_kernel_equals_the_general_one(orc, monkeypatch):
+    """The FP64 recompute has a fast kernel (one strip per pair, no flush test per operation, a range check on M instead) and a
+    general one (any shape, flushes after every operation as the reference's FTZ does).  Same bits from both on junk reads of
+    1 to 5 rows per lane, on reads beyond the fast kernel's 159 bases, and on pairs the fast kernel hands back because its
+    range check trips (forced here by raising the check's floor from 2^-830 to 2^+900: with the default gap-continuation
+    quality a read of <= 159 bases cannot get anywhere near the real floor); all within 1e-12 of the scalar FP64 oracle."""
+    rng = np.random.default_rng(91)
+    regs = [wl._one_region(rng, 40, 6, 300, 420, 100, 151, junk=0.6), wl._one_region(rng, 30, 5, 80, 120, 10, 100, junk=0.7),
+            wl._one_region(rng, 12, 3, 500, 700, 140, 250, junk=0.8)]                     # some reads over 159 bases
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+    haps = [np.full(400, ord("C"), np.uint8), np.full(350, ord("G"), np.uint8), acgt[rng.integers(0, 4, 380)]]
+    reads = [dict(bases=np.full(n, ord("A"), np.uint8), qual=np.full(n, 40, np.uint8), mapq=60) for n in (150, 151, 120, 159, 90)]
+    regs.append((reads, haps))                                                            # every base a mismatch
+    batch = wl.RegionBatch.from_regions(regs)
+    eng = PairHmmEngine(fp64_mode=FP64_ALWAYS)
+    try:
+        fast = eng.run_flat(batch, raw=True)
+        monkeypatch.setenv("PHMM_B200_FP64_GENERAL", "1")
+        general = eng.run_flat(batch, raw=True)
+        monkeypatch.delenv("PHMM_B200_FP64_GENERAL")
+        monkeypatch.setenv("PHMM_B200_FP64_TRIP_HI", hex((1023 + 900) << 20))
+        tripped = eng.run_flat(batch, raw=True)
+        monkeypatch.delenv("PHMM_B200_FP64_TRIP_HI")
+    finally:
+        eng.close()
+    took = fast.raw_f32 < np.float32(1e-28)
+    assert took.sum() == fast.n_fp64 == general.n_fp64 == tripped.n_fp64 > 200
+    for other in (general, tripped):
+        assert np.array_equal(fast.raw_f64[took].view(np.uint64), other.raw_f64[took].view(np.uint64))
+        assert np.array_equal(fast.likelihoods.view(np.uint64), other.likelihoods.view(np.uint64))
+    assert np.isnan(fast.raw_f64[~took]).all()
+    assert (fast.raw_f64[took] < 2.0 ** 900).sum() > 150, "most pairs must fall under the raised floor"
+    for g in range(batch.n_regions):
+        rd, hp = batch.region(g)
+        _, _, o32, o64, n64 = orc.region(rd, hp)
+        t = o32 < np.float32(1e-28)
+        a, b = fast.raw64(g)[t], o64[t]
+        nz = b != 0
+        assert np.all(np.abs(a[nz] - b[nz]) <= 1e-12 * np.abs(b[nz])) and np.all(a[~nz] == 0)

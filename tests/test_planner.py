@@ -50,10 +50,13 @@ def test_an_idle_device_gets_the_wide_layouts():
 def test_small_batches_are_cut_finer():
     """A batch with fewer than sixteen waves of warps gets shorter chunks (its last warps would otherwise finish alone); a batch
     that fills the device many times over keeps one full-length chunk per cfg2 region."""
-    few, many = ph.plan_audit(wl.cfg2(2, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2048, seed=3), busy_batches=1)
+    few, many = ph.plan_audit(wl.cfg2(4, seed=3), busy_batches=1), ph.plan_audit(wl.cfg2(2048, seed=3), busy_batches=1)
     _sound(few)
     _sound(many)
-    assert few["chunks"] == 2 * 4 and many["chunks"] == 2048          # 8 haplotypes: at most four chunks of one pair each
+    assert few["chunks"] == 4 * 4 and many["chunks"] == 2048          # 8 haplotypes: four chunks of one pair each
+    lone = ph.plan_audit(wl.cfg2(1, seed=3), busy_batches=1)          # a lone call on an idle device: a haplotype per chunk,
+    _sound(lone)                                                      # half the sweep (and half the lanes idle, which nobody needs)
+    assert lone["chunks"] == 8 and lone["warps"] == 8 * 64
     mid = ph.plan_audit(wl.cfg2(256, seed=3), busy_batches=1)
     _sound(mid)
     assert 256 < mid["chunks"] <= 4 * 256

@@ -1,8 +1,28 @@
 #!/bin/bash
-# 8-GPU weak-scaling check of bench.py (cfg2, 4096 regions per rank): device step and end-to-end GCUPS, host phases
+# multi-GPU evidence on one box (run under gpurun --gpus N): GPU tests (incl. the torchrun sharded-stream test and the
+# multi-device engine tests), bench.py at 1/2/4/N ranks with the sharded-stream record, a 1 M-region sharded stream at N ranks,
+# and ONE process driving all N GPUs.  Usage: bash tools/gpu_scale8.sh <tag> <N>
+TAG=${1:-r02_scale}; N=${2:-8}
 mkdir -p gpurun_out
-run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node ${3:-8} --master-addr 127.0.0.1 --master-port $1 bench.py --gpus ${3:-8} --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); e=d['e2e']; print('$2', d['n_gpus'], d['value'], e['value'], e['ms_per_step'], e['host_plan_ms_per_step'], e['host_epilogue_ms_per_step'])"; }
-run 29521 default 8
-run 29522 default 8
-nproc
+nvidia-smi --query-gpu=index,name,clocks.max.sm --format=csv > gpurun_out/${TAG}_gpus.csv; nproc >> gpurun_out/${TAG}_gpus.csv
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest exit $?"; tail -4 gpurun_out/${TAG}_pytest.log
+: > gpurun_out/${TAG}_bench.jsonl
+P=29600
+for n in 1 2 4 $N; do
+  [ $n -gt $N ] && continue
+  P=$((P+1))
+  if [ $n -eq 1 ]; then timeout 900 python bench.py --gpus 1 --steps 5 --warmup 3 --no-workloads >> gpurun_out/${TAG}_bench.jsonl 2>> gpurun_out/${TAG}_bench.err
+  else timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $P bench.py --gpus $n --steps 5 --warmup 3 2>> gpurun_out/${TAG}_bench.err | grep '^{' >> gpurun_out/${TAG}_bench.jsonl; fi
+  echo "bench n=$n exit $?"
+done
+P=$((P+1))
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N --steps 2 --warmup 3 --regions 1024 --sustain 0 --stream-regions 1048576 2>> gpurun_out/${TAG}_bench.err | grep '^{' > gpurun_out/${TAG}_stream1M.json; echo "1M stream exit $?"
+timeout 900 python tools/multi_gpu_stream.py 524288 0.5 all > gpurun_out/${TAG}_one_process.json 2>> gpurun_out/${TAG}_bench.err; echo "one process exit $?"
+python - <<PY
+import json
+for ln in open("gpurun_out/${TAG}_bench.jsonl"):
+    d = json.loads(ln); s = d.get("sharded_stream") or {}
+    print("n", d["n_gpus"], "value", d["value"], "e2e", d["e2e"]["value"], "| sharded stream e2e", s.get("e2e_gcups"), "identical", s.get("identical_to_single_gpu"))
+d = json.loads(open("gpurun_out/${TAG}_stream1M.json").read()); print("1M:", json.dumps(d["sharded_stream"]))
+print(open("gpurun_out/${TAG}_one_process.json").read())
+PY

@@ -18,8 +18,9 @@ constexpr uint32_t kRowCost[PHMM_MAX_RPT + 1] = {0,    4680, 2188, 1603, 1531, 1
 inline uint32_t step_cost(int rpt) { return (uint32_t)rpt * kRowCost[rpt]; }
 // Rows-per-lane counts the throughput policy chooses among: every distinct count in a batch is a launch of its own with its own
 // tail, and neighbouring counts differ by a per cent or two — so a few well-separated ones.
-constexpr int kRptChoices[] = {12, 16, 19};
-constexpr int kRptChoicesGeneric[] = {8, 10, 12};
+constexpr int kRptChoices[] = {12, 16, 19};            // first choice first
+constexpr int kRptChoicesGeneric[] = {12, 10, 8};
+constexpr uint32_t kRptMargin = 6;
 
 // Pack reads that need lanes_of[k] consecutive lanes each into warps of 32 lanes, biggest first into the first warp that still
 // has room (by_lanes[n] = how many reads need n lanes).  Returns the warps needed; with `out`, also which reads go where:
@@ -401,16 +402,34 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 // a region of equal-length reads (the usual short-read case): remembered from the last such region
             } else {
                 // the few candidate counts, each packed for real: least warps x step cost (ties: more rows per lane)
-                uint32_t best = UINT32_MAX;
+                // The first choice is the most efficient instantiation; another count has to beat it by kRptMargin per cent to
+                // be worth a launch of its own (reads that pack badly at the first choice do: 150-bp reads take 13 lanes at
+                // 12 rows, two per warp, but 8 lanes at 19 rows, four per warp).
+                uint64_t best = UINT64_MAX;
                 const int* choices = refgaps ? kRptChoices : kRptChoicesGeneric;
-                for (int q = 2; q >= 0; --q) {
+                const bool uniform = shortest_read == longest_read;
+                for (int q = 0; q < 3; ++q) {
                     const int c = std::max(rpt_lo, choices[q]);
                     if (c > max_rpt || c == rpt) continue;
-                    const uint32_t cost = exact_cost(c);
+                    uint64_t cost;
+                    if (uniform) {
+                        cost = exact_cost(c);                                   // packed for real, and remembered below
+                    } else {
+                        // mixed lengths: all lanes over what a warp holds on average — 32 less half a read's lanes minus one,
+                        // the room the next read does not fit into (an estimate: packing every candidate for every region
+                        // of a stream of small regions costs more host time than it saves device time)
+                        const uint8_t* lut = lanes_lut[c];
+                        uint32_t lanes = 0;
+                        for (uint32_t k = 0; k < r.n_reads; ++k) lanes += lut[lens[k]];
+                        lanes -= r.n_reads - fast_reads;
+                        const uint32_t room64 = 64u * 32u - 32u * (lanes - fast_reads) / fast_reads;      // capacity per warp x 64
+                        cost = (uint64_t)((64u * lanes + room64 - 1) / room64) * step_cost(c);
+                    }
+                    cost *= (q == 0 ? 100u - kRptMargin : 100u);
                     if (cost < best) { best = cost; rpt = c; }
                 }
                 if (rpt == 0) rpt = max_rpt;
-                if (shortest_read == longest_read) uniform_rpt[std::min<uint32_t>(fast_reads, 255u)][longest_read] = (uint8_t)rpt;
+                if (uniform) uniform_rpt[std::min<uint32_t>(fast_reads, 255u)][longest_read] = (uint8_t)rpt;
             }
             // the packing itself: read ids by lane count (a counting sort that keeps the caller's order), then warp after warp
             {

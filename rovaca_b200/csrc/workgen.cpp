@@ -226,9 +226,10 @@ void wg_counts(const wg_spec* sp, uint64_t first, uint32_t n, uint32_t* n_reads,
     });
 }
 
-// Cells (sum of read lengths x sum of haplotype lengths) of every region of [first, first + n), without generating a byte:
+// Cells (sum of read lengths x sum of haplotype lengths) and pairs (reads x haplotypes) of every region of [first, first + n),
+// without generating a byte:
 // what a sharding plan needs of a stream.
-void wg_region_cells(const wg_spec* sp, uint64_t first, uint32_t n, uint64_t* cells, uint32_t threads)
+void wg_region_cells(const wg_spec* sp, uint64_t first, uint32_t n, uint64_t* cells, uint64_t* pairs, uint32_t threads)
 {
     parallel_regions(n, threads, [=](uint32_t a, uint32_t b) {
         Shape sh;
@@ -238,6 +239,7 @@ void wg_region_cells(const wg_spec* sp, uint64_t first, uint32_t n, uint64_t* ce
             for (uint32_t v : sh.read_len) rb += v;
             for (const HapPlan& h : sh.haps) hb += h.len;
             cells[g] = rb * hb;
+            if (pairs) pairs[g] = (uint64_t)sh.n_reads * sh.n_haps;
         }
     });
 }

@@ -20,6 +20,7 @@ from . import sharding, workloads
 from .pairhmm import FlatResult, PairHmmEngine
 
 BLOCK = 512              # regions per block of a stream: the unit ranks / devices are dealt
+PAIR_WEIGHT = 16384      # cells a pair is charged for the host's work on it (kPairWeight in the engine)
 PIECE = 65536            # regions per phmm_run_flat call (one pinned input set, one result set: ~0.6 GB for cfg5)
 
 
@@ -42,6 +43,15 @@ class StreamSpec:
         c = workloads.stream_cells(self.kind, self.n_regions, 0, self.seed, self.post_trim_fraction).astype(np.int64)
         pad = self.n_blocks * BLOCK - self.n_regions
         return np.concatenate([c, np.zeros(pad, np.int64)]).reshape(self.n_blocks, BLOCK).sum(axis=1)
+
+    def block_work(self) -> np.ndarray:
+        """What a block costs end to end, in cell units: its cells plus a per-pair charge for the host's share (planning and
+        result hand-over cost about as much per pair as PAIR_WEIGHT cells cost the GPU — phmm_run_flat cuts its sub-batches by
+        the same measure).  Small post-trim regions are host-heavy: balancing ranks by cells alone leaves them uneven."""
+        c, p = workloads.stream_work(self.kind, self.n_regions, 0, self.seed, self.post_trim_fraction)
+        w = c.astype(np.int64) + PAIR_WEIGHT * p.astype(np.int64)
+        pad = self.n_blocks * BLOCK - self.n_regions
+        return np.concatenate([w, np.zeros(pad, np.int64)]).reshape(self.n_blocks, BLOCK).sum(axis=1)
 
     def describe(self) -> str:
         return (f"{self.kind} stream of {self.n_regions} regions (seed {self.seed}, {self.post_trim_fraction:.0%} post-trim shapes), "
@@ -124,7 +134,7 @@ def run_stream(eng: PairHmmEngine, spec: StreamSpec, blocks: Optional[Sequence[i
 def sharded_stream(eng: PairHmmEngine, spec: StreamSpec, rank: int, world: int, piece_regions: int = PIECE) -> Optional[dict]:
     """One common stream sharded over ``world`` ranks (one engine each) with no data-path collective; rank 0 then runs the
     whole stream alone on its own GPU and compares every region's digest.  -> the record (rank 0) or None."""
-    mine = sharding.shard_blocks(spec.block_cells(), rank, world)
+    mine = sharding.shard_blocks(spec.block_work(), rank, world)
     sharding.barrier()
     run = run_stream(eng, spec, mine, piece_regions)
     secs = sharding.max_over_ranks(run.seconds)
@@ -136,7 +146,7 @@ def sharded_stream(eng: PairHmmEngine, spec: StreamSpec, rank: int, world: int, 
         return None
     rec = {"stream": spec.describe(), "regions": spec.n_regions, "cells": int(cells), "n_gpus": world,
            "e2e_gcups": round(cells / secs / 1e9, 2), "seconds_max_over_ranks": round(secs, 4),
-           "seconds_per_rank": [round(float(x), 4) for x in rank_secs], "sharding": f"LPT over blocks of {BLOCK} regions, no collective",
+           "seconds_per_rank": [round(float(x), 4) for x in rank_secs], "sharding": f"LPT by work (cells + {PAIR_WEIGHT} per pair) over blocks of {BLOCK} regions, no collective",
            "what_travels": "one 64-bit digest per region to rank 0 (host-side gather)"}
     if world > 1:
         solo = run_stream(eng, spec, None, piece_regions, warm=False)

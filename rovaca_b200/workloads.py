@@ -341,7 +341,7 @@ def _workgen():
         L.wg_lengths.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, vp, vp, u32]
         L.wg_fill.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, vp, vp, vp, vp, vp, vp, u32]
         L.wg_digest_regions.argtypes = [u32, vp, vp, vp, vp, vp, vp, vp, u32]
-        L.wg_region_cells.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, u32]
+        L.wg_region_cells.argtypes = [_C.POINTER(_WgSpec), u64, u32, vp, vp, u32]
         for f in (L.wg_counts, L.wg_lengths, L.wg_fill, L.wg_digest_regions, L.wg_region_cells):
             f.restype = None
         _wg = L
@@ -365,10 +365,16 @@ def _spec(kind: str, seed: int, post_trim_fraction: float) -> _WgSpec:
 def stream_cells(kind: str, n_regions: int, first: int = 0, seed: int = 5, post_trim_fraction: float = 0.0,
                  threads: Optional[int] = None) -> np.ndarray:
     """Cells of every region of [first, first + n_regions) of the stream, without generating it (for sharding plans)."""
+    return stream_work(kind, n_regions, first, seed, post_trim_fraction, threads)[0]
+
+
+def stream_work(kind: str, n_regions: int, first: int = 0, seed: int = 5, post_trim_fraction: float = 0.0,
+                threads: Optional[int] = None):
+    """(cells, pairs) of every region of [first, first + n_regions) of the stream, without generating it."""
     sp = _spec(kind, seed, post_trim_fraction)
-    out = np.zeros(max(int(n_regions), 1), np.uint64)
-    _workgen().wg_region_cells(_C.byref(sp), first, int(n_regions), out.ctypes.data, _threads(threads))
-    return out[: int(n_regions)]
+    cells, pairs = np.zeros(max(int(n_regions), 1), np.uint64), np.zeros(max(int(n_regions), 1), np.uint64)
+    _workgen().wg_region_cells(_C.byref(sp), first, int(n_regions), cells.ctypes.data, pairs.ctypes.data, _threads(threads))
+    return cells[: int(n_regions)], pairs[: int(n_regions)]
 
 
 def stream(kind: str, n_regions: int, first: int = 0, seed: int = 5, post_trim_fraction: float = 0.0, pinned: bool = False,

@@ -47,7 +47,7 @@ typedef struct phmm_config
 {
     int32_t device;               /* CUDA ordinal; -1 = current device */
     int32_t fma_mode;             /* PHMM_FMA_* (0 = the AVX-512 flavour) */
-    uint32_t n_workers;           /* host worker threads = batches in flight, per device (0 = three quarters of the cores / visible GPUs, clamped to 2..12) */
+    uint32_t n_workers;           /* host worker threads = batches in flight, per device (0 = cores / visible GPUs, clamped to 2..12) */
     uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 32e9) */
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
@@ -206,7 +206,7 @@ void phmm_destroy(phmm_engine* e);
  * one device.  Regions are independent, so there is no collective and no peer access, and the result
  * of a region does not depend on the device that computed it.  devices[k] are CUDA ordinals (-1 = the current device; an
  * ordinal may be listed twice: two independent queues on one GPU); n_devices = 0 means every visible device.  cfg->device is
- * ignored, cfg->n_workers counts per device (0 = three quarters of the cores / max(devices used, devices visible), clamped to 2..12). */
+ * ignored, cfg->n_workers counts per device (0 = cores / max(devices used, devices visible), clamped to 2..12). */
 int phmm_create_multi(const phmm_config* cfg, const int32_t* devices, uint32_t n_devices, phmm_engine** out);
 uint32_t phmm_device_count(const phmm_engine* e);
 int phmm_device_ordinal(const phmm_engine* e, uint32_t index);   /* CUDA ordinal of the engine's index-th device, -1 if out of range */

@@ -232,7 +232,7 @@ int phmm_create_multi(const phmm_config* cfg, const int32_t* devices, uint32_t n
     // host workers per device: the box's cores are shared by the devices this process drives and — one rank per GPU being the
     // other deployment — by the ranks beside it
     const unsigned sharers = (unsigned)std::max<size_t>(std::max<size_t>(ords.size(), (size_t)ndev), 1);
-    s.n_workers = std::max(2u, std::min(12u, std::thread::hardware_concurrency() * 3 / 4 / sharers));
+    s.n_workers = std::max(2u, std::min(12u, std::thread::hardware_concurrency() / sharers));
     if (const char* env = std::getenv("PHMM_B200_WORKERS"))          // deployment override of the default only
         if (std::atoi(env) > 0) s.n_workers = std::min(32, std::atoi(env));
     if (cfg) {

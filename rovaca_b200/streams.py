@@ -98,6 +98,7 @@ def run_stream(eng: PairHmmEngine, spec: StreamSpec, blocks: Optional[Sequence[i
     ``warm``: the first piece is run once untimed first (arena growth, clocks)."""
     if blocks is None:
         blocks = np.arange(spec.n_blocks)
+    piece_regions *= max(1, int(getattr(eng, "n_devices", 1)))      # an engine over N devices takes N times the piece per call
     if pinned:                                  # page-locked inputs need the CUDA runtime (the CPU tests stand the engine in)
         import torch
         pinned = torch.cuda.is_available()

@@ -350,6 +350,7 @@ int PhmmDevice::init(const PhmmSettings* settings, int cuda_ordinal, uint32_t id
                                        "; this library carries sm_100a code only");
     warp_slots = (uint32_t)prop.multiProcessorCount * 8;
     smem_optin = prop.sharedMemPerBlockOptin;
+    smem_sm = prop.sharedMemPerMultiprocessor;
     int rc = d_tables.ensure(sizeof(PhmmTables));
     if (rc != PHMM_OK) return rc;
     CU(cudaMemcpy(d_tables.p, &tables, sizeof(PhmmTables), cudaMemcpyHostToDevice));

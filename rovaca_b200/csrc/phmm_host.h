@@ -310,6 +310,7 @@ struct PhmmDevice
     uint32_t index = 0;          // position in phmm_engine::devs
     uint32_t warp_slots = 148 * 8; // warps of the widest forward kernel the device holds at once (8 per SM at 231 registers)
     size_t smem_optin = 227 * 1024;  // dynamic shared memory one CTA may ask for (cudaDevAttrMaxSharedMemoryPerBlockOptin)
+    size_t smem_sm = 228 * 1024;     // shared memory of one SM (cudaDevAttrMaxSharedMemoryPerMultiprocessor)
     std::atomic<uint32_t> busy_batches{0};   // batches somewhere between plan and the end of their epilogue
     std::atomic<uint64_t> outstanding{0};    // work (weighted cells) queued on or running on this device: the dispatch key
     std::atomic<size_t> high_water[8] = {};   // per arena kind, see grow_to()

@@ -228,8 +228,8 @@ __device__ __forceinline__ uint32_t class_onehot(uint32_t b) { return b < 4u ? (
 
 // occupancy targets found with tools/phmm_ablate.cu: the kernel is bound by register-file reads and issue slots, not by
 // latency, so it wants enough registers to hold RPT rows x 2 streams x 3 states plus the row parameters without spilling.
-constexpr int fwd_min_blocks(int rpt) { return rpt <= 3 ? 6 : rpt <= 5 ? 5 : (rpt == 6 || rpt == 8) ? 4 : rpt <= 10 ? 3 : 2; }
-constexpr int fwd_min_blocks_rg(int rpt) { return rpt <= 3 ? 6 : rpt <= 6 ? 5 : rpt <= 9 ? 4 : rpt <= 12 ? 3 : 2; }
+constexpr int fwd_min_blocks(int rpt) { return phmm_fwd_blocks_per_sm(rpt, false); }
+constexpr int fwd_min_blocks_rg(int rpt) { return phmm_fwd_blocks_per_sm(rpt, true); }
 
 // VAR: PHMM_VAR_GENERIC_NOFMA — any per-base qualities, un-contracted AVX2 arithmetic (core/avx2_s.cpp:207-216);
 //      PHMM_VAR_GENERIC       — any per-base qualities, AVX-512 contraction;
@@ -320,6 +320,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     const uint32_t rid = __shfl_sync(0xffffffffu, my_rid, ridx);
     const uint32_t nl = __shfl_sync(0xffffffffu, my_nl, ridx);
     const uint32_t lane = live ? wlane - first : 0u;                               // my lane within the read
+    constexpr int shfl_w = 32;                                                     // (segmenting the shuffles per read where the lane counts allow it measured slower)
     const PhmmRead rd = p.reads[rid];
     const int npad = (int)(nl * RPT) - (int)rd.len;   // >= 1
 
@@ -494,12 +495,12 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             sumM.x = __fadd_rn(sumM.x, Ml[RPT - 1].x); sumM.y = __fadd_rn(sumM.y, Ml[RPT - 1].y);
             sumI.x = __fadd_rn(sumI.x, Il[RPT - 1].x); sumI.y = __fadd_rn(sumI.y, Il[RPT - 1].y);
         }
-        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1);
-        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1);
-        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1);
-        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1);
-        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1);
-        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1);
+        upM.x = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].x, 1, shfl_w);
+        upM.y = __shfl_up_sync(0xffffffffu, Ml[RPT - 1].y, 1, shfl_w);
+        upI.x = __shfl_up_sync(0xffffffffu, Il[RPT - 1].x, 1, shfl_w);
+        upI.y = __shfl_up_sync(0xffffffffu, Il[RPT - 1].y, 1, shfl_w);
+        upD.x = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].x, 1, shfl_w);
+        upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1, shfl_w);
     }
 #undef PHMM_BOUNDARY
 }

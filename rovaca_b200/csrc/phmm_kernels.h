@@ -69,6 +69,16 @@ cudaError_t phmm_launch_log10_probe(const float* x, double* out, uint32_t n, cud
 #define PHMM_VAR_GENERIC 1
 #define PHMM_VAR_REFGAPS 2
 
+// CTAs of PHMM_WARPS warps the register file of an SM holds of the instantiation with `rpt` rows per lane (the occupancy
+// targets the kernels are compiled for, __launch_bounds__ in phmm_kernels.cu)
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int phmm_fwd_blocks_per_sm(int rpt, bool refgaps)
+{
+    return refgaps ? (rpt <= 3 ? 6 : rpt <= 6 ? 5 : rpt <= 9 ? 4 : rpt <= 12 ? 3 : 2)
+                   : (rpt <= 3 ? 6 : rpt <= 5 ? 5 : (rpt == 6 || rpt == 8) ? 4 : rpt <= 10 ? 3 : 2);
+}
 static inline int phmm_max_rpt(bool refgaps) { return refgaps ? PHMM_MAX_RPT : PHMM_MAX_RPT_GENERIC; }
 static inline uint32_t phmm_read_lanes(uint32_t len, int rpt) { return (len + (uint32_t)rpt) / (uint32_t)rpt; }   // ceil((len + 1) / rpt)
 // longest read the wavefront kernel takes (longer ones go to the per-pair kernel)

@@ -478,10 +478,17 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         fl.refgaps = refgaps;
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
-        // warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but a
+        // Warps per CTA of this launch: bigger CTAs stage each chunk's streams fewer times and run a little faster, but a
         // region's warps then come in bigger lumps; take the biggest size that wastes at most 8 % more warp slots than
-        // single-warp CTAs
+        // single-warp CTAs.  (A rule that maximised resident warps per SM from the shared memory and the registers a CTA size
+        // needs picked smaller CTAs for short chunks and measured 5 % slower on post-trim streams, equal elsewhere:
+        // profiles/r02_experiments.txt.)
         uint32_t cta_warps = cfg->cta_warps;
+        uint32_t longest_stream = 0, most_haps = 0;
+        for (const Group& g : groups[b]) {
+            longest_stream = std::max(longest_stream, chunks[g.chunk].stream_len);
+            most_haps = std::max(most_haps, chunks[g.chunk].n_haps);
+        }
         if (cta_warps == 0) {
             uint64_t slots[3] = {0, 0, 0};
             for (const Group& g : groups[b])
@@ -495,9 +502,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         // ... that still fits the device's shared memory with this launch's longest chunk (streams of very long haplotypes)
         for (;;) {
-            smem = 0;
-            for (const Group& g : groups[b])
-                smem = std::max(smem, phmm_fwd_smem_bytes(chunks[g.chunk].stream_len, chunks[g.chunk].n_haps, b, cta_warps));
+            smem = phmm_fwd_smem_bytes(longest_stream, most_haps, b, cta_warps);
             if (smem <= smem_optin || cta_warps == 1) break;
             cta_warps >>= 1;
         }

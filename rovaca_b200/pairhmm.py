@@ -107,7 +107,7 @@ EXPORTS = ["phmm_resident_marginalize", "phmm_create_multi", "phmm_device_count"
 
 
 def library_path() -> str:
-    return os.path.join(_HERE, "libphmm_b200.so")
+    return os.environ.get("PHMM_B200_LIB") or os.path.join(_HERE, "libphmm_b200.so")      # the override is for kernel experiments
 
 
 def build_library(force: bool = False) -> str:

@@ -1,8 +1,10 @@
-python -m pytest tests/test_gpu_configs.py tests/test_gpu_parity.py -x -q -m gpu -k "fp64 or fast_fp64 or kernel_info" 2>&1 | tail -5
+for i in 1 2; do
+python tools/resident_bench.py cfg5 32768 1.0
+PHMM_B200_CTA_RULE=old python tools/resident_bench.py cfg5 32768 1.0
+done
+python tools/resident_bench.py cfg5 16384 0.5
+PHMM_B200_CTA_RULE=old python tools/resident_bench.py cfg5 16384 0.5
 python tools/resident_bench.py cfg3 96
-FP64_ALWAYS=1 python tools/resident_bench.py cfg3 96
-FP64_ALWAYS=1 PHMM_B200_FP64_GENERAL=1 python tools/resident_bench.py cfg3 96
+PHMM_B200_CTA_RULE=old python tools/resident_bench.py cfg3 96
 python tools/resident_bench.py cfg5 16384
-FP64_ALWAYS=1 python tools/resident_bench.py cfg5 16384
-FP64_ALWAYS=1 PHMM_B200_FP64_GENERAL=1 python tools/resident_bench.py cfg5 16384
-bash tools/gpu_callers.sh r02_callers 2>&1 | tail -14
+PHMM_B200_CTA_RULE=old python tools/resident_bench.py cfg5 16384

@@ -58,6 +58,7 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
                     const PhmmRead& rd = R[tasks[at + k]];
                     const uint32_t nl = phmm_read_lanes(rd.len, (int)rpt);
                     if (nl * rpt < rd.len + 1 || rd.len == 0) ++out[8];
+                    if (fl.fixed_lanes && nl != fl.fixed_lanes) ++out[13];   // the fixed-lanes kernel takes reads of that lane count only
                     lanes += nl;
                     widest = std::max(widest, nl);
                 }

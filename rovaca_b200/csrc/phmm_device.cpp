@@ -46,7 +46,7 @@ int PhmmDevice::launch(Slot& s, bool copy_in)
         const FwdLaunch& fl = s.launches[i];
         const size_t lane = i % (n_side + 1);
         cudaStream_t st = lane == 0 ? s.stream : s.aux[lane - 1];
-        const cudaError_t le = phmm_launch_fwd(s.dev, fl.rpt, fl.refgaps, cfg->fma, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, st);
+        const cudaError_t le = phmm_launch_fwd(s.dev, fl.rpt, fl.refgaps, cfg->fma, fl.fixed_lanes, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, st);
         if (le != cudaSuccess)
             return fail(PHMM_ERR_CUDA, std::string("forward kernel launch (") + std::to_string(fl.rpt) + " rows per lane, " +
                                            std::to_string(fl.n_ctas) + " CTAs of " + std::to_string(fl.cta_warps) + " warps, " +

@@ -164,6 +164,7 @@ struct FwdLaunch
 {
     int rpt;                 // rows per lane: which instantiation of the forward kernel
     bool refgaps;            // ... and which variant (the reference's own gap qualities, or per-base ones)
+    uint32_t fixed_lanes;    // every read of the launch takes exactly this many lanes: the fixed-lanes specialisation (0 = general kernel)
     uint32_t cta_base, n_ctas, cta_warps;
     size_t smem;
 };

@@ -238,7 +238,10 @@ constexpr int fwd_min_blocks_rg(int rpt) { return phmm_fwd_blocks_per_sm(rpt, tr
 //                               pairhmm_internal.cpp:425,559), so md == mi and gapm / ii / dd are per-read scalars: half the
 //                               parameter registers, which is what lets 19 rows per lane (8 lanes x 19 = 152 rows for 150/151-bp
 //                               reads, 1 % padding instead of 6 %) fit the register file.
-template <int RPT, int VAR>
+// FIXED: 0 = every read on the lanes it needs (the general kernel); else every read of the launch takes exactly FIXED lanes (a
+// power of two) — the round-1 layout, kept as a specialisation for the commonest shape (150/151-bp reads on 8 lanes x 19 rows):
+// read slot and lane are the thread's position, the shuffles are segmented per read; ptxas schedules this hot loop 1.5 % better.
+template <int RPT, int VAR, int FIXED>
 __global__ void __launch_bounds__(PHMM_WARPS * 32, VAR == PHMM_VAR_REFGAPS ? fwd_min_blocks_rg(RPT) : fwd_min_blocks(RPT))
 phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 {
@@ -298,29 +301,38 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     uint32_t wbeg = cta.read_begin;                                                // ... and where they start in the task list
 #pragma unroll
     for (uint32_t w = 0; w < PHMM_WARPS; ++w) wbeg += w < warp ? ((cta.warp_reads >> (8 * w)) & 0xffu) : 0u;
-    uint32_t my_rid = 0, my_nl = 0;
-    if (wlane < wcnt) {
-        my_rid = p.task_reads[wbeg + wlane];
-        my_nl = (p.reads[my_rid].len + RPT) / RPT;                                 // ceil((len + 1) / RPT): at least one pad row on top
-    }
-    uint32_t start = my_nl;                                                        // exclusive prefix sum: first lane of read i
+    uint32_t rid, nl, lane, nl_max;
+    bool live;
+    if (FIXED) {
+        live = wlane / (FIXED ? FIXED : 1) < wcnt;                                 // a dead group shadows the warp's last read, never writes
+        rid = p.task_reads[wbeg + (live ? wlane / (FIXED ? FIXED : 1) : wcnt - 1)];
+        lane = wlane & ((FIXED ? FIXED : 1) - 1);
+        nl = nl_max = FIXED;
+    } else {
+        uint32_t my_rid = 0, my_nl = 0;
+        if (wlane < wcnt) {
+            my_rid = p.task_reads[wbeg + wlane];
+            my_nl = (p.reads[my_rid].len + RPT) / RPT;                             // ceil((len + 1) / RPT): at least one pad row on top
+        }
+        uint32_t start = my_nl;                                                    // exclusive prefix sum: first lane of read i
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, start, d);
-        if (wlane >= (uint32_t)d) start += v;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, start, d);
+            if (wlane >= (uint32_t)d) start += v;
+        }
+        const uint32_t used = __shfl_sync(0xffffffffu, start, 31);                 // lanes with a read (<= 32 by the host's packing)
+        start -= my_nl;
+        const uint32_t starts = __reduce_or_sync(0xffffffffu, wlane < wcnt ? (1u << start) : 0u);
+        nl_max = __reduce_max_sync(0xffffffffu, my_nl);
+        live = wlane < used;                                                       // a lane without a read shadows lane 0 of the last read, never writes
+        const uint32_t below = starts & (0xffffffffu >> (31 - (live ? wlane : used - 1)));
+        const uint32_t ridx = (uint32_t)__popc(below) - 1u;                       // which of the warp's reads covers me
+        const uint32_t first = 31u - (uint32_t)__clz((int)below);
+        rid = __shfl_sync(0xffffffffu, my_rid, ridx);
+        nl = __shfl_sync(0xffffffffu, my_nl, ridx);
+        lane = live ? wlane - first : 0u;                                          // my lane within the read
     }
-    const uint32_t used = __shfl_sync(0xffffffffu, start, 31);                     // lanes with a read (<= 32 by the host's packing)
-    start -= my_nl;
-    const uint32_t starts = __reduce_or_sync(0xffffffffu, wlane < wcnt ? (1u << start) : 0u);
-    const uint32_t nl_max = __reduce_max_sync(0xffffffffu, my_nl);
-    const bool live = wlane < used;                                                // a lane without a read shadows lane 0 of the last read, never writes
-    const uint32_t below = starts & (0xffffffffu >> (31 - (live ? wlane : used - 1)));
-    const uint32_t ridx = (uint32_t)__popc(below) - 1u;                           // which of the warp's reads covers me
-    const uint32_t first = 31u - (uint32_t)__clz((int)below);
-    const uint32_t rid = __shfl_sync(0xffffffffu, my_rid, ridx);
-    const uint32_t nl = __shfl_sync(0xffffffffu, my_nl, ridx);
-    const uint32_t lane = live ? wlane - first : 0u;                               // my lane within the read
-    constexpr int shfl_w = 32;                                                     // (segmenting the shuffles per read where the lane counts allow it measured slower)
+    constexpr int shfl_w = FIXED ? FIXED : 32;       // (segmenting the shuffles at run time where the lane counts allow it measured slower)
     const PhmmRead rd = p.reads[rid];
     const int npad = (int)(nl * RPT) - (int)rd.len;   // >= 1
 
@@ -1041,10 +1053,10 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
     if (acc == 123.456f) out[0] = acc;
 }
 
-template <int RPT, int VAR>
+template <int RPT, int VAR, int FIXED = 0>
 cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps, size_t smem, cudaStream_t st)
 {
-    auto kern = phmm_fwd_kernel<RPT, VAR>;
+    auto kern = phmm_fwd_kernel<RPT, VAR, FIXED>;
     // Raise the dynamic shared-memory limit of this instantiation once, to the device maximum: several host workers launch
     // concurrently, and a per-launch "set to what I need" lets one worker lower the limit under another's launch.
     static std::atomic<uint64_t> limit_set{0};            // one bit per device ordinal
@@ -1067,7 +1079,7 @@ template <int RPT, int VAR>
 cudaError_t info_t(PhmmKernelInfo* info)
 {
     cudaFuncAttributes a;
-    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, VAR>);
+    cudaError_t e = cudaFuncGetAttributes(&a, phmm_fwd_kernel<RPT, VAR, 0>);
     if (e != cudaSuccess) return e;
     info->regs = a.numRegs;
     info->local_bytes = (int)a.localSizeBytes;
@@ -1104,11 +1116,15 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     PHMM_CASE(17, FN, __VA_ARGS__) PHMM_CASE(18, FN, __VA_ARGS__) PHMM_CASE(19, FN, __VA_ARGS__)                                \
     return cudaErrorInvalidValue;
 
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
-                            size_t smem_bytes, cudaStream_t st)
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, uint32_t cta_base, uint32_t n_ctas,
+                            uint32_t cta_warps, size_t smem_bytes, cudaStream_t st)
 {
     if (n_ctas == 0) return cudaSuccess;
     if (rpt < 1 || rpt > phmm_max_rpt(refgaps) || cta_warps < 1 || cta_warps > PHMM_WARPS) return cudaErrorInvalidValue;
+    if (fixed_lanes) {                               // the one specialisation: see phmm_fixed_lanes()
+        if (fixed_lanes != phmm_fixed_lanes(rpt, refgaps) || !fma) return cudaErrorInvalidValue;
+        return launch_fwd_t<PHMM_MAX_RPT, PHMM_VAR_REFGAPS, 8>(b, cta_base, n_ctas, cta_warps, smem_bytes, st);
+    }
     PHMM_DISPATCH_RPT(launch_fwd_t, b, cta_base, n_ctas, cta_warps, smem_bytes, st)
 }
 

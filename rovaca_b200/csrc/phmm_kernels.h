@@ -103,9 +103,12 @@ static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, i
 }
 
 cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st);
+// The one fixed-lanes specialisation of the forward kernel: reads of 133..151 bases take 8 lanes at 19 rows per lane (the
+// reference-gap variant); a launch in which every read does may use it (fixed_lanes = 8), else 0.
+static inline uint32_t phmm_fixed_lanes(int rpt, bool refgaps) { return (refgaps && rpt == PHMM_MAX_RPT) ? 8u : 0u; }
 // Forward wavefront kernel over ctas[cta_base .. cta_base + n_ctas) (all of one rows-per-lane count).
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps,
-                            size_t smem_bytes, cudaStream_t st);
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, uint32_t cta_base, uint32_t n_ctas,
+                            uint32_t cta_warps, size_t smem_bytes, cudaStream_t st);
 // Per-pair kernels.  count_dev != null: the pair count is read on the device (FP64 recompute list).
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
                                   uint32_t threads, uint32_t max_cols, cudaStream_t st);

@@ -180,10 +180,11 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::vector<std::vector<Group>>& groups = ps.groups;
     std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;       // read ids, warp after warp
     std::vector<std::vector<uint8_t>>& group_warps = ps.group_warps;        // reads per warp
-    groups.resize(PHMM_MAX_RPT + 1);
-    group_reads.resize(PHMM_MAX_RPT + 1);
-    group_warps.resize(PHMM_MAX_RPT + 1);
-    for (int b = 0; b <= PHMM_MAX_RPT; ++b) {
+    constexpr int kFixedBin = PHMM_MAX_RPT + 1;                              // regions whose reads all take phmm_fixed_lanes() lanes
+    groups.resize(PHMM_MAX_RPT + 2);
+    group_reads.resize(PHMM_MAX_RPT + 2);
+    group_warps.resize(PHMM_MAX_RPT + 2);
+    for (int b = 0; b <= PHMM_MAX_RPT + 1; ++b) {
         groups[b].clear();
         group_reads[b].clear();
         group_warps[b].clear();
@@ -444,10 +445,13 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 for (uint32_t k = 0; k < r.n_reads; ++k)
                     if (lens[k]) packer.slots[cur[lut[lens[k]]]++] = rp.read_begin + k;
             }
-            const uint32_t first_read = (uint32_t)group_reads[rpt].size(), first_warp = (uint32_t)group_warps[rpt].size();
-            const uint32_t n_warps = packer.pack(&group_reads[rpt], &group_warps[rpt]);
+            // a region whose reads all take the fixed lane count of this rows-per-lane count goes to the fixed-lanes kernel
+            const uint32_t fixed = cfg->fma ? phmm_fixed_lanes(rpt, refgaps) : 0u;
+            const int bin = (fixed && packer.count[fixed] == fast_reads) ? kFixedBin : rpt;
+            const uint32_t first_read = (uint32_t)group_reads[bin].size(), first_warp = (uint32_t)group_warps[bin].size();
+            const uint32_t n_warps = packer.pack(&group_reads[bin], &group_warps[bin]);
             // every chunk of the region sweeps the same warps: one copy of the lists, one group per chunk
-            for (uint32_t ci : region_chunks) groups[rpt].push_back(Group{ci, chunks[ci].stream_len, first_read, first_warp, n_warps});
+            for (uint32_t ci : region_chunks) groups[bin].push_back(Group{ci, chunks[ci].stream_len, first_read, first_warp, n_warps});
         }
         out_off += (uint64_t)r.n_reads * r.n_haps;
     }
@@ -460,21 +464,24 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     ctas.clear();
     task_reads.clear();
     s.launches.clear();
-    for (int b = 1; b <= max_rpt; ++b) {
-        if (groups[b].empty()) continue;
+    for (int bin = 1; bin <= kFixedBin; ++bin) {
+        const int b = bin == kFixedBin ? PHMM_MAX_RPT : bin;              // rows per lane of this launch
+        if (bin != kFixedBin && bin > max_rpt) continue;
+        if (groups[bin].empty()) continue;
         {
             // stable, longest stream first: a counting sort on the stream length (at most kMaxStreamCols + 33 values)
             uint32_t longest = 0;
-            for (const Group& g : groups[b]) longest = std::max(longest, g.stream_len);
+            for (const Group& g : groups[bin]) longest = std::max(longest, g.stream_len);
             ps.bucket.assign((size_t)longest + 2, 0u);
-            for (const Group& g : groups[b]) ++ps.bucket[longest - g.stream_len + 1];
+            for (const Group& g : groups[bin]) ++ps.bucket[longest - g.stream_len + 1];
             for (uint32_t k = 1; k <= longest + 1; ++k) ps.bucket[k] += ps.bucket[k - 1];
-            ps.sorted.resize(groups[b].size());
-            for (const Group& g : groups[b]) ps.sorted[ps.bucket[longest - g.stream_len]++] = g;
-            groups[b].swap(ps.sorted);
+            ps.sorted.resize(groups[bin].size());
+            for (const Group& g : groups[bin]) ps.sorted[ps.bucket[longest - g.stream_len]++] = g;
+            groups[bin].swap(ps.sorted);
         }
         FwdLaunch fl{};
         fl.rpt = b;
+        fl.fixed_lanes = bin == kFixedBin ? phmm_fixed_lanes(b, refgaps) : 0u;
         fl.refgaps = refgaps;
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
@@ -485,13 +492,13 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         // profiles/r02_experiments.txt.)
         uint32_t cta_warps = cfg->cta_warps;
         uint32_t longest_stream = 0, most_haps = 0;
-        for (const Group& g : groups[b]) {
+        for (const Group& g : groups[bin]) {
             longest_stream = std::max(longest_stream, chunks[g.chunk].stream_len);
             most_haps = std::max(most_haps, chunks[g.chunk].n_haps);
         }
         if (cta_warps == 0) {
             uint64_t slots[3] = {0, 0, 0};
-            for (const Group& g : groups[b])
+            for (const Group& g : groups[bin])
                 for (int k = 0; k < 3; ++k) {
                     const uint32_t per = 1u << k;
                     slots[k] += (uint64_t)((g.n_warps + per - 1) / per) * per;
@@ -506,9 +513,9 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             if (smem <= smem_optin || cta_warps == 1) break;
             cta_warps >>= 1;
         }
-        const std::vector<uint32_t>& gr = group_reads[b];
-        const std::vector<uint8_t>& gw = group_warps[b];
-        for (const Group& g : groups[b]) {
+        const std::vector<uint32_t>& gr = group_reads[bin];
+        const std::vector<uint8_t>& gw = group_warps[bin];
+        for (const Group& g : groups[bin]) {
             uint32_t at_read = g.first_read;
             for (uint32_t w0 = 0; w0 < g.n_warps; w0 += cta_warps) {
                 PhmmCta c{};

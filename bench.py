@@ -186,7 +186,7 @@ def workload_specs(quick):
         ("cfg5_trim0", "region stream, Poisson(41) reads of 60-151 bp x ~8.8 haplotypes of 201-499 bp", lambda: wl.stream("cfg5", 16384 // q, seed=5)),
         ("cfg5_trim50", "region stream, 50 % of the regions with post-trim shapes (H 41-120, R <= H)",
          lambda: wl.stream("cfg5", 16384 // q, seed=5, post_trim_fraction=0.5)),
-        ("cfg5_trim100", "region stream, post-trim shapes only", lambda: wl.stream("cfg5", 32768 // q, seed=5, post_trim_fraction=1.0)),
+        ("cfg5_trim100", "region stream, post-trim shapes only", lambda: wl.stream("cfg5", 65536 // q, seed=5, post_trim_fraction=1.0)),
     ]
 
 

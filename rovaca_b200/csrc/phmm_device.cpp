@@ -100,10 +100,11 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
         // short batches (the synchronous per-region callers) finish in tens of microseconds: poll before paying a blocking
         // sync's wake-up latency
         cudaError_t q = cudaErrorNotReady;
+        constexpr int poll_us = 400;                // (no polling, or blocking syncs, measured the same or worse with 16-128 callers)
         if (s.n_cells < 1500000000ull) {            // < ~0.5 ms of device work; big batches sleep instead of burning a core
             const auto t_poll = std::chrono::steady_clock::now();
             while ((q = cudaStreamQuery(s.stream)) == cudaErrorNotReady) {
-                if (std::chrono::steady_clock::now() - t_poll > std::chrono::microseconds(400)) break;
+                if (std::chrono::steady_clock::now() - t_poll > std::chrono::microseconds(poll_us)) break;
                 _mm_pause();
             }
             if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PHMM_ERR_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));

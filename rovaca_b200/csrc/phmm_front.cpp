@@ -132,13 +132,27 @@ void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g
 std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb)
 {
     std::vector<uint64_t> pre(fb->n_regions + 1, 0);
-    for (uint32_t g = 0; g < fb->n_regions; ++g) {
-        uint64_t rb = 0, hb = 0;
-        for (uint64_t k = fb->reg_read_off[g]; k < fb->reg_read_off[g + 1]; ++k) rb += fb->read_len[k];
-        for (uint64_t j = fb->reg_hap_off[g]; j < fb->reg_hap_off[g + 1]; ++j) hb += fb->hap_len[j];
-        const uint64_t pairs = (fb->reg_read_off[g + 1] - fb->reg_read_off[g]) * (fb->reg_hap_off[g + 1] - fb->reg_hap_off[g]);
-        pre[g + 1] = pre[g] + rb * hb + pairs * kPairWeight;
+    auto work_of = [&](uint32_t g0, uint32_t g1) {                  // pre[g + 1] = work of region g, for g in [g0, g1)
+        for (uint32_t g = g0; g < g1; ++g) {
+            uint64_t rb = 0, hb = 0;
+            for (uint64_t k = fb->reg_read_off[g]; k < fb->reg_read_off[g + 1]; ++k) rb += fb->read_len[k];
+            for (uint64_t j = fb->reg_hap_off[g]; j < fb->reg_hap_off[g + 1]; ++j) hb += fb->hap_len[j];
+            const uint64_t pairs = (fb->reg_read_off[g + 1] - fb->reg_read_off[g]) * (fb->reg_hap_off[g + 1] - fb->reg_hap_off[g]);
+            pre[g + 1] = rb * hb + pairs * kPairWeight;
+        }
+    };
+    // this runs on the caller's thread before any sub-batch can start: big streams (one engine over several GPUs takes
+    // hundreds of thousands of regions per call) spread the pass over a few threads
+    const uint32_t n = fb->n_regions, n_thr = n >= 131072 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+    if (n_thr > 1) {
+        std::vector<std::thread> pool;
+        for (uint32_t t = 0; t < n_thr; ++t)
+            pool.emplace_back(work_of, (uint32_t)((uint64_t)n * t / n_thr), (uint32_t)((uint64_t)n * (t + 1) / n_thr));
+        for (auto& t : pool) t.join();
+    } else {
+        work_of(0, n);
     }
+    for (uint32_t g = 0; g < n; ++g) pre[g + 1] += pre[g];
     return pre;
 }
 

@@ -740,58 +740,58 @@ __device__ __forceinline__ bool pair64_sweep(const PhmmBatchDev& p, const PhmmRe
     __syncwarp();
     const double init = __ddiv_rn(__longlong_as_double(0x7FB0000000000000LL), (double)H);      // 2^1020 / H
     const bool above_pad = (int)lane * RPT - 1 < npad;
+    // column -1 state: M = I = D = 0, generator rows hold D = init.  A lane starts on column 0 at step `lane` and does nothing
+    // before (so this state is still intact then); what it computes past column H - 1 is never kept.
     double Ml[RPT], Il[RPT], Dl[RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) { Ml[k] = 0.0; Il[k] = 0.0; Dl[k] = 0.0; }
-    double upM = 0.0, upI = 0.0, upD = 0.0, dgM = 0.0, dgI = 0.0, dgD = 0.0, sumM = 0.0, sumI = 0.0;
+    for (int k = 0; k < RPT; ++k) { Ml[k] = 0.0; Il[k] = 0.0; Dl[k] = (((int)lane * RPT + k) < npad) ? init : 0.0; }
+    double upM = 0.0, upI = 0.0, upD = 0.0, dgM = 0.0, dgI = 0.0, dgD = above_pad ? init : 0.0, sumM = 0.0, sumI = 0.0;
     const unsigned char* tl = s_tbl + lane * PAIR64_TSTRIDE;
     bool small = false;
+#pragma unroll 2
     for (int s = 0; s < H + 31; ++s) {
-        const int c = s - (int)lane;                             // my column this step; outside [0, H): idle work, never kept
-        if (c == 0) {                                            // column -1 state: M = I = D = 0, generator rows hold D = init
+        const int c = s - (int)lane;                             // my column this step
+        if (c >= 0) {
+            const bool valid = c < H;
+            const double* pr = reinterpret_cast<const double*>(tl + (valid ? (uint32_t)s_cls[c] : 5u) * (32 * PAIR64_TSTRIDE));
+            double prior[RPT];
+            if (RPT >= 2) {
+                const double2 v = *reinterpret_cast<const double2*>(pr);
+                prior[0] = v.x;
+                prior[RPT >= 2 ? 1 : 0] = v.y;
+            } else {
+                prior[0] = pr[0];
+            }
+            if (RPT >= 4) {
+                const double2 v = *reinterpret_cast<const double2*>(pr + 2);
+                prior[RPT >= 4 ? 2 : 0] = v.x;
+                prior[RPT >= 4 ? 3 : 0] = v.y;
+            } else if (RPT == 3) {
+                prior[RPT >= 3 ? 2 : 0] = pr[2];
+            }
+            if (RPT == 5) prior[RPT >= 5 ? 4 : 0] = pr[4];
+            double pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
+            bool step_small = false;
 #pragma unroll
-            for (int k = 0; k < RPT; ++k) { Ml[k] = 0.0; Il[k] = 0.0; Dl[k] = (((int)lane * RPT + k) < npad) ? init : 0.0; }
-            dgM = 0.0; dgI = 0.0; dgD = above_pad ? init : 0.0;
-        }
-        const bool valid = c >= 0 && c < H;
-        const double* pr = reinterpret_cast<const double*>(tl + (valid ? (uint32_t)s_cls[c] : 5u) * (32 * PAIR64_TSTRIDE));
-        double prior[RPT];
-        if (RPT >= 2) {
-            const double2 v = *reinterpret_cast<const double2*>(pr);
-            prior[0] = v.x;
-            prior[RPT >= 2 ? 1 : 0] = v.y;
-        } else {
-            prior[0] = pr[0];
-        }
-        if (RPT >= 4) {
-            const double2 v = *reinterpret_cast<const double2*>(pr + 2);
-            prior[RPT >= 4 ? 2 : 0] = v.x;
-            prior[RPT >= 4 ? 3 : 0] = v.y;
-        } else if (RPT == 3) {
-            prior[RPT >= 3 ? 2 : 0] = pr[2];
-        }
-        if (RPT == 5) prior[RPT >= 5 ? 4 : 0] = pr[4];
-        double pM = dgM, pI = dgI, pD = dgD, uM = upM, uI = upI;
-        bool step_small = false;
-#pragma unroll
-        for (int k = 0; k < RPT; ++k) {
-            const double oM = Ml[k], oI = Il[k], oD = Dl[k];
-            double t = __dmul_rn(pM, mm[k]);
-            t = __fma_rn(pI, gapm, t);
-            t = __fma_rn(pD, gapm, t);
-            const double m = __dmul_rn(t, prior[k]);
-            const double i = __fma_rn(uI, gcp_p, __dmul_rn(uM, mi[k]));
-            const double d = __fma_rn(oD, dd[k], __dmul_rn(oM, mi[k]));
-            step_small |= (uint32_t)(__double2hiint(m) - 1) < trip_hi - 1u;         // 0 < m < 2^-830 (trip_hi = 0x0C100000)
-            Ml[k] = m; Il[k] = i; Dl[k] = d;
-            pM = oM; pI = oI; pD = oD;
-            uM = m; uI = i;
-        }
-        dgM = upM; dgI = upI; dgD = upD;
-        if (valid) {
-            small |= step_small;
-            sumM = __dadd_rn(sumM, Ml[RPT - 1]);                 // only the last lane's sums are read
-            sumI = __dadd_rn(sumI, Il[RPT - 1]);
+            for (int k = 0; k < RPT; ++k) {
+                const double oM = Ml[k], oI = Il[k], oD = Dl[k];
+                double t = __dmul_rn(pM, mm[k]);
+                t = __fma_rn(pI, gapm, t);
+                t = __fma_rn(pD, gapm, t);
+                const double m = __dmul_rn(t, prior[k]);
+                const double i = __fma_rn(uI, gcp_p, __dmul_rn(uM, mi[k]));
+                const double d = __fma_rn(oD, dd[k], __dmul_rn(oM, mi[k]));
+                step_small |= (uint32_t)(__double2hiint(m) - 1) < trip_hi - 1u;         // 0 < m < 2^-830 (trip_hi = 0x0C100000)
+                Ml[k] = m; Il[k] = i; Dl[k] = d;
+                pM = oM; pI = oI; pD = oD;
+                uM = m; uI = i;
+            }
+            dgM = upM; dgI = upI; dgD = upD;
+            if (valid) {
+                small |= step_small;
+                sumM = __dadd_rn(sumM, Ml[RPT - 1]);             // only the last lane's sums are read
+                sumI = __dadd_rn(sumI, Il[RPT - 1]);
+            }
         }
         const double nuM = __shfl_up_sync(0xffffffffu, Ml[RPT - 1], 1);
         const double nuI = __shfl_up_sync(0xffffffffu, Il[RPT - 1], 1);

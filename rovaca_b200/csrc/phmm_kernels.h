@@ -137,7 +137,7 @@ struct PhmmSwTask
     uint64_t bt_off;               // first back-track word of this alignment, [step = row - 1 + lane][lane][ceil(cpt/8)] u32
     uint64_t aux_off;              // last row (read_len ints) then last column (ref_len ints) of H
     uint32_t cpt;                  // columns per lane of the fill kernel that serves it
-    uint32_t rsv;
+    uint32_t narrow;               // 1: its scores fit 16 bits, the two-alignments-per-warp kernel takes it
 };
 struct PhmmSwOut
 {
@@ -160,6 +160,10 @@ struct PhmmSwBatchDev
 static const int kPhmmSwCpt[] = {2, 5, 8, 16, 32, 64};     // columns per lane: reads up to 64, 160, 256, 512, 1024, 2048 bases
 static const int kPhmmSwNumCpt = sizeof(kPhmmSwCpt) / sizeof(kPhmmSwCpt[0]);
 cudaError_t phmm_launch_sw_fill(const PhmmSwBatchDev& b, int cpt, uint32_t first, uint32_t count, uint32_t warps, cudaStream_t st);
+// the same for tasks whose scores fit 16 bits (PhmmSwTask.narrow): two alignments per warp in packed 16-bit halves
+cudaError_t phmm_launch_sw_fill16(const PhmmSwBatchDev& b, int cpt, uint32_t first, uint32_t count, uint32_t warps, cudaStream_t st);
+// a task may take the 16-bit kernel if min(rows, columns) x max(|match|, |mismatch|) + |open| + |extend| stays under this
+static const int kPhmmSwNarrowBound = 12000;
 cudaError_t phmm_launch_sw_trace(const PhmmSwBatchDev& b, uint32_t first, uint32_t count, cudaStream_t st);
 
 // FP32 issue-rate micro-benchmark; each thread executes iters*32 FMA instructions on 2 lanes (see .cu).

@@ -20,6 +20,7 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
     constexpr size_t kBtBudget = (size_t)6 << 30;                        // back-track words one sub-batch may hold on the device
     constexpr uint32_t kSubBatch = 32768;                                // alignments per sub-batch: several per big call, so that packing,
                                                                          // kernels and the hand-back of results overlap
+    const bool wide_only = std::getenv("PHMM_B200_SW_WIDE") != nullptr;   // tests: the 32-bit fill kernel for everything
     std::lock_guard<std::mutex> lk(e->sw_m);
     // sub-batches go round the devices' slots (two per device): the host packs one while the others run
     struct Lane { PhmmDevice* d; SwSlot* ss; };
@@ -136,6 +137,11 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             t.bt_off = bt_words; bt_words += words;
             t.aux_off = aux_ints; aux_ints += (size_t)p.ref_len + p.read_len;
             t.cpt = (uint32_t)cpt;
+            {
+                const int big = std::max(std::max(std::abs(params->match), std::abs(params->mismatch)), 1);
+                const long bound = (long)std::min(p.ref_len, p.read_len) * big + std::abs(params->gap_open) + std::abs(params->gap_extend);
+                t.narrow = (!wide_only && cpt <= 32 && params->match > params->mismatch && bound <= kPhmmSwNarrowBound) ? 1u : 0u;
+            }
             if (bytes >= ((size_t)1 << 32)) { rc = fail(PHMM_ERR_ARG, "phmm_sw_align: more than 4 GiB of sequence in one sub-batch"); break; }
             tasks.push_back(t);
             src.push_back(at);
@@ -149,11 +155,11 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
         std::vector<uint32_t>& order = ss.order;
         order.resize(n);
         {
-            uint32_t count[kPhmmSwNumCpt + 1] = {};
-            auto group_of = [&](uint32_t cpt) { int q = 0; while (kPhmmSwCpt[q] != (int)cpt) ++q; return q; };
-            for (uint32_t k = 0; k < n; ++k) ++count[group_of(tasks[k].cpt) + 1];
-            for (int q = 0; q < kPhmmSwNumCpt; ++q) count[q + 1] += count[q];
-            for (uint32_t k = 0; k < n; ++k) order[count[group_of(tasks[k].cpt)]++] = k;
+            uint32_t count[2 * kPhmmSwNumCpt + 1] = {};               // groups: (cpt, 32-bit) then (cpt, 16-bit) per cpt
+            auto group_of = [&](const PhmmSwTask& t) { int q = 0; while (kPhmmSwCpt[q] != (int)t.cpt) ++q; return 2 * q + (int)t.narrow; };
+            for (uint32_t k = 0; k < n; ++k) ++count[group_of(tasks[k]) + 1];
+            for (int q = 0; q < 2 * kPhmmSwNumCpt; ++q) count[q + 1] += count[q];
+            for (uint32_t k = 0; k < n; ++k) order[count[group_of(tasks[k])]++] = k;
         }
         size_t off = 0;
         auto place = [&](size_t nbytes) { size_t o = off; off = align_up(off + nbytes, 256); return o; };
@@ -190,11 +196,17 @@ int phmm_sw_align(phmm_engine* e, const phmm_sw_pair* pairs, uint32_t n_pairs, c
             CU(cudaSetDevice(ln.d->ordinal));
             CU(cudaMemcpyAsync(ss.d_in.p, ss.h_in.p, off, cudaMemcpyHostToDevice, ss.stream));
             CU(cudaEventRecord(ss.ev[0], ss.stream));
-            for (uint32_t g0 = 0; g0 < n;) {                             // one fill launch per cpt group
+            for (uint32_t g0 = 0; g0 < n;) {                             // one fill launch per (cpt, width) group
                 uint32_t g1 = g0;
-                while (g1 < n && tasks[order[g1]].cpt == tasks[order[g0]].cpt) ++g1;
-                const uint32_t warps = std::min<uint32_t>(g1 - g0, ln.d->warp_slots * 4);
-                CU(phmm_launch_sw_fill(b, (int)tasks[order[g0]].cpt, g0, g1 - g0, warps, ss.stream));
+                const PhmmSwTask& lead = tasks[order[g0]];
+                while (g1 < n && tasks[order[g1]].cpt == lead.cpt && tasks[order[g1]].narrow == lead.narrow) ++g1;
+                if (lead.narrow) {
+                    const uint32_t warps = std::min<uint32_t>((g1 - g0 + 1) / 2, ln.d->warp_slots * 4);
+                    CU(phmm_launch_sw_fill16(b, (int)lead.cpt, g0, g1 - g0, warps, ss.stream));
+                } else {
+                    const uint32_t warps = std::min<uint32_t>(g1 - g0, ln.d->warp_slots * 4);
+                    CU(phmm_launch_sw_fill(b, (int)lead.cpt, g0, g1 - g0, warps, ss.stream));
+                }
                 g0 = g1;
             }
             CU(phmm_launch_sw_trace(b, 0, n, ss.stream));

@@ -101,6 +101,116 @@ __global__ void __launch_bounds__(128) sw_fill_kernel(PhmmSwBatchDev b, uint32_t
     }
 }
 
+// The same fill for TWO alignments per warp in the 16-bit halves of packed registers (VIADD.16x2, VIMNMX.S16x2 with its two
+// predicate outputs: the back-track bits are the predicates of the maxima).  For alignments whose scores fit 16 bits with
+// room to spare — the host sends a task here only if min(rows, columns) x max(|match|, |mismatch|) + |open| + |extend| <= 12000
+// (H is bounded by a diagonal run of matches above and of mismatches below; E and F by H + open), which holds for the
+// realignment parameter set up to ~800-base reads and never for the assembler's.  LOW is -16384 here: like the 32-bit
+// LOW_INIT_VALUE it only ever loses the comparison it enters (LOW + extend < any H + open), so every predicate — every
+// back-track bit — and every H is the 32-bit kernel's.  Results per alignment go where sw_fill_kernel puts them.
+template <int CPT>
+__global__ void __launch_bounds__(128) sw_fill16_kernel(PhmmSwBatchDev b, uint32_t first, uint32_t count)
+{
+    constexpr int W = (CPT + 7) / 8;
+    constexpr uint32_t LOW2 = 0xC000C000u;                 // -16384 in both halves
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t npair = (count + 1) / 2;
+    auto pack = [](int v) { return ((uint32_t)v & 0xffffu) * 0x00010001u; };
+    const uint32_t open2 = pack(b.gap_open), ext2 = pack(b.gap_extend), match2 = pack(b.match);
+    const uint32_t drop = (uint32_t)(b.match - b.mismatch);            // match - mismatch > 0: what a mismatch loses
+    for (uint32_t t = wid; t < npair; t += nwarps) {
+        const bool hasB = 2 * t + 1 < count;
+        const PhmmSwTask ta = b.tasks[b.order[first + 2 * t]];
+        const PhmmSwTask tb = b.tasks[b.order[first + 2 * t + (hasB ? 1 : 0)]];
+        const int nrowA = (int)ta.ref_len, ncolA = (int)ta.read_len, nrowB = (int)tb.ref_len, ncolB = (int)tb.read_len;
+        const int nrow = max(nrowA, nrowB);
+        const uint8_t* seq1A = b.bytes + ta.ref_off;
+        const uint8_t* seq1B = b.bytes + tb.ref_off;
+        const uint8_t* seq2A = b.bytes + ta.read_off;
+        const uint8_t* seq2B = b.bytes + tb.read_off;
+        uint32_t* btA = b.bt + ta.bt_off;
+        uint32_t* btB = b.bt + tb.bt_off;
+        int32_t* hrowA = b.aux + ta.aux_off;
+        int32_t* hcolA = hrowA + ncolA;
+        int32_t* hrowB = b.aux + tb.aux_off;
+        int32_t* hcolB = hrowB + ncolB;
+        const int j0 = (int)lane * CPT;
+        uint32_t c2[CPT], Hp[CPT], Fv[CPT];
+#pragma unroll
+        for (int k = 0; k < CPT; ++k) {
+            const uint32_t a = (j0 + k < ncolA) ? seq2A[j0 + k] : 0x100u;      // never equal to a byte of seq1
+            const uint32_t bb = (j0 + k < ncolB) ? seq2B[j0 + k] : 0x100u;
+            c2[k] = a | (bb << 16);
+            Hp[k] = 0u;
+            Fv[k] = LOW2;
+        }
+        const int kcolA = ncolA - 1 - j0, kcolB = ncolB - 1 - j0;
+        uint32_t lastH = 0u, lastE = LOW2, diagH = 0u;
+        for (int s = 0; s < nrow + 31; ++s) {
+            uint32_t inH = __shfl_up_sync(0xffffffffu, lastH, 1);
+            uint32_t inE = __shfl_up_sync(0xffffffffu, lastE, 1);
+            if (lane == 0) { inH = 0u; inE = LOW2; }
+            const int i = s - (int)lane + 1;
+            if (i >= 1 && i <= nrow) {
+                const bool rowA = i <= nrowA, rowB = i <= nrowB;
+                const uint32_t c1 = (rowA ? (uint32_t)seq1A[i - 1] : 0x200u) | ((rowB ? (uint32_t)seq1B[i - 1] : 0x200u) << 16);
+                uint32_t hl = inH, e = inE, hd = diagH;
+                uint32_t wa[W], wb[W];
+#pragma unroll
+                for (int w = 0; w < W; ++w) { wa[w] = 0u; wb[w] = 0u; }
+                uint32_t hc = 0u;
+#pragma unroll
+                for (int k = 0; k < CPT; ++k) {            // MAIN_CODE, sw_avx.c:40-76, two alignments per instruction
+                    bool eh_b, eh_a, ev_b, ev_a, kh_b, kh_a, kf_b, kf_a;          // (high half = alignment B, low half = A)
+                    const uint32_t e11 = __vibmax_s16x2(__vadd2(e, ext2), __vadd2(hl, open2), &eh_b, &eh_a);       // extension wins or ties
+                    const uint32_t f11 = __vibmax_s16x2(__vadd2(Fv[k], ext2), __vadd2(Hp[k], open2), &ev_b, &ev_a);
+                    const uint32_t ne = __vminu2(c1 ^ c2[k], 0x00010001u);        // 1 where the bases differ
+                    const uint32_t m11 = __vsub2(__vadd2(hd, match2), ne * drop); // diagonal + (match or mismatch); no carry: ne is 0 / 1 per half
+                    uint32_t h11 = __vibmax_s16x2(m11, e11, &kh_b, &kh_a);        // diagonal >= E (the cut-off at -1e8 cannot bind here)
+                    h11 = __vibmax_s16x2(h11, f11, &kf_b, &kf_a);                 // max so far >= F
+                    const uint32_t ca = (eh_a ? (uint32_t)BT_INS_EXT : 0u) | (ev_a ? (uint32_t)BT_DEL_EXT : 0u) |
+                                        (kf_a ? (kh_a ? (uint32_t)BT_MATCH : (uint32_t)BT_INS) : (uint32_t)BT_DEL);
+                    const uint32_t cb = (eh_b ? (uint32_t)BT_INS_EXT : 0u) | (ev_b ? (uint32_t)BT_DEL_EXT : 0u) |
+                                        (kf_b ? (kh_b ? (uint32_t)BT_MATCH : (uint32_t)BT_INS) : (uint32_t)BT_DEL);
+                    wa[k / 8] += ca << (4 * (k % 8));
+                    wb[k / 8] += cb << (4 * (k % 8));
+                    hd = Hp[k];
+                    Hp[k] = h11;
+                    Fv[k] = f11;
+                    hl = h11;
+                    e = e11;
+                    if (k == kcolA) hc = (hc & 0xffff0000u) | (h11 & 0xffffu);
+                    if (k == kcolB) hc = (hc & 0x0000ffffu) | (h11 & 0xffff0000u);
+                }
+                lastH = hl;
+                lastE = e;
+                diagH = inH;
+                if (rowA) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) btA[((size_t)s * 32 + lane) * W + w] = wa[w];
+                    if (kcolA >= 0 && kcolA < CPT) hcolA[i - 1] = (int32_t)(int16_t)(hc & 0xffffu);
+                    if (i == nrowA) {
+#pragma unroll
+                        for (int k = 0; k < CPT; ++k)
+                            if (j0 + k < ncolA) hrowA[j0 + k] = (int32_t)(int16_t)(Hp[k] & 0xffffu);
+                    }
+                }
+                if (rowB && hasB) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) btB[((size_t)s * 32 + lane) * W + w] = wb[w];
+                    if (kcolB >= 0 && kcolB < CPT) hcolB[i - 1] = (int32_t)(int16_t)(hc >> 16);
+                    if (i == nrowB) {
+#pragma unroll
+                        for (int k = 0; k < CPT; ++k)
+                            if (j0 + k < ncolB) hrowB[j0 + k] = (int32_t)(int16_t)(Hp[k] >> 16);
+                    }
+                }
+            }
+        }
+    }
+}
+
 __device__ __forceinline__ uint32_t bt_code(const uint32_t* bt, int cpt, int i, int j)
 {
     const int w = (cpt + 7) / 8, lane = (j - 1) / cpt, k = (j - 1) % cpt;
@@ -198,6 +308,21 @@ cudaError_t phmm_launch_sw_fill(const PhmmSwBatchDev& b, int cpt, uint32_t first
         case 32: sw_fill_kernel<32><<<blocks, 128, 0, st>>>(b, first, count); break;
         case 64: sw_fill_kernel<64><<<blocks, 128, 0, st>>>(b, first, count); break;
         default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t phmm_launch_sw_fill16(const PhmmSwBatchDev& b, int cpt, uint32_t first, uint32_t count, uint32_t warps, cudaStream_t st)
+{
+    if (count == 0) return cudaSuccess;
+    const uint32_t blocks = (warps + 3) / 4;
+    switch (cpt) {
+        case 2: sw_fill16_kernel<2><<<blocks, 128, 0, st>>>(b, first, count); break;
+        case 5: sw_fill16_kernel<5><<<blocks, 128, 0, st>>>(b, first, count); break;
+        case 8: sw_fill16_kernel<8><<<blocks, 128, 0, st>>>(b, first, count); break;
+        case 16: sw_fill16_kernel<16><<<blocks, 128, 0, st>>>(b, first, count); break;
+        case 32: sw_fill16_kernel<32><<<blocks, 128, 0, st>>>(b, first, count); break;
+        default: return cudaErrorInvalidValue;                 // 64 columns per lane: reads over 1024 bases never qualify
     }
     return cudaGetLastError();
 }

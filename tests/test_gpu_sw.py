@@ -106,3 +106,41 @@ def test_sw_many_alignments_cross_the_sub_batches(engine, orc):
             assert g[3] == 1 and g[1] == 1 and len(g[0]) == 0
         else:
             assert g[3] == 0 and _same(g, want[int(pick[k])]), k
+
+
+def test_sw_narrow_and_wide_kernels_agree(engine, orc, monkeypatch):
+    """Alignments whose scores fit 16 bits take the two-alignments-per-warp kernel (packed 16-bit halves), the rest the
+    32-bit one: identical CIGAR, offset and score from both, and from the oracle — pairs of unequal shapes in one warp (so
+    that one alignment's rows run on after the other's end), odd counts, reads near the 16-bit kernel's bound, the
+    assembler's parameter set (never narrow)."""
+    rng = np.random.default_rng(123)
+    acgt = np.frombuffer(b"ACGT", np.uint8)
+
+    def seq(n):
+        return acgt[rng.integers(0, 4, n)]
+    pairs = []
+    for _ in range(101):                                    # odd count: the last warp holds one alignment
+        h = seq(int(rng.integers(30, 420)))
+        n = int(rng.integers(8, 159))
+        if rng.random() < 0.7 and len(h) > n:               # a read of the haplotype with substitutions and an indel
+            o = int(rng.integers(0, len(h) - n + 1))
+            r = h[o:o + n].copy()
+            m = rng.random(n) < 0.05
+            r[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+            if n > 20 and rng.random() < 0.5:
+                p = int(rng.integers(5, n - 5))
+                r = np.concatenate([r[:p], seq(int(rng.integers(1, 6))), r[p:]]) if rng.random() < 0.5 else np.concatenate([r[:p], r[p + 3:]])
+        else:
+            r = seq(n)
+        pairs.append((h, r))
+    pairs += [(seq(900), seq(790)), (seq(790), seq(900)), (seq(1200), seq(810)), (seq(60), seq(1000))]   # around the bound (798)
+    for prm in (ph.SW_REALIGN, ph.SW_ASSEMBLE):
+        got = engine.sw_align(pairs, prm, cigar_cap=128)
+        monkeypatch.setenv("PHMM_B200_SW_WIDE", "1")
+        wide = engine.sw_align(pairs, prm, cigar_cap=128)
+        monkeypatch.delenv("PHMM_B200_SW_WIDE")
+        for k, ((h, r), g, w) in enumerate(zip(pairs, got, wide)):
+            assert np.array_equal(g[0], w[0]) and g[1:] == w[1:], (k, len(h), len(r), prm)
+        for k in range(0, len(pairs), 7):
+            want = orc.sw_align(pairs[k][0], pairs[k][1], prm)
+            assert np.array_equal(got[k][0], want[0]) and got[k][1:3] == want[1:3], k

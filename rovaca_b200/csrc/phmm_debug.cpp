@@ -23,10 +23,9 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
     e.busy_batches.store(busy_batches);
     Slot s;
     s.set_host_only();
-    std::vector<phmm_read> reads;
     std::vector<phmm_hap> haps;
     std::vector<RegionIn> regs;
-    flat_to_regions(fb, nullptr, 0, fb->n_regions, reads, haps, regs);
+    flat_to_regions(fb, nullptr, 0, fb->n_regions, haps, regs);
     int rc = e.plan(s, regs);
     if (rc != PHMM_OK) return rc;
     const uint8_t* h = static_cast<const uint8_t*>(s.h_in.p);
@@ -140,10 +139,9 @@ int phmm_debug_epilogue(const phmm_flat_batch* fb, const float* raw_f32, const d
     e.cfg = &cfg;
     Slot s;
     s.set_host_only();
-    std::vector<phmm_read> reads;
     std::vector<phmm_hap> haps;
     std::vector<RegionIn> regs;
-    flat_to_regions(fb, fr, 0, fb->n_regions, reads, haps, regs);
+    flat_to_regions(fb, fr, 0, fb->n_regions, haps, regs);
     int rc = e.plan(s, regs);
     if (rc != PHMM_OK) return rc;
     for (size_t g = 0; g < regs.size(); ++g)

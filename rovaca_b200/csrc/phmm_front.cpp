@@ -73,26 +73,15 @@ void phmm_engine::seal_locked()
 // Flat batches
 // ------------------------------------------------------------------------------------------------
 
-// Regions [g0, g1) of a flat batch as RegionIn records (pointers into the caller's blobs).  reads/haps are resized to the
-// range; region g's reads start at reads[reg_read_off[g] - reg_read_off[g0]].
-void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_read>& reads,
-                            std::vector<phmm_hap>& haps, std::vector<RegionIn>& regs)
+// Regions [g0, g1) of a flat batch as RegionIn records.  The reads stay where they are (RegionIn.flat: the planner reads the
+// caller's flat arrays directly — a view struct per read cost more than the planning it feeds); the haplotypes, few per region,
+// get their views in `haps`.
+void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_hap>& haps,
+                     std::vector<RegionIn>& regs)
 {
-    const uint64_t rbeg = fb->reg_read_off[g0], hbeg = fb->reg_hap_off[g0];
-    const uint64_t nr = fb->reg_read_off[g1] - rbeg, nh = fb->reg_hap_off[g1] - hbeg;
-    reads.resize(nr);
+    const uint64_t hbeg = fb->reg_hap_off[g0];
+    const uint64_t nh = fb->reg_hap_off[g1] - hbeg;
     haps.resize(nh);
-    for (uint64_t k = 0; k < nr; ++k) {
-        phmm_read& r = reads[k];
-        const uint64_t o = fb->read_off[rbeg + k];
-        r.bases = fb->read_bases + o;
-        r.qual = fb->read_qual + o;
-        r.ins = fb->read_ins ? fb->read_ins + o : nullptr;
-        r.del = fb->read_del ? fb->read_del + o : nullptr;
-        r.gcp = fb->read_gcp ? fb->read_gcp + o : nullptr;
-        r.len = fb->read_len[rbeg + k];
-        r.mapq = fb->read_mapq[rbeg + k];
-    }
     for (uint64_t j = 0; j < nh; ++j) {
         haps[j].bases = fb->hap_bases + fb->hap_off[hbeg + j];
         haps[j].len = fb->hap_len[hbeg + j];
@@ -102,7 +91,9 @@ void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g
     for (uint32_t g = g0; g < g1; ++g) {
         RegionIn& r = regs[g - g0];
         const uint64_t r0 = fb->reg_read_off[g], h0 = fb->reg_hap_off[g];
-        r.reads = reads.data() + (r0 - rbeg);
+        r.reads = nullptr;
+        r.flat = fb;
+        r.flat_r0 = r0;
         r.n_reads = (uint32_t)(fb->reg_read_off[g + 1] - r0);
         r.haps = haps.data() + (h0 - hbeg);
         r.n_haps = (uint32_t)(fb->reg_hap_off[g + 1] - h0);
@@ -185,7 +176,7 @@ std::vector<std::pair<uint32_t, uint32_t>> flat_partition(const std::vector<uint
 uint64_t region_cells(const RegionIn& r)
 {
     uint64_t rb = 0, hb = 0;
-    for (uint32_t k = 0; k < r.n_reads; ++k) rb += r.reads[k].len;
+    for (uint32_t k = 0; k < r.n_reads; ++k) rb += region_read_len(r, k);
     for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
     return rb * hb;
 }
@@ -325,6 +316,7 @@ int phmm_submit(phmm_engine* e, const phmm_region* region, phmm_result* result, 
         return fail(PHMM_ERR_ARG, "phmm_submit: best_hap and second_hap go together");
     RegionIn r{};
     r.reads = region->reads;
+    r.flat = nullptr;
     r.n_reads = region->n_reads;
     r.haps = region->haps;
     r.n_haps = region->n_haps;
@@ -422,10 +414,9 @@ int phmm_run_flat(phmm_engine* e, const phmm_flat_batch* fb, phmm_flat_result* f
     for (const auto& part : parts) {
         PhmmDevice& d = e->pick_device();
         d.enqueue([&, part, dp = &d](Slot& s) {
-            std::vector<phmm_read> reads;
             std::vector<phmm_hap> haps;
             std::vector<RegionIn> regs;
-            flat_to_regions(fb, fr, part.first, part.second, reads, haps, regs);
+            flat_to_regions(fb, fr, part.first, part.second, haps, regs);
             const int rc = dp->execute(s, regs);
             std::lock_guard<std::mutex> lk(m);
             if (rc != PHMM_OK && rc_all == PHMM_OK) {
@@ -472,7 +463,8 @@ int phmm_resident_upload_on(phmm_engine* e, uint32_t device_index, const phmm_fl
     r->dev = &d;
     int rc = r->slot.init();
     if (rc != PHMM_OK) return rc;
-    flat_to_regions(fb, nullptr, 0, fb->n_regions, r->reads, r->haps, r->regs);
+    r->fb = *fb;
+    flat_to_regions(&r->fb, nullptr, 0, fb->n_regions, r->haps, r->regs);
     r->slot.force_dev_epi = true;
     if ((rc = d.plan(r->slot, r->regs)) != PHMM_OK) return rc;
     CU(cudaMemcpyAsync(r->slot.d_in.p, r->slot.h_in.p, r->slot.staged_bytes, cudaMemcpyHostToDevice, r->slot.stream));
@@ -568,7 +560,7 @@ int phmm_resident_download(phmm_engine* e, phmm_resident* r, phmm_flat_result* f
     fr->n_fp64 = 0;
     for (size_t g = 0; g < r->regs.size(); ++g) {
         RegionIn& x = r->regs[g];
-        const uint64_t r0 = (uint64_t)(x.reads - r->reads.data());
+        const uint64_t r0 = x.flat_r0;
         x.out = phmm_result{};
         x.out.likelihoods = fr->likelihoods + fr->lik_off[g];
         x.out.kept_idx = fr->kept_idx + r0;

@@ -72,7 +72,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct RegionIn
 {
-    const phmm_read* reads;
+    const phmm_read* reads;     // null for a region of a flat batch: its reads are read straight from the caller's flat arrays
+    const phmm_flat_batch* flat;   // ... this batch, reads flat_r0 .. flat_r0 + n_reads (no per-read view structs are built)
+    uint64_t flat_r0;
     uint32_t n_reads;
     const phmm_hap* haps;
     uint32_t n_haps;
@@ -84,6 +86,26 @@ struct RegionIn
     uint32_t* n_fp64_out32; // per-region (may be null)
     bool pinned_src;        // the read / haplotype bytes live in page-locked memory the device can read directly
 };
+
+// one read of a region, wherever it lives
+struct ReadView
+{
+    const uint8_t *bases, *qual, *ins, *del, *gcp;
+    uint32_t len;
+    uint8_t mapq;
+};
+inline uint32_t region_read_len(const RegionIn& r, uint32_t k) { return r.flat ? r.flat->read_len[r.flat_r0 + k] : r.reads[k].len; }
+inline ReadView region_read(const RegionIn& r, uint32_t k)
+{
+    if (r.flat) {
+        const phmm_flat_batch* fb = r.flat;
+        const uint64_t i = r.flat_r0 + k, o = fb->read_off[i];
+        return ReadView{fb->read_bases + o, fb->read_qual + o, fb->read_ins ? fb->read_ins + o : nullptr, fb->read_del ? fb->read_del + o : nullptr,
+                        fb->read_gcp ? fb->read_gcp + o : nullptr, fb->read_len[i], fb->read_mapq[i]};
+    }
+    const phmm_read& in = r.reads[k];
+    return ReadView{in.bases, in.qual, in.ins, in.del, in.gcp, in.len, in.mapq};
+}
 
 struct RegionPlan
 {
@@ -150,6 +172,18 @@ struct HostBuf
         cap = want;
         return PHMM_OK;
     }
+    // grow, keeping the first `keep` bytes (the planner writes the read records into the arena as it makes them)
+    int ensure_keep(size_t bytes, size_t keep, std::atomic<size_t>* high_water = nullptr)
+    {
+        if (bytes <= cap) return PHMM_OK;
+        HostBuf old = *this;
+        p = nullptr;
+        cap = 0;
+        const int rc = ensure(bytes, high_water);
+        if (rc == PHMM_OK && old.p && keep) std::memcpy(p, old.p, std::min(keep, old.cap));
+        old.release();
+        return rc;
+    }
     void release()
     {
         if (p) {
@@ -187,7 +221,6 @@ struct Slot
     struct Group { uint32_t chunk; uint32_t stream_len; uint32_t first_read; uint32_t first_warp; uint32_t n_warps; };
     struct PlanScratch
     {
-        std::vector<PhmmRead> reads;
         std::vector<PhmmHap> haps;
         std::vector<PhmmChunk> chunks;
         std::vector<PhmmPair> slow;
@@ -352,12 +385,12 @@ struct PhmmDevice
 struct phmm_resident
 {
     PhmmDevice* dev = nullptr;
+    phmm_flat_batch fb{};                // a copy of the caller's batch descriptor (its arrays must outlive the resident batch)
     Slot slot;
     bool ran = false;                    // the device holds results of a phmm_resident_run
     DevBuf d_marg;                       // phmm_resident_marginalize: sites + maps in, marginal matrices out
     HostBuf h_marg;
     std::vector<RegionIn> regs;
-    std::vector<phmm_read> reads;
     std::vector<phmm_hap> haps;
 };
 
@@ -416,8 +449,8 @@ struct phmm_engine
 int phmm_plan_rpt_for_uniform_reads(uint32_t read_len, bool refgaps);
 
 // flat batches (phmm_front.cpp)
-void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_read>& reads,
-                     std::vector<phmm_hap>& haps, std::vector<RegionIn>& regs);
+void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_hap>& haps,
+                     std::vector<RegionIn>& regs);
 constexpr uint64_t kPairWeight = 16384;
 std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb);
 std::vector<std::pair<uint32_t, uint32_t>> flat_partition(const std::vector<uint64_t>& pre, uint32_t n_regions, uint64_t batch_cells, uint32_t n_workers);

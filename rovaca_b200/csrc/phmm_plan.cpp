@@ -93,17 +93,45 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     bool any_ins = false, any_del = false, any_gcp = false;
     s.want_f64 = cfg->fp64_always;
     s.want_best = s.want_raw = false;
+    const RegionIn *flat_first = nullptr, *flat_last = nullptr;
+    bool flat_contig = true;         // the batch's read bytes are one contiguous range of every blob of one flat batch
     for (const RegionIn& r : regs) {
-        if (r.n_reads == 0 || r.n_haps == 0) continue;           // pairhmm_internal.cpp:508-510
+        if (r.n_reads == 0 || r.n_haps == 0) {                   // pairhmm_internal.cpp:508-510
+            flat_contig &= r.n_reads == 0;                       // reads that are skipped would sit inside the range
+            continue;
+        }
         s.want_f64 |= r.out.raw_f64 != nullptr;
         s.want_raw |= r.out.raw_f32 != nullptr || r.out.raw_f64 != nullptr;
         s.want_best |= r.out.best_hap != nullptr;
         uint64_t rb = 0, hb = 0;
-        for (uint32_t k = 0; k < r.n_reads; ++k) {
-            rb += r.reads[k].len;
-            any_ins |= r.reads[k].ins != nullptr;
-            any_del |= r.reads[k].del != nullptr;
-            any_gcp |= r.reads[k].gcp != nullptr;
+        if (r.flat) {
+            const uint32_t* len = r.flat->read_len + r.flat_r0;
+            const uint64_t* off = r.flat->read_off + r.flat_r0;
+            uint64_t gaps = 0;                                       // bytes between consecutive reads in the caller's blobs
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                rb += len[k];
+                gaps += (k + 1 < r.n_reads) ? off[k + 1] - (off[k] + len[k]) : 0;
+            }
+            any_ins |= r.flat->read_ins != nullptr;
+            any_del |= r.flat->read_del != nullptr;
+            any_gcp |= r.flat->read_gcp != nullptr;
+            // one run per blob for the whole batch?  Regions of one flat batch, consecutive, their reads back to back
+            if (flat_first == nullptr) {
+                flat_first = &r;
+            } else {
+                flat_contig &= r.flat == flat_last->flat && r.flat_r0 == flat_last->flat_r0 + flat_last->n_reads &&
+                               off[0] == flat_last->flat->read_off[r.flat_r0 - 1] + flat_last->flat->read_len[r.flat_r0 - 1];
+            }
+            flat_contig &= gaps == 0;
+            flat_last = &r;
+        } else {
+            flat_contig = false;
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                rb += r.reads[k].len;
+                any_ins |= r.reads[k].ins != nullptr;
+                any_del |= r.reads[k].del != nullptr;
+                any_gcp |= r.reads[k].gcp != nullptr;
+            }
         }
         for (uint32_t j = 0; j < r.n_haps; ++j) hb += r.haps[j].len;
         n_reads += r.n_reads;
@@ -158,16 +186,28 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             target_cols = (uint32_t)std::max<uint64_t>(kMinStreamCols, (uint64_t)full_cols * est_warps / want_chunks);
     }
     Slot::PlanScratch& ps = s.ps;
-    std::vector<PhmmRead>& reads = ps.reads;
+    // The read records go straight into the pinned arena (they are first in it): room for them and, as far as it can be told
+    // now, for the rest — records per read and haplotype, the task list, the byte blobs — so that the arena is not moved later.
+    {
+        const size_t blobs = (size_t)(2 + (any_ins ? 1 : 0) + (any_del ? 1 : 0) + (any_gcp ? 1 : 0)) * (read_bytes + 272) + hap_bytes + 272;
+        const size_t guess = (size_t)n_reads * (sizeof(PhmmRead) + 16) + (size_t)n_haps * 96 + blobs + ((size_t)1 << 16);
+        const int rc0 = s.h_in.ensure(guess, &high_water[0]);
+        if (rc0 != PHMM_OK) return rc0;
+    }
+    struct ReadRecords                               // the arena's head, written in place
+    {
+        HostBuf* buf;
+        uint32_t n = 0;
+        size_t size() const { return n; }
+        void push_back(const PhmmRead& d) { static_cast<PhmmRead*>(buf->p)[n++] = d; }
+    } reads{&s.h_in};
     std::vector<PhmmHap>& haps = ps.haps;
     std::vector<PhmmChunk>& chunks = ps.chunks;
     std::vector<PhmmPair>& slow = ps.slow;
-    reads.clear();
     haps.clear();
     chunks.clear();
     slow.clear();
     ps.pri.clear();
-    reads.reserve(n_reads);
     haps.reserve(n_haps);
     s.regions.clear();
     s.regions.reserve(regs.size());
@@ -336,7 +376,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         // reads
         uint32_t longest_read = 0, shortest_read = UINT32_MAX, fast_reads = 0;
         for (uint32_t k = 0; k < r.n_reads; ++k) {
-            const phmm_read& in = r.reads[k];
+            const ReadView in = region_read(r, k);
             PhmmRead d{};
             d.raw_off = (uint32_t)raw_off;
             d.word_off = (uint32_t)raw_off;
@@ -384,7 +424,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             std::vector<uint16_t>& lens = ps.fast_len;
             lens.resize(r.n_reads);
             for (uint32_t k = 0; k < r.n_reads; ++k) {
-                const uint32_t len = r.reads[k].len;
+                const uint32_t len = region_read_len(r, k);
                 lens[k] = (len - 1u < max_read) ? (uint16_t)len : (uint16_t)0;
             }
             auto exact_cost = [&](int c) {                                      // warps after packing x step cost
@@ -570,10 +610,11 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     s.o_reads = o_reads; s.o_haps = o_haps; s.o_chunks = o_chunks; s.o_ctas = o_ctas; s.o_tasks = o_tasks; s.o_slow = o_slow;
     s.n_chunks = chunks.size(); s.n_ctas = ctas.size(); s.n_tasks = task_reads.size();
     int rc;
-    if ((rc = s.h_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
+    if ((rc = s.h_in.ensure_keep(off, reads.size() * sizeof(PhmmRead), &high_water[0])) != PHMM_OK) return rc;
     if ((rc = s.d_in.ensure(off, &high_water[0])) != PHMM_OK) return rc;
     uint8_t* h = static_cast<uint8_t*>(s.h_in.p);
-    std::memcpy(h + o_reads, reads.data(), reads.size() * sizeof(PhmmRead));
+    static_assert(sizeof(PhmmRead) == 32, "the arena's head is an array of PhmmRead");
+    if (o_reads != 0) return fail(PHMM_ERR_STATE, "planner: the read records must be first in the arena");
     std::memcpy(h + o_haps, haps.data(), haps.size() * sizeof(PhmmHap));
     std::memcpy(h + o_chunks, chunks.data(), chunks.size() * sizeof(PhmmChunk));
     std::memcpy(h + o_ctas, ctas.data(), ctas.size() * sizeof(PhmmCta));
@@ -615,11 +656,21 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         Run rb_run{nullptr, 0, 0, &runs}, rq_run = rb_run, ri_run = rb_run, rd_run = rb_run, rg_run = rb_run, hb_run = rb_run;
         bool pinned = true;
         size_t ro = 0, ho = 0;
+        const bool one_run = flat_contig && flat_first != nullptr;
+        if (one_run) {                               // a flat batch with its reads back to back: one run per blob, no per-read walk
+            const phmm_flat_batch* fb = flat_first->flat;
+            const uint64_t o = fb->read_off[flat_first->flat_r0];
+            rb_run.add(fb->read_bases + o, read_bytes, o_rb);
+            rq_run.add(fb->read_qual + o, read_bytes, o_rq);
+            if (fb->read_ins) ri_run.add(fb->read_ins + o, read_bytes, o_ri);
+            if (fb->read_del) rd_run.add(fb->read_del + o, read_bytes, o_rd);
+            if (fb->read_gcp) rg_run.add(fb->read_gcp + o, read_bytes, o_rg);
+        }
         for (const RegionIn& r : regs) {
             if (r.n_reads == 0 || r.n_haps == 0) continue;
             pinned &= r.pinned_src;
-            for (uint32_t k = 0; k < r.n_reads; ++k) {
-                const phmm_read& in = r.reads[k];
+            for (uint32_t k = 0; k < r.n_reads && !one_run; ++k) {
+                const ReadView in = region_read(r, k);
                 rb_run.add(in.bases, in.len, o_rb + ro);
                 rq_run.add(in.qual, in.len, o_rq + ro);
                 if (in.ins) ri_run.add(in.ins, in.len, o_ri + ro);

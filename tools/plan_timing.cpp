@@ -31,20 +31,29 @@ int main(int argc, char** argv)
     for (auto& x : rb) x = "ACGT"[rng() & 3];
     for (auto& x : rq) x = 30 + rng() % 10;
     for (auto& x : hb) x = "ACGT"[rng() & 3];
-    std::vector<phmm_read> reads(n_reads);
-    std::vector<phmm_hap> haps(n_haps);
-    std::vector<double> out(n_pairs);
-    std::vector<uint32_t> kept(n_reads);
-    std::vector<RegionIn> regs(G);
-    size_t ro = 0, ho = 0, ri = 0, hi = 0, po = 0;
-    for (int g = 0; g < G; ++g) {
-        regs[g] = RegionIn{};
-        regs[g].reads = reads.data() + ri; regs[g].n_reads = nr[g]; regs[g].haps = haps.data() + hi; regs[g].n_haps = nh[g];
-        regs[g].thr = 18; regs[g].pcr = 3; regs[g].out.likelihoods = out.data() + po; regs[g].out.kept_idx = kept.data() + ri;
-        for (uint32_t k = 0; k < nr[g]; ++k) { reads[ri++] = phmm_read{rb.data() + ro, rq.data() + ro, nullptr, nullptr, nullptr, rl[g][k], 60}; ro += rl[g][k]; }
-        for (uint32_t j = 0; j < nh[g]; ++j) { haps[hi++] = phmm_hap{hb.data() + ho, hl[g][j]}; ho += hl[g][j]; }
-        po += (size_t)nr[g] * nh[g];
+    // a flat batch over the arrays above: what phmm_run_flat hands the planner (reads are not materialised as view structs)
+    std::vector<uint64_t> rro(G + 1, 0), rho(G + 1, 0), roff(n_reads), hoff(n_haps);
+    std::vector<uint32_t> rlen(n_reads), hlen(n_haps);
+    std::vector<uint8_t> mapq(n_reads, 60);
+    {
+        size_t ri = 0, hi = 0;
+        uint64_t ro = 0, ho = 0;
+        for (int g = 0; g < G; ++g) {
+            for (uint32_t k = 0; k < nr[g]; ++k) { rlen[ri] = rl[g][k]; roff[ri] = ro; ro += rl[g][k]; ++ri; }
+            for (uint32_t j = 0; j < nh[g]; ++j) { hlen[hi] = hl[g][j]; hoff[hi] = ho; ho += hl[g][j]; ++hi; }
+            rro[g + 1] = ri;
+            rho[g + 1] = hi;
+        }
     }
+    phmm_flat_batch fb{};
+    fb.n_regions = (uint32_t)G; fb.reg_read_off = rro.data(); fb.reg_hap_off = rho.data(); fb.read_len = rlen.data(); fb.read_mapq = mapq.data();
+    fb.read_off = roff.data(); fb.read_bases = rb.data(); fb.read_qual = rq.data(); fb.hap_len = hlen.data(); fb.hap_off = hoff.data();
+    fb.hap_bases = hb.data(); fb.min_quality_threshold = 18; fb.pcr_model = 3;
+    std::vector<phmm_hap> haps;
+    std::vector<RegionIn> regs;
+    const auto tf = PT_NOW();
+    for (int it = 0; it < 5; ++it) flat_to_regions(&fb, nullptr, 0, (uint32_t)G, haps, regs);
+    const double flat_ms = std::chrono::duration<double, std::milli>(PT_NOW() - tf).count() / 5;
     PhmmSettings cfg;
     PhmmDevice e;
     e.cfg = &cfg;
@@ -57,6 +66,7 @@ int main(int argc, char** argv)
         if (e.plan(s, regs) != PHMM_OK) return 1;
         PT_ADD(7, a, PT_NOW());
     }
+    std::printf("flat_to_regions %.2f ms; ", flat_ms);
     std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f\n", G,
                 n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5);
     return 0;

@@ -48,6 +48,15 @@ def test_fails_loudly_without_gpu():
     assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
 
 
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-GPU behaviour")
+def test_multi_device_engine_fails_loudly_without_gpu():
+    """phmm_create_multi — one engine over several GPUs — has no CPU fallback either, for any device list."""
+    for devices in ("all", [0], [0, 1], [0, 0]):
+        with pytest.raises(ph.PhmmError) as ei:
+            ph.PairHmmEngine(devices=devices)
+        assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
 def test_tables_match_oracle(orc):
     p, mm, pd, mmd = ph.host_tables()
     assert np.array_equal(p.view(np.uint32), orc.ph2pr_f32().view(np.uint32))

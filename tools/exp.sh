@@ -1,9 +1,3 @@
-python tools/bench_sw.py 65536 > gpurun_out/sw_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/sw_launches.csv python tools/bench_sw.py 65536 > gpurun_out/sw_ncu.log 2>&1
-python - <<'PY'
-import csv
-rows=list(csv.reader(open('gpurun_out/sw_launches.csv')))
-h=next(i for i,r in enumerate(rows) if r and r[0]=="ID")
-hdr=rows[h]; ik,iv=hdr.index("Kernel Name"),hdr.index("Metric Value")
-for r in rows[h+1:h+25]:
-    print(r[ik][:60], r[iv])
-PY
+lscpu | grep -E "Model name|^CPU\(s\)|Thread|Core|Socket" 
+for w in 4 6 8 12 16; do PHMM_B200_WORKERS=$w python tools/stream_bench.py 131072 1.0 | cut -c1-330; done
+for w in 6 8 12 16; do PHMM_B200_WORKERS=$w python tools/stream_bench.py 131072 0.5 | cut -c1-330; done

@@ -45,7 +45,9 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
         for (uint32_t c = fl.cta_base; c < fl.cta_base + fl.n_ctas; ++c) {
             const PhmmCta& cta = T[c];
             const PhmmChunk& ch = C[cta.chunk];
-            if (cta.n_reads == 0 || cta.read_begin + cta.n_reads > s.n_tasks) ++out[13];
+            const uint32_t ts = fl.duo ? 2u : 1u;                             // paired reads: two task entries per read slot
+            if (cta.n_reads == 0 || cta.read_begin + ts * cta.n_reads > s.n_tasks) ++out[13];
+            if (fl.duo && (rpt != PHMM_DUO_RPT || ch.n_haps != 1 || (ch.n_xy >> 16) != 0)) ++out[13];
             uint32_t at = cta.read_begin, in_warps = 0;
             for (uint32_t w = 0; w < PHMM_WARPS; ++w) {
                 const uint32_t n = (cta.warp_reads >> (8 * w)) & 0xffu;
@@ -54,10 +56,14 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
                 if (w >= fl.cta_warps) ++out[13];                         // a warp the launch does not have
                 uint32_t lanes = 0, widest = 0;
                 for (uint32_t k = 0; k < n; ++k) {
-                    const PhmmRead& rd = R[tasks[at + k]];
+                    const PhmmRead& rd = R[tasks[at + ts * k]];
                     const uint32_t nl = phmm_read_lanes(rd.len, (int)rpt);
                     if (nl * rpt < rd.len + 1 || rd.len == 0) ++out[8];
                     if (fl.fixed_lanes && nl != fl.fixed_lanes) ++out[13];   // the fixed-lanes kernel takes reads of that lane count only
+                    if (fl.duo && tasks[at + 2 * k + 1] != UINT32_MAX) {     // its partner must take the same lanes
+                        const PhmmRead& rb = R[tasks[at + 2 * k + 1]];
+                        if (rb.len == 0 || phmm_read_lanes(rb.len, (int)rpt) != nl) ++out[8];
+                    }
                     lanes += nl;
                     widest = std::max(widest, nl);
                 }
@@ -67,7 +73,8 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
                 out[6] += 32;
                 out[7] += lanes;
                 out[11] += (uint64_t)32u * rpt * steps;
-                for (uint32_t k = 0; k < n; ++k) {
+                for (uint32_t k = 0; k < ts * n; ++k) {
+                    if (tasks[at + k] == UINT32_MAX) continue;               // a pair of one
                     const PhmmRead& rd = R[tasks[at + k]];
                     for (uint32_t j = 0; j < ch.n_haps; ++j) {
                         const PhmmHap& hp = H[ch.hap_begin + j];
@@ -79,7 +86,7 @@ int phmm_debug_plan(const phmm_flat_batch* fb, int fma_mode, uint32_t cta_warps,
                         out[12] += (uint64_t)rd.len * hp.len;
                     }
                 }
-                at += n;
+                at += ts * n;
             }
             if (in_warps != cta.n_reads) ++out[13];
         }

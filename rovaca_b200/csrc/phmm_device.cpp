@@ -3,6 +3,28 @@
 // :161-193, when the device epilogue is not used), and the worker threads that drive batches through both.
 #include "phmm_host.h"
 
+// PHMM_B200_PHASES=1: where a batch's wall time goes (plan / CUDA calls of launch() / waiting for the device / epilogue and
+// the rest of finish()), summed over the process and printed by the last device's shutdown — tools/caller_bench's latency table.
+static const bool g_phases = std::getenv("PHMM_B200_PHASES") != nullptr;
+static std::atomic<uint64_t> g_phase_ns[4], g_phase_batches;
+thread_local uint64_t tl_wait_ns = 0;
+
+// One allocation stream per device for the whole process (engines come and go; the stream is a few hundred bytes).
+cudaStream_t phmm_alloc_stream()
+{
+    static std::mutex m;
+    static std::vector<cudaStream_t> streams;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return nullptr;
+    std::lock_guard<std::mutex> lk(m);
+    if (streams.size() <= (size_t)dev) streams.resize((size_t)dev + 1, nullptr);
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        cudaGetLastError();
+        streams[dev] = nullptr;                    // the legacy default stream still gives stream-ordered allocations
+    }
+    return streams[dev];
+}
+
 // ------------------------------------------------------------------------------------------------
 // Device side of one batch
 // ------------------------------------------------------------------------------------------------
@@ -30,14 +52,14 @@ int PhmmDevice::launch(Slot& s, bool copy_in)
             CU(cudaMemcpyAsync(static_cast<uint8_t*>(s.d_in.p) + c.dst, c.src, c.len, cudaMemcpyHostToDevice, s.stream));
         stats.h2d += s.in_bytes;
     }
-    CU(cudaMemsetAsync(s.d_cnt.p, 0, 4, s.stream));
+    // (the prep kernel empties the list of underflowing pairs: one call less per batch)
     // PHMM_B200_POISON=1 (the GPU tests set it): every raw sum starts as NaN, so a pair no kernel wrote is loud instead of
     // keeping a stale value from an earlier batch
     static const bool poison = std::getenv("PHMM_B200_POISON") != nullptr;
-    if (poison && s.n_pairs) CU(cudaMemsetAsync(s.d_f32.p, 0xFF, s.n_pairs * sizeof(float), s.stream));
+    if (poison && s.n_pairs) CU(cudaMemsetAsync(s.dev.out_f32, 0xFF, s.n_pairs * sizeof(float), s.stream));
     CU(cudaEventRecord(s.ev[0], s.stream));
     CU(phmm_launch_prep(s.dev, s.stream));
-    CU(cudaEventRecord(s.ev[1], s.stream));
+    if (!s.lite) CU(cudaEventRecord(s.ev[1], s.stream));
     // One launch per read-length bin.  A batch of mixed lengths has many of them, none big enough to fill the GPU to the
     // end of its last wave, so they go out on up to four streams (forked after the prep kernel, joined before the FP64 pass).
     const size_t n_side = std::min<size_t>(Slot::kAux, s.launches.size() > 1 ? s.launches.size() - 1 : 0);
@@ -46,7 +68,7 @@ int PhmmDevice::launch(Slot& s, bool copy_in)
         const FwdLaunch& fl = s.launches[i];
         const size_t lane = i % (n_side + 1);
         cudaStream_t st = lane == 0 ? s.stream : s.aux[lane - 1];
-        const cudaError_t le = phmm_launch_fwd(s.dev, fl.rpt, fl.refgaps, cfg->fma, fl.fixed_lanes, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, st);
+        const cudaError_t le = phmm_launch_fwd(s.dev, fl.rpt, fl.refgaps, cfg->fma, fl.fixed_lanes, fl.duo, fl.cta_base, fl.n_ctas, fl.cta_warps, fl.smem, st);
         if (le != cudaSuccess)
             return fail(PHMM_ERR_CUDA, std::string("forward kernel launch (") + std::to_string(fl.rpt) + " rows per lane, " +
                                            std::to_string(fl.n_ctas) + " CTAs of " + std::to_string(fl.cta_warps) + " warps, " +
@@ -56,7 +78,7 @@ int PhmmDevice::launch(Slot& s, bool copy_in)
         CU(cudaEventRecord(s.aux_done[a], s.aux[a]));
         CU(cudaStreamWaitEvent(s.stream, s.aux_done[a], 0));
     }
-    CU(cudaEventRecord(s.ev[2], s.stream));
+    if (!s.lite) CU(cudaEventRecord(s.ev[2], s.stream));
     if (s.n_slow)
         CU(phmm_launch_pairs_f32(s.dev, cfg->fma, s.dev.slow_pairs, s.n_slow, static_cast<float*>(s.d_scr32.p), kPairThreads, s.max_cols,
                                  s.stream));
@@ -83,8 +105,8 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
     // a resident batch was planned before anyone said what to download: without best / second-best buffers on the device
     // the host epilogue serves that call
     const bool dev = s.dev_epi && (!asks_best || s.want_best);
-    const bool need_f32 = !dev || asks_raw;
-    if (copy_out && s.n_pairs) {
+    const bool need_f32 = (!dev || asks_raw) && !s.host_out;       // host_out: the kernels wrote the raw sums into h_f32 themselves
+    if (copy_out && s.n_pairs && !s.host_out) {
         if (need_f32) {
             CU(cudaMemcpyAsync(s.h_f32.p, s.d_f32.p, s.n_pairs * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
             stats.d2h += s.n_pairs * sizeof(float);
@@ -100,6 +122,7 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
         // short batches (the synchronous per-region callers) finish in tens of microseconds: poll before paying a blocking
         // sync's wake-up latency
         cudaError_t q = cudaErrorNotReady;
+        const auto t_wait = std::chrono::steady_clock::now();
         constexpr int poll_us = 400;                // (no polling, or blocking syncs, measured the same or worse with 16-128 callers)
         if (s.n_cells < 1500000000ull) {            // < ~0.5 ms of device work; big batches sleep instead of burning a core
             const auto t_poll = std::chrono::steady_clock::now();
@@ -110,10 +133,11 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
             if (q != cudaSuccess && q != cudaErrorNotReady) return fail(PHMM_ERR_CUDA, std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
         }
         if (q == cudaErrorNotReady) CU(cudaStreamSynchronize(s.stream));
+        if (g_phases) tl_wait_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t_wait).count();
     }
     // The FP64 sums are read only by a caller that asked for them (raw_f64) or under PHMM_FP64_ALWAYS; see `have64` below.
     bool have64 = s.f64_done;
-    if (s.n_pairs) {
+    if (s.n_pairs && !s.host_out) {
         n64 = *static_cast<uint32_t*>(s.h_cnt.p);
         if (n64 > 0 && !have64) {
             if (asks_f64) {                                     // a resident batch learns at download time who wants raw sums
@@ -128,15 +152,20 @@ int PhmmDevice::finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out
         }
     }
     CU(cudaEventElapsedTime(&s.gpu_ms, s.ev[0], s.ev[3]));
-    CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
+    if (s.lite)
+        s.fwd_ms = s.gpu_ms;                                   // (prep included: a few microseconds)
+    else
+        CU(cudaEventElapsedTime(&s.fwd_ms, s.ev[1], s.ev[2]));
 
     const auto t_epi = std::chrono::steady_clock::now();
     if (dev) {
         epilogue_from_device(s, regs, have64);
         stats.dev_epilogues += 1;
     }
-    else
-        epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
+    else {
+        const uint64_t under = epilogue(s, regs, static_cast<const float*>(s.h_f32.p), static_cast<const double*>(s.h_f64.p), have64);
+        if (s.host_out) n64 = (uint32_t)under;                 // the device's count stayed on the device
+    }
     stats.regions += regs.size();
     stats.pairs += s.n_pairs;
     stats.cells += s.n_cells;
@@ -189,8 +218,9 @@ void PhmmDevice::epilogue_from_device(const Slot& s, const std::vector<RegionIn>
 
 // The reference's host side after the kernels (pairhmm_internal.cpp:578-584 conversion, :53-63 normalize, :161-182 filter,
 // :184-193 transpose), region by region, from the raw sums in batch order.
-void PhmmDevice::epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const
+uint64_t PhmmDevice::epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const
 {
+    uint64_t under = 0;                            // pairs below MIN_ACCEPTED in this batch
     const unsigned old_csr = _mm_getcsr();
     _mm_setcsr(old_csr | 0x8000u);                 // init_native, pairhmm_internal.cpp:21-25
     std::vector<double> lk;
@@ -234,8 +264,10 @@ void PhmmDevice::epilogue(const Slot& s, const std::vector<RegionIn>& regs, cons
         if (r.n_kept_out) *r.n_kept_out = kept;
         if (r.n_fp64_out32) *r.n_fp64_out32 = reg64;
         if (r.n_fp64_out) __atomic_fetch_add(r.n_fp64_out, (uint64_t)reg64, __ATOMIC_RELAXED);
+        under += reg64;
     }
     _mm_setcsr(old_csr);
+    return under;
 }
 
 // After an error part-way through a batch: copies or kernels of this slot may still be reading its pinned arena and its
@@ -272,6 +304,7 @@ int PhmmDevice::execute(Slot& s, const std::vector<RegionIn>& regs)
     int rc;
     const auto t0 = std::chrono::steady_clock::now();
     busy_batches.fetch_add(1, std::memory_order_relaxed);
+    s.small_ok = true;
     {
         PhmmRange r("phmm plan");
         rc = plan(s, regs);
@@ -285,9 +318,19 @@ int PhmmDevice::execute(Slot& s, const std::vector<RegionIn>& regs)
         PhmmRange r("phmm launch");
         rc = launch(s, true);
     }
+    const auto t2 = std::chrono::steady_clock::now();
     if (rc == PHMM_OK) {
         PhmmRange r("phmm finish");
         rc = finish(s, regs, true);
+    }
+    if (g_phases) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ns = [](auto a, auto b) { return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count(); };
+        g_phase_ns[0] += ns(t0, t1);
+        g_phase_ns[1] += ns(t1, t2);
+        g_phase_ns[2] += tl_wait_ns;
+        g_phase_ns[3] += ns(t2, t3) - tl_wait_ns;
+        g_phase_batches += 1;
     }
     if (rc != PHMM_OK) {
         const std::string keep = g_phmm_err;
@@ -321,6 +364,22 @@ void PhmmDevice::worker_main(uint32_t idx)
         }
         job(s);
     }
+}
+
+Slot* PhmmDevice::take_caller_slot()
+{
+    for (uint32_t i = 0; i < kCallerSlots; ++i) {
+        if (!caller_slots[i]) continue;
+        bool idle = false;
+        if (caller_slot_busy[i].compare_exchange_strong(idle, true, std::memory_order_acquire)) return caller_slots[i].get();
+    }
+    return nullptr;
+}
+
+void PhmmDevice::return_caller_slot(Slot* s)
+{
+    for (uint32_t i = 0; i < kCallerSlots; ++i)
+        if (caller_slots[i].get() == s) caller_slot_busy[i].store(false, std::memory_order_release);
 }
 
 // `work` (weighted cells, flat_work_prefix's unit) counts as outstanding on this device from now until the job has run: the
@@ -364,6 +423,10 @@ int PhmmDevice::init(const PhmmSettings* settings, int cuda_ordinal, uint32_t id
         slots.emplace_back(new Slot());
         if ((rc = slots.back()->init()) != PHMM_OK) return rc;
     }
+    for (uint32_t i = 0; i < std::min<uint32_t>(kCallerSlots, std::max<uint32_t>(cfg->pipeline_depth, 1)); ++i) {
+        caller_slots[i].reset(new Slot());
+        if ((rc = caller_slots[i]->init()) != PHMM_OK) return rc;
+    }
     for (uint32_t i = 0; i < cfg->n_workers; ++i) workers.emplace_back([this, i] { worker_main(i); });
     return PHMM_OK;
 }
@@ -380,6 +443,11 @@ void PhmmDevice::shutdown()
     cudaSetDevice(ordinal);
     for (auto& s : slots) s->destroy();
     slots.clear();
+    for (auto& s : caller_slots)
+        if (s) {
+            s->destroy();
+            s.reset();
+        }
     for (auto& ss : sw.slot) {
         for (auto* b : {&ss.h_in, &ss.h_out}) b->release();
         for (auto* b : {&ss.d_in, &ss.d_bt, &ss.d_aux, &ss.d_cig, &ss.d_out}) b->release();
@@ -396,4 +464,11 @@ void PhmmDevice::shutdown()
     if (ub_stream) cudaStreamDestroy(ub_stream);
     if (epoch) cudaEventDestroy(epoch);
     d_tables.release();
+    cudaStreamSynchronize(phmm_alloc_stream());    // the arenas go back to the device now, not at some later synchronisation
+    if (g_phases && g_phase_batches.load()) {
+        const double n = (double)g_phase_batches.exchange(0);
+        std::fprintf(stderr, "{\"phases_us_per_batch\": {\"plan\": %.1f, \"launch_calls\": %.1f, \"wait_for_device\": %.1f, \"finish_and_epilogue\": %.1f}, \"batches\": %.0f}\n",
+                     g_phase_ns[0].exchange(0) / n / 1e3, g_phase_ns[1].exchange(0) / n / 1e3, g_phase_ns[2].exchange(0) / n / 1e3,
+                     g_phase_ns[3].exchange(0) / n / 1e3, n);
+    }
 }

@@ -127,6 +127,10 @@ inline size_t grow_to(size_t bytes, std::atomic<size_t>* high_water)
     return want;
 }
 
+// Device arenas come from the stream-ordered allocator on a stream of their own (one per device, phmm_device.cpp): growing one
+// slot's arena must not stall the batches other slots have in flight, which cudaFree's device-wide synchronisation did.
+cudaStream_t phmm_alloc_stream();   // of the calling thread's current device
+
 struct DevBuf
 {
     void* p = nullptr;
@@ -135,18 +139,25 @@ struct DevBuf
     int ensure(size_t bytes, std::atomic<size_t>* high_water = nullptr)
     {
         if (bytes <= cap || host_only) return PHMM_OK;
-        if (p) cudaFree(p);
+        static const bool sync_alloc = std::getenv("PHMM_B200_SYNC_ALLOC") != nullptr;   // A/B: plain cudaMalloc / cudaFree
+        cudaStream_t st = phmm_alloc_stream();
+        if (p) sync_alloc ? cudaFree(p) : cudaFreeAsync(p, st);   // (the slot is idle: nothing in flight reads the old arena)
         p = nullptr;
         cap = 0;
         size_t want = grow_to(bytes, high_water);
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) return fail(PHMM_ERR_MEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        cudaError_t e = sync_alloc ? cudaMalloc(&p, want) : cudaMallocAsync(&p, want, st);
+        if (e == cudaSuccess && !sync_alloc) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            return fail(PHMM_ERR_MEM, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
+        }
         cap = want;
         return PHMM_OK;
     }
     void release()
     {
-        if (p && !host_only) cudaFree(p);
+        static const bool sync_alloc = std::getenv("PHMM_B200_SYNC_ALLOC") != nullptr;
+        if (p && !host_only) sync_alloc ? cudaFree(p) : cudaFreeAsync(p, phmm_alloc_stream());
         p = nullptr;
         cap = 0;
     }
@@ -199,6 +210,7 @@ struct FwdLaunch
     int rpt;                 // rows per lane: which instantiation of the forward kernel
     bool refgaps;            // ... and which variant (the reference's own gap qualities, or per-base ones)
     uint32_t fixed_lanes;    // every read of the launch takes exactly this many lanes: the fixed-lanes specialisation (0 = general kernel)
+    bool duo;                // paired reads against one stream (two task entries per read slot), PHMM_DUO_RPT rows per lane
     uint32_t cta_base, n_ctas, cta_warps;
     size_t smem;
 };
@@ -228,6 +240,7 @@ struct Slot
         std::vector<PhmmRegionDev> regions_dev;
         std::vector<double> pri;
         std::vector<uint32_t> task_reads, order, region_chunks, idx, bucket, rec_of, hap_boff, stream_sum, stream_of, stream_idx;
+        std::vector<uint32_t> duo_a, duo_b, duo_order;          // paired reads: the two reads of every slot, slots warp after warp
         std::vector<std::vector<Group>> groups;
         std::vector<Group> sorted;
         std::vector<std::vector<uint32_t>> group_reads;
@@ -254,6 +267,9 @@ struct Slot
     bool want_raw = false;               // ... for the raw FP32 sums
     bool want_f64 = false;               // the FP64 recompute goes out with the batch (someone will read its values)
     bool f64_done = false;               // ... and has been launched for the sums now on the device
+    bool small_ok = false;               // set by the ticket path before plan(): a small batch may take the short device path
+    bool host_out = false;               // this batch's raw sums are written straight into h_f32 (mapped pinned memory): no D2H
+    bool lite = false;                   // one forward launch, no side streams: no forward-only timing events either
     float gpu_ms = 0.f, fwd_ms = 0.f;
     size_t o_reads = 0, o_haps = 0, o_chunks = 0, o_ctas = 0, o_tasks = 0, o_slow = 0;   // arena offsets of the record arrays
     size_t n_chunks = 0, n_ctas = 0, n_tasks = 0;
@@ -366,6 +382,13 @@ struct PhmmDevice
     std::condition_variable qcv;
     std::deque<std::function<void(Slot&)>> jobs;
     bool stopping = false;
+    // Slots for batches that run on their caller's own thread (phmm_wait on an idle pipeline: no hand-over to a worker and
+    // back, which is two thread wake-ups per call).  Taken and returned with one atomic each.
+    static constexpr uint32_t kCallerSlots = 4;
+    std::unique_ptr<Slot> caller_slots[kCallerSlots];
+    std::atomic<bool> caller_slot_busy[kCallerSlots] = {};
+    Slot* take_caller_slot();
+    void return_caller_slot(Slot* s);
 
     int init(const PhmmSettings* settings, int cuda_ordinal, uint32_t idx, const PhmmTables& tables);
     void shutdown();
@@ -373,7 +396,7 @@ struct PhmmDevice
     int launch(Slot& s, bool copy_in);
     cudaError_t launch_f64(Slot& s);
     int finish(Slot& s, const std::vector<RegionIn>& regs, bool copy_out);
-    void epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const;
+    uint64_t epilogue(const Slot& s, const std::vector<RegionIn>& regs, const float* f32, const double* f64, bool have64) const;
     void epilogue_from_device(const Slot& s, const std::vector<RegionIn>& regs, bool have64) const;
     int execute(Slot& s, const std::vector<RegionIn>& regs);
     void drain(Slot& s);                       // after an error: nothing of this slot may still be in flight when it is reused
@@ -418,7 +441,7 @@ struct phmm_engine
     {
         std::mutex m;
         std::condition_variable cv;
-        bool done = false;
+        std::atomic<bool> done{false};   // set (release) after rc and err; a waiter polls it before it blocks on cv
         int rc = PHMM_OK;
         std::string err;
     };
@@ -438,7 +461,10 @@ struct phmm_engine
     // return from earlier batches and goes out when one of those completes, when it is big (batch_cells), or after linger_us.
     uint32_t in_flight = 0;            // sealed batches that have not completed
     uint32_t depth() const { return cfg.pipeline_depth * (uint32_t)std::max<size_t>(devs.size(), 1); }
-    void seal_locked();
+    // Seals the open batch.  With `caller_runs` the batch may come back as a job for the calling thread (to be run after bm has
+    // been released) instead of going to a worker.
+    std::function<void()> seal_locked(bool caller_runs = false);
+    bool caller_runs = true;             // PHMM_B200_CALLER_RUNS=0: every batch goes to a worker (the round-1 hand-over; A/B and tests)
 
     std::mutex sw_m;                   // phmm_sw_align: one call at a time
     float sw_last_ms = 0.f;
@@ -452,6 +478,7 @@ int phmm_plan_rpt_for_uniform_reads(uint32_t read_len, bool refgaps);
 void flat_to_regions(const phmm_flat_batch* fb, phmm_flat_result* fr, uint32_t g0, uint32_t g1, std::vector<phmm_hap>& haps,
                      std::vector<RegionIn>& regs);
 constexpr uint64_t kPairWeight = 16384;
+constexpr size_t kHostOutBytes = 256 << 10;   // raw sums of a batch up to this size are written straight to mapped host memory
 std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb);
 std::vector<std::pair<uint32_t, uint32_t>> flat_partition(const std::vector<uint64_t>& pre, uint32_t n_regions, uint64_t batch_cells, uint32_t n_workers);
 uint64_t region_cells(const RegionIn& r);

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
     __shared__ uint32_t s_eq[8][8][PREP_WORDS];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.f64_count = 0u;   // the forward kernels' list of underflowing pairs starts empty
     if (warp >= p.n_reads) return;
     const PhmmRead rd = p.reads[warp];
     const int n = (int)rd.len;
@@ -177,11 +178,22 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
     const int thr = rd.thr;
     const bool fast = model != 0 && n <= PREP_MAX;
     const int nwords = (n + 31) >> 5;
+    // A small batch (a synchronous caller's region) is one warp's latency here, so the qualities of the first 160 bases are
+    // fetched before the staging and the ballots below, not one global load per round of the loop that needs them.
+    constexpr int kPre = 5;
+    uint32_t qpre[kPre];
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) {
+        const int i = (int)lane + 32 * k;
+        qpre[k] = i < n ? q[i] : 0u;
+    }
     if (fast) {
         uint8_t* sb = s_bases[wib];
+#pragma unroll 4
         for (int i = (int)lane; i < nwords * 32 + 8; i += 32) sb[i] = i < n ? b[i] : 0;
         __syncwarp();
         for (int str = 1; str <= 8; ++str)
+#pragma unroll 2
             for (int w = 0; w < nwords; ++w) {
                 const int pos = w * 32 + (int)lane;
                 const uint32_t m = __ballot_sync(0xffffffffu, pos + str < n && sb[pos] == sb[pos + str]);
@@ -189,8 +201,7 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
             }
         __syncwarp();
     }
-    for (int i = (int)lane; i < n; i += 32) {
-        uint32_t qq = q[i];
+    auto one_base = [&](int i, uint32_t qq) {
         qq = qq < rd.mapq ? qq : rd.mapq;
         qq = ((int)qq < thr) ? 6u : qq;                                     // MIN_QUALITY, adapter.h:5
         uint32_t gi = (flags & PHMM_RD_HAS_INS) ? p.read_ins[rd.raw_off + i] : 45u;   // read_record.cpp:191-196
@@ -203,7 +214,13 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
         const uint32_t gc = (flags & PHMM_RD_HAS_GCP) ? p.read_gcp[rd.raw_off + i] : 10u; // read_record.cpp:205-210
         const uint32_t base = fast ? s_bases[wib][i] : b[i];
         p.words[rd.word_off + i] = (qq & 127u) | ((gi & 127u) << 7) | ((gd & 127u) << 14) | ((gc & 127u) << 21) | (onehot(base) << 28);
+    };
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) {
+        const int i = (int)lane + 32 * k;
+        if (i < n) one_base(i, qpre[k]);
     }
+    for (int i = (int)lane + 32 * kPre; i < n; i += 32) one_base(i, q[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,12 +258,17 @@ constexpr int fwd_min_blocks_rg(int rpt) { return phmm_fwd_blocks_per_sm(rpt, tr
 // FIXED: 0 = every read on the lanes it needs (the general kernel); else every read of the launch takes exactly FIXED lanes (a
 // power of two) — the round-1 layout, kept as a specialisation for the commonest shape (150/151-bp reads on 8 lanes x 19 rows):
 // read slot and lane are the thread's position, the shuffles are segmented per read; ptxas schedules this hot loop 1.5 % better.
-template <int RPT, int VAR, int FIXED>
-__global__ void __launch_bounds__(PHMM_WARPS * 32, VAR == PHMM_VAR_REFGAPS ? fwd_min_blocks_rg(RPT) : fwd_min_blocks(RPT))
+// DUO: the two halves of every packed register hold two READS of the same lane count sweeping ONE haplotype stream (instead of
+// one read sweeping two streams).  For the haplotype a region has left over when its count is odd: dealt into the two streams it
+// would make one of them longer, and the other half of every lane idle for that long.  Each half has its own row parameters (as
+// true packed operands), its own prior tables and pad rows; a seam is crossed by both at once.  Reference-gap variant only.
+template <int RPT, int VAR, int FIXED, int DUO = 0>
+__global__ void __launch_bounds__(PHMM_WARPS * 32, DUO ? 2 : VAR == PHMM_VAR_REFGAPS ? fwd_min_blocks_rg(RPT) : fwd_min_blocks(RPT))
 phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
 {
     constexpr bool FMA = VAR != PHMM_VAR_GENERIC_NOFMA;
     constexpr bool RG = VAR == PHMM_VAR_REFGAPS;
+    static_assert(!DUO || (RG && FIXED == 0), "paired reads: reference-gap variant, general lane layout");
     constexpr int NP = RG ? 1 : RPT;                      // per-row (generic) or per-read (reference gaps) gap parameters
     constexpr int G = (RPT + 3) / 4;                     // float4 groups of the prior table
     constexpr uint32_t TSTRIDE = phmm_prior_table_stride(RPT);   // bytes per thread and base class: G float4, padded to an odd count
@@ -299,9 +321,11 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     const uint32_t wcnt = (cta.warp_reads >> (8 * warp)) & 0xffu;                  // reads of this warp
     if (wcnt == 0) return;                                                         // (the host packs warps so that this is rare)
     uint32_t wbeg = cta.read_begin;                                                // ... and where they start in the task list
+    constexpr uint32_t TS = DUO ? 2u : 1u;                                         // (paired reads: two task entries per slot)
 #pragma unroll
-    for (uint32_t w = 0; w < PHMM_WARPS; ++w) wbeg += w < warp ? ((cta.warp_reads >> (8 * w)) & 0xffu) : 0u;
+    for (uint32_t w = 0; w < PHMM_WARPS; ++w) wbeg += w < warp ? TS * ((cta.warp_reads >> (8 * w)) & 0xffu) : 0u;
     uint32_t rid, nl, lane, nl_max;
+    uint32_t ridB = 0xffffffffu;                                                   // DUO: the read in the .y halves (none: ~0)
     bool live;
     if (FIXED) {
         live = wlane / (FIXED ? FIXED : 1) < wcnt;                                 // a dead group shadows the warp's last read, never writes
@@ -309,9 +333,10 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         lane = wlane & ((FIXED ? FIXED : 1) - 1);
         nl = nl_max = FIXED;
     } else {
-        uint32_t my_rid = 0, my_nl = 0;
+        uint32_t my_rid = 0, my_nl = 0, my_ridB = 0xffffffffu;
         if (wlane < wcnt) {
-            my_rid = p.task_reads[wbeg + wlane];
+            my_rid = p.task_reads[wbeg + TS * wlane];
+            if (DUO) my_ridB = p.task_reads[wbeg + TS * wlane + 1];                // (same lane count as its partner: the host pairs them so)
             my_nl = (p.reads[my_rid].len + RPT) / RPT;                             // ceil((len + 1) / RPT): at least one pad row on top
         }
         uint32_t start = my_nl;                                                    // exclusive prefix sum: first lane of read i
@@ -329,12 +354,16 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         const uint32_t ridx = (uint32_t)__popc(below) - 1u;                       // which of the warp's reads covers me
         const uint32_t first = 31u - (uint32_t)__clz((int)below);
         rid = __shfl_sync(0xffffffffu, my_rid, ridx);
+        if (DUO) ridB = __shfl_sync(0xffffffffu, my_ridB, ridx);
         nl = __shfl_sync(0xffffffffu, my_nl, ridx);
         lane = live ? wlane - first : 0u;                                          // my lane within the read
     }
     constexpr int shfl_w = FIXED ? FIXED : 32;       // (segmenting the shuffles at run time where the lane counts allow it measured slower)
     const PhmmRead rd = p.reads[rid];
     const int npad = (int)(nl * RPT) - (int)rd.len;   // >= 1
+    const bool hasB = DUO && ridB != 0xffffffffu;     // a slot with one read only: the .y halves shadow it and never write
+    const PhmmRead rdB = DUO ? p.reads[hasB ? ridB : rid] : rd;
+    const int npadB = (int)(nl * RPT) - (int)rdB.len;
 
     // ---- per-row parameters (pairhmm_internal.cpp:463-481) into registers, priors into my table ----
     float mm[RPT], mi[RPT], dd[RPT], gapm[NP], ii[NP], md[NP];
@@ -396,6 +425,50 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         }
     }
 
+    // ---- paired reads: the same for the read in the .y halves, with tables of its own behind the first six ----
+    constexpr int RB = DUO ? RPT : 1;
+    float mmB[RB], miB[RB], ddB[RB];
+    uint32_t padmaskB = 0u;
+    if constexpr (DUO != 0) {
+        const PhmmTables* __restrict__ T = p.tables;
+        float pm[G * 4], pmm[G * 4];
+        uint32_t rr[G * 4];
+#pragma unroll
+        for (int k = 0; k < G * 4; ++k) { pm[k] = 0.f; pmm[k] = 0.f; rr[k] = 0u; }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            const int r = (int)lane * RPT + k - npadB;
+            if (r >= 0) {
+                const uint32_t w = p.words[rdB.word_off + r];
+                const uint32_t q = w & 127u, qi = (w >> 7) & 127u, qd = (w >> 14) & 127u, qc = (w >> 21) & 127u;
+                const uint32_t lo = qi < qd ? qi : qd, hi = qi < qd ? qd : qi;
+                mmB[k] = __ldg(&T->mm[((hi * (hi + 1)) >> 1) + lo]);
+                miB[k] = __ldg(&T->ph2pr[qi]);
+                ddB[k] = __ldg(&T->ph2pr[qc]);
+                pm[k] = __ldg(&T->pm[q]);
+                pmm[k] = __ldg(&T->pmm[q]);
+                rr[k] = w >> 28;
+            } else {
+                mmB[k] = 0.f; miB[k] = 0.f; ddB[k] = 1.f;
+                padmaskB |= 1u << k;
+            }
+        }
+        if ((int)lane * RPT - 1 < npadB) padmaskB |= 1u << RPT;
+#pragma unroll
+        for (uint32_t b = 0; b < 6; ++b) {
+            const uint32_t hb = class_onehot(b);
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4 v;
+                v.x = (rr[4 * g] & hb) ? pm[4 * g] : pmm[4 * g];
+                v.y = (rr[4 * g + 1] & hb) ? pm[4 * g + 1] : pmm[4 * g + 1];
+                v.z = (rr[4 * g + 2] & hb) ? pm[4 * g + 2] : pmm[4 * g + 2];
+                v.w = (rr[4 * g + 3] & hb) ? pm[4 * g + 3] : pmm[4 * g + 3];
+                *reinterpret_cast<float4*>(tbl + (6 + b) * CSTRIDE + threadIdx.x * TSTRIDE + g * 16) = v;
+            }
+        }
+    }
+
     // ---- state ------------------------------------------------------------------------------
     float2 Ml[RPT], Il[RPT], Dl[RPT];              // previous column, my rows
 #pragma unroll
@@ -408,6 +481,42 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     const unsigned char* tb = tbl + threadIdx.x * TSTRIDE;
     const uint32_t nsteps = L - 1 - (32 - nl_max); // the last lane of the warp's widest read reaches the end sentinel at step L - 33 + nl_max
     const bool writer = live && (lane == nl - 1);
+    const bool writerB = writer && hasB;
+
+    // paired reads: one stream, both halves cross a seam together
+#define PHMM_BOUNDARY_DUO()                                                                             \
+    {                                                                                                   \
+        if (writer && jx > 0) {                                                                         \
+            const uint32_t col = info_col[jx - 1], hap = info_hap[jx - 1];                              \
+            const float resA = __fadd_rn(sumM.x, sumI.x);                                               \
+            p.out_f32[rd.out_off + col] = resA;                                                         \
+            if (resA < 1e-28f) {                                                                        \
+                const uint32_t slot64 = atomicAdd(p.f64_count, 1u);                                     \
+                PhmmPair pr; pr.read = rid; pr.hap = hap; pr.out_idx = rd.out_off + col;                \
+                p.f64_pairs[slot64] = pr;                                                               \
+            }                                                                                           \
+            if (writerB) {                                                                              \
+                const float resB = __fadd_rn(sumM.y, sumI.y);                                           \
+                p.out_f32[rdB.out_off + col] = resB;                                                    \
+                if (resB < 1e-28f) {                                                                    \
+                    const uint32_t slot64 = atomicAdd(p.f64_count, 1u);                                 \
+                    PhmmPair pr; pr.read = ridB; pr.hap = hap; pr.out_idx = rdB.out_off + col;          \
+                    p.f64_pairs[slot64] = pr;                                                           \
+                }                                                                                       \
+            }                                                                                           \
+        }                                                                                               \
+        const float init = info_init[jx];                                                               \
+        ++jx;                                                                                           \
+        sumM = bc(0.f); sumI = bc(0.f);                                                                 \
+        _Pragma("unroll") for (int k = 0; k < RPT; ++k) {                                               \
+            Ml[k] = bc(0.f); Il[k] = bc(0.f);                                                           \
+            Dl[k].x = ((padmask >> k) & 1u) ? init : 0.f;                                               \
+            Dl[k].y = ((padmaskB >> k) & 1u) ? init : 0.f;                                              \
+        }                                                                                               \
+        dgM = bc(0.f); dgI = bc(0.f);                                                                   \
+        dgD.x = ((padmask >> RPT) & 1u) ? init : 0.f;                                                   \
+        dgD.y = ((padmaskB >> RPT) & 1u) ? init : 0.f;                                                  \
+    }
 
 #define PHMM_BOUNDARY(E, J, EI)                                                                         \
     {                                                                                                   \
@@ -430,24 +539,17 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         dgM.E = 0.f; dgI.E = 0.f; dgD.E = ((padmask >> RPT) & 1u) ? init : 0.f;                         \
     }
 
-    // two steps per trip let the registers of a step's inputs and outputs alternate (one step per trip costs a third of the
-    // throughput in moves); four pay for their code size only in the middle (measured: +1-3 % at 9-13 rows, -2-4 % below 9, 0 above;
-    // at 9 rows and its 128-register cap four steps spill, so it stays at two)
-#pragma unroll(RPT >= 10 && RPT <= 13 ? 4 : 2)
-    for (uint32_t s = 0; s < nsteps; ++s) {
-        uint2 w = sp[s];
-        if ((int)(w.x | w.y) < 0) {
-            if ((int)w.x < 0) PHMM_BOUNDARY(x, jx, 0)
-            if ((int)w.y < 0) PHMM_BOUNDARY(y, jy, 1)
-            w.x &= ~PHMM_FLAG_BIT;
-            w.y &= ~PHMM_FLAG_BIT;
-        }
-        // priors of my RPT rows against this column's base class, four rows per LDS (pairhmm_internal.cpp:479-480 values)
-        float px[G * 4], py[G * 4];
+    // Few rows per lane is the layout of a batch too small to fill the device (the latency policy of the planner): one warp per
+    // scheduler, every step waiting for its own stream word (LDS) and then for its priors (LDS again).  There the word and the
+    // priors of the next step are fetched one step ahead; the throughput layouts (more rows, other warps to issue from) keep the
+    // shorter live ranges.
+    constexpr bool PIPE = RG && RPT <= 8;
+    auto load_priors = [&](uint32_t wx, uint32_t wy, float* px, float* py) {
+        // priors of my RPT rows against a column's base class, four rows per LDS (pairhmm_internal.cpp:479-480 values)
 #pragma unroll
         for (int g = 0; g < G; ++g) {
-            const unsigned char* ax = tb + w.x + g * 16;
-            const unsigned char* ay = tb + w.y + g * 16;
+            const unsigned char* ax = tb + wx + g * 16;
+            const unsigned char* ay = tb + wy + g * 16;
             if (RPT - 4 * g >= 3) {
                 const float4 vx = *reinterpret_cast<const float4*>(ax), vy = *reinterpret_cast<const float4*>(ay);
                 px[4 * g] = vx.x; px[4 * g + 1] = vx.y; px[4 * g + 2] = vx.z; px[4 * g + 3] = vx.w;
@@ -461,13 +563,66 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
                 py[4 * g] = *reinterpret_cast<const float*>(ay);
             }
         }
+    };
+    // at the top of step s: wc = word(s) and pxn / pyn = its priors, wn = word(s + 1) — all in registers; the step asks for the
+    // priors of wn and for word(s + 2), and nobody waits for either before the next step
+    uint2 wc = make_uint2(0u, 0u), wn = make_uint2(0u, 0u);
+    float pxn[G * 4], pyn[G * 4];
+#pragma unroll
+    for (int k = 0; k < G * 4; ++k) { pxn[k] = 0.f; pyn[k] = 0.f; }
+    if (PIPE && nsteps > 0) {
+        wc = sp[0];
+        wn = sp[1];
+        load_priors(wc.x & ~PHMM_FLAG_BIT, wc.y & ~PHMM_FLAG_BIT, pxn, pyn);
+    }
+
+    // two steps per trip let the registers of a step's inputs and outputs alternate (one step per trip costs a third of the
+    // throughput in moves); four pay for their code size only in the middle (measured: +1-3 % at 9-13 rows, -2-4 % below 9, 0 above;
+    // at 9 rows and its 128-register cap four steps spill, so it stays at two)
+#pragma unroll(RPT >= 10 && RPT <= 13 ? 4 : 2)
+    for (uint32_t s = 0; s < nsteps; ++s) {
+        uint2 w;
+        float px[G * 4], py[G * 4];
+        if (PIPE) {
+            w = wc;
+#pragma unroll
+            for (int k = 0; k < G * 4; ++k) { px[k] = pxn[k]; py[k] = pyn[k]; }
+            load_priors(wn.x & ~PHMM_FLAG_BIT, wn.y & ~PHMM_FLAG_BIT, pxn, pyn);
+            wc = wn;
+            wn = sp[s + 2];                        // (32 zero words follow the end sentinel; a word beyond them is never used)
+        } else {
+            w = sp[s];
+        }
+        if constexpr (DUO != 0) {
+            if ((int)w.x < 0) {
+                PHMM_BOUNDARY_DUO()
+                w.x &= ~PHMM_FLAG_BIT;
+            }
+            load_priors(w.x, w.x + 6u * CSTRIDE, px, py);       // the same column for both reads, each in its own tables
+        } else {
+            if ((int)(w.x | w.y) < 0) {
+                if ((int)w.x < 0) PHMM_BOUNDARY(x, jx, 0)
+                if ((int)w.y < 0) PHMM_BOUNDARY(y, jy, 1)
+                w.x &= ~PHMM_FLAG_BIT;
+                w.y &= ~PHMM_FLAG_BIT;
+            }
+            if (!PIPE) load_priors(w.x, w.y, px, py);
+        }
         float2 pM = dgM, pI = dgI, pD = dgD;       // diagonal inputs of row 0
         float2 uM = upM, uI = upI;                 // inputs from above of row 0
 #pragma unroll
         for (int k = 0; k < RPT; ++k) {
             const float2 oM = Ml[k], oI = Il[k], oD = Dl[k];
             float2 nM, nI, nD;
-            if (RG) {                               // same operations, md == mi and one gapm / ii per read
+            if constexpr (DUO != 0) {               // two reads: every row parameter is a true pair
+                float2 t = __fmul2_rn(pM, make_float2(mm[k], mmB[k]));
+                t = __ffma2_rn(pI, bc(p.rg_gapm), t);
+                t = __ffma2_rn(pD, bc(p.rg_gapm), t);
+                nM.x = __fmul_rn(t.x, px[k]);
+                nM.y = __fmul_rn(t.y, py[k]);
+                nI = __ffma2_rn(uI, bc(k == 0 ? ii0 : p.rg_ii), __fmul2_rn(uM, make_float2(mi[k], miB[k])));
+                nD = __ffma2_rn(oD, make_float2(dd[k], ddB[k]), __fmul2_rn(oM, make_float2(mi[k], miB[k])));
+            } else if (RG) {                        // same operations, md == mi and one gapm / ii per read
                 float2 t = __fmul2_rn(pM, bc(mm[k]));
                 t = __ffma2_rn(pI, bc(p.rg_gapm), t);
                 t = __ffma2_rn(pD, bc(p.rg_gapm), t);
@@ -515,6 +670,7 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
         upD.y = __shfl_up_sync(0xffffffffu, Dl[RPT - 1].y, 1, shfl_w);
     }
 #undef PHMM_BOUNDARY
+#undef PHMM_BOUNDARY_DUO
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1053,10 +1209,10 @@ __global__ void __launch_bounds__(256) phmm_ubench_kernel(float* out, uint32_t i
     if (acc == 123.456f) out[0] = acc;
 }
 
-template <int RPT, int VAR, int FIXED = 0>
+template <int RPT, int VAR, int FIXED = 0, int DUO = 0>
 cudaError_t launch_fwd_t(const PhmmBatchDev& b, uint32_t cta_base, uint32_t n_ctas, uint32_t cta_warps, size_t smem, cudaStream_t st)
 {
-    auto kern = phmm_fwd_kernel<RPT, VAR, FIXED>;
+    auto kern = phmm_fwd_kernel<RPT, VAR, FIXED, DUO>;
     // Raise the dynamic shared-memory limit of this instantiation once, to the device maximum: several host workers launch
     // concurrently, and a per-launch "set to what I need" lets one worker lower the limit under another's launch.
     static std::atomic<uint64_t> limit_set{0};            // one bit per device ordinal
@@ -1116,11 +1272,15 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
     PHMM_CASE(17, FN, __VA_ARGS__) PHMM_CASE(18, FN, __VA_ARGS__) PHMM_CASE(19, FN, __VA_ARGS__)                                \
     return cudaErrorInvalidValue;
 
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, uint32_t cta_base, uint32_t n_ctas,
-                            uint32_t cta_warps, size_t smem_bytes, cudaStream_t st)
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, bool duo, uint32_t cta_base,
+                            uint32_t n_ctas, uint32_t cta_warps, size_t smem_bytes, cudaStream_t st)
 {
     if (n_ctas == 0) return cudaSuccess;
     if (rpt < 1 || rpt > phmm_max_rpt(refgaps) || cta_warps < 1 || cta_warps > PHMM_WARPS) return cudaErrorInvalidValue;
+    if (duo) {                                       // paired reads: one instantiation, see PHMM_DUO_RPT
+        if (rpt != PHMM_DUO_RPT || !refgaps || !fma || fixed_lanes) return cudaErrorInvalidValue;
+        return launch_fwd_t<PHMM_DUO_RPT, PHMM_VAR_REFGAPS, 0, 1>(b, cta_base, n_ctas, cta_warps, smem_bytes, st);
+    }
     if (fixed_lanes) {                               // the one specialisation: see phmm_fixed_lanes()
         if (fixed_lanes != phmm_fixed_lanes(rpt, refgaps) || !fma) return cudaErrorInvalidValue;
         return launch_fwd_t<PHMM_MAX_RPT, PHMM_VAR_REFGAPS, 8>(b, cta_base, n_ctas, cta_warps, smem_bytes, st);

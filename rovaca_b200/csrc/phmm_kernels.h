@@ -76,7 +76,9 @@ __host__ __device__
 #endif
 constexpr int phmm_fwd_blocks_per_sm(int rpt, bool refgaps)
 {
-    return refgaps ? (rpt <= 3 ? 6 : rpt <= 6 ? 5 : rpt <= 9 ? 4 : rpt <= 12 ? 3 : 2)
+    // (reference gaps, 4-8 rows: layouts of the latency policy only — a batch too small to fill the device — whose kernels keep
+    // the next step's stream word and priors in registers: they get the registers rather than the occupancy)
+    return refgaps ? (rpt <= 3 ? 6 : rpt <= 6 ? 4 : rpt <= 8 ? 3 : rpt == 9 ? 4 : rpt <= 12 ? 3 : 2)
                    : (rpt <= 3 ? 6 : rpt <= 5 ? 5 : (rpt == 6 || rpt == 8) ? 4 : rpt <= 10 ? 3 : 2);
 }
 static inline int phmm_max_rpt(bool refgaps) { return refgaps ? PHMM_MAX_RPT : PHMM_MAX_RPT_GENERIC; }
@@ -94,21 +96,25 @@ constexpr uint32_t phmm_prior_table_stride(int rpt) { return (uint32_t)(((rpt + 
 
 // Shared memory one CTA of the forward kernel needs for a chunk: the two column streams, the per-haplotype seam records and
 // the per-thread prior tables (6 base classes x ceil(RPT/4) float4 per thread).
-static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int rpt, uint32_t cta_warps)
+// (paired reads — two reads in the halves of every lane — keep a second set of tables)
+static inline size_t phmm_fwd_smem_bytes(uint32_t stream_len, uint32_t n_haps, int rpt, uint32_t cta_warps, bool duo = false)
 {
     const size_t streams = (size_t)(stream_len + 32) * 8;
     const size_t info = (((streams + (size_t)(n_haps + 1) * 2 * 12) + 15) & ~(size_t)15) - streams;
-    const size_t tables = (size_t)6 * phmm_prior_table_stride(rpt) * cta_warps * 32;
+    const size_t tables = (size_t)(duo ? 12 : 6) * phmm_prior_table_stride(rpt) * cta_warps * 32;
     return streams + info + tables;
 }
+// Rows per lane of the paired-reads kernel (phmm_fwd_kernel<.., DUO>): the most efficient count of the throughput layouts; a
+// region whose reads need more than 32 lanes at it keeps its odd haplotype in the two-stream chunks.
+#define PHMM_DUO_RPT 12
 
 cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st);
 // The one fixed-lanes specialisation of the forward kernel: reads of 133..151 bases take 8 lanes at 19 rows per lane (the
 // reference-gap variant); a launch in which every read does may use it (fixed_lanes = 8), else 0.
 static inline uint32_t phmm_fixed_lanes(int rpt, bool refgaps) { return (refgaps && rpt == PHMM_MAX_RPT) ? 8u : 0u; }
 // Forward wavefront kernel over ctas[cta_base .. cta_base + n_ctas) (all of one rows-per-lane count).
-cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, uint32_t cta_base, uint32_t n_ctas,
-                            uint32_t cta_warps, size_t smem_bytes, cudaStream_t st);
+cudaError_t phmm_launch_fwd(const PhmmBatchDev& b, int rpt, bool refgaps, bool fma, uint32_t fixed_lanes, bool duo, uint32_t cta_base,
+                            uint32_t n_ctas, uint32_t cta_warps, size_t smem_bytes, cudaStream_t st);
 // Per-pair kernels.  count_dev != null: the pair count is read on the device (FP64 recompute list).
 cudaError_t phmm_launch_pairs_f32(const PhmmBatchDev& b, bool fma, const PhmmPair* pairs, uint32_t count, float* scratch,
                                   uint32_t threads, uint32_t max_cols, cudaStream_t st);

@@ -221,10 +221,11 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     std::vector<std::vector<uint32_t>>& group_reads = ps.group_reads;       // read ids, warp after warp
     std::vector<std::vector<uint8_t>>& group_warps = ps.group_warps;        // reads per warp
     constexpr int kFixedBin = PHMM_MAX_RPT + 1;                              // regions whose reads all take phmm_fixed_lanes() lanes
-    groups.resize(PHMM_MAX_RPT + 2);
-    group_reads.resize(PHMM_MAX_RPT + 2);
-    group_warps.resize(PHMM_MAX_RPT + 2);
-    for (int b = 0; b <= PHMM_MAX_RPT + 1; ++b) {
+    constexpr int kDuoBin = PHMM_MAX_RPT + 2;                                // paired reads against a region's odd haplotype
+    groups.resize(PHMM_MAX_RPT + 3);
+    group_reads.resize(PHMM_MAX_RPT + 3);
+    group_warps.resize(PHMM_MAX_RPT + 3);
+    for (int b = 0; b <= PHMM_MAX_RPT + 2; ++b) {
         groups[b].clear();
         group_reads[b].clear();
         group_warps[b].clear();
@@ -248,6 +249,16 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         const uint8_t* operator[](int c) const { return v[c]; }
     } lanes_lut;
+
+    static const int env_rpt = std::getenv("PHMM_B200_RPT") ? std::atoi(std::getenv("PHMM_B200_RPT")) : 0;   // experiments only
+    // Paired reads (phmm_fwd_kernel<.., DUO>): a region with an odd number of haplotypes would leave the second stream of one
+    // chunk a haplotype short — half of every lane idle for that long.  Its shortest haplotype is taken out of the two-stream
+    // chunks and swept by the region's reads two at a time instead, when enough of them pair up (equal lane counts).
+    static const bool env_no_duo = std::getenv("PHMM_B200_NO_DUO") != nullptr;                              // A/B and tests
+    const bool duo_ok = !env_no_duo && refgaps && cfg->fma && !single_stream && min_lanes == 8 && env_rpt == 0;
+    static thread_local LanePacker tl_duo_packer;
+    LanePacker& duo_packer = tl_duo_packer;
+    std::vector<uint32_t>&duo_a = ps.duo_a, &duo_b = ps.duo_b, &duo_order = ps.duo_order;
 
     uint64_t raw_off = 0, hap_off = 0, out_off = 0;
     uint32_t max_cols = 0;
@@ -282,6 +293,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             }
         }
         const bool all_haps_in_stream = order.size() == r.n_haps;
+        uint32_t duo_hap = UINT32_MAX, duo_chunk = UINT32_MAX;
         region_chunks.clear();
         std::vector<uint32_t>& rec_of = ps.rec_of;                     // caller's haplotype index -> its record in haps[]
         rec_of.assign(r.n_haps, 0u);
@@ -313,58 +325,91 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     }
                     order[at2] = v;
                 }
+                if (duo_ok && (order.size() & 1)) {
+                    // do enough reads pair up?  lanes at PHMM_DUO_RPT rows, read by read and pair by pair
+                    const uint8_t* lut = lanes_lut[PHMM_DUO_RPT];
+                    uint32_t cls[33] = {0}, solo = 0, paired = 0;
+                    bool fits = true;
+                    for (uint32_t k = 0; k < r.n_reads; ++k) {
+                        const uint32_t len = region_read_len(r, k);
+                        if (len - 1u >= max_read) continue;              // not a wavefront read
+                        fits &= len <= 32u * PHMM_DUO_RPT - 1u;
+                        ++cls[std::min<uint32_t>(lut[len], 32u)];
+                    }
+                    for (uint32_t n = 1; n <= 32; ++n) {
+                        solo += n * cls[n];
+                        paired += n * ((cls[n] + 1) / 2);
+                    }
+                    if (fits && solo > 0 && paired * 10 <= solo * 7) {
+                        duo_hap = order.back();                          // the shortest
+                        order.pop_back();
+                        total -= r.haps[duo_hap].len;
+                    }
+                }
                 // never more chunks than pairs of haplotypes: a chunk with a single haplotype leaves its second stream empty —
                 // unless the batch is so small that most of the device would idle anyway (the one-region calls of a lone
                 // synchronous caller): then a haplotype per chunk halves the sweep, i.e. the call's latency
-                const uint32_t per_chunk = single_stream ? 1u : 2u;
-                uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / per_chunk),
-                                                                 std::max<uint64_t>(1, (total + per_chunk * (uint64_t)target_cols - 1) / (per_chunk * (uint64_t)target_cols)));
-                std::vector<uint32_t>&ssum = ps.stream_sum, &sown = ps.stream_of, &sidx = ps.stream_idx;
-                for (;;) {
+                if (!order.empty()) {                                         // (the odd haplotype may have been the only one)
+                    const uint32_t per_chunk = single_stream ? 1u : 2u;
+                    uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / per_chunk),
+                                                                     std::max<uint64_t>(1, (total + per_chunk * (uint64_t)target_cols - 1) / (per_chunk * (uint64_t)target_cols)));
+                    std::vector<uint32_t>&ssum = ps.stream_sum, &sown = ps.stream_of, &sidx = ps.stream_idx;
+                    for (;;) {
+                        const uint32_t S = per_chunk * n_chunks;
+                        ssum.assign(S, 0u);
+                        sown.resize(order.size());
+                        bool fits = true;
+                        for (size_t a = 0; a < order.size(); ++a) {
+                            uint32_t best = 0;
+                            for (uint32_t q = 1; q < S; ++q)
+                                if (ssum[q] < ssum[best]) best = q;
+                            sown[a] = best;
+                            ssum[best] += r.haps[order[a]].len;
+                            fits &= ssum[best] <= kMaxStreamCols;              // what one CTA can stage in shared memory
+                        }
+                        if (fits || per_chunk * n_chunks >= order.size()) break;
+                        ++n_chunks;                                            // several very long haplotypes: spread them further
+                    }
                     const uint32_t S = per_chunk * n_chunks;
-                    ssum.assign(S, 0u);
-                    sown.resize(order.size());
-                    bool fits = true;
-                    for (size_t a = 0; a < order.size(); ++a) {
-                        uint32_t best = 0;
-                        for (uint32_t q = 1; q < S; ++q)
-                            if (ssum[q] < ssum[best]) best = q;
-                        sown[a] = best;
-                        ssum[best] += r.haps[order[a]].len;
-                        fits &= ssum[best] <= kMaxStreamCols;              // what one CTA can stage in shared memory
+                    sidx.resize(S);
+                    for (uint32_t q = 0; q < S; ++q) sidx[q] = q;
+                    for (uint32_t a = 1; a < S; ++a) {                         // streams by length, longest first
+                        const uint32_t v = sidx[a];
+                        uint32_t at2 = a;
+                        while (at2 > 0 && ssum[sidx[at2 - 1]] < ssum[v]) {
+                            sidx[at2] = sidx[at2 - 1];
+                            --at2;
+                        }
+                        sidx[at2] = v;
                     }
-                    if (fits || per_chunk * n_chunks >= order.size()) break;
-                    ++n_chunks;                                            // several very long haplotypes: spread them further
-                }
-                const uint32_t S = per_chunk * n_chunks;
-                sidx.resize(S);
-                for (uint32_t q = 0; q < S; ++q) sidx[q] = q;
-                for (uint32_t a = 1; a < S; ++a) {                         // streams by length, longest first
-                    const uint32_t v = sidx[a];
-                    uint32_t at2 = a;
-                    while (at2 > 0 && ssum[sidx[at2 - 1]] < ssum[v]) {
-                        sidx[at2] = sidx[at2 - 1];
-                        --at2;
+                    for (uint32_t c = 0; c < n_chunks; ++c) {
+                        const uint32_t sx = sidx[per_chunk * c], sy = single_stream ? UINT32_MAX : sidx[2 * c + 1];
+                        if (ssum[sx] == 0) break;                              // fewer haplotypes than streams
+                        PhmmChunk ch{};
+                        ch.hap_begin = (uint32_t)haps.size();
+                        uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
+                        for (size_t a = 0; a < order.size(); ++a) {
+                            if (sown[a] != sx && sown[a] != sy) continue;
+                            const uint32_t e = sown[a] == sx ? 0u : 1u;
+                            emit(order[a], 32 + sum[e], (cnt[e] << 1) | e);
+                            sum[e] += r.haps[order[a]].len;
+                            ++cnt[e];
+                        }
+                        ch.n_haps = cnt[0] + cnt[1];
+                        ch.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
+                        ch.n_xy = cnt[0] | (cnt[1] << 16);
+                        region_chunks.push_back((uint32_t)chunks.size());
+                        chunks.push_back(ch);
                     }
-                    sidx[at2] = v;
                 }
-                for (uint32_t c = 0; c < n_chunks; ++c) {
-                    const uint32_t sx = sidx[per_chunk * c], sy = single_stream ? UINT32_MAX : sidx[2 * c + 1];
-                    if (ssum[sx] == 0) break;                              // fewer haplotypes than streams
+                if (duo_hap != UINT32_MAX) {
                     PhmmChunk ch{};
                     ch.hap_begin = (uint32_t)haps.size();
-                    uint32_t sum[2] = {0, 0}, cnt[2] = {0, 0};
-                    for (size_t a = 0; a < order.size(); ++a) {
-                        if (sown[a] != sx && sown[a] != sy) continue;
-                        const uint32_t e = sown[a] == sx ? 0u : 1u;
-                        emit(order[a], 32 + sum[e], (cnt[e] << 1) | e);
-                        sum[e] += r.haps[order[a]].len;
-                        ++cnt[e];
-                    }
-                    ch.n_haps = cnt[0] + cnt[1];
-                    ch.stream_len = 32 + std::max(sum[0], sum[1]) + 1;
-                    ch.n_xy = cnt[0] | (cnt[1] << 16);
-                    region_chunks.push_back((uint32_t)chunks.size());
+                    emit(duo_hap, 32u, 0u);
+                    ch.n_haps = 1;
+                    ch.stream_len = 32 + r.haps[duo_hap].len + 1;
+                    ch.n_xy = 1u;
+                    duo_chunk = (uint32_t)chunks.size();
                     chunks.push_back(ch);
                 }
             }
@@ -395,7 +440,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             const uint32_t rid = (uint32_t)reads.size();
             reads.push_back(d);
             s.read_len.push_back(in.len);
-            const bool fast = in.len > 0 && in.len <= max_read && !region_chunks.empty();   // the wavefront kernel takes it
+            const bool fast = in.len > 0 && in.len <= max_read && (!region_chunks.empty() || duo_chunk != UINT32_MAX);   // the wavefront kernel takes it
             if (fast) {
                 ++fast_reads;
                 longest_read = std::max(longest_read, in.len);
@@ -413,7 +458,43 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     }
                 }
         }
-        if (fast_reads) {
+        if (fast_reads && duo_chunk != UINT32_MAX) {
+            // the odd haplotype's sweep: reads of equal lane count two by two (neighbours in the caller's order, which is by
+            // length), pairs packed into warps like single reads
+            const uint8_t* lut = lanes_lut[PHMM_DUO_RPT];
+            uint32_t cls[33] = {0}, at[34];
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const uint32_t len = region_read_len(r, k);
+                if (len - 1u < max_read) ++cls[lut[len]];
+            }
+            at[1] = 0;
+            for (int n = 1; n <= 32; ++n) at[n + 1] = at[n] + (cls[n] + 1) / 2;
+            duo_a.assign(at[33], UINT32_MAX);
+            duo_b.assign(at[33], UINT32_MAX);
+            uint32_t seen[33] = {0};
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const uint32_t len = region_read_len(r, k);
+                if (len - 1u >= max_read) continue;
+                const uint32_t n = lut[len], q = seen[n]++;
+                ((q & 1) ? duo_b : duo_a)[at[n] + q / 2] = rp.read_begin + k;
+            }
+            duo_packer.slots.resize(at[33]);
+            for (uint32_t q = 0; q < at[33]; ++q) duo_packer.slots[q] = q;
+            duo_packer.count[0] = 0;
+            for (int n = 1; n <= 32; ++n) {
+                duo_packer.count[n] = (cls[n] + 1) / 2;
+                duo_packer.first[n] = at[n];
+            }
+            duo_order.clear();
+            const uint32_t first_read = (uint32_t)group_reads[kDuoBin].size(), first_warp = (uint32_t)group_warps[kDuoBin].size();
+            const uint32_t n_warps = duo_packer.pack(&duo_order, &group_warps[kDuoBin]);
+            for (uint32_t q : duo_order) {
+                group_reads[kDuoBin].push_back(duo_a[q]);
+                group_reads[kDuoBin].push_back(duo_b[q]);
+            }
+            groups[kDuoBin].push_back(Group{duo_chunk, chunks[duo_chunk].stream_len, first_read, first_warp, n_warps});
+        }
+        if (fast_reads && !region_chunks.empty()) {
             // Rows per lane for this region.  A read of len bases takes ceil((len + 1) / rpt) consecutive lanes; the region's
             // reads are packed into warps lane by lane.  Throughput: the rpt with the least warps x step cost (many rows per
             // lane amortise a step's shuffles and loads, but pad every read up to a whole lane).  Latency (a small batch on an
@@ -434,7 +515,6 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 packer.count[1] -= r.n_reads - fast_reads;
                 return packer.pack(nullptr, nullptr) * step_cost(c);
             };
-            static const int env_rpt = std::getenv("PHMM_B200_RPT") ? std::atoi(std::getenv("PHMM_B200_RPT")) : 0;   // experiments only
             if (env_rpt > 0) {
                 rpt = std::max(rpt_lo, std::min(max_rpt, env_rpt));
             } else if (min_lanes > 8) {
@@ -504,9 +584,10 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     ctas.clear();
     task_reads.clear();
     s.launches.clear();
-    for (int bin = 1; bin <= kFixedBin; ++bin) {
-        const int b = bin == kFixedBin ? PHMM_MAX_RPT : bin;              // rows per lane of this launch
-        if (bin != kFixedBin && bin > max_rpt) continue;
+    for (int bin = 1; bin <= kDuoBin; ++bin) {
+        const bool duo = bin == kDuoBin;
+        const int b = duo ? PHMM_DUO_RPT : bin == kFixedBin ? PHMM_MAX_RPT : bin;   // rows per lane of this launch
+        if (bin < kFixedBin && bin > max_rpt) continue;
         if (groups[bin].empty()) continue;
         {
             // stable, longest stream first: a counting sort on the stream length (at most kMaxStreamCols + 33 values)
@@ -522,6 +603,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         FwdLaunch fl{};
         fl.rpt = b;
         fl.fixed_lanes = bin == kFixedBin ? phmm_fixed_lanes(b, refgaps) : 0u;
+        fl.duo = duo;
         fl.refgaps = refgaps;
         fl.cta_base = (uint32_t)ctas.size();
         size_t smem = 0;
@@ -549,7 +631,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         // ... that still fits the device's shared memory with this launch's longest chunk (streams of very long haplotypes)
         for (;;) {
-            smem = phmm_fwd_smem_bytes(longest_stream, most_haps, b, cta_warps);
+            smem = phmm_fwd_smem_bytes(longest_stream, most_haps, b, cta_warps, duo);
             if (smem <= smem_optin || cta_warps == 1) break;
             cta_warps >>= 1;
         }
@@ -567,8 +649,9 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     c.warp_reads |= n << (8 * (w - w0));
                     c.n_reads += n;
                 }
-                task_reads.insert(task_reads.end(), gr.begin() + at_read, gr.begin() + at_read + c.n_reads);
-                at_read += c.n_reads;
+                const uint32_t entries = c.n_reads * (duo ? 2u : 1u);     // paired reads: two task entries per read slot
+                task_reads.insert(task_reads.end(), gr.begin() + at_read, gr.begin() + at_read + entries);
+                at_read += entries;
                 ctas.push_back(c);
             }
         }
@@ -739,6 +822,20 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
     b.hap_bases = d + o_hb;
     b.words = static_cast<uint32_t*>(s.d_words.p);
     b.out_f32 = static_cast<float*>(s.d_f32.p);
+    // A small batch of the ticket path (synchronous callers: one or a few regions) is all latency.  Its kernels write the raw
+    // sums straight into the pinned result buffer (a few KB of posted PCIe writes) — no copy back, no counter to fetch (the host
+    // epilogue sees which sums are under MIN_ACCEPTED anyway) — and a single forward launch is not timed on its own.
+    s.lite = s.small_ok && s.launches.size() <= 1 && slow.empty() && !s.want_f64 && !s.dev_epi;
+    s.host_out = false;
+    if (s.small_ok && !s.dev_epi && !s.want_f64 && !s.h_in.host_only && n_pairs && n_pairs * sizeof(float) <= kHostOutBytes) {
+        void* mapped = nullptr;
+        if (cudaHostGetDevicePointer(&mapped, s.h_f32.p, 0) == cudaSuccess && mapped) {
+            b.out_f32 = static_cast<float*>(mapped);
+            s.host_out = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     b.out_f64 = static_cast<double*>(s.d_f64.p);
     b.f64_pairs = static_cast<PhmmPair*>(s.d_pairs.p);
     b.f64_count = static_cast<uint32_t*>(s.d_cnt.p);

@@ -130,7 +130,8 @@ def test_sass_audit():
         assert c["FMUL"] >= 2 * rpt * steps, (name, c)
         assert c["FADD2"] == 2 * steps, (name, c)
         assert c["SHFL"] >= 6 * steps, (name, c)
-    assert seen == 12 + 19 + 1           # 1..12 rows per lane for any gap qualities, 1..19 for the reference's own, + fixed 8 x 19
+    # 1..12 rows per lane for any gap qualities, 1..19 for the reference's own, + fixed 8 x 19, + paired reads at 12 rows
+    assert seen == 12 + 19 + 1 + 1
 
 
 @pytest.mark.skipif(shutil.which("g++") is None, reason="g++ not on PATH")

@@ -234,6 +234,41 @@ def test_latency_lane_families(orc, lanes):
         eng.close()
 
 
+def test_paired_reads_on_the_odd_haplotype(orc):
+    """Throughput layout (8 lanes pinned, as a big batch gets): a region with an odd number of haplotypes has its shortest one
+    swept by pairs of reads — one read in each half of every lane, row parameters and prior tables per half.  Same bits as the
+    oracle for 1 / 3 / 5 / 9 haplotypes, full and odd read counts (a pair of one), reads on either side of every lane-count
+    boundary of the 12-row layout, short post-trim shapes, junk reads that underflow in either half (FP64 list), and a region
+    whose longest read does not fit 32 lanes at 12 rows (which keeps the two-stream chunks)."""
+    eng = PairHmmEngine(lanes_per_read=8)
+    try:
+        rng = np.random.default_rng(77)
+        for n_haps in (1, 3, 5, 9):
+            reads, haps = wl._one_region(rng, 64, n_haps, 280, 330, 150, 150)
+            _check_region_vs_oracle(eng, orc, reads, haps)
+            _check_region_vs_oracle(eng, orc, reads[:63], haps)
+            reads, haps = wl._one_region(rng, 41, n_haps, 250, 450, 30, 151, junk=0.15)
+            _check_region_vs_oracle(eng, orc, reads, haps)
+            reads, haps = wl._one_region(rng, 37, n_haps, 41, 120, 10, 100)                  # post-trim shapes
+            _check_region_vs_oracle(eng, orc, reads, haps, 18, PCR_HOSTILE)
+        hap = B[rng.integers(0, 4, 500)]
+        haps = [hap, hap[5:480].copy(), hap[::-1][:300].copy()]
+        edge = [11, 11, 12, 12, 23, 23, 24, 24, 35, 36, 36, 371, 371, 372, 372, 383, 383, 1, 1, 2]
+        reads = [dict(bases=hap[o:o + n].copy(), qual=rng.integers(5, 41, n).astype(np.uint8), mapq=int(rng.integers(20, 61)))
+                 for n, o in zip(edge, rng.integers(0, 100, len(edge)))]
+        _check_region_vs_oracle(eng, orc, reads, haps)
+        reads.append(dict(bases=hap[:400].copy(), qual=np.full(400, 30, np.uint8), mapq=60))   # 34 lanes at 12 rows: no pairs here
+        _check_region_vs_oracle(eng, orc, reads, haps)
+        # a flat batch of many such regions equals the per-region calls (CTAs of several warps, several regions per launch)
+        regs = [wl._one_region(rng, int(rng.integers(1, 60)), int(rng.integers(1, 12)), 60, 400, 10, 151, junk=0.05) for _ in range(48)]
+        flat = eng.run_flat(wl.RegionBatch.from_regions(regs))
+        for g, (rd, hp) in enumerate(regs):
+            m0, k0, *_ = orc.region(rd, hp)
+            assert np.array_equal(k0, flat.kept(g)) and np.array_equal(_bits64(m0), _bits64(flat.matrix(g))), g
+    finally:
+        eng.close()
+
+
 def test_fp64_recompute_exercised(engine, orc):
     """cfg3-style: junk reads underflow FP32 (< 1e-28f) and are recomputed in FP64 on the device."""
     rng = np.random.default_rng(12)

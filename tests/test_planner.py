@@ -137,8 +137,35 @@ def test_planner_quality_does_not_regress():
     """How well a plan uses the lanes it occupies (useful cells / lane-steps, lanes that hold a read) on the shapes the workload
     table watches: a guard for later planner changes — the numbers of the round-2 planner, rounded down.  (Lane utilisation
     is per padded row; the planner trades some of it for more rows per lane, i.e. fewer shuffles and loads per cell.)"""
-    for name, util, fill in (("cfg2", 0.97, 0.999), ("cfg5", 0.82, 0.93), ("cfg5t", 0.74, 0.90), ("cfg3", 0.80, 0.85)):
+    for name, util, fill in (("cfg2", 0.97, 0.999), ("cfg5", 0.86, 0.92), ("cfg5t", 0.77, 0.89), ("cfg3", 0.80, 0.85)):
         a = ph.plan_audit(_stream(name), busy_batches=6)
         _sound(a)
         assert a["lane_utilisation"] >= util and a["slot_fill"] >= fill, (name, a["lane_utilisation"], a["slot_fill"])
-        assert a["launches"] <= 3, (name, a["launches"])              # a few well-separated rows-per-lane counts, not one per length
+        assert a["launches"] <= 4, (name, a["launches"])    # a few well-separated rows-per-lane counts (+ the paired reads), not one per length
+
+
+def test_an_odd_haplotype_is_swept_by_pairs_of_reads():
+    """A region with an odd number of haplotypes: the shortest one leaves the two-stream chunks (which then balance) and is
+    swept by the reads two at a time, one read in each half of every lane — a launch of its own, every pair still covered
+    exactly once, fewer lane-steps than the same region pays for one haplotype more (which makes its count even)."""
+    rng = np.random.default_rng(21)
+
+    def region(n_haps, lens):
+        hap = B[rng.integers(0, 4, 320)]
+        haps = [hap[: 300 + 2 * j].copy() for j in range(n_haps)]
+        return ([dict(bases=B[rng.integers(0, 4, n)], qual=np.full(n, 30, np.uint8), mapq=60) for n in lens], haps)
+
+    mixed = [int(x) for x in rng.integers(30, 152, 41)]
+    for n_haps in (1, 3, 5, 9):
+        for lens in ([150] * 64, [150] * 63, mixed, [100, 101] * 20 + [17]):
+            odd = ph.plan_audit(wl.RegionBatch.from_regions([region(n_haps, lens)] * 40), lanes_per_read=8, busy_batches=4)
+            even = ph.plan_audit(wl.RegionBatch.from_regions([region(n_haps + 1, lens)] * 40), lanes_per_read=8, busy_batches=4)
+            _sound(odd)
+            _sound(even)
+            assert odd["pairs"] == 40 * n_haps * len(lens)
+            assert odd["launches"] == even["launches"] + (1 if n_haps > 1 else 0), (n_haps, odd["launches"], even["launches"])
+            assert odd["lane_steps"] < even["lane_steps"], (n_haps, odd["lane_steps"], even["lane_steps"])
+    # reads that do not pair up (every one its own lane count): the odd haplotype stays in the two-stream chunks
+    lone = ph.plan_audit(wl.RegionBatch.from_regions([region(3, [20, 40, 60, 80, 100, 120, 140])] * 40), lanes_per_read=8, busy_batches=4)
+    _sound(lone)
+    assert lone["launches"] == 1

@@ -117,7 +117,7 @@ int main(int argc, char** argv)
             ++calls;
         }
     };
-    for (int pass = 0; pass < 2; ++pass) {                       // pass 0 warms the arenas up
+    for (int pass = -1; pass < 2; ++pass) {                      // two passes warm the arenas of every slot up
         const int count = per_thread;
         lat_ns = 0;
         calls = 0;

@@ -212,7 +212,10 @@ uint32_t phmm_device_count(const phmm_engine* e);
 int phmm_device_ordinal(const phmm_engine* e, uint32_t index);   /* CUDA ordinal of the engine's index-th device, -1 if out of range */
 
 /* Replaces one synchronous rovaca::call_pairhmm call (haplotypecaller_engine.cpp:250).
- * = phmm_submit + phmm_wait.  Thread-safe; efficient only when many callers are in flight. */
+ * = phmm_submit + phmm_wait.  Thread-safe; efficient only when many callers are in flight.
+ * While the engine has room, a caller's own region is planned, launched and finished on the CALLING thread (no hand-over to
+ * a worker and back); that thread's current CUDA device is switched to the engine's for the call and restored before it
+ * returns. */
 int phmm_call_region(phmm_engine* e, const phmm_region* region, phmm_result* result);
 
 /* Asynchronous form of the same call, so that the caller's region loop

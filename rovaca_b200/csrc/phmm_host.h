@@ -60,6 +60,7 @@ struct PhmmRange
 };
 
 constexpr uint32_t kTargetStreamCols = 2400;    // per stream and chunk: keeps streams + prior tables under ~64 KB per CTA (3+ CTAs/SM)
+constexpr uint32_t kMixedStreamCols = 1600;     // ... for regions whose reads differ in length (phmm_plan.cpp)
 constexpr uint32_t kWavesWanted = 16;          // warps per warp slot a batch should have before its chunks may be full length
 constexpr uint32_t kMinStreamCols = 200;        // small batches are cut finer (more, shorter warps), but never below this
 constexpr uint32_t kMaxStreamCols = 22000;      // hard limit of one haplotype in the wavefront kernel (176 KB of streams + 37 KB of prior tables)

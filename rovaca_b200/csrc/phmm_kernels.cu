@@ -107,6 +107,7 @@ __device__ int repeat_length(const uint8_t* b, int n, int offset)
 // E[str-1] starting at t is at least s long; the backward count is the run of set bits ending at `offset`.
 constexpr int PREP_MAX = 1024;                 // bases per read on the fast path
 constexpr int PREP_WORDS = PREP_MAX / 32;
+constexpr uint32_t kPrepSplitReads = 2048;     // batches of at most this many reads get four warps per read in the prep kernel
 
 __device__ __forceinline__ int run_up(const uint32_t* e, int nwords, int p0, int cap)     // consecutive ones at p0, p0+1, ...
 {
@@ -138,37 +139,58 @@ __device__ __forceinline__ int run_down(const uint32_t* e, int p0, int cap)     
     return run;
 }
 
+// x / d for 0 <= x < 4096 and 1 <= d <= 8 (runs of at most 199 bits over unit lengths 1..8) without the integer-division
+// sequence: (x + 0.5) / d lies at least 1/16 inside the integer interval of x / d, far beyond the approximate divide's error.
+__device__ __forceinline__ int div_small(int x, int d) { return __float2int_rz(__fdividef((float)x + 0.5f, (float)d)); }
+
 __device__ __forceinline__ int repeat_length_bits(const uint32_t (*E)[PREP_WORDS], int nwords, int n, int offset)
 {
-    int fw_len = 1, max_fw = 0;
     const int test_len = n - offset - 1;
     const int p0 = offset + 1, w0 = p0 >> 5, b0 = p0 & 31;
+    // The shortest unit that repeats at all (the next `str` periodicity bits all set), all eight lengths looked at without a
+    // branch: the lanes of a warp find theirs at different lengths, and counting the whole run inside the loop made the warp
+    // walk that (divergent) path at nearly every length.  Only then the run itself, once.
+    int fw = 0;
+#pragma unroll
     for (int str = 1; str <= 8; ++str) {
-        if (str > test_len) break;                                   // :126-127 offsets only; unit must fit
-        // does the unit repeat at all?  (the next `str` periodicity bits all set)  Only then count the whole run.
         const uint32_t lo = E[str - 1][w0], hi = (w0 + 1 < nwords) ? E[str - 1][w0 + 1] : 0u;
         const uint32_t need = (1u << str) - 1u;
-        max_fw = 1;
-        if ((__funnelshift_r(lo, hi, b0) & need) == need) {
-            const int run = run_up(E[str - 1], nwords, p0, 21 * str);
-            max_fw = run / str + 1;                                  // bounded by test_len / str through E's validity bit
-            fw_len = str;
-            break;
-        }
+        const bool hit = str <= test_len && (__funnelshift_r(lo, hi, b0) & need) == need;   // :126-127 offsets only; unit must fit
+        fw = (fw == 0 && hit) ? str : fw;
     }
-    const int max_bw = run_down(E[fw_len - 1], offset, 21 * fw_len) / fw_len;
+    int fw_len = 1, max_fw = 1;
+    if (fw) {
+        const int run = run_up(E[fw - 1], nwords, p0, 21 * fw);
+        max_fw = div_small(run, fw) + 1;                                 // bounded by test_len / str through E's validity bit
+        fw_len = fw;
+    }
+    const int max_bw = div_small(run_down(E[fw_len - 1], offset, 21 * fw_len), fw_len);
     const int rl = max_bw + max_fw;
     return rl > 20 ? 20 : rl;
 }
 
+// WPR warps per read: 1 for a batch that fills the device with reads; 4 for a small one (a synchronous caller's region), where
+// the kernel is one warp's latency — the staging, the periodicity masks and the bases are then dealt to four warps that meet at
+// a named barrier of their own.
+template <int WPR>
 __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
 {
-    __shared__ uint8_t s_bases[8][PREP_MAX + 16];
-    __shared__ uint32_t s_eq[8][8][PREP_WORDS];
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    constexpr int RPB = 8 / WPR;                            // reads per block
+    constexpr int TS = 32 * WPR;                            // threads per read
+    __shared__ uint8_t s_bases[RPB][PREP_MAX + 16];
+    __shared__ uint32_t s_eq[RPB][8][PREP_WORDS];
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t warp = gw / WPR, part = gw % WPR;        // my read, and which of its warps I am
+    const uint32_t lane = threadIdx.x & 31, wib = (threadIdx.x >> 5) / WPR;
+    const int t0 = (int)(part * 32 + lane);                 // my first base
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.f64_count = 0u;   // the forward kernels' list of underflowing pairs starts empty
-    if (warp >= p.n_reads) return;
+    if (warp >= p.n_reads) return;                          // (all warps of a read leave together)
+    auto sync_read = [&] {
+        if (WPR == 1)
+            __syncwarp();
+        else
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + wib), "r"(TS) : "memory");
+    };
     const PhmmRead rd = p.reads[warp];
     const int n = (int)rd.len;
     const uint8_t* b = p.read_bases + rd.raw_off;
@@ -178,28 +200,30 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
     const int thr = rd.thr;
     const bool fast = model != 0 && n <= PREP_MAX;
     const int nwords = (n + 31) >> 5;
-    // A small batch (a synchronous caller's region) is one warp's latency here, so the qualities of the first 160 bases are
-    // fetched before the staging and the ballots below, not one global load per round of the loop that needs them.
+    // the qualities of my first bases are fetched before the staging and the ballots below, not one global load per round of
+    // the loop that needs them
     constexpr int kPre = 5;
     uint32_t qpre[kPre];
 #pragma unroll
     for (int k = 0; k < kPre; ++k) {
-        const int i = (int)lane + 32 * k;
+        const int i = t0 + TS * k;
         qpre[k] = i < n ? q[i] : 0u;
     }
     if (fast) {
         uint8_t* sb = s_bases[wib];
 #pragma unroll 4
-        for (int i = (int)lane; i < nwords * 32 + 8; i += 32) sb[i] = i < n ? b[i] : 0;
-        __syncwarp();
+        for (int i = t0; i < nwords * 32 + 8; i += TS) sb[i] = i < n ? b[i] : 0;
+        sync_read();
+        uint32_t turn = 0;
         for (int str = 1; str <= 8; ++str)
 #pragma unroll 2
-            for (int w = 0; w < nwords; ++w) {
+            for (int w = 0; w < nwords; ++w, ++turn) {
+                if (WPR > 1 && (turn & (WPR - 1)) != part) continue;
                 const int pos = w * 32 + (int)lane;
                 const uint32_t m = __ballot_sync(0xffffffffu, pos + str < n && sb[pos] == sb[pos + str]);
                 if (lane == 0) s_eq[wib][str - 1][w] = m;
             }
-        __syncwarp();
+        sync_read();
     }
     auto one_base = [&](int i, uint32_t qq) {
         qq = qq < rd.mapq ? qq : rd.mapq;
@@ -217,10 +241,10 @@ __global__ void __launch_bounds__(256) phmm_prep_kernel(PhmmBatchDev p)
     };
 #pragma unroll
     for (int k = 0; k < kPre; ++k) {
-        const int i = (int)lane + 32 * k;
+        const int i = t0 + TS * k;
         if (i < n) one_base(i, qpre[k]);
     }
-    for (int i = (int)lane + 32 * kPre; i < n; i += 32) one_base(i, q[i]);
+    for (int i = t0 + TS * kPre; i < n; i += TS) one_base(i, q[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1249,8 +1273,13 @@ cudaError_t phmm_launch_prep(const PhmmBatchDev& b, cudaStream_t st)
 {
     if (b.n_reads == 0) return cudaSuccess;
     const uint32_t warps_per_block = 8;
-    const uint32_t blocks = (b.n_reads + warps_per_block - 1) / warps_per_block;
-    phmm_prep_kernel<<<blocks, warps_per_block * 32, 0, st>>>(b);
+    if (b.n_reads <= kPrepSplitReads) {                   // a small batch: four warps per read (latency)
+        const uint32_t blocks = (b.n_reads * 4 + warps_per_block - 1) / warps_per_block;
+        phmm_prep_kernel<4><<<blocks, warps_per_block * 32, 0, st>>>(b);
+    } else {
+        const uint32_t blocks = (b.n_reads + warps_per_block - 1) / warps_per_block;
+        phmm_prep_kernel<1><<<blocks, warps_per_block * 32, 0, st>>>(b);
+    }
     return cudaGetLastError();
 }
 

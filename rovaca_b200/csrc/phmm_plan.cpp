@@ -294,6 +294,21 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         const bool all_haps_in_stream = order.size() == r.n_haps;
         uint32_t duo_hap = UINT32_MAX, duo_chunk = UINT32_MAX;
+        // Reads of mixed lengths mostly end up at 12 rows per lane in CTAs of one or two warps, where a full-length stream (a CTA
+        // stages its chunk's streams whatever its size) keeps the SM's shared memory from holding the twelve warps the registers
+        // allow; their chunks are cut at two thirds (measured: cfg5 streams +1.2 %, equal-length shapes want the full length).
+        uint32_t region_cols = target_cols;
+        if (!env_cols && target_cols > kMixedStreamCols) {
+            uint32_t lo = UINT32_MAX, hi = 0;
+            for (uint32_t k = 0; k < r.n_reads; ++k) {
+                const uint32_t len = region_read_len(r, k);
+                if (len - 1u < max_read) {
+                    lo = std::min(lo, len);
+                    hi = std::max(hi, len);
+                }
+            }
+            if (lo < hi) region_cols = kMixedStreamCols;
+        }
         region_chunks.clear();
         std::vector<uint32_t>& rec_of = ps.rec_of;                     // caller's haplotype index -> its record in haps[]
         rec_of.assign(r.n_haps, 0u);
@@ -352,7 +367,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 if (!order.empty()) {                                         // (the odd haplotype may have been the only one)
                     const uint32_t per_chunk = single_stream ? 1u : 2u;
                     uint32_t n_chunks = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(1, order.size() / per_chunk),
-                                                                     std::max<uint64_t>(1, (total + per_chunk * (uint64_t)target_cols - 1) / (per_chunk * (uint64_t)target_cols)));
+                                                                     std::max<uint64_t>(1, (total + per_chunk * (uint64_t)region_cols - 1) / (per_chunk * (uint64_t)region_cols)));
                     std::vector<uint32_t>&ssum = ps.stream_sum, &sown = ps.stream_of, &sidx = ps.stream_idx;
                     for (;;) {
                         const uint32_t S = per_chunk * n_chunks;

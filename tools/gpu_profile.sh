@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 3 -c
 echo "forward (cfg2) capture exit $?"
 CMD2="python tools/resident_bench.py cfg5 8192 0.5 1"
 $CMD2 > gpurun_out/${TAG}_cfg5_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 3 -c 3 -f -o gpurun_out/${TAG}_fwd_cfg5 $CMD2 > gpurun_out/${TAG}_ncu3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 4 -c 4 -f -o gpurun_out/${TAG}_fwd_cfg5 $CMD2 > gpurun_out/${TAG}_ncu3.log 2>&1
 echo "forward (cfg5) capture exit $?"
 export FP64_ALWAYS=1
 CMD3="python tools/resident_bench.py cfg3 48 0 1"

@@ -157,6 +157,32 @@ def test_one_engine_over_several_devices_synchronous_callers(orc):
         many.close()
 
 
+def test_a_callers_own_region_runs_on_its_thread_and_leaves_its_device_alone(monkeypatch):
+    """A synchronous caller whose batch is its own single region runs it on the calling thread (caller slots, results
+    written to mapped pinned memory): same bytes as with every batch handed to a worker (PHMM_B200_CALLER_RUNS=0), the calling
+    thread's current CUDA device — switched to the engine's for the call — is what it was afterwards, whichever device served."""
+    import torch
+    b = wl.stream("cfg5", 24, seed=13, post_trim_fraction=0.5)
+    regions = [b.region(g) for g in range(b.n_regions)]
+    ords = _ordinals()
+    before = torch.cuda.current_device()
+    eng = PairHmmEngine(devices=list(reversed(ords)))                # the engine's first device is not the caller's when there are two
+    try:
+        got = [eng.call_pairhmm(haps, reads) for reads, haps in regions]       # (no raw sums asked: the short device path)
+        assert torch.cuda.current_device() == before
+        assert eng.stats()["batches"] == len(regions)
+    finally:
+        eng.close()
+    monkeypatch.setenv("PHMM_B200_CALLER_RUNS", "0")
+    eng = PairHmmEngine(devices=ords)
+    try:
+        for (reads, haps), (m1, k1) in zip(regions, got):
+            m0, k0 = eng.call_pairhmm(haps, reads)
+            assert np.array_equal(m0.view(np.uint64), m1.view(np.uint64)) and np.array_equal(k0, k1)
+    finally:
+        eng.close()
+
+
 def test_sharded_stream_under_torchrun():
     """bench.py's `sharded_stream` record with one rank per GPU: needs two GPUs."""
     import torch

@@ -297,18 +297,27 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         // Reads of mixed lengths mostly end up at 12 rows per lane in CTAs of one or two warps, where a full-length stream (a CTA
         // stages its chunk's streams whatever its size) keeps the SM's shared memory from holding the twelve warps the registers
         // allow; their chunks are cut at two thirds (measured: cfg5 streams +1.2 %, equal-length shapes want the full length).
-        uint32_t region_cols = target_cols;
-        if (!env_cols && target_cols > kMixedStreamCols) {
-            uint32_t lo = UINT32_MAX, hi = 0;
+        [[maybe_unused]] const auto ptp0 = PT_NOW();
+        // one look at the read lengths for everything below that asks about them: which reads the wavefront kernel can take
+        // (lens[k] != 0), their range, and how many of them take how many lanes at the paired-reads kernel's rows per lane
+        std::vector<uint16_t>& lens = ps.fast_len;
+        lens.resize(r.n_reads);
+        uint32_t len_lo = UINT32_MAX, len_hi = 0, cls12[33] = {0};
+        {
+            const uint8_t* lut = lanes_lut[PHMM_DUO_RPT];
             for (uint32_t k = 0; k < r.n_reads; ++k) {
                 const uint32_t len = region_read_len(r, k);
-                if (len - 1u < max_read) {
-                    lo = std::min(lo, len);
-                    hi = std::max(hi, len);
+                const bool ok = len - 1u < max_read;
+                lens[k] = ok ? (uint16_t)len : (uint16_t)0;
+                if (ok) {
+                    len_lo = std::min(len_lo, len);
+                    len_hi = std::max(len_hi, len);
+                    ++cls12[std::min<uint32_t>(lut[len], 32u)];
                 }
             }
-            if (lo < hi) region_cols = kMixedStreamCols;
         }
+        const uint32_t region_cols = (!env_cols && target_cols > kMixedStreamCols && len_lo < len_hi) ? kMixedStreamCols : target_cols;
+        PT_ADD(5, ptp0, PT_NOW());
         region_chunks.clear();
         std::vector<uint32_t>& rec_of = ps.rec_of;                     // caller's haplotype index -> its record in haps[]
         rec_of.assign(r.n_haps, 0u);
@@ -342,20 +351,12 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 }
                 if (duo_ok && (order.size() & 1)) {
                     // do enough reads pair up?  lanes at PHMM_DUO_RPT rows, read by read and pair by pair
-                    const uint8_t* lut = lanes_lut[PHMM_DUO_RPT];
-                    uint32_t cls[33] = {0}, solo = 0, paired = 0;
-                    bool fits = true;
-                    for (uint32_t k = 0; k < r.n_reads; ++k) {
-                        const uint32_t len = region_read_len(r, k);
-                        if (len - 1u >= max_read) continue;              // not a wavefront read
-                        fits &= len <= 32u * PHMM_DUO_RPT - 1u;
-                        ++cls[std::min<uint32_t>(lut[len], 32u)];
-                    }
+                    uint32_t solo = 0, paired = 0;
                     for (uint32_t n = 1; n <= 32; ++n) {
-                        solo += n * cls[n];
-                        paired += n * ((cls[n] + 1) / 2);
+                        solo += n * cls12[n];
+                        paired += n * ((cls12[n] + 1) / 2);
                     }
-                    if (fits && solo > 0 && paired * 10 <= solo * 7) {
+                    if (len_hi <= 32u * PHMM_DUO_RPT - 1u && solo > 0 && paired * 10 <= solo * 7) {
                         duo_hap = order.back();                          // the shortest
                         order.pop_back();
                         total -= r.haps[duo_hap].len;
@@ -473,24 +474,21 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     }
                 }
         }
+        [[maybe_unused]] const auto ptd0 = PT_NOW();
         if (fast_reads && duo_chunk != UINT32_MAX) {
             // the odd haplotype's sweep: reads of equal lane count two by two (neighbours in the caller's order, which is by
             // length), pairs packed into warps like single reads
             const uint8_t* lut = lanes_lut[PHMM_DUO_RPT];
-            uint32_t cls[33] = {0}, at[34];
-            for (uint32_t k = 0; k < r.n_reads; ++k) {
-                const uint32_t len = region_read_len(r, k);
-                if (len - 1u < max_read) ++cls[lut[len]];
-            }
+            const uint32_t* cls = cls12;
+            uint32_t at[34];
             at[1] = 0;
             for (int n = 1; n <= 32; ++n) at[n + 1] = at[n] + (cls[n] + 1) / 2;
             duo_a.assign(at[33], UINT32_MAX);
             duo_b.assign(at[33], UINT32_MAX);
             uint32_t seen[33] = {0};
             for (uint32_t k = 0; k < r.n_reads; ++k) {
-                const uint32_t len = region_read_len(r, k);
-                if (len - 1u >= max_read) continue;
-                const uint32_t n = lut[len], q = seen[n]++;
+                if (!lens[k]) continue;
+                const uint32_t n = lut[lens[k]], q = seen[n]++;
                 ((q & 1) ? duo_b : duo_a)[at[n] + q / 2] = rp.read_begin + k;
             }
             duo_packer.slots.resize(at[33]);
@@ -509,6 +507,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             }
             groups[kDuoBin].push_back(Group{duo_chunk, chunks[duo_chunk].stream_len, first_read, first_warp, n_warps});
         }
+        PT_ADD(6, ptd0, PT_NOW());
         if (fast_reads && !region_chunks.empty()) {
             // Rows per lane for this region.  A read of len bases takes ceil((len + 1) / rpt) consecutive lanes; the region's
             // reads are packed into warps lane by lane.  Throughput: the rpt with the least warps x step cost (many rows per
@@ -516,13 +515,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             // idle device): the longest read spread over about min_lanes lanes, so that a step is short.
             int rpt = 0;
             const int rpt_lo = (int)((longest_read + 32) / 32);                 // the longest read must fit 32 lanes
-            // the lengths of the reads the wavefront kernel takes, compact (0 = not one of them)
-            std::vector<uint16_t>& lens = ps.fast_len;
-            lens.resize(r.n_reads);
-            for (uint32_t k = 0; k < r.n_reads; ++k) {
-                const uint32_t len = region_read_len(r, k);
-                lens[k] = (len - 1u < max_read) ? (uint16_t)len : (uint16_t)0;
-            }
+            // (lens[]: the lengths of the reads the wavefront kernel takes, 0 = not one of them)
             auto exact_cost = [&](int c) {                                      // warps after packing x step cost
                 for (int n = 0; n <= 32; ++n) packer.count[n] = 0;
                 const uint8_t* lut = lanes_lut[c];

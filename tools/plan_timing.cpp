@@ -67,7 +67,7 @@ int main(int argc, char** argv)
         PT_ADD(7, a, PT_NOW());
     }
     std::printf("flat_to_regions %.2f ms; ", flat_ms);
-    std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f\n", G,
-                n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5);
+    std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f (inside the regions loop: read-length scan %.2f, paired-reads packing %.2f)\n", G,
+                n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5, g_t[5] / 5, g_t[6] / 5);
     return 0;
 }

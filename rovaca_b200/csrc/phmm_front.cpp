@@ -153,7 +153,9 @@ std::vector<uint64_t> flat_work_prefix(const phmm_flat_batch* fb)
     };
     // this runs on the caller's thread before any sub-batch can start: big streams (one engine over several GPUs takes
     // hundreds of thousands of regions per call) spread the pass over a few threads
-    const uint32_t n = fb->n_regions, n_thr = n >= 131072 ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
+    const uint32_t n = fb->n_regions;
+    const bool big = n >= 131072 || (n > 0 && fb->reg_read_off[n] - fb->reg_read_off[0] >= 1000000);   // (~0.5 ms of adds per million reads)
+    const uint32_t n_thr = big ? std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 1u;
     if (n_thr > 1) {
         std::vector<std::thread> pool;
         for (uint32_t t = 0; t < n_thr; ++t)

@@ -179,11 +179,15 @@ std::vector<std::pair<uint32_t, uint32_t>> flat_partition(const std::vector<uint
     const uint64_t full = std::max<uint64_t>(1, std::min<uint64_t>(batch_cells, std::max<uint64_t>(total / (2ull * std::max(n_workers, 1u)), batch_cells >> 2)));
     std::vector<std::pair<uint32_t, uint32_t>> parts;
     uint32_t g = 0;
-    int ramp = 2;                                    // next sizes: full/4, full/2, then full
+    // Ramp up: the workers plan the first sub-batches side by side, and the device has nothing to do until the first plan is done —
+    // so the first ones are small (an eighth of the full size: planned in an eighth of the time), and there are several of each
+    // size, so that the device still has work when the next size up arrives: 4 x full/8, 2 x full/4, 2 x full/2, then full.
+    static const uint8_t kRamp[8] = {3, 3, 3, 3, 2, 2, 1, 1};
+    uint32_t step = 0;
     while (g < n_regions) {
         const uint64_t left = total - pre[g];
-        uint64_t want = ramp > 0 ? (full >> ramp) : full;
-        if (ramp > 0) --ramp;
+        uint64_t want = step < 8 ? (full >> kRamp[step]) : full;
+        ++step;
         // ramp down: never take more than half of what is left while more than full/4 remains
         if (left > (full >> 2)) want = std::min<uint64_t>(want, std::max<uint64_t>(left / 2, full >> 2));
         uint32_t end = g + 1;

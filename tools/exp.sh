@@ -1,12 +1,13 @@
 #!/bin/bash
-# scratch experiments on the GPU box (output: gpurun_out/<tag>.txt)
+# scratch: ncu of the forward launches of a post-trim-only cfg5 step
 mkdir -p gpurun_out
-OUT=gpurun_out/${1:-exp}.txt
-: > $OUT
-echo "## chunk length (PHMM_B200_STREAM_COLS) against shared-memory-limited occupancy, final round-2 kernels" >> $OUT
-for spec in "cfg5 16384 0.0" "cfg5 16384 0.5" "cfg5 32768 1.0" "cfg3 96 0.0" "cfg4 192 0.0"; do
-  for cols in 2400 2200 1600 1000; do
-    PHMM_B200_STREAM_COLS=$cols python tools/resident_bench.py $spec 3 >> $OUT 2>&1
-  done
-done
-cat $OUT | cut -c1-200
+python tools/resident_bench.py cfg5 16384 1.0 1 > gpurun_out/${1:-exp}_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 4 -c 4 -f -o gpurun_out/${1:-exp}_fwd_trim100 python tools/resident_bench.py cfg5 16384 1.0 1 > gpurun_out/${1:-exp}_ncu.log 2>&1
+echo "ncu exit $?"; cat gpurun_out/${1:-exp}_plain.log
+python - <<PY
+import sys; sys.path.insert(0, '.')
+from rovaca_b200 import workloads as wl, pairhmm as ph
+b = wl.stream("cfg5", 16384, seed=5, post_trim_fraction=1.0)
+a = ph.plan_audit(b, busy_batches=1)
+print({k: a[k] for k in ("warps", "lane_steps", "lane_utilisation", "slot_fill", "launches", "chunks", "cells")})
+PY

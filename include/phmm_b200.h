@@ -51,7 +51,7 @@ typedef struct phmm_config
     uint64_t batch_cells;         /* seal a batch at this many read x haplotype cells (0 = 32e9) */
     uint32_t linger_us;           /* phmm_wait lets an open batch collect regions this long (0 = 200) */
     uint32_t cta_warps;           /* warps per forward-kernel CTA, 1..4; 0 = chosen per launch; tuning knob */
-    uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 3) */
+    uint32_t pipeline_depth;      /* batches phmm_submit/phmm_wait keep in flight before they start batching up (0 = 6) */
     uint32_t lanes_per_read;      /* 8, 16 or 32 lanes per read in the forward kernel; 0 = by batch size (small batches on an idle
                                      device get the wide, low-latency layouts); tuning / test knob */
     uint32_t fp64_mode;           /* PHMM_FP64_*: when pairs whose FP32 sum underflows (< 1e-28f) are recomputed in FP64 */

@@ -63,7 +63,7 @@ static void make_region(Region& r, std::mt19937_64& rng, int n_reads, int n_haps
 int main(int argc, char** argv)
 {
     int threads = 64, per_thread = 64, window = 1, n_reads = 64, n_haps = 8, R = 150, H = 300;
-    uint32_t linger = 0, workers = 0, depth = 0;
+    uint32_t linger = 0, workers = 0, depth = 0, lanes = 0;
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string k = argv[i];
         const int v = std::atoi(argv[i + 1]);
@@ -73,6 +73,7 @@ int main(int argc, char** argv)
         else if (k == "--linger") linger = (uint32_t)v;
         else if (k == "--workers") workers = (uint32_t)v;
         else if (k == "--depth") depth = (uint32_t)v;
+        else if (k == "--lanes") lanes = (uint32_t)v;             // phmm_config.lanes_per_read: pins the layout policy (experiments)
         else if (k == "--reads") n_reads = v;
         else if (k == "--haps") n_haps = v;
     }
@@ -82,6 +83,7 @@ int main(int argc, char** argv)
     cfg.linger_us = linger;
     cfg.n_workers = workers;
     cfg.pipeline_depth = depth;
+    cfg.lanes_per_read = lanes;
     phmm_engine* eng = nullptr;
     if (phmm_create(&cfg, &eng) != PHMM_OK) {
         std::fprintf(stderr, "phmm_create: %s\n", phmm_last_error());

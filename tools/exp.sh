@@ -1,13 +1,15 @@
 #!/bin/bash
-# scratch: ncu of the forward launches of a post-trim-only cfg5 step
+# scratch: synchronous callers, pipeline depth x pinned layout
 mkdir -p gpurun_out
-python tools/resident_bench.py cfg5 16384 1.0 1 > gpurun_out/${1:-exp}_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:phmm_fwd -s 4 -c 4 -f -o gpurun_out/${1:-exp}_fwd_trim100 python tools/resident_bench.py cfg5 16384 1.0 1 > gpurun_out/${1:-exp}_ncu.log 2>&1
-echo "ncu exit $?"; cat gpurun_out/${1:-exp}_plain.log
-python - <<PY
-import sys; sys.path.insert(0, '.')
-from rovaca_b200 import workloads as wl, pairhmm as ph
-b = wl.stream("cfg5", 16384, seed=5, post_trim_fraction=1.0)
-a = ph.plan_audit(b, busy_batches=1)
-print({k: a[k] for k in ("warps", "lane_steps", "lane_utilisation", "slot_fill", "launches", "chunks", "cells")})
-PY
+OUT=gpurun_out/${1:-exp}.txt
+: > $OUT
+g++ -O2 -std=c++17 -Iinclude tools/caller_bench.cpp -Lrovaca_b200 -lphmm_b200 -Wl,-rpath,'$ORIGIN/../rovaca_b200' -lpthread -o tools/caller_bench || exit 1
+for t in 16 32 64; do
+  for d in 3 6 8 12; do
+    for lanes in 0 8 16; do
+      echo "threads $t depth $d lanes $lanes" >> $OUT
+      tools/caller_bench --threads $t --regions $((8192 / t)) --lanes $lanes --depth $d >> $OUT 2>&1
+    done
+  done
+done
+cut -c1-200 $OUT

@@ -363,6 +363,31 @@ void PhmmDevice::worker_main(uint32_t idx)
             jobs.pop_front();
         }
         job(s);
+        // Arenas grow to the biggest size any slot of the device has needed (pinning host pages takes milliseconds): a worker with
+        // nothing queued does that now, not under the first big batch it is handed.
+        bool idle;
+        {
+            std::lock_guard<std::mutex> lk(qm);
+            idle = jobs.empty() && !stopping;
+        }
+        if (idle) catch_up(s);
+    }
+}
+
+void PhmmDevice::catch_up(Slot& s)
+{
+    s.h_in.catch_up(high_water[0]);
+    s.d_in.catch_up(high_water[0]);
+    s.d_words.catch_up(high_water[1]);
+    s.d_f32.catch_up(high_water[2]);
+    s.h_f32.catch_up(high_water[2]);
+    s.d_f64.catch_up(high_water[3]);
+    s.h_f64.catch_up(high_water[3]);
+    s.d_pairs.catch_up(high_water[4]);
+    s.d_scr64.catch_up(high_water[5]);
+    if (s.d_epi.cap) {                                 // (a slot that has never run a device epilogue keeps none)
+        s.d_epi.catch_up(high_water[7]);
+        s.h_epi.catch_up(high_water[7]);
     }
 }
 

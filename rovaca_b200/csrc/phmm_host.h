@@ -162,6 +162,14 @@ struct DevBuf
         p = nullptr;
         cap = 0;
     }
+    // bring an idle slot's arena up to the device-wide mark of its kind (contents are not kept; errors are left to the next ensure)
+    void catch_up(const std::atomic<size_t>& high_water)
+    {
+        const size_t mark = high_water.load(std::memory_order_relaxed);
+        if (mark <= cap || host_only) return;
+        release();
+        if (ensure(mark * 2 / 3) != PHMM_OK) g_phmm_err.clear();      // (grow_to gives 1.5 x what is asked for: the mark)
+    }
 };
 
 struct HostBuf
@@ -203,6 +211,13 @@ struct HostBuf
         }
         p = nullptr;
         cap = 0;
+    }
+    void catch_up(const std::atomic<size_t>& high_water)      // as DevBuf::catch_up
+    {
+        const size_t mark = high_water.load(std::memory_order_relaxed);
+        if (mark <= cap || host_only) return;
+        release();
+        if (ensure(mark * 2 / 3) != PHMM_OK) g_phmm_err.clear();      // (grow_to gives 1.5 x what is asked for: the mark)
     }
 };
 
@@ -388,6 +403,7 @@ struct PhmmDevice
     static constexpr uint32_t kCallerSlots = 4;
     std::unique_ptr<Slot> caller_slots[kCallerSlots];
     std::atomic<bool> caller_slot_busy[kCallerSlots] = {};
+    void catch_up(Slot& s);                  // an idle worker brings its slot's arenas up to the device's high-water marks
     Slot* take_caller_slot();
     void return_caller_slot(Slot* s);
 

@@ -590,6 +590,11 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
     };
     // at the top of step s: wc = word(s) and pxn / pyn = its priors, wn = word(s + 1) — all in registers; the step asks for the
     // priors of wn and for word(s + 2), and nobody waits for either before the next step
+    // The next step's stream word alone, fetched a step ahead: measured on every throughput instantiation (ptxas schedules each its own
+    // way) — 16 rows +1.1 % (cfg4), 12 rows -3.4 %, the fixed-lanes 19-row kernel -1.0 % (profiles/r02_word_prefetch_ab.txt).
+    constexpr bool PREW = !PIPE && !DUO && RG && FIXED == 0 && RPT == 16;
+    uint2 wpre = make_uint2(0u, 0u);
+    if (PREW && nsteps > 0) wpre = sp[0];
     uint2 wc = make_uint2(0u, 0u), wn = make_uint2(0u, 0u);
     float pxn[G * 4], pyn[G * 4];
 #pragma unroll
@@ -614,6 +619,9 @@ phmm_fwd_kernel(PhmmBatchDev p, uint32_t cta_base)
             load_priors(wn.x & ~PHMM_FLAG_BIT, wn.y & ~PHMM_FLAG_BIT, pxn, pyn);
             wc = wn;
             wn = sp[s + 2];                        // (32 zero words follow the end sentinel; a word beyond them is never used)
+        } else if (PREW) {
+            w = wpre;
+            wpre = sp[s + 1];
         } else {
             w = sp[s];
         }

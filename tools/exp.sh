@@ -1,15 +1,12 @@
 #!/bin/bash
-# scratch: synchronous callers, pipeline depth x pinned layout
+# scratch: stream word fetched a step ahead in the throughput kernels (library variants built with -DPHMM_EXP_WORD_PREFETCH=1|2)
 mkdir -p gpurun_out
 OUT=gpurun_out/${1:-exp}.txt
 : > $OUT
-g++ -O2 -std=c++17 -Iinclude tools/caller_bench.cpp -Lrovaca_b200 -lphmm_b200 -Wl,-rpath,'$ORIGIN/../rovaca_b200' -lpthread -o tools/caller_bench || exit 1
-for t in 16 32 64; do
-  for d in 3 6 8 12; do
-    for lanes in 0 8 16; do
-      echo "threads $t depth $d lanes $lanes" >> $OUT
-      tools/caller_bench --threads $t --regions $((8192 / t)) --lanes $lanes --depth $d >> $OUT 2>&1
-    done
+for spec in "cfg2 4096 0.0" "cfg5 16384 0.5" "cfg4 192 0.0"; do
+  python tools/resident_bench.py $spec 3 >> $OUT 2>&1
+  for v in 1 2; do
+    PHMM_B200_LIB=$PWD/rovaca_b200/libphmm_b200_exp$v.so python tools/resident_bench.py $spec 3 >> $OUT 2>&1
   done
 done
-cut -c1-200 $OUT
+cut -c1-220 $OUT

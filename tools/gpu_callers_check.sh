@@ -1,6 +1,6 @@
 #!/bin/bash
 # last check: smoke, the whole GPU suite, the callers table
-TAG=${1:-r02final4}
+TAG=${1:-callers_check}
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log

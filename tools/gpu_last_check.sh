@@ -1,6 +1,6 @@
 #!/bin/bash
 # last check of the round on one GPU: smoke, the whole GPU suite, the default bench line
-TAG=${1:-r02final2}
+TAG=${1:-last_check}
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log

@@ -169,3 +169,35 @@ def test_an_odd_haplotype_is_swept_by_pairs_of_reads():
     lone = ph.plan_audit(wl.RegionBatch.from_regions([region(3, [20, 40, 60, 80, 100, 120, 140])] * 40), lanes_per_read=8, busy_batches=4)
     _sound(lone)
     assert lone["launches"] == 1
+
+
+def test_random_batches_are_covered_exactly_once():
+    """Seeded random batches of awkward shapes — odd and even haplotype counts, haplotypes of length 0, 1 and beyond one stream, reads of
+    length 0 up to beyond the wavefront envelope, regions without reads or haplotypes, explicit gap qualities now and then — through
+    every layout policy and both arithmetic flavours: every pair computed exactly once, every read on enough lanes, every CTA in shape."""
+    rng = np.random.default_rng(2024)
+    pool = B[rng.integers(0, 4, 24000)]
+    for trial in range(300):
+        regs = []
+        for _ in range(int(rng.integers(1, 12))):
+            n_reads, n_haps = int(rng.integers(0, 70)), int(rng.integers(0, 12))
+            hap_lens = [int(rng.choice([0, 1, 7, 40, 80, 300, 301, 450, 1000, 2399, 23000], p=[.02, .02, .04, .1, .2, .3, .1, .1, .06, .04, .02]))
+                        for _ in range(n_haps)]
+            if rng.random() < 0.3:
+                read_lens = [int(rng.choice([100, 150, 151, 250]))] * n_reads
+            else:
+                read_lens = sorted(int(rng.choice([0, 1, 11, 12, 23, 24, 60, 100, 150, 151, 250, 383, 384, 607, 608, 900])) for _ in range(n_reads))
+            explicit = rng.random() < 0.1
+            reads = []
+            for n in read_lens:
+                r = dict(bases=pool[:n].copy(), qual=np.full(n, 30, np.uint8), mapq=60)
+                if explicit:
+                    r["gcp"] = np.full(n, 10, np.uint8)
+                reads.append(r)
+            regs.append((reads, [pool[:h].copy() for h in hap_lens]))
+        b = wl.RegionBatch.from_regions(regs)
+        lanes = int(rng.choice([0, 8, 16, 32]))
+        a = ph.plan_audit(b, fma_mode=ph.FMA_AVX512 if trial % 5 else ph.FMA_NONE, cta_warps=int(rng.choice([0, 1, 2, 4])),
+                          busy_batches=int(rng.choice([1, 4, 32])), lanes_per_read=lanes)
+        _sound(a)
+        assert a["pairs"] == b.pairs(), trial

@@ -269,6 +269,51 @@ def test_paired_reads_on_the_odd_haplotype(orc):
         eng.close()
 
 
+def test_random_awkward_batches_vs_oracle(engine, orc):
+    """Seeded random flat batches of awkward shapes — odd and even haplotype counts, haplotypes of 1 to 2399 columns, reads of 1 to 400
+    bases sorted or of one length, junk reads, N bases — through the default engine and one pinned to the throughput layout (paired
+    reads, fixed lanes, mixed rows per lane): every region byte-identical to the oracle."""
+    rng = np.random.default_rng(4242)
+    pinned = PairHmmEngine(lanes_per_read=8)
+    try:
+        for trial in range(6):
+            regs = []
+            for _ in range(int(rng.integers(6, 14))):
+                n_reads, n_haps = int(rng.integers(1, 50)), int(rng.integers(1, 10))
+                H = int(rng.choice([1, 7, 40, 80, 120, 300, 450, 1000, 2399], p=[.03, .05, .1, .2, .1, .3, .1, .08, .04]))
+                ref = B[rng.integers(0, 4, H)]
+                haps = []
+                for j in range(n_haps):
+                    h = ref.copy()
+                    if H > 4:
+                        h[rng.integers(0, H, 2)] = B[rng.integers(0, 4, 2)]
+                        if rng.random() < 0.3:
+                            h = h[: H - int(rng.integers(1, min(8, H - 1)))]
+                        if rng.random() < 0.05:
+                            h[int(rng.integers(0, len(h)))] = ord("N")
+                    haps.append(h)
+                lens = [int(rng.choice([100, 150, 151, 250]))] * n_reads if rng.random() < 0.3 else \
+                    sorted(int(rng.choice([1, 2, 11, 12, 23, 24, 35, 36, 60, 100, 150, 151, 250, 383, 384, 400])) for _ in range(n_reads))
+                reads = []
+                for n in lens:
+                    if rng.random() < 0.1 or n > H:
+                        rs = B[rng.integers(0, 4, n)]
+                    else:
+                        o = int(rng.integers(0, H - n + 1))
+                        rs = ref[o:o + n].copy()
+                    reads.append(dict(bases=rs, qual=rng.integers(2, 41, n).astype(np.uint8), mapq=int(rng.integers(0, 61))))
+                regs.append((reads, haps))
+            batch = wl.RegionBatch.from_regions(regs)
+            for eng in (engine, pinned):
+                flat = eng.run_flat(batch)
+                for g, (rd, hp) in enumerate(regs):
+                    m0, k0, *_ = orc.region(rd, hp)
+                    assert np.array_equal(k0, flat.kept(g)), (trial, g)
+                    assert np.array_equal(_bits64(m0), _bits64(flat.matrix(g))), (trial, g)
+    finally:
+        pinned.close()
+
+
 def test_fp64_recompute_exercised(engine, orc):
     """cfg3-style: junk reads underflow FP32 (< 1e-28f) and are recomputed in FP64 on the device."""
     rng = np.random.default_rng(12)

@@ -114,7 +114,7 @@ struct RegionPlan
     uint64_t out_off;
 };
 
-// Growing an arena means cudaFree + cudaMalloc (a device-wide sync) or re-pinning host pages (milliseconds), so arenas grow
+// Growing an arena means a stream-ordered free + allocation (DevBuf) or re-pinning host pages (milliseconds), so arenas grow
 // in big steps and straight to the biggest size any worker of the engine has needed for that buffer (the high-water mark):
 // after a change of workload every slot reallocates at most once.
 inline size_t grow_to(size_t bytes, std::atomic<size_t>* high_water)

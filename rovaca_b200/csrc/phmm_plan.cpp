@@ -318,6 +318,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         const uint32_t region_cols = (!env_cols && target_cols > kMixedStreamCols && len_lo < len_hi) ? kMixedStreamCols : target_cols;
         PT_ADD(5, ptp0, PT_NOW());
+        [[maybe_unused]] const auto pth0 = PT_NOW();
         region_chunks.clear();
         std::vector<uint32_t>& rec_of = ps.rec_of;                     // caller's haplotype index -> its record in haps[]
         rec_of.assign(r.n_haps, 0u);
@@ -434,6 +435,8 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                 for (uint32_t j = 0; j < r.n_haps; ++j)
                     if (!(r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols)) emit(j, 0u, 0u);
         }
+        [[maybe_unused]] const auto ptr0 = PT_NOW();
+        PT_ADD(8, pth0, ptr0);
         // reads
         uint32_t longest_read = 0, shortest_read = UINT32_MAX, fast_reads = 0;
         for (uint32_t k = 0; k < r.n_reads; ++k) {
@@ -474,6 +477,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
                     }
                 }
         }
+        PT_ADD(9, ptr0, PT_NOW());
         [[maybe_unused]] const auto ptd0 = PT_NOW();
         if (fast_reads && duo_chunk != UINT32_MAX) {
             // the odd haplotype's sweep: reads of equal lane count two by two (neighbours in the caller's order, which is by
@@ -508,6 +512,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             groups[kDuoBin].push_back(Group{duo_chunk, chunks[duo_chunk].stream_len, first_read, first_warp, n_warps});
         }
         PT_ADD(6, ptd0, PT_NOW());
+        [[maybe_unused]] const auto ptm0 = PT_NOW();
         if (fast_reads && !region_chunks.empty()) {
             // Rows per lane for this region.  A read of len bases takes ceil((len + 1) / rpt) consecutive lanes; the region's
             // reads are packed into warps lane by lane.  Throughput: the rpt with the least warps x step cost (many rows per
@@ -581,6 +586,7 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
             // every chunk of the region sweeps the same warps: one copy of the lists, one group per chunk
             for (uint32_t ci : region_chunks) groups[bin].push_back(Group{ci, chunks[ci].stream_len, first_read, first_warp, n_warps});
         }
+        PT_ADD(10, ptm0, PT_NOW());
         out_off += (uint64_t)r.n_reads * r.n_haps;
     }
 

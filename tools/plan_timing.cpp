@@ -1,7 +1,7 @@
 // Times the sections of PhmmDevice::plan on the CPU (host-only slot, no GPU), cfg2- or cfg5-shaped synthetic regions (NOT product).
 //   nvcc -O2 -std=c++17 -x cu -Irovaca_b200/csrc -Iinclude -o build/plan_timing tools/plan_timing.cpp -Lrovaca_b200 -lphmm_b200 -Xlinker -rpath=$PWD/rovaca_b200
 #include <chrono>
-static double g_t[8];
+static double g_t[12];
 #define PT_NOW() std::chrono::steady_clock::now()
 #define PT_ADD(i, a, b) g_t[i] += std::chrono::duration<double, std::milli>(b - a).count()
 #define PHMM_PLAN_TIMING 1
@@ -67,7 +67,7 @@ int main(int argc, char** argv)
         PT_ADD(7, a, PT_NOW());
     }
     std::printf("flat_to_regions %.2f ms; ", flat_ms);
-    std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f (inside the regions loop: read-length scan %.2f, paired-reads packing %.2f)\n", G,
-                n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5, g_t[5] / 5, g_t[6] / 5);
+    std::printf("%d regions, %zu reads, %zu pairs: plan total %.2f ms/call (%.2f us/region): count %.2f, regions loop %.2f, ctas %.2f, records copy %.2f, gather %.2f (inside the regions loop: read-length scan %.2f, haplotype chunks %.2f, read records %.2f, paired-reads packing %.2f, rows per lane + packing %.2f)\n", G,
+                n_reads, n_pairs, g_t[7] / 5, g_t[7] / 5 * 1e3 / G, g_t[0] / 5, g_t[1] / 5, g_t[2] / 5, g_t[3] / 5, g_t[4] / 5, g_t[5] / 5, g_t[8] / 5, g_t[9] / 5, g_t[6] / 5, g_t[10] / 5);
     return 0;
 }

@@ -437,45 +437,65 @@ int PhmmDevice::plan(Slot& s, const std::vector<RegionIn>& regs)
         }
         [[maybe_unused]] const auto ptr0 = PT_NOW();
         PT_ADD(8, pth0, ptr0);
-        // reads
+        // reads: one 32-byte record each, written straight into the pinned arena.  Everything but the length, the mapping quality
+        // and the running offsets is the same for all reads of a region (of a flat batch: also which optional qualities exist).
         uint32_t longest_read = 0, shortest_read = UINT32_MAX, fast_reads = 0;
-        for (uint32_t k = 0; k < r.n_reads; ++k) {
-            const ReadView in = region_read(r, k);
+        {
             PhmmRead d{};
-            d.raw_off = (uint32_t)raw_off;
-            d.word_off = (uint32_t)raw_off;
-            d.len = in.len;
-            d.out_off = (uint32_t)(out_off + (uint64_t)k * r.n_haps);
             d.n_haps = r.n_haps;
             d.hap_begin = rp.hap_begin;
             d.thr = (int16_t)std::max(-32768, std::min(32767, r.thr));
-            d.mapq = in.mapq;
-            const uint32_t fl = (in.ins ? PHMM_RD_HAS_INS : 0u) | (in.del ? PHMM_RD_HAS_DEL : 0u) | (in.gcp ? PHMM_RD_HAS_GCP : 0u);
             // apply_pcr_error_model's switch takes HOSTILE / AGGRESSIVE / CONSERVATIVE and leaves the read alone for anything
             // else (pairhmm_internal.cpp:121-159, default: break)
             const uint32_t pcr = (r.pcr >= PHMM_PCR_HOSTILE && r.pcr <= PHMM_PCR_CONSERVATIVE) ? (uint32_t)r.pcr : (uint32_t)PHMM_PCR_NONE;
-            d.model_flags = (uint8_t)(pcr | (fl << 4));
-            raw_off += in.len;
-            const uint32_t rid = (uint32_t)reads.size();
-            reads.push_back(d);
-            s.read_len.push_back(in.len);
-            const bool fast = in.len > 0 && in.len <= max_read && (!region_chunks.empty() || duo_chunk != UINT32_MAX);   // the wavefront kernel takes it
-            if (fast) {
-                ++fast_reads;
-                longest_read = std::max(longest_read, in.len);
-                shortest_read = std::min(shortest_read, in.len);
-            }
-            if (!fast || !all_haps_in_stream)
-                for (uint32_t j = 0; j < r.n_haps; ++j) {
-                    const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
-                    if (!fast || !hap_ok) {
-                        PhmmPair p{};
-                        p.read = rid;
-                        p.hap = rec_of[j];
-                        p.out_idx = d.out_off + j;
-                        slow.push_back(p);
-                    }
+            const phmm_flat_batch* fb = r.flat;
+            const uint32_t* flat_len = fb ? fb->read_len + r.flat_r0 : nullptr;
+            const uint8_t* flat_mapq = fb ? fb->read_mapq + r.flat_r0 : nullptr;
+            const uint32_t flat_fl = fb ? ((fb->read_ins ? PHMM_RD_HAS_INS : 0u) | (fb->read_del ? PHMM_RD_HAS_DEL : 0u) | (fb->read_gcp ? PHMM_RD_HAS_GCP : 0u)) : 0u;
+            const bool has_chunk = !region_chunks.empty() || duo_chunk != UINT32_MAX;
+            const size_t len_at = s.read_len.size();
+            s.read_len.resize(len_at + r.n_reads);
+            uint32_t* len_out = s.read_len.data() + len_at;
+            uint64_t oo = out_off;
+            for (uint32_t k = 0; k < r.n_reads; ++k, oo += r.n_haps) {
+                uint32_t len, fl;
+                if (fb) {
+                    len = flat_len[k];
+                    d.mapq = flat_mapq[k];
+                    fl = flat_fl;
+                } else {
+                    const phmm_read& in = r.reads[k];
+                    len = in.len;
+                    d.mapq = in.mapq;
+                    fl = (in.ins ? PHMM_RD_HAS_INS : 0u) | (in.del ? PHMM_RD_HAS_DEL : 0u) | (in.gcp ? PHMM_RD_HAS_GCP : 0u);
                 }
+                d.raw_off = (uint32_t)raw_off;
+                d.word_off = (uint32_t)raw_off;
+                d.len = len;
+                d.out_off = (uint32_t)oo;
+                d.model_flags = (uint8_t)(pcr | (fl << 4));
+                raw_off += len;
+                const uint32_t rid = (uint32_t)reads.size();
+                reads.push_back(d);
+                len_out[k] = len;
+                const bool fast = lens[k] != 0 && has_chunk;                  // the wavefront kernel takes it
+                if (fast) {
+                    ++fast_reads;
+                    longest_read = std::max(longest_read, len);
+                    shortest_read = std::min(shortest_read, len);
+                }
+                if (!fast || !all_haps_in_stream)
+                    for (uint32_t j = 0; j < r.n_haps; ++j) {
+                        const bool hap_ok = r.haps[j].len > 0 && r.haps[j].len <= kMaxStreamCols;
+                        if (!fast || !hap_ok) {
+                            PhmmPair p{};
+                            p.read = rid;
+                            p.hap = rec_of[j];
+                            p.out_idx = d.out_off + j;
+                            slow.push_back(p);
+                        }
+                    }
+            }
         }
         PT_ADD(9, ptr0, PT_NOW());
         [[maybe_unused]] const auto ptd0 = PT_NOW();
